@@ -1,0 +1,985 @@
+// ff_engine.cu — host side of libfacfake.so: weight folding/layout, workspace, TMA descriptors, the launch
+// schedule of the CViT forward and the C-ABI declared in include/facfake.h.
+//
+// Reference path being replaced (all under /root/reference/CViT-main/):
+//   model/cvit.py:80-179 (CViT), cvit_prediction.py:209-242 (model half of predict()), :258-281 (reduction).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/facfake.h"
+#include "ff_fp32.cuh"
+#include "ff_pre.cuh"
+#include "ff_small.cuh"
+#include "ff_tc.cuh"
+
+namespace {
+
+using namespace ff;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------ model plan
+struct ConvPlan { int cin, cout, hw; bool pool; int conv_idx; };
+const ConvPlan kConv[17] = {
+    {3, 32, 224, false, 0},    {32, 32, 224, false, 3},   {32, 32, 224, true, 6},
+    {32, 64, 112, false, 10},  {64, 64, 112, false, 13},  {64, 64, 112, true, 16},
+    {64, 128, 56, false, 20},  {128, 128, 56, false, 23}, {128, 128, 56, true, 26},
+    {128, 256, 28, false, 30}, {256, 256, 28, false, 33}, {256, 256, 28, false, 36}, {256, 256, 28, true, 39},
+    {256, 512, 14, false, 43}, {512, 512, 14, false, 46}, {512, 512, 14, false, 49}, {512, 512, 14, true, 52},
+};
+constexpr int DIM = 1024, DEPTH = 6, MLP = 2048, PATCH = 25088, SLOTS = 32;
+constexpr float BN_EPS = 1e-5f;
+
+std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+struct ConvLayerDev {
+  bf16* w = nullptr;        // [cout][3][3][cin] bf16
+  float* wf = nullptr;      // fp32 path: [cout][3][3][cin]
+  float* scale = nullptr;
+  float* shift = nullptr;
+  CUtensorMap tmA, tmB;
+  int rowb = 128, bn = 128;
+  int bw = 16, bh = 8, bi = 1;
+};
+struct LinearDev {
+  bf16* w = nullptr;        // [out][in] bf16
+  float* wf = nullptr;      // fp32 copy (fp32 path / head2)
+  float* b = nullptr;
+  int out_f = 0, in_f = 0;
+  CUtensorMap tmB;          // box {64, bn}
+  int bn = 128;
+};
+struct XfLayerDev {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  LinearDev qkv, out, ff1, ff2;
+};
+
+}  // namespace
+
+struct ff_cvit {
+  int device = 0;
+  int cap = 0;             // crops per pass (multiple of 32)
+  int rows_cap = 0;        // token rows capacity (multiple of 128)
+  int s12 = 16;            // crops per stage-1/2 sub-pass
+  int s12_cap = 32;
+  int compute = FF_COMPUTE_BF16;
+  int variant = 0;         // tile-shape variant (tuning)
+  bool finalized = false;
+  std::mutex mu;
+  mutable std::string err;
+  int64_t launches = 0;
+  cudaEvent_t done_ev = nullptr;
+
+  std::map<std::string, std::vector<float>> host_w;
+  std::map<std::string, std::vector<int64_t>> host_shape;
+
+  Conv1Params conv1;
+  ConvLayerDev conv[17];
+  LinearDev embed, head1, head2;
+  XfLayerDev xf[DEPTH];
+  float *pos = nullptr, *cls = nullptr;
+
+  // workspace
+  bf16 *bufA = nullptr, *bufB = nullptr;   // stage 1/2 ping-pong, s12_cap crops
+  bf16 *P = nullptr, *Q = nullptr;         // stage 3..5 ping-pong, cap crops
+  bf16* feat = nullptr;                    // [cap_rows128][25088]
+  float* emb = nullptr;                    // [cap][1024]
+  float* x = nullptr;                      // [rows_cap][1024] residual stream
+  bf16* xn = nullptr;                      // [rows_cap][1024]
+  float* qkv = nullptr;                    // [rows_cap][3072]
+  bf16* att = nullptr;                     // [rows_cap][1024]
+  bf16* ffh = nullptr;                     // [rows_cap][2048]
+  bf16* clsb = nullptr;                    // [cap128][1024]
+  float* hid = nullptr;                    // [cap128][2048]
+  CUtensorMap tm_feat, tm_xn, tm_att, tm_ffh, tm_cls;
+  // fp32-path workspace
+  float *fA = nullptr, *fB = nullptr;
+  // grow-only scratch for predict()
+  int32_t* slot_buf = nullptr; size_t slot_cap = 0;
+  uint8_t* xin_buf = nullptr; size_t xin_cap = 0;
+  float* logit_buf = nullptr; size_t logit_cap = 0;
+  int32_t* off_buf = nullptr; size_t off_cap = 0;
+  float* score_buf = nullptr; size_t score_cap = 0;
+  std::vector<void*> allocs;
+  // optional per-launch timing (bench.py roofline): event pairs tagged with a kernel class
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<int> ev_class;       // class of pair i (events 2i, 2i+1)
+  double prof_ms[4] = {0, 0, 0, 0};
+  int64_t prof_launches[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(const ff_cvit* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+enum { KC_CONV1 = 0, KC_TC_CONV = 1, KC_TC_GEMM = 2, KC_SMALL = 3 };
+
+void prof_mark(ff_cvit* h, cudaStream_t st, int cls, bool begin) {
+  if (!h->profiling) return;
+  if (h->ev_used >= h->ev_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    h->ev_pool.push_back(e);
+  }
+  cudaEventRecord(h->ev_pool[h->ev_used++], st);
+  if (begin) h->ev_class.push_back(cls);
+}
+struct ProfScope {
+  ff_cvit* h; cudaStream_t st; int cls;
+  ProfScope(ff_cvit* h_, cudaStream_t st_, int cls_) : h(h_), st(st_), cls(cls_) { prof_mark(h, st, cls, true); }
+  ~ProfScope() { prof_mark(h, st, cls, false); }
+};
+
+#define FF_CUDA(h, call)                                                                             \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail(h, FF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define FF_LAUNCH_CHECK(h, what)                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = cudaGetLastError();                                                             \
+    if (e_ != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e_)); \
+    ++(h)->launches;                                                                                 \
+  } while (0)
+
+template <typename T>
+int dev_alloc(ff_cvit* h, T** p, size_t count) {
+  void* q = nullptr;
+  FF_CUDA(h, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return FF_OK;
+}
+template <typename T>
+int dev_upload(ff_cvit* h, T** p, const std::vector<T>& v) {
+  int rc = dev_alloc(h, p, v.size());
+  if (rc) return rc;
+  FF_CUDA(h, cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return FF_OK;
+}
+template <typename T>
+int grow(ff_cvit* h, T** p, size_t* cap, size_t need) {
+  if (need <= *cap) return FF_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  void* q = nullptr;
+  FF_CUDA(h, cudaMalloc(&q, need * sizeof(T)));
+  *p = reinterpret_cast<T*>(q);
+  *cap = need;
+  return FF_OK;
+}
+
+std::vector<bf16> to_bf16(const std::vector<float>& v) {
+  std::vector<bf16> o(v.size());
+  for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16(v[i]);
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+int tmap_2d(ff_cvit* h, CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner,
+            uint32_t box_rows) {
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = box_inner * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(2d %llu x %llu) failed: %d",
+                                     (unsigned long long)inner, (unsigned long long)rows, (int)r);
+  return FF_OK;
+}
+int tmap_4d(ff_cvit* h, CUtensorMap* m, const void* base, int C, int W, int H, int N, int boxC, int bw, int bh, int bi) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bi};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle sw = boxC * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(4d C%d W%d H%d N%d) failed: %d", C, W, H, N, (int)r);
+  return FF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ tc launch dispatch
+template <int MODE, int ROWB, int BN, bool POOL, int STAGES>
+cudaError_t launch_tc_t(dim3 grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
+  using L = TcSmem<ROWB, BN, STAGES>;
+  auto k = tc_kernel<MODE, ROWB, BN, POOL, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  k<<<grid, 192, L::TOTAL, st>>>(a, b, args);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv(int rowb, int bn, bool pool, int variant, dim3 grid, cudaStream_t st, const CUtensorMap& a,
+                        const CUtensorMap& b, const TcArgs& args) {
+#define FF_CONV_CASE(R, N, S)                                                              \
+  if (rowb == R && bn == N)                                                                \
+    return pool ? launch_tc_t<MODE_CONV, R, N, true, S>(grid, st, a, b, args)              \
+                : launch_tc_t<MODE_CONV, R, N, false, S>(grid, st, a, b, args);
+  FF_CONV_CASE(64, 32, 4)
+  FF_CONV_CASE(64, 64, 4)
+  FF_CONV_CASE(128, 64, 4)
+  if (variant == 2) { FF_CONV_CASE(128, 256, 2) }
+  FF_CONV_CASE(128, 128, 3)
+  FF_CONV_CASE(128, 256, 4)
+#undef FF_CONV_CASE
+  return cudaErrorInvalidValue;
+}
+
+int conv_bn_for(int cout, int variant) {
+  const int bn_max = (variant == 1) ? 128 : 256;
+  return std::min(cout, bn_max);
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+const std::vector<float>* get_w(ff_cvit* h, const std::string& key, std::initializer_list<int64_t> shape) {
+  auto it = h->host_w.find(key);
+  if (it == h->host_w.end()) {
+    fail(h, FF_ERR_STATE, "missing weight '%s'", key.c_str());
+    return nullptr;
+  }
+  const auto& s = h->host_shape[key];
+  if (s.size() != shape.size() || !std::equal(s.begin(), s.end(), shape.begin())) {
+    fail(h, FF_ERR_SHAPE, "weight '%s' has the wrong shape", key.c_str());
+    return nullptr;
+  }
+  return &it->second;
+}
+
+int upload_linear(ff_cvit* h, LinearDev* L, const std::string& name, int out_f, int in_f, bool bias, int bn) {
+  const auto* w = get_w(h, name + ".weight", {out_f, in_f});
+  if (!w) return h->err.find("missing") != std::string::npos ? FF_ERR_STATE : FF_ERR_SHAPE;
+  L->out_f = out_f;
+  L->in_f = in_f;
+  L->bn = bn;
+  int rc;
+  if (out_f >= 32) {
+    if ((rc = dev_upload(h, &L->w, to_bf16(*w)))) return rc;
+    if ((rc = tmap_2d(h, &L->tmB, L->w, in_f, out_f, 64, bn))) return rc;
+  }
+  if (h->compute == FF_COMPUTE_FP32 || out_f < 32)
+    if ((rc = dev_upload(h, &L->wf, *w))) return rc;
+  if (bias) {
+    const auto* b = get_w(h, name + ".bias", {out_f});
+    if (!b) return FF_ERR_STATE;
+    if ((rc = dev_upload(h, &L->b, *b))) return rc;
+  }
+  return FF_OK;
+}
+
+int upload_vec(ff_cvit* h, float** p, const std::string& key, int64_t n) {
+  const auto* v = get_w(h, key, {n});
+  if (!v) return FF_ERR_STATE;
+  return dev_upload(h, p, *v);
+}
+
+void conv_tile_geometry(int hw, int* bw, int* bh, int* bi) {
+  if (hw >= 112) { *bw = 16; *bh = 8; *bi = 1; }
+  else if (hw == 56) { *bw = 8; *bh = 8; *bi = 2; }
+  else if (hw == 28) { *bw = 4; *bh = 4; *bi = 8; }
+  else { *bw = 2; *bh = 2; *bi = 32; }
+}
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// Which buffer conv layer li (1..16; layer 0 is conv1) reads, per the ping-pong schedule in forward_pass().
+const bf16* conv_input_buffer(const ff_cvit* h, int li) {
+  switch (li) {
+    case 1: return h->bufA; case 2: return h->bufB; case 3: return h->bufA; case 4: return h->bufB; case 5: return h->bufA;
+    case 6: return h->P; case 7: return h->Q; case 8: return h->P;
+    case 9: return h->Q; case 10: return h->P; case 11: return h->Q; case 12: return h->P;
+    case 13: return h->Q; case 14: return h->P; case 15: return h->Q; case 16: return h->P;
+  }
+  return nullptr;
+}
+bf16* conv_output_buffer(const ff_cvit* h, int li) {
+  switch (li) {
+    case 0: return h->bufA; case 1: return h->bufB; case 2: return h->bufA; case 3: return h->bufB; case 4: return h->bufA;
+    case 5: return h->P;
+    case 6: return h->Q; case 7: return h->P; case 8: return h->Q;
+    case 9: return h->P; case 10: return h->Q; case 11: return h->P; case 12: return h->Q;
+    case 13: return h->P; case 14: return h->Q; case 15: return h->P; case 16: return h->feat;
+  }
+  return nullptr;
+}
+
+int build_conv_maps(ff_cvit* h) {
+  for (int li = 1; li < 17; ++li) {
+    const ConvPlan& p = kConv[li];
+    ConvLayerDev& L = h->conv[li];
+    L.rowb = p.cin == 32 ? 64 : 128;
+    L.bn = conv_bn_for(p.cout, h->variant);
+    conv_tile_geometry(p.hw, &L.bw, &L.bh, &L.bi);
+    const int ncap = li <= 5 ? h->s12_cap : h->cap;
+    int rc = tmap_4d(h, &L.tmA, conv_input_buffer(h, li), p.cin, p.hw, p.hw, ncap, L.rowb / 2, L.bw, L.bh, L.bi);
+    if (rc) return rc;
+    rc = tmap_2d(h, &L.tmB, L.w, (uint64_t)9 * p.cin, p.cout, L.rowb / 2, L.bn);
+    if (rc) return rc;
+  }
+  return FF_OK;
+}
+
+int finalize(ff_cvit* h) {
+  int rc;
+  // ---- conv stack: fold bias + eval BN into (scale, shift); weights -> [cout][kh][kw][cin]
+  for (int li = 0; li < 17; ++li) {
+    const ConvPlan& p = kConv[li];
+    const std::string c = "features." + std::to_string(p.conv_idx), b = "features." + std::to_string(p.conv_idx + 1);
+    const auto* w = get_w(h, c + ".weight", {p.cout, p.cin, 3, 3});
+    const auto* bias = get_w(h, c + ".bias", {p.cout});
+    const auto* g = get_w(h, b + ".weight", {p.cout});
+    const auto* be = get_w(h, b + ".bias", {p.cout});
+    const auto* mu = get_w(h, b + ".running_mean", {p.cout});
+    const auto* var = get_w(h, b + ".running_var", {p.cout});
+    if (!w || !bias || !g || !be || !mu || !var) return h->err.find("shape") != std::string::npos ? FF_ERR_SHAPE : FF_ERR_STATE;
+    std::vector<float> scale(p.cout), shift(p.cout), wr((size_t)p.cout * 9 * p.cin);
+    for (int o = 0; o < p.cout; ++o) {
+      const float s = (*g)[o] / std::sqrt((*var)[o] + BN_EPS);
+      scale[o] = s;
+      shift[o] = ((*bias)[o] - (*mu)[o]) * s + (*be)[o];
+      for (int ci = 0; ci < p.cin; ++ci)
+        for (int t = 0; t < 9; ++t) wr[((size_t)o * 9 + t) * p.cin + ci] = (*w)[((size_t)o * p.cin + ci) * 9 + t];
+    }
+    ConvLayerDev& L = h->conv[li];
+    if ((rc = dev_upload(h, &L.scale, scale))) return rc;
+    if ((rc = dev_upload(h, &L.shift, shift))) return rc;
+    if (li == 0) {
+      for (int o = 0; o < 32; ++o) {
+        for (int k = 0; k < 27; ++k) h->conv1.w[o][k] = wr[(size_t)o * 27 + k];
+        h->conv1.scale[o] = scale[o];
+        h->conv1.shift[o] = shift[o];
+      }
+    }
+    if (h->compute == FF_COMPUTE_FP32) {
+      if ((rc = dev_upload(h, &L.wf, wr))) return rc;
+    } else if (li > 0) {
+      if ((rc = dev_upload(h, &L.w, to_bf16(wr)))) return rc;
+    }
+  }
+  // ---- embedding / tokens
+  if ((rc = upload_linear(h, &h->embed, "patch_to_embedding", DIM, PATCH, true, 128))) return rc;
+  {
+    const auto* pos = get_w(h, "pos_embedding", {SLOTS, 1, DIM});
+    const auto* cls = get_w(h, "cls_token", {1, 1, DIM});
+    if (!pos || !cls) return FF_ERR_STATE;
+    if ((rc = dev_upload(h, &h->pos, *pos))) return rc;
+    if ((rc = dev_upload(h, &h->cls, *cls))) return rc;
+  }
+  // ---- transformer
+  for (int l = 0; l < DEPTH; ++l) {
+    const std::string p = "transformer.layers." + std::to_string(l);
+    XfLayerDev& X = h->xf[l];
+    if ((rc = upload_vec(h, &X.ln1_g, p + ".0.fn.norm.weight", DIM))) return rc;
+    if ((rc = upload_vec(h, &X.ln1_b, p + ".0.fn.norm.bias", DIM))) return rc;
+    if ((rc = upload_vec(h, &X.ln2_g, p + ".1.fn.norm.weight", DIM))) return rc;
+    if ((rc = upload_vec(h, &X.ln2_b, p + ".1.fn.norm.bias", DIM))) return rc;
+    if ((rc = upload_linear(h, &X.qkv, p + ".0.fn.fn.to_qkv", 3 * DIM, DIM, false, 128))) return rc;
+    if ((rc = upload_linear(h, &X.out, p + ".0.fn.fn.to_out", DIM, DIM, true, 64))) return rc;
+    if ((rc = upload_linear(h, &X.ff1, p + ".1.fn.fn.net.0", MLP, DIM, true, 128))) return rc;
+    if ((rc = upload_linear(h, &X.ff2, p + ".1.fn.fn.net.2", DIM, MLP, true, 64))) return rc;
+  }
+  if ((rc = upload_linear(h, &h->head1, "mlp_head.0", MLP, DIM, true, 64))) return rc;
+  if ((rc = upload_linear(h, &h->head2, "mlp_head.2", 2, MLP, true, 64))) return rc;
+
+  if (h->compute == FF_COMPUTE_BF16) {
+    if ((rc = build_conv_maps(h))) return rc;
+    const int cap128 = (h->cap + 127) / 128 * 128;
+    if ((rc = tmap_2d(h, &h->tm_feat, h->feat, PATCH, cap128, 64, 128))) return rc;
+    if ((rc = tmap_2d(h, &h->tm_xn, h->xn, DIM, h->rows_cap, 64, 128))) return rc;
+    if ((rc = tmap_2d(h, &h->tm_att, h->att, DIM, h->rows_cap, 64, 128))) return rc;
+    if ((rc = tmap_2d(h, &h->tm_ffh, h->ffh, MLP, h->rows_cap, 64, 128))) return rc;
+    if ((rc = tmap_2d(h, &h->tm_cls, h->clsb, DIM, cap128, 64, 128))) return rc;
+  }
+  h->host_w.clear();
+  h->host_shape.clear();
+  h->finalized = true;
+  return FF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+int launch_gemm(ff_cvit* h, cudaStream_t st, const CUtensorMap& tmA, const LinearDev& L, int M, void* out, int ldo, int epi,
+                int act, int splits, const char* what) {
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M;
+  a.N = L.out_f;
+  a.ldo = ldo;
+  a.kb_total = L.in_f / 64;
+  a.kb_per_split = (a.kb_total + splits - 1) / splits;
+  a.shift = (epi == EPI_ATOMIC_F32) ? nullptr : L.b;
+  a.out = out;
+  a.epi = epi;
+  a.act = act;
+  const int zs = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
+  dim3 grid((M + 127) / 128, L.out_f / L.bn, zs);
+  ProfScope ps(h, st, KC_TC_GEMM);
+  cudaError_t e = L.bn == 128 ? launch_tc_t<MODE_GEMM, 128, 128, false, 4>(grid, st, tmA, L.tmB, a)
+                              : launch_tc_t<MODE_GEMM, 128, 64, false, 6>(grid, st, tmA, L.tmB, a);
+  if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of gemm %s failed: %s", what, cudaGetErrorString(e));
+  ++h->launches;
+  return FF_OK;
+}
+
+struct DebugTap {
+  int stop_after = 0;       // 0 = run everything
+  const void* ptr = nullptr;
+  int64_t elems = 0;
+  bool is_bf16 = false;
+  bool hit = false;
+};
+
+int forward_fp32(ff_cvit* h, const void* x, int layout, const int32_t* slot, int slot_base, int n, float* logits,
+                 cudaStream_t st, DebugTap* tap);
+
+// One pass over n <= cap crops.  x points at the first crop of the pass.
+int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int slot_base, int n, float* logits,
+                 cudaStream_t st, DebugTap* tap) {
+  if (h->compute == FF_COMPUTE_FP32) return forward_fp32(h, x, layout, slot, slot_base, n, logits, st, tap);
+  const int stop = tap ? tap->stop_after : 0;
+  auto tap_hit = [&](int step, const void* p, int64_t elems, bool is_b) {
+    if (stop == step) { tap->ptr = p; tap->elems = elems; tap->is_bf16 = is_b; tap->hit = true; return true; }
+    return false;
+  };
+  const size_t crop_in_bytes = layout == FF_X_NHWC_U8 ? (size_t)224 * 224 * 3 : (size_t)224 * 224 * 3 * 4;
+
+  auto run_conv = [&](int li, int n_img, int img_off_out) -> int {
+    const ConvPlan& p = kConv[li];
+    const ConvLayerDev& L = h->conv[li];
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.H = p.hw; a.W = p.hw;
+    a.tiles_w = p.hw / L.bw; a.tiles_h = p.hw / L.bh;
+    a.lg_bw = ilog2(L.bw); a.lg_bh = ilog2(L.bh);
+    a.n_img = n_img;
+    a.img_off_out = img_off_out;
+    a.cout = p.cout;
+    a.cin = p.cin;
+    a.kb_per_tap = p.cin / (L.rowb / 2);
+    a.kb_total = 9 * a.kb_per_tap;
+    a.kb_per_split = a.kb_total;
+    a.scale = L.scale; a.shift = L.shift;
+    a.out = conv_output_buffer(h, li);
+    dim3 grid(a.tiles_w * a.tiles_h * ((n_img + L.bi - 1) / L.bi), p.cout / L.bn, 1);
+    ProfScope ps(h, st, KC_TC_CONV);
+    cudaError_t e = launch_conv(L.rowb, L.bn, p.pool, h->variant, grid, st, L.tmA, L.tmB, a);
+    if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
+    ++h->launches;
+    return FF_OK;
+  };
+
+  // ---- stages 1-2 in sub-passes of s12 crops (activations of 3.2 MB/crop stay L2-resident between layers)
+  const int sub = stop ? std::min(n, h->s12_cap) : h->s12;
+  if (stop && n > h->s12_cap) return fail(h, FF_ERR_BAD_ARG, "debug tap needs n <= %d", h->s12_cap);
+  for (int s0 = 0; s0 < n; s0 += sub) {
+    const int ns = std::min(sub, n - s0);
+    const uint8_t* xin = reinterpret_cast<const uint8_t*>(x) + (size_t)s0 * crop_in_bytes;
+    dim3 g1(14, 14, ns);
+    {
+      ProfScope ps(h, st, KC_CONV1);
+      if (layout == FF_X_NHWC_U8) conv1_kernel<2><<<g1, 256, 0, st>>>(xin, h->bufA, ns, h->conv1);
+      else conv1_kernel<0><<<g1, 256, 0, st>>>(xin, h->bufA, ns, h->conv1);
+    }
+    FF_LAUNCH_CHECK(h, "conv1");
+    if (tap_hit(1, h->bufA, (int64_t)ns * 224 * 224 * 32, true)) return FF_OK;
+    for (int li = 1; li <= 5; ++li) {
+      int rc = run_conv(li, ns, li == 5 ? s0 : 0);
+      if (rc) return rc;
+      const ConvPlan& p = kConv[li];
+      const int ohw = p.pool ? p.hw / 2 : p.hw;
+      if (tap_hit(li + 1, conv_output_buffer(h, li), (int64_t)ns * ohw * ohw * p.cout, true)) return FF_OK;
+    }
+  }
+  // ---- stages 3-5 on the whole pass
+  for (int li = 6; li < 17; ++li) {
+    int rc = run_conv(li, n, 0);
+    if (rc) return rc;
+    const ConvPlan& p = kConv[li];
+    const int ohw = p.pool ? p.hw / 2 : p.hw;
+    if (tap_hit(li + 1, conv_output_buffer(h, li), (int64_t)n * ohw * ohw * p.cout, true)) return FF_OK;
+  }
+  // ---- patch embedding (split-K, fp32 atomics) + token assembly
+  FF_CUDA(h, cudaMemsetAsync(h->emb, 0, (size_t)n * DIM * sizeof(float), st));
+  int rc = launch_gemm(h, st, h->tm_feat, h->embed, n, h->emb, DIM, EPI_ATOMIC_F32, ACT_NONE, 8, "patch_to_embedding");
+  if (rc) return rc;
+  { ProfScope ps(h, st, KC_SMALL); tokens_kernel<<<n, 256, 0, st>>>(h->emb, h->embed.b, h->cls, h->pos, slot, slot_base, h->x, n); }
+  FF_LAUNCH_CHECK(h, "tokens");
+  const int rows = 2 * n;
+  if (tap_hit(18, h->x, (int64_t)rows * DIM, false)) return FF_OK;
+  // ---- transformer
+  for (int l = 0; l < DEPTH; ++l) {
+    const XfLayerDev& X = h->xf[l];
+    { ProfScope ps(h, st, KC_SMALL); layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(h->x, X.ln1_g, X.ln1_b, h->xn, rows); }
+    FF_LAUNCH_CHECK(h, "layernorm1");
+    if ((rc = launch_gemm(h, st, h->tm_xn, X.qkv, rows, h->qkv, 3 * DIM, EPI_STORE_F32, ACT_NONE, 1, "to_qkv"))) return rc;
+    { ProfScope ps(h, st, KC_SMALL); attention2_kernel<<<(n * 8 + 7) / 8, 256, 0, st>>>(h->qkv, h->att, n); }
+    FF_LAUNCH_CHECK(h, "attention2");
+    if ((rc = launch_gemm(h, st, h->tm_att, X.out, rows, h->x, DIM, EPI_RESID_F32, ACT_NONE, 1, "to_out"))) return rc;
+    { ProfScope ps(h, st, KC_SMALL); layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(h->x, X.ln2_g, X.ln2_b, h->xn, rows); }
+    FF_LAUNCH_CHECK(h, "layernorm2");
+    if ((rc = launch_gemm(h, st, h->tm_xn, X.ff1, rows, h->ffh, MLP, EPI_STORE_BF16, ACT_GELU, 1, "ff1"))) return rc;
+    if ((rc = launch_gemm(h, st, h->tm_ffh, X.ff2, rows, h->x, DIM, EPI_RESID_F32, ACT_NONE, 1, "ff2"))) return rc;
+    if (tap_hit(19 + l, h->x, (int64_t)rows * DIM, false)) return FF_OK;
+  }
+  // ---- head
+  { ProfScope ps(h, st, KC_SMALL); cls_gather_kernel<<<n, 256, 0, st>>>(h->x, h->clsb, n); }
+  FF_LAUNCH_CHECK(h, "cls_gather");
+  if ((rc = launch_gemm(h, st, h->tm_cls, h->head1, n, h->hid, MLP, EPI_STORE_F32, ACT_RELU, 1, "mlp_head.0"))) return rc;
+  { ProfScope ps(h, st, KC_SMALL); head2_kernel<<<(n + 7) / 8, 256, 0, st>>>(h->hid, h->head2.wf, h->head2.b, logits, n); }
+  FF_LAUNCH_CHECK(h, "head2");
+  if (tap_hit(25, logits, (int64_t)n * 2, false)) return FF_OK;
+  return FF_OK;
+}
+
+// ---- fp32 CUDA-core path (parity to 1e-4; reuses LN/attention-like kernels in fp32)
+int forward_fp32(ff_cvit* h, const void* x, int layout, const int32_t* slot, int slot_base, int n, float* logits,
+                 cudaStream_t st, DebugTap* tap) {
+  const int stop = tap ? tap->stop_after : 0;
+  auto tap_hit = [&](int step, const void* p, int64_t elems) {
+    if (stop == step) { tap->ptr = p; tap->elems = elems; tap->is_bf16 = false; tap->hit = true; return true; }
+    return false;
+  };
+  // conv stack, NHWC fp32, ping-pong fA/fB; processed `chunk` crops at a time to bound the workspace
+  const int chunk = h->s12_cap;
+  const size_t crop_in_bytes = layout == FF_X_NHWC_U8 ? (size_t)224 * 224 * 3 : (size_t)224 * 224 * 3 * 4;
+  float* featf = h->fB + (size_t)chunk * 224 * 224 * 32;    // tail of fB is reserved for [cap][25088]
+  if (stop && n > chunk) return fail(h, FF_ERR_BAD_ARG, "debug tap needs n <= %d", chunk);
+  for (int s0 = 0; s0 < n; s0 += chunk) {
+    const int ns = std::min(chunk, n - s0);
+    const uint8_t* xin = reinterpret_cast<const uint8_t*>(x) + (size_t)s0 * crop_in_bytes;
+    float* cur = h->fA;
+    float* nxt = h->fB;
+    for (int li = 0; li < 17; ++li) {
+      const ConvPlan& p = kConv[li];
+      const ConvLayerDev& L = h->conv[li];
+      float* dst = (li == 16) ? featf + (size_t)s0 * PATCH : nxt;
+      const int ohw = p.pool ? p.hw / 2 : p.hw;
+      const size_t total = (size_t)ns * ohw * ohw * p.cout;
+      const int blocks = (int)std::min<size_t>((total + 255) / 256, 1u << 30);
+      if (li == 0)
+        conv3x3_fp32_kernel<<<blocks, 256, 0, st>>>(xin, layout == FF_X_NHWC_U8 ? 2 : 1, nullptr, L.wf, L.scale, L.shift, dst,
+                                                   ns, p.hw, p.cin, p.cout, p.pool ? 1 : 0);
+      else
+        conv3x3_fp32_kernel<<<blocks, 256, 0, st>>>(nullptr, 0, cur, L.wf, L.scale, L.shift, dst, ns, p.hw, p.cin, p.cout,
+                                                   p.pool ? 1 : 0);
+      FF_LAUNCH_CHECK(h, "conv3x3_fp32");
+      if (tap_hit(li + 1, dst, (int64_t)total)) return FF_OK;
+      std::swap(cur, nxt);
+    }
+  }
+  const int rows = 2 * n;
+  float* xn = reinterpret_cast<float*>(h->fA);                  // [rows][1024]
+  float* att = xn + (size_t)h->rows_cap * DIM;                  // [rows][1024]
+  float* ffh = att + (size_t)h->rows_cap * DIM;                 // [rows][2048]
+  auto lin = [&](const float* A, const LinearDev& L, int M, float* out, int act, int resid, const char* what) -> int {
+    dim3 grid((L.out_f + 63) / 64, (M + 63) / 64);
+    linear_fp32_kernel<<<grid, 256, 0, st>>>(A, L.wf, L.b, out, M, L.out_f, L.in_f, act, resid);
+    FF_LAUNCH_CHECK(h, what);
+    return FF_OK;
+  };
+  int rc;
+  if ((rc = lin(featf, h->embed, n, h->emb, 0, 0, "embed_fp32"))) return rc;
+  tokens_kernel<<<n, 256, 0, st>>>(h->emb, nullptr, h->cls, h->pos, slot, slot_base, h->x, n);
+  FF_LAUNCH_CHECK(h, "tokens");
+  if (tap_hit(18, h->x, (int64_t)rows * DIM)) return FF_OK;
+  for (int l = 0; l < DEPTH; ++l) {
+    const XfLayerDev& X = h->xf[l];
+    layernorm_f32_kernel<<<(rows + 7) / 8, 256, 0, st>>>(h->x, X.ln1_g, X.ln1_b, xn, rows);
+    FF_LAUNCH_CHECK(h, "layernorm_f32");
+    if ((rc = lin(xn, X.qkv, rows, h->qkv, 0, 0, "qkv_fp32"))) return rc;
+    attention2_f32_kernel<<<(n * 8 + 7) / 8, 256, 0, st>>>(h->qkv, att, n);
+    FF_LAUNCH_CHECK(h, "attention2_f32");
+    if ((rc = lin(att, X.out, rows, h->x, 0, 1, "out_fp32"))) return rc;
+    layernorm_f32_kernel<<<(rows + 7) / 8, 256, 0, st>>>(h->x, X.ln2_g, X.ln2_b, xn, rows);
+    FF_LAUNCH_CHECK(h, "layernorm_f32");
+    if ((rc = lin(xn, X.ff1, rows, ffh, 2, 0, "ff1_fp32"))) return rc;
+    if ((rc = lin(ffh, X.ff2, rows, h->x, 0, 1, "ff2_fp32"))) return rc;
+    if (tap_hit(19 + l, h->x, (int64_t)rows * DIM)) return FF_OK;
+  }
+  cls_gather_f32_kernel<<<n, 256, 0, st>>>(h->x, xn, n);
+  FF_LAUNCH_CHECK(h, "cls_gather_f32");
+  if ((rc = lin(xn, h->head1, n, h->hid, 1, 0, "head1_fp32"))) return rc;
+  head2_kernel<<<(n + 7) / 8, 256, 0, st>>>(h->hid, h->head2.wf, h->head2.b, logits, n);
+  FF_LAUNCH_CHECK(h, "head2");
+  if (tap_hit(25, logits, (int64_t)n * 2)) return FF_OK;
+  return FF_OK;
+}
+
+int forward_all(ff_cvit* h, const void* x, int layout, const int32_t* slot, int n, float* logits, cudaStream_t st,
+                DebugTap* tap) {
+  if (!h->finalized) return fail(h, FF_ERR_STATE, "weights not finalized");
+  if (n < 0 || (n > 0 && (!x || !logits))) return fail(h, FF_ERR_BAD_ARG, "bad forward arguments");
+  if (layout != FF_X_NCHW_F32 && layout != FF_X_NHWC_U8) return fail(h, FF_ERR_BAD_ARG, "unknown x_layout %d", layout);
+  int dev = -1;
+  FF_CUDA(h, cudaGetDevice(&dev));
+  if (dev != h->device) FF_CUDA(h, cudaSetDevice(h->device));
+  // the workspace is shared by all calls on this handle: order this call after the previous one (any stream)
+  FF_CUDA(h, cudaStreamWaitEvent(st, h->done_ev, 0));
+  const size_t crop_in_bytes = layout == FF_X_NHWC_U8 ? (size_t)224 * 224 * 3 : (size_t)224 * 224 * 3 * 4;
+  int rc = FF_OK;
+  for (int p0 = 0; p0 < n && rc == FF_OK; p0 += h->cap) {
+    const int np = std::min(h->cap, n - p0);
+    rc = forward_pass(h, reinterpret_cast<const uint8_t*>(x) + (size_t)p0 * crop_in_bytes, layout,
+                      slot ? slot + p0 : nullptr, p0, np, logits + (size_t)2 * p0, st, tap);
+    if (tap && tap->hit) break;
+  }
+  cudaEventRecord(h->done_ev, st);
+  if (dev != h->device && dev >= 0) cudaSetDevice(dev);
+  return rc;
+}
+
+__global__ void slots_from_offsets_kernel(const int* __restrict__ off, int n_videos, int* __restrict__ slot) {
+  const int v = blockIdx.x;
+  if (v >= n_videos) return;
+  const int a = off[v], e = off[v + 1];
+  for (int i = a + threadIdx.x; i < e; i += blockDim.x) slot[i] = (i - a) & 31;
+}
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+}  // namespace
+
+// ================================================================================================ C-ABI
+extern "C" {
+
+const char* ff_last_error(const ff_cvit_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype) {
+  if (!out || max_crops <= 0) return fail(nullptr, FF_ERR_BAD_ARG, "ff_cvit_create: bad arguments");
+  if (compute_dtype != FF_COMPUTE_BF16 && compute_dtype != FF_COMPUTE_FP32)
+    return fail(nullptr, FF_ERR_BAD_ARG, "ff_cvit_create: unknown compute_dtype %d", compute_dtype);
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return fail(nullptr, FF_ERR_CUDA, "no CUDA device (%s): libfacfake has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, FF_ERR_BAD_ARG, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, FF_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, FF_ERR_CUDA, "device %d is sm_%d%d; libfacfake is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, FF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn) return fail(nullptr, FF_ERR_CUDA, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  ff_cvit* h = new ff_cvit();
+  h->device = device;
+  h->compute = compute_dtype;
+  h->cap = (max_crops + 31) / 32 * 32;
+  h->rows_cap = (2 * h->cap + 127) / 128 * 128;
+  h->s12_cap = 32;
+  h->s12 = std::min(16, h->cap);
+  if (const char* v = getenv("FF_TC_VARIANT")) h->variant = atoi(v);
+  if (const char* v = getenv("FF_S12")) h->s12 = std::max(1, std::min(h->s12_cap, atoi(v)));
+  int rc = FF_OK;
+  const int cap128 = (h->cap + 127) / 128 * 128;
+  do {
+    if (cudaEventCreateWithFlags(&h->done_ev, cudaEventDisableTiming) != cudaSuccess) { rc = fail(h, FF_ERR_CUDA, "event create failed"); break; }
+    if ((rc = dev_alloc(h, &h->emb, (size_t)h->cap * DIM))) break;
+    if ((rc = dev_alloc(h, &h->x, (size_t)h->rows_cap * DIM))) break;
+    if ((rc = dev_alloc(h, &h->qkv, (size_t)h->rows_cap * 3 * DIM))) break;
+    if ((rc = dev_alloc(h, &h->hid, (size_t)cap128 * MLP))) break;
+    if (compute_dtype == FF_COMPUTE_BF16) {
+      if ((rc = dev_alloc(h, &h->bufA, (size_t)h->s12_cap * 224 * 224 * 32))) break;
+      if ((rc = dev_alloc(h, &h->bufB, (size_t)h->s12_cap * 224 * 224 * 32))) break;
+      if ((rc = dev_alloc(h, &h->P, (size_t)h->cap * 56 * 56 * 128))) break;
+      if ((rc = dev_alloc(h, &h->Q, (size_t)h->cap * 56 * 56 * 128))) break;
+      if ((rc = dev_alloc(h, &h->feat, (size_t)cap128 * PATCH))) break;
+      if ((rc = dev_alloc(h, &h->xn, (size_t)h->rows_cap * DIM))) break;
+      if ((rc = dev_alloc(h, &h->att, (size_t)h->rows_cap * DIM))) break;
+      if ((rc = dev_alloc(h, &h->ffh, (size_t)h->rows_cap * MLP))) break;
+      if ((rc = dev_alloc(h, &h->clsb, (size_t)cap128 * DIM))) break;
+      // rows beyond the valid ones are read by TMA (results masked): keep them finite
+      cudaMemset(h->feat, 0, (size_t)cap128 * PATCH * 2);
+      cudaMemset(h->xn, 0, (size_t)h->rows_cap * DIM * 2);
+      cudaMemset(h->att, 0, (size_t)h->rows_cap * DIM * 2);
+      cudaMemset(h->ffh, 0, (size_t)h->rows_cap * MLP * 2);
+      cudaMemset(h->clsb, 0, (size_t)cap128 * DIM * 2);
+    } else {
+      const size_t act = (size_t)h->s12_cap * 224 * 224 * 32;
+      const size_t tail = std::max((size_t)h->rows_cap * DIM * 4, (size_t)1);
+      if ((rc = dev_alloc(h, &h->fA, std::max(act, tail)))) break;
+      if ((rc = dev_alloc(h, &h->fB, act + (size_t)h->cap * PATCH))) break;
+    }
+  } while (0);
+  if (rc != FF_OK) {
+    g_create_error = h->err;
+    ff_cvit_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return FF_OK;
+}
+
+void ff_cvit_destroy(ff_cvit_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->slot_buf) cudaFree(h->slot_buf);
+  if (h->xin_buf) cudaFree(h->xin_buf);
+  if (h->logit_buf) cudaFree(h->logit_buf);
+  if (h->off_buf) cudaFree(h->off_buf);
+  if (h->score_buf) cudaFree(h->score_buf);
+  if (h->done_ev) cudaEventDestroy(h->done_ev);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  delete h;
+}
+
+int ff_cvit_load_weight(ff_cvit_t* h, const char* key, const float* host_fp32, const int64_t* shape, int ndim) {
+  if (!h) return FF_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!key || (!host_fp32 && ndim > 0) || ndim < 0 || ndim > 4) return fail(h, FF_ERR_BAD_ARG, "ff_cvit_load_weight: bad arguments");
+  if (h->finalized) return fail(h, FF_ERR_STATE, "weights already finalized");
+  const std::string k(key);
+  if (k.size() > 19 && k.compare(k.size() - 19, 19, "num_batches_tracked") == 0) return FF_OK;
+  int64_t cnt = 1;
+  std::vector<int64_t> shp;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] <= 0) return fail(h, FF_ERR_SHAPE, "weight '%s': non-positive dimension", key);
+    cnt *= shape[i];
+    shp.push_back(shape[i]);
+  }
+  if (cnt > (int64_t)1024 * 25088) return fail(h, FF_ERR_SHAPE, "weight '%s' too large for CViT", key);
+  h->host_w[k].assign(host_fp32, host_fp32 + cnt);
+  h->host_shape[k] = shp;
+  return FF_OK;
+}
+
+int ff_cvit_finalize_weights(ff_cvit_t* h) {
+  if (!h) return FF_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->finalized) return fail(h, FF_ERR_STATE, "weights already finalized");
+  cudaSetDevice(h->device);
+  return finalize(h);
+}
+
+int ff_cvit_forward(ff_cvit_t* h, const void* x, int x_layout, const int32_t* slot, int n, float* logits, void* stream) {
+  if (!h) return FF_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  return forward_all(h, x, x_layout, slot, n, logits, reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+int ff_video_scores(ff_cvit_t* h, const float* logits, const int32_t* video_offsets, int n_videos, int mode, float* scores,
+                    void* stream) {
+  if (!h) return FF_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (n_videos < 0 || (n_videos > 0 && (!video_offsets || !scores))) return fail(h, FF_ERR_BAD_ARG, "ff_video_scores: bad arguments");
+  if (mode != FF_REDUCE_REFERENCE && mode != FF_REDUCE_SOFTMAX_MEAN) return fail(h, FF_ERR_BAD_ARG, "unknown reduction mode %d", mode);
+  if (n_videos == 0) return FF_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  video_reduce_kernel<<<(n_videos + 7) / 8, 256, 0, st>>>(logits, video_offsets, n_videos, mode, scores);
+  FF_LAUNCH_CHECK(h, "video_reduce");
+  return FF_OK;
+}
+
+int ff_cvit_predict(ff_cvit_t* h, const void* x, int x_layout, const int32_t* off_host, const int32_t* off_dev, int n_videos,
+                    int mode, float* logits_out, float* scores, void* stream) {
+  if (!h) return FF_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (n_videos < 0 || (n_videos > 0 && (!off_host || !off_dev || !scores))) return fail(h, FF_ERR_BAD_ARG, "ff_cvit_predict: bad arguments");
+  if (mode != FF_REDUCE_REFERENCE && mode != FF_REDUCE_SOFTMAX_MEAN) return fail(h, FF_ERR_BAD_ARG, "unknown reduction mode %d", mode);
+  if (n_videos == 0) return FF_OK;
+  for (int v = 0; v < n_videos; ++v)
+    if (off_host[v + 1] < off_host[v]) return fail(h, FF_ERR_BAD_ARG, "video_offsets must be non-decreasing");
+  if (off_host[0] != 0) return fail(h, FF_ERR_BAD_ARG, "video_offsets[0] must be 0");
+  const int n = off_host[n_videos];
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaSetDevice(h->device);
+  int rc;
+  if ((rc = grow(h, &h->slot_buf, &h->slot_cap, (size_t)std::max(n, 1)))) return rc;
+  float* lg = logits_out;
+  if (!lg) {
+    if ((rc = grow(h, &h->logit_buf, &h->logit_cap, (size_t)std::max(n, 1) * 2))) return rc;
+    lg = h->logit_buf;
+  }
+  if (n > 0) {
+    slots_from_offsets_kernel<<<n_videos, 64, 0, st>>>(off_dev, n_videos, h->slot_buf);
+    FF_LAUNCH_CHECK(h, "slots_from_offsets");
+    if ((rc = forward_all(h, x, x_layout, h->slot_buf, n, lg, st, nullptr))) return rc;
+  }
+  video_reduce_kernel<<<(n_videos + 7) / 8, 256, 0, st>>>(lg, off_dev, n_videos, mode, scores);
+  FF_LAUNCH_CHECK(h, "video_reduce");
+  return FF_OK;
+}
+
+int ff_cvit_predict_host(ff_cvit_t* h, const uint8_t* x_host, const int32_t* off_host, int n_videos, int mode, float* scores_host,
+                         void* stream) {
+  if (!h) return FF_ERR_BAD_ARG;
+  if (n_videos < 0 || (n_videos > 0 && (!off_host || !scores_host))) return fail(h, FF_ERR_BAD_ARG, "ff_cvit_predict_host: bad arguments");
+  if (n_videos == 0) return FF_OK;
+  const int n = off_host[n_videos];
+  if (n < 0 || (n > 0 && !x_host)) return fail(h, FF_ERR_BAD_ARG, "ff_cvit_predict_host: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);
+    if ((rc = grow(h, &h->xin_buf, &h->xin_cap, (size_t)std::max(n, 1) * 224 * 224 * 3))) return rc;
+    if ((rc = grow(h, &h->off_buf, &h->off_cap, (size_t)n_videos + 1))) return rc;
+    if ((rc = grow(h, &h->score_buf, &h->score_cap, (size_t)n_videos))) return rc;
+    FF_CUDA(h, cudaStreamWaitEvent(st, h->done_ev, 0));
+    if (n > 0) FF_CUDA(h, cudaMemcpyAsync(h->xin_buf, x_host, (size_t)n * 224 * 224 * 3, cudaMemcpyHostToDevice, st));
+    FF_CUDA(h, cudaMemcpyAsync(h->off_buf, off_host, ((size_t)n_videos + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  if ((rc = ff_cvit_predict(h, h->xin_buf, FF_X_NHWC_U8, off_host, h->off_buf, n_videos, mode, nullptr, h->score_buf, stream))) return rc;
+  FF_CUDA(h, cudaMemcpyAsync(scores_host, h->score_buf, (size_t)n_videos * sizeof(float), cudaMemcpyDeviceToHost, st));
+  FF_CUDA(h, cudaStreamSynchronize(st));
+  return FF_OK;
+}
+
+int ff_preprocess_crops(ff_cvit_t* h, const uint8_t* const* crop_ptrs, const int32_t* hw, const int32_t* pitch, int n, int swap_rb,
+                        uint8_t* out_u8, float* out_norm_nchw, void* stream) {
+  if (!h) return FF_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (n < 0 || (n > 0 && (!crop_ptrs || !hw || !pitch || (!out_u8 && !out_norm_nchw)))) return fail(h, FF_ERR_BAD_ARG, "ff_preprocess_crops: bad arguments");
+  if (n == 0) return FF_OK;
+  std::vector<CropDesc> d(n);
+  for (int i = 0; i < n; ++i) {
+    const int ch = hw[2 * i], cw = hw[2 * i + 1];
+    if (!crop_ptrs[i] || ch <= 0 || cw <= 0 || pitch[i] < cw * 3) return fail(h, FF_ERR_SHAPE, "crop %d: bad pointer/size/pitch", i);
+    d[i].ptr = crop_ptrs[i]; d[i].h = ch; d[i].w = cw; d[i].pitch = pitch[i];
+    const double sx = (double)cw / 224.0, sy = (double)ch / 224.0;
+    if (sx >= 1.0 && sy >= 1.0) {
+      const int isx = (int)std::lrint(sx), isy = (int)std::lrint(sy);
+      const bool fast = std::fabs(sx - isx) < 2.220446049250313e-16 && std::fabs(sy - isy) < 2.220446049250313e-16;
+      d[i].mode = fast ? PRE_FAST : PRE_FRAC; d[i].isx = isx; d[i].isy = isy;
+    } else {
+      d[i].mode = PRE_LINEAR; d[i].isx = d[i].isy = 1;
+    }
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaSetDevice(h->device);
+  CropDesc* dd = nullptr;
+  FF_CUDA(h, cudaMalloc(&dd, sizeof(CropDesc) * n));
+  cudaError_t e = cudaMemcpyAsync(dd, d.data(), sizeof(CropDesc) * n, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    preprocess_kernel<<<dim3((224 * 224 + 255) / 256, n), 256, 0, st>>>(dd, n, swap_rb, out_u8, out_norm_nchw);
+    e = cudaGetLastError();
+    ++h->launches;
+  }
+  cudaError_t e2 = cudaStreamSynchronize(st);   // descriptors are stack-lifetime host memory
+  cudaFree(dd);
+  if (e != cudaSuccess || e2 != cudaSuccess) return fail(h, FF_ERR_CUDA, "preprocess failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+  return FF_OK;
+}
+
+int64_t ff_cvit_launch_count(const ff_cvit_t* h) { return h ? h->launches : 0; }
+
+int64_t ff_cvit_debug_activation(ff_cvit_t* h, const void* x, int x_layout, const int32_t* slot, int n, int stop_after,
+                                 float* out_host, int64_t out_elems, void* stream) {
+  if (!h) return FF_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (stop_after < 1 || stop_after > 25 || !out_host || n <= 0 || n > h->cap) return fail(h, FF_ERR_BAD_ARG, "ff_cvit_debug_activation: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DebugTap tap;
+  tap.stop_after = stop_after;
+  float* lg = nullptr;
+  if (cudaMalloc(&lg, (size_t)n * 2 * sizeof(float)) != cudaSuccess) return fail(h, FF_ERR_CUDA, "debug alloc failed");
+  int rc = forward_all(h, x, x_layout, slot, n, lg, st, &tap);
+  int64_t ret = rc;
+  if (rc == FF_OK) {
+    if (!tap.hit) ret = fail(h, FF_ERR_STATE, "debug tap %d not reached", stop_after);
+    else if (tap.elems > out_elems) ret = fail(h, FF_ERR_BAD_ARG, "debug buffer too small: need %lld floats", (long long)tap.elems);
+    else {
+      cudaError_t e;
+      if (tap.is_bf16) {
+        float* tmp = nullptr;
+        e = cudaMalloc(&tmp, (size_t)tap.elems * sizeof(float));
+        if (e == cudaSuccess) {
+          bf16_to_f32_kernel<<<(unsigned)((tap.elems + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(tap.ptr), tmp, (size_t)tap.elems);
+          e = cudaMemcpyAsync(out_host, tmp, (size_t)tap.elems * sizeof(float), cudaMemcpyDeviceToHost, st);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+          cudaFree(tmp);
+        }
+      } else {
+        e = cudaMemcpyAsync(out_host, tap.ptr, (size_t)tap.elems * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      }
+      ret = (e == cudaSuccess) ? tap.elems : fail(h, FF_ERR_CUDA, "debug copy failed: %s", cudaGetErrorString(e));
+    }
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(lg);
+  return ret;
+}
+
+int ff_cvit_set_profiling(ff_cvit_t* h, int enable) {
+  if (!h) return FF_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->profiling = enable != 0;
+  h->ev_used = 0;
+  h->ev_class.clear();
+  for (int i = 0; i < 4; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
+  return FF_OK;
+}
+
+int ff_cvit_get_profile(ff_cvit_t* h, double* ms_by_class, int64_t* launches_by_class) {
+  if (!h || !ms_by_class || !launches_by_class) return FF_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  const size_t pairs = std::min(h->ev_class.size(), h->ev_used / 2);
+  if (pairs > 0) FF_CUDA(h, cudaEventSynchronize(h->ev_pool[2 * pairs - 1]));
+  for (size_t i = 0; i < pairs; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]) == cudaSuccess) {
+      h->prof_ms[h->ev_class[i]] += ms;
+      h->prof_launches[h->ev_class[i]] += 1;
+    }
+  }
+  h->ev_used = 0;
+  h->ev_class.clear();
+  for (int i = 0; i < 4; ++i) { ms_by_class[i] = h->prof_ms[i]; launches_by_class[i] = h->prof_launches[i]; }
+  return FF_OK;
+}
+
+int ff_cvit_set_tuning(ff_cvit_t* h, int stage12_sub_batch, int use_cuda_graph) {
+  if (!h) return FF_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  (void)use_cuda_graph;
+  if (stage12_sub_batch < 0 || stage12_sub_batch > h->s12_cap) return fail(h, FF_ERR_BAD_ARG, "stage12_sub_batch must be in [1,%d]", h->s12_cap);
+  if (stage12_sub_batch > 0) h->s12 = std::min(stage12_sub_batch, h->cap);
+  return FF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// ff_pre.cuh — K0: crop preprocessing.  cv2.resize(face,(224,224),INTER_AREA) + cv2.cvtColor(RGB2BGR)
+// (/root/reference/CViT-main/cvit_prediction.py:114-115, :96-97, :141-142) for a batch of variable-size uint8
+// HWC crops, optionally also emitting the normalised fp32 NCHW tensor of cvit_prediction.py:209-215.
+//
+// OpenCV's INTER_AREA has three regimes (modules/imgproc/src/resize.cpp); each is restated so that the uint8
+// result matches OpenCV's (see oracle/resize_oracle.py for the CPU restatement it is tested against):
+//   FAST   both scales integer >= 1 : block sum * (1/area) in fp32, round-half-even; 2x2 -> (s+2)>>2
+//   FRAC   both scales >= 1         : computeResizeAreaTab weights (fp64 -> fp32), fp32 accumulate in table order
+//   LINEAR any up-scaling           : bilinear in "area mode", 11-bit fixed-point taps, integer arithmetic
+#pragma once
+#include "ff_ptx.cuh"
+
+namespace ff {
+
+enum { PRE_FAST = 0, PRE_FRAC = 1, PRE_LINEAR = 2 };
+
+struct CropDesc {
+  const uint8_t* ptr;
+  int h, w, pitch;
+  int mode, isx, isy;
+};
+
+struct AreaSpan {
+  int n;        // number of table entries for this destination index
+  int sx1, sx2;
+  double fs1, fs2, cell;
+  bool head, tail;
+};
+
+__device__ __forceinline__ AreaSpan area_span(int d, double scale, int ssize) {
+  AreaSpan s;
+  s.fs1 = d * scale;
+  s.fs2 = s.fs1 + scale;
+  s.cell = fmin(scale, ssize - s.fs1);
+  int sx1 = static_cast<int>(ceil(s.fs1)), sx2 = static_cast<int>(floor(s.fs2));
+  sx2 = min(sx2, ssize - 1);
+  sx1 = min(sx1, sx2);
+  s.sx1 = sx1;
+  s.sx2 = sx2;
+  s.head = (sx1 - s.fs1) > 1e-3;
+  s.tail = (s.fs2 - sx2) > 1e-3;
+  s.n = (s.head ? 1 : 0) + (sx2 - sx1) + (s.tail ? 1 : 0);
+  return s;
+}
+// entry e of the span: source index and fp32 weight, in OpenCV's table order
+__device__ __forceinline__ void area_entry(const AreaSpan& s, int e, int* si, float* alpha) {
+  if (s.head && e == 0) {
+    *si = s.sx1 - 1;
+    *alpha = static_cast<float>((s.sx1 - s.fs1) / s.cell);
+    return;
+  }
+  const int m = e - (s.head ? 1 : 0);
+  if (m < s.sx2 - s.sx1) {
+    *si = s.sx1 + m;
+    *alpha = static_cast<float>(1.0 / s.cell);
+    return;
+  }
+  *si = s.sx2;
+  *alpha = static_cast<float>(fmin(fmin(s.fs2 - s.sx2, 1.0), s.cell) / s.cell);
+}
+
+__device__ __forceinline__ void linear_tap(int d, int ssize, int dsize, int* sx, int* a0, int* a1, bool* edge) {
+  const double scale = static_cast<double>(ssize) / dsize, inv = static_cast<double>(dsize) / ssize;
+  int s = static_cast<int>(floor(d * scale));
+  float fx = static_cast<float>((d + 1) - (s + 1) * inv);
+  fx = fx <= 0.0f ? 0.0f : fx - floorf(fx);
+  if (s < 0) { fx = 0.0f; s = 0; }
+  bool e = false;
+  if (s + 1 >= ssize) {
+    e = true;
+    if (s >= ssize - 1) { fx = 0.0f; s = ssize - 1; }
+  }
+  const float c0 = 1.0f - fx;
+  *a0 = max(-32768, min(32767, __float2int_rn(c0 * 2048.0f)));
+  *a1 = max(-32768, min(32767, __float2int_rn(fx * 2048.0f)));
+  *sx = s;
+  *edge = e;
+}
+
+__device__ __forceinline__ uint8_t sat_u8_rn(float v) { return static_cast<uint8_t>(max(0, min(255, __float2int_rn(v)))); }
+
+__global__ void __launch_bounds__(256)
+preprocess_kernel(const CropDesc* __restrict__ crops, int n, int swap_rb, uint8_t* __restrict__ out_u8,
+                  float* __restrict__ out_norm) {
+  constexpr int D = 224;
+  const int i = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n || pix >= D * D) return;
+  const int dy = pix / D, dx = pix % D;
+  const CropDesc c = crops[i];
+  int res[3];
+  if (c.mode == PRE_FAST) {
+    int sum[3] = {0, 0, 0};
+    for (int sy = 0; sy < c.isy; ++sy) {
+      const uint8_t* row = c.ptr + static_cast<size_t>(dy * c.isy + sy) * c.pitch + static_cast<size_t>(dx) * c.isx * 3;
+      for (int sx = 0; sx < c.isx; ++sx) {
+        sum[0] += row[sx * 3]; sum[1] += row[sx * 3 + 1]; sum[2] += row[sx * 3 + 2];
+      }
+    }
+    if (c.isx == 2 && c.isy == 2) {
+      for (int k = 0; k < 3; ++k) res[k] = (sum[k] + 2) >> 2;
+    } else {
+      const float scale = 1.0f / static_cast<float>(c.isx * c.isy);
+      for (int k = 0; k < 3; ++k) res[k] = sat_u8_rn(__fmul_rn(static_cast<float>(sum[k]), scale));
+    }
+  } else if (c.mode == PRE_FRAC) {
+    const AreaSpan xs = area_span(dx, static_cast<double>(c.w) / D, c.w);
+    const AreaSpan ys = area_span(dy, static_cast<double>(c.h) / D, c.h);
+    float sum[3] = {0.f, 0.f, 0.f};
+    for (int ey = 0; ey < ys.n; ++ey) {
+      int sy; float beta;
+      area_entry(ys, ey, &sy, &beta);
+      const uint8_t* row = c.ptr + static_cast<size_t>(sy) * c.pitch;
+      float buf[3] = {0.f, 0.f, 0.f};
+      for (int ex = 0; ex < xs.n; ++ex) {
+        int sx; float alpha;
+        area_entry(xs, ex, &sx, &alpha);
+        const uint8_t* p = row + static_cast<size_t>(sx) * 3;
+        for (int k = 0; k < 3; ++k) buf[k] = __fadd_rn(buf[k], __fmul_rn(static_cast<float>(p[k]), alpha));
+      }
+      for (int k = 0; k < 3; ++k)
+        sum[k] = (ey == 0) ? __fmul_rn(beta, buf[k]) : __fadd_rn(sum[k], __fmul_rn(beta, buf[k]));
+    }
+    for (int k = 0; k < 3; ++k) res[k] = sat_u8_rn(sum[k]);
+  } else {
+    int sx, a0, a1, sy, b0, b1;
+    bool ex, ey;
+    linear_tap(dx, c.w, D, &sx, &a0, &a1, &ex);
+    linear_tap(dy, c.h, D, &sy, &b0, &b1, &ey);
+    const int sx1 = min(sx + 1, c.w - 1), sy1 = min(sy + 1, c.h - 1);
+    const uint8_t* r0 = c.ptr + static_cast<size_t>(sy) * c.pitch;
+    const uint8_t* r1 = c.ptr + static_cast<size_t>(sy1) * c.pitch;
+    for (int k = 0; k < 3; ++k) {
+      int h0, h1;
+      if (ex) { h0 = r0[sx * 3 + k] * 2048; h1 = r1[sx * 3 + k] * 2048; }
+      else {
+        h0 = r0[sx * 3 + k] * a0 + r0[sx1 * 3 + k] * a1;
+        h1 = r1[sx * 3 + k] * a0 + r1[sx1 * 3 + k] * a1;
+      }
+      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      res[k] = max(0, min(255, v));
+    }
+  }
+  if (swap_rb) { const int t = res[0]; res[0] = res[2]; res[2] = t; }
+  if (out_u8) {
+    uint8_t* o = out_u8 + (static_cast<size_t>(i) * D * D + pix) * 3;
+    o[0] = static_cast<uint8_t>(res[0]); o[1] = static_cast<uint8_t>(res[1]); o[2] = static_cast<uint8_t>(res[2]);
+  }
+  if (out_norm) {
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+    for (int k = 0; k < 3; ++k)
+      out_norm[(static_cast<size_t>(i) * 3 + k) * D * D + pix] =
+          __fdiv_rn(__fdiv_rn(static_cast<float>(res[k]), 255.0f) - mean[k], sd[k]);
+  }
+}
+
+}  // namespace ff

@@ -1,0 +1,237 @@
+// ff_small.cuh — the non-tensor-core kernels of the CViT path (HBM- or latency-bound):
+//   conv1 (3->32, K=27) with the crop normalisation fused, LayerNorm, 2-token attention, token assembly,
+//   cls gather, the 2048->2 head GEMV and the per-video score reduction.
+// Reference lines are /root/reference/CViT-main/{model/cvit.py, cvit_prediction.py}.
+#pragma once
+#include "ff_ptx.cuh"
+
+namespace ff {
+
+// ------------------------------------------------------------------------------------------------
+// conv1: Conv2d(3,32,3,p=1)+BN+ReLU (cvit.py:88-90) on CUDA cores, fp32 FMA with the 864 weights in the
+// kernel-parameter constant bank (every thread of a warp uses the same weight at the same time).
+// IN_KIND 0: fp32 NCHW normalised input (what model(x) receives, cvit_prediction.py:229)
+// IN_KIND 2: uint8 NHWC crops; (x/255 - mean)/std of cvit_prediction.py:41-45,214-215 fused into the load.
+// Output: bf16 NHWC [n,224,224,32].
+struct Conv1Params {
+  float w[32][27];   // [cout][(kh*3+kw)*3 + cin]
+  float scale[32];
+  float shift[32];
+};
+
+template <int IN_KIND>
+__global__ void __launch_bounds__(256)
+conv1_kernel(const void* __restrict__ xin, __nv_bfloat16* __restrict__ out, int n_img,
+             const __grid_constant__ Conv1Params p) {
+  constexpr int HW = 224, T = 16, P = T + 2;
+  __shared__ float patch[P * P * 3];
+  const int n = blockIdx.z;
+  const int h0 = blockIdx.y * T, w0 = blockIdx.x * T;
+  for (int idx = threadIdx.x; idx < P * P * 3; idx += 256) {
+    int py, px, c;
+    if (IN_KIND == 2) { c = idx % 3; const int pi = idx / 3; px = pi % P; py = pi / P; }
+    else              { px = idx % P; const int t = idx / P; py = t % P; c = t / P; }
+    const int gy = h0 - 1 + py, gx = w0 - 1 + px;
+    float v = 0.0f;                                   // zero padding applies AFTER normalisation
+    if (gy >= 0 && gy < HW && gx >= 0 && gx < HW) {
+      if (IN_KIND == 2) {
+        const uint8_t* x = reinterpret_cast<const uint8_t*>(xin);
+        const float u = static_cast<float>(x[((static_cast<size_t>(n) * HW + gy) * HW + gx) * 3 + c]);
+        const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+        const float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+        v = __fdiv_rn(__fdiv_rn(u, 255.0f) - mean, sd);
+      } else {
+        const float* x = reinterpret_cast<const float*>(xin);
+        v = x[((static_cast<size_t>(n) * 3 + c) * HW + gy) * HW + gx];
+      }
+    }
+    patch[(py * P + px) * 3 + c] = v;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float in[27];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) in[(kh * 3 + kw) * 3 + c] = patch[((ty + kh) * P + (tx + kw)) * 3 + c];
+  float acc[32];
+#pragma unroll
+  for (int co = 0; co < 32; ++co) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) s = fmaf(in[k], p.w[co][k], s);
+    acc[co] = fmaxf(fmaf(s, p.scale[co], p.shift[co]), 0.0f);
+  }
+  if (n < n_img) {
+    uint4* o = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * HW + (h0 + ty)) * HW + (w0 + tx)) * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      o[i] = make_uint4(pack_bf16x2(acc[8 * i], acc[8 * i + 1]), pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]),
+                        pack_bf16x2(acc[8 * i + 4], acc[8 * i + 5]), pack_bf16x2(acc[8 * i + 6], acc[8 * i + 7]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// LayerNorm(1024), eps 1e-5, affine (cvit.py:16,20).  One warp per row; fp32 in, bf16 out (next GEMM's A operand).
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ y, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * 1024);
+  float4 v[8];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = xr[i * 32 + lane];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / 1024.0f);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / 1024.0f) + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * 1024);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 g = g4[i * 32 + lane], b = b4[i * 32 + lane];
+    const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+    const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+    const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
+    const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
+    yr[i * 32 + lane] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+  }
+}
+
+// 2-token attention (cvit.py:43-60): one warp per (crop, head).  qkv fp32 [2n][3072] with feature index
+// which*1024 + head*128 + d (cvit.py:46); scale = dim**-0.5 = 1/32 (cvit.py:38); out bf16 [2n][1024] '(h d)'.
+__global__ void __launch_bounds__(256)
+attention2_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_crops) {
+  const int wid = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= n_crops * 8) return;
+  const int b = wid >> 3, h = wid & 7;
+  const float* r0 = qkv + static_cast<size_t>(2 * b) * 3072 + h * 128 + lane * 4;
+  const float* r1 = r0 + 3072;
+  const float4 q0 = *reinterpret_cast<const float4*>(r0), q1 = *reinterpret_cast<const float4*>(r1);
+  const float4 k0 = *reinterpret_cast<const float4*>(r0 + 1024), k1 = *reinterpret_cast<const float4*>(r1 + 1024);
+  const float4 v0 = *reinterpret_cast<const float4*>(r0 + 2048), v1 = *reinterpret_cast<const float4*>(r1 + 2048);
+  auto dot = [](const float4& a, const float4& c) { return (a.x * c.x + a.y * c.y) + (a.z * c.z + a.w * c.w); };
+  const float s = 0.03125f;
+  const float d00 = warp_sum(dot(q0, k0)) * s, d01 = warp_sum(dot(q0, k1)) * s;
+  const float d10 = warp_sum(dot(q1, k0)) * s, d11 = warp_sum(dot(q1, k1)) * s;
+  const float m0 = fmaxf(d00, d01), m1 = fmaxf(d10, d11);
+  const float e00 = expf(d00 - m0), e01 = expf(d01 - m0), e10 = expf(d10 - m1), e11 = expf(d11 - m1);
+  const float i0 = 1.0f / (e00 + e01), i1 = 1.0f / (e10 + e11);
+  const float a00 = e00 * i0, a01 = e01 * i0, a10 = e10 * i1, a11 = e11 * i1;
+  __nv_bfloat16* o0 = out + static_cast<size_t>(2 * b) * 1024 + h * 128 + lane * 4;
+  *reinterpret_cast<uint2*>(o0) = make_uint2(pack_bf16x2(a00 * v0.x + a01 * v1.x, a00 * v0.y + a01 * v1.y),
+                                              pack_bf16x2(a00 * v0.z + a01 * v1.z, a00 * v0.w + a01 * v1.w));
+  *reinterpret_cast<uint2*>(o0 + 1024) = make_uint2(pack_bf16x2(a10 * v0.x + a11 * v1.x, a10 * v0.y + a11 * v1.y),
+                                                     pack_bf16x2(a10 * v0.z + a11 * v1.z, a10 * v0.w + a11 * v1.w));
+}
+
+// Token assembly (cvit.py:171-175): tok0 = cls + pos[slot], tok1 = (patch embedding + bias) + pos[slot].
+__global__ void __launch_bounds__(256)
+tokens_kernel(const float* __restrict__ emb, const float* __restrict__ bias, const float* __restrict__ cls,
+              const float* __restrict__ pos, const int* __restrict__ slot, int slot_base, float* __restrict__ x, int n) {
+  const int b = blockIdx.x;
+  if (b >= n) return;
+  const int s = slot ? slot[b] : ((slot_base + b) & 31);
+  const int i = threadIdx.x;   // 256 threads x float4 = 1024
+  const float4 p = reinterpret_cast<const float4*>(pos + static_cast<size_t>(s) * 1024)[i];
+  const float4 c = reinterpret_cast<const float4*>(cls)[i];
+  const float4 e = reinterpret_cast<const float4*>(emb + static_cast<size_t>(b) * 1024)[i];
+  const float4 bb = bias ? reinterpret_cast<const float4*>(bias)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4* x0 = reinterpret_cast<float4*>(x + static_cast<size_t>(2 * b) * 1024);
+  x0[i] = make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);
+  x0[256 + i] = make_float4((e.x + bb.x) + p.x, (e.y + bb.y) + p.y, (e.z + bb.z) + p.z, (e.w + bb.w) + p.w);
+}
+
+// cls select (cvit.py:177): bf16 copy of token 0 of every crop -> A operand of mlp_head.0.
+__global__ void __launch_bounds__(256)
+cls_gather_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int n) {
+  const int b = blockIdx.x;
+  if (b >= n) return;
+  const float4 v = reinterpret_cast<const float4*>(x + static_cast<size_t>(2 * b) * 1024)[threadIdx.x];
+  reinterpret_cast<uint2*>(out + static_cast<size_t>(b) * 1024)[threadIdx.x] =
+      make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+// mlp_head.2: Linear(2048 -> 2) (cvit.py:164) — one warp per crop, fp32.
+__global__ void __launch_bounds__(256)
+head2_kernel(const float* __restrict__ hid, const float* __restrict__ w, const float* __restrict__ bias,
+             float* __restrict__ logits, int n) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= n) return;
+  const float4* h4 = reinterpret_cast<const float4*>(hid + static_cast<size_t>(b) * 2048);
+  const float4* w0 = reinterpret_cast<const float4*>(w);
+  const float4* w1 = reinterpret_cast<const float4*>(w + 2048);
+  float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll 4
+  for (int i = lane; i < 512; i += 32) {
+    const float4 hv = h4[i], a = w0[i], c = w1[i];
+    s0 += (hv.x * a.x + hv.y * a.y) + (hv.z * a.z + hv.w * a.w);
+    s1 += (hv.x * c.x + hv.y * c.y) + (hv.z * c.z + hv.w * c.w);
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if (lane == 0) {
+    logits[2 * b] = s0 + bias[0];
+    logits[2 * b + 1] = s1 + bias[1];
+  }
+}
+
+// Per-video reduction (cvit_prediction.py:258-281): sigmoid per logit, mean over the video's frames,
+// f if f > r else |1 - r|; <= 2 frames (or none) -> 0.5.  One warp per video.
+// mode 1: mean of softmax(logits)[0] (extra).
+__global__ void __launch_bounds__(256)
+video_reduce_kernel(const float* __restrict__ logits, const int* __restrict__ off, int n_videos, int mode,
+                    float* __restrict__ scores) {
+  const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (v >= n_videos) return;
+  const int a = off[v], e = off[v + 1];
+  const int cnt = e - a;
+  float f = 0.0f, r = 0.0f;
+  for (int i = a + lane; i < e; i += 32) {
+    const float2 z = *reinterpret_cast<const float2*>(logits + 2 * static_cast<size_t>(i));
+    if (mode == 0) {
+      f += 1.0f / (1.0f + expf(-z.x));
+      r += 1.0f / (1.0f + expf(-z.y));
+    } else {
+      f += 1.0f / (1.0f + expf(z.y - z.x));
+    }
+  }
+  f = warp_sum(f);
+  r = warp_sum(r);
+  if (lane == 0) {
+    float s = 0.5f;
+    if (mode == 0) {
+      if (cnt > 2) {
+        const float fc = f / static_cast<float>(cnt), rc = r / static_cast<float>(cnt);
+        s = (fc > rc) ? fc : fabsf(1.0f - rc);
+      }
+    } else if (cnt > 0) {
+      s = f / static_cast<float>(cnt);
+    }
+    scores[v] = s;
+  }
+}
+
+}  // namespace ff

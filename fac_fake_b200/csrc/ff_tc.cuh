@@ -1,0 +1,322 @@
+// ff_tc.cuh — the tensor-core kernel of the engine: one warp-specialised tcgen05 mainloop used as
+//   * MODE_CONV: implicit-GEMM 3x3 / pad 1 / stride 1 convolution over NHWC bf16 activations
+//                (reference op: nn.Conv2d + BatchNorm2d(eval) + ReLU [+ MaxPool2d(2)],
+//                 /root/reference/CViT-main/model/cvit.py:88-147), and
+//   * MODE_GEMM: y = x W^T (+bias, activation, residual) for the patch embedding, the ViT
+//                encoder linears and the MLP head (cvit.py:26-28,40-41,155,161-165).
+//
+// Tile: 128 (M: output pixels / token rows) x BN (output channels) per CTA, fp32 accumulator in TMEM.
+// K loop: one k-block = 64 (SW128) or 32 (SW64) bf16 input channels of one filter tap.
+//
+//   warp 0   TMA producer   A tile: 4-D box {chan, BW, BH, BI} of the NHWC input at (c0, w0+kw-1, h0+kh-1, n0)
+//                           — out-of-bounds coordinates are zero-filled by TMA, which IS the conv padding;
+//                           B tile: 2-D box {chan, BN} of the [Cout][tap][Cin] weights.
+//   warp 1   TMEM alloc + single-thread tcgen05.mma issue (cta_group::1, kind::f16, M=128, N=BN, K=16),
+//            tcgen05.commit releases smem stages / signals the epilogue.
+//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns, fp32 scale/shift (+ReLU), bf16 pack, XOR-swizzled smem
+//            staging, optional 2x2 max-pool, coalesced 16-byte global stores.
+#pragma once
+#include "ff_ptx.cuh"
+
+namespace ff {
+
+enum { MODE_CONV = 0, MODE_GEMM = 1 };
+enum { EPI_STORE_F32 = 0, EPI_STORE_BF16 = 1, EPI_RESID_F32 = 2, EPI_ATOMIC_F32 = 3 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+struct TcArgs {
+  // ---- conv geometry
+  int H, W;               // conv input == output spatial size (before pooling)
+  int tiles_w, tiles_h;   // M-tiles per image along w / h
+  int lg_bw, lg_bh;       // log2 of the tile box (BW x BH pixels x BI images = 128 rows)
+  int n_img;              // valid images in this launch
+  int img_off_out;        // image offset added on output (placement inside a larger buffer)
+  int cout;               // total output channels (row pitch of the NHWC output)
+  int kb_per_tap;         // Cin / (channels per k-block)
+  int cin;                // input channels
+  // ---- gemm geometry
+  int M, N;               // valid rows / columns
+  int ldo;                // row pitch of the outputs (elements)
+  // ---- k range
+  int kb_total;           // number of k-blocks of the whole reduction
+  int kb_per_split;       // k-blocks handled by one blockIdx.z
+  // ---- epilogue
+  const float* scale;     // conv: per-channel scale (gamma / sqrt(var+eps))
+  const float* shift;     // conv: per-channel shift;  gemm: bias or nullptr
+  void* out;              // conv: bf16 NHWC;  gemm: see epi
+  int epi;                // gemm: EPI_*
+  int act;                // gemm: ACT_*
+};
+
+template <int ROWB, int BN, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = 128 * ROWB;
+  static constexpr int B_BYTES = BN * ROWB;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_BYTES = 128 * BN * 2;
+  static constexpr int MAIN_BYTES = PIPE_BYTES > STAGING_BYTES ? PIPE_BYTES : STAGING_BYTES;
+  static constexpr int SS_OFF = MAIN_BYTES;                 // scale/shift floats [2*BN]
+  static constexpr int BAR_OFF = SS_OFF + 2 * BN * 4;       // full[S], empty[S], tmem_full
+  static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 1) * 8;
+  static constexpr int TOTAL = SLOT_OFF + 16 + 1024;        // + manual 1024-B alignment slack
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int MODE, int ROWB, int BN, bool POOL, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  using L = TcSmem<ROWB, BN, STAGES>;
+  constexpr int BKE = ROWB / 2;        // bf16 elements per k-block row
+  constexpr int KSTEPS = ROWB / 32;    // UMMA K=16 steps per k-block
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int CPR = BN / 8;          // 16-byte chunks per staged row
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
+  static_assert(ROWB == 64 || ROWB == 128, "ROWB");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  float* ss = reinterpret_cast<float*>(base_ptr + L::SS_OFF);
+  const uint32_t bar_full = base + L::BAR_OFF;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_tmem = bar_empty + STAGES * 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  int w0 = 0, h0 = 0, n0 = 0, m0 = 0;
+  if (MODE == MODE_CONV) {
+    const int t = blockIdx.x;
+    const int tw = t % a.tiles_w;
+    const int th = (t / a.tiles_w) % a.tiles_h;
+    const int nb = t / (a.tiles_w * a.tiles_h);
+    w0 = tw << a.lg_bw;
+    h0 = th << a.lg_bh;
+    n0 = nb << (7 - a.lg_bw - a.lg_bh);
+  } else {
+    m0 = blockIdx.x * 128;
+  }
+  const int col0 = blockIdx.y * BN;   // first output channel / column of this CTA
+  const int kb_begin = blockIdx.z * a.kb_per_split;
+  const int kb_end = min(a.kb_total, kb_begin + a.kb_per_split);
+
+  // ---- one-time setup
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tmem, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  }
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    for (int i = t; i < BN; i += 128) {
+      const int c = col0 + i;
+      if (MODE == MODE_CONV) {
+        ss[i] = a.scale[c];
+        ss[BN + i] = a.shift[c];
+      } else {
+        ss[i] = 1.0f;
+        ss[BN + i] = (a.shift != nullptr && c < a.N) ? a.shift[c] : 0.0f;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int it = 0, s = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        if (it > 0) mbar_wait(bar_empty + 8 * s, (it - 1) & 1);
+        const uint32_t sa = base + s * L::STAGE_BYTES;
+        const uint32_t sb = sa + L::A_BYTES;
+        const uint32_t bar = bar_full + 8 * s;
+        mbar_arrive_expect_tx(bar, L::STAGE_BYTES);
+        if (MODE == MODE_CONV) {
+          const int tap = kb / a.kb_per_tap;
+          const int cc = kb - tap * a.kb_per_tap;
+          const int kh = tap / 3, kw = tap - kh * 3;
+          tma_load_4d(sa, &tmA, bar, cc * BKE, w0 + kw - 1, h0 + kh - 1, n0);
+        } else {
+          tma_load_2d(sa, &tmA, bar, kb * BKE, m0);
+        }
+        tma_load_2d(sb, &tmB, bar, kb * BKE, col0);
+        if (++s == STAGES) { s = 0; ++it; }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+      int it = 0, s = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(bar_full + 8 * s, it & 1);
+        tcgen05_fence_after();
+        const uint32_t sa = base + s * L::STAGE_BYTES;
+        const uint64_t adesc = make_kmajor_desc<ROWB>(sa);
+        const uint64_t bdesc = make_kmajor_desc<ROWB>(sa + L::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < KSTEPS; ++k) {
+          // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the 16-byte address field
+          umma_bf16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * s);   // frees this smem stage once the MMAs above have read it
+        if (++s == STAGES) { s = 0; ++it; }
+      }
+      umma_commit(bar_tmem);              // accumulator complete
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int g = warp & 3;               // TMEM lane group this warp may access
+    const int r = g * 32 + lane;          // accumulator row == TMEM lane
+    const int te = threadIdx.x - 64;      // 0..127
+    mbar_wait(bar_tmem, 0);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
+
+    if (MODE == MODE_CONV) {
+      uint8_t* stg = base_ptr;            // pipeline stages are idle now: reuse as staging [128][BN] bf16
+      const int swz = (CPR >= 8) ? (r & 7) : ((r >> 1) & (CPR - 1));
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t p[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c0 + j * 8 + e * 2;
+            float x0 = fmaf(__uint_as_float(v[j * 8 + e * 2]), ss[c], ss[BN + c]);
+            float x1 = fmaf(__uint_as_float(v[j * 8 + e * 2 + 1]), ss[c + 1], ss[BN + c + 1]);
+            p[e] = pack_bf16x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f));
+          }
+          const int q = (c0 >> 3) + j;
+          *reinterpret_cast<uint4*>(stg + r * (BN * 2) + ((q ^ swz) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+        }
+      }
+      named_bar_sync(1, 128);
+      const int BW = 1 << a.lg_bw, BH = 1 << a.lg_bh;
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
+      if (!POOL) {
+        for (int idx = te; idx < 128 * CPR; idx += 128) {
+          const int row = idx / CPR, q = idx % CPR;
+          const int rs = (CPR >= 8) ? (row & 7) : ((row >> 1) & (CPR - 1));
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + row * (BN * 2) + ((q ^ rs) << 4));
+          const int wl = row & (BW - 1);
+          const int hl = (row >> a.lg_bw) & (BH - 1);
+          const int nl = row >> (a.lg_bw + a.lg_bh);
+          const int n = n0 + nl;
+          if (n < a.n_img) {
+            const size_t pix = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * a.W + (w0 + wl);
+            *reinterpret_cast<uint4*>(out + pix * a.cout + col0 + q * 8) = val;
+          }
+        }
+      } else {
+        const int PW = BW >> 1, PH = BH >> 1;
+        const int Ho = a.H >> 1, Wo = a.W >> 1;
+        for (int idx = te; idx < 32 * CPR; idx += 128) {
+          const int p = idx / CPR, q = idx % CPR;
+          const int pw = p % PW;
+          const int ph = (p / PW) % PH;
+          const int pn = p / (PW * PH);
+          const int r00 = ((pn << a.lg_bh) + 2 * ph) * BW + 2 * pw;
+          uint4 m;
+          {
+            const int rows[4] = {r00, r00 + 1, r00 + BW, r00 + BW + 1};
+            uint4 x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = rows[i];
+              const int rs = (CPR >= 8) ? (row & 7) : ((row >> 1) & (CPR - 1));
+              x[i] = *reinterpret_cast<const uint4*>(stg + row * (BN * 2) + ((q ^ rs) << 4));
+            }
+            auto mx = [](uint32_t a0, uint32_t b0) {
+              __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a0), *reinterpret_cast<__nv_bfloat162*>(&b0));
+              return *reinterpret_cast<uint32_t*>(&r2);
+            };
+            m.x = mx(mx(x[0].x, x[1].x), mx(x[2].x, x[3].x));
+            m.y = mx(mx(x[0].y, x[1].y), mx(x[2].y, x[3].y));
+            m.z = mx(mx(x[0].z, x[1].z), mx(x[2].z, x[3].z));
+            m.w = mx(mx(x[0].w, x[1].w), mx(x[2].w, x[3].w));
+          }
+          const int n = n0 + pn;
+          if (n < a.n_img) {
+            const size_t pix = (static_cast<size_t>(a.img_off_out + n) * Ho + ((h0 >> 1) + ph)) * Wo + ((w0 >> 1) + pw);
+            *reinterpret_cast<uint4*>(out + pix * a.cout + col0 + q * 8) = m;
+          }
+        }
+      }
+    } else {
+      // ---- GEMM epilogue: direct stores, one accumulator row per thread
+      const int m = m0 + r;
+      const bool row_ok = m < a.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+        const int nb = col0 + c0;
+        if (row_ok && nb < a.N) {   // N is a multiple of 32 for every linear on the path
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(v[i]) + ss[BN + c0 + i];
+            if (a.act == ACT_RELU) x = fmaxf(x, 0.0f);
+            else if (a.act == ACT_GELU) x = gelu_erf(x);
+            f[i] = x;
+          }
+          const size_t off = static_cast<size_t>(m) * a.ldo + nb;
+          if (a.epi == EPI_STORE_F32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + off);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else if (a.epi == EPI_STORE_BF16) {
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + off);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
+                                pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+          } else if (a.epi == EPI_RESID_F32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + off);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 t = o[i];
+              t.x += f[4 * i]; t.y += f[4 * i + 1]; t.z += f[4 * i + 2]; t.w += f[4 * i + 3];
+              o[i] = t;
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(a.out) + off;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(o + i, f[i]);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace ff

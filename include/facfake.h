@@ -1,0 +1,137 @@
+/*
+ * facfake.h — C-ABI of libfacfake.so: the B200 (sm_100a) engine for FAC_fake's CViT hot path.
+ *
+ * The reference (xiaomo9/FAC_fake) has no FFI of its own; its seam for this path is Python
+ * (SURVEY.md §8b).  Each entry point below names the reference interface it replaces
+ * (paths relative to /root/reference/CViT-main/).  Plain pointers and sizes only — no torch
+ * types.  Unless stated otherwise every data pointer is a DEVICE pointer on the engine's
+ * GPU and `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *
+ * Every function returns FF_OK (0) or a negative FF_ERR_* code and never throws;
+ * `ff_last_error()` gives the message of the most recent failure on that handle.
+ * There is no CPU fallback: without a usable sm_100 device `ff_cvit_create` fails.
+ */
+#ifndef FACFAKE_H_
+#define FACFAKE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ff_cvit ff_cvit_t;
+
+enum {
+  FF_OK = 0,
+  FF_ERR_BAD_ARG = -1, /* NULL pointer, negative size, unknown enum value                     */
+  FF_ERR_SHAPE = -2,   /* weight / input shape does not match the CViT configuration           */
+  FF_ERR_CUDA = -3,    /* a CUDA runtime / driver call failed (message has the CUDA error)    */
+  FF_ERR_STATE = -4    /* call order violated (e.g. forward before finalize, missing weights) */
+};
+
+/* input layouts accepted by ff_cvit_forward / ff_cvit_predict */
+enum {
+  FF_X_NCHW_F32 = 0, /* [n,3,224,224] fp32, already normalised — what `model(x)` receives at
+                        cvit_prediction.py:229                                                  */
+  FF_X_NHWC_U8 = 2   /* [n,224,224,3] uint8 crops exactly as stored by cvit_prediction.py:108-117;
+                        the (x/255-mean)/std of cvit_prediction.py:41-45,214-215 is fused in    */
+};
+
+/* compute types */
+enum {
+  FF_COMPUTE_BF16 = 0, /* bf16 operands, fp32 accumulate (tcgen05), fp32 epilogues/residual     */
+  FF_COMPUTE_FP32 = 1  /* fp32 CUDA-core path (parity to 1e-4; slow)                            */
+};
+
+/* per-video reduction modes for ff_video_scores / ff_cvit_predict */
+enum {
+  FF_REDUCE_REFERENCE = 0,   /* sigmoid per logit, mean, decision rule: cvit_prediction.py:258-281 */
+  FF_REDUCE_SOFTMAX_MEAN = 1 /* mean over frames of softmax(logits)[fake] (extra, not the oracle)  */
+};
+
+/* ---- lifetime ----------------------------------------------------------------------------
+ * Replaces `CViT(image_size=224, patch_size=7, num_classes=2, channels=512, dim=1024, depth=6,
+ * heads=8, mlp_dim=2048)` + `.to(device)` (cvit_prediction.py:62-64; model/cvit.py:80-165).
+ * The engine is specialised for exactly that configuration.  `max_crops` is the number of
+ * crops one internal pass holds (workspace is allocated here; none on the forward path);
+ * larger batches are processed in several passes.                                          */
+int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype);
+void ff_cvit_destroy(ff_cvit_t* h);
+const char* ff_last_error(const ff_cvit_t* h); /* h may be NULL: last create() error */
+
+/* ---- weights ------------------------------------------------------------------------------
+ * Replaces `model.load_state_dict(checkpoint)` + `model.eval()` (cvit_prediction.py:66-70).
+ * One call per state_dict entry, with the reference's key names, HOST fp32
+ * data, C-contiguous.  `num_batches_tracked` entries are accepted and ignored.
+ * `ff_cvit_finalize_weights` folds conv bias + eval BatchNorm (eps 1e-5) into per-channel
+ * (scale, shift), converts to the kernels' layouts ([Cout][kh][kw][Cin] bf16, linears as
+ * stored) and builds the TMA descriptors.                                                   */
+int ff_cvit_load_weight(ff_cvit_t* h, const char* state_dict_key, const float* host_fp32,
+                        const int64_t* shape, int ndim);
+int ff_cvit_finalize_weights(ff_cvit_t* h);
+
+/* ---- crop preprocessing (K0) ----------------------------------------------------------------
+ * Replaces `cv2.resize(face, (224,224), interpolation=cv2.INTER_AREA)` + `cv2.cvtColor(RGB2BGR)`
+ * (cvit_prediction.py:114-115; same at :96-97, :141-142) for n variable-size crops.
+ * crop_ptrs[i] (HOST array of DEVICE pointers) -> uint8 HWC crop i with hw[2i], hw[2i+1] =
+ * (height, width) and pitch[i] bytes per row (HOST arrays).  out_u8 = [n,224,224,3] uint8.
+ * If out_norm_nchw != NULL it additionally receives the normalised fp32 [n,3,224,224] tensor
+ * of cvit_prediction.py:209-215.                                                               */
+int ff_preprocess_crops(ff_cvit_t* h, const uint8_t* const* crop_ptrs, const int32_t* hw,
+                        const int32_t* pitch, int n, int swap_rb, uint8_t* out_u8,
+                        float* out_norm_nchw, void* stream);
+
+/* ---- forward (K1..K7) ------------------------------------------------------------------------
+ * Replaces `model(dfdc_tensor[a:b])` (cvit_prediction.py:229,234,238; model/cvit.py:167-179).
+ * slot[i] in [0,32) is the index crop i would have inside the <=32 batch the reference passes
+ * to forward() — it selects pos_embedding[slot] (model/cvit.py:175).  slot may be NULL
+ * (= i % 32).  `slot` is a DEVICE pointer.  logits = [n,2] fp32 (fake, real).  Any n >= 0.    */
+int ff_cvit_forward(ff_cvit_t* h, const void* x, int x_layout, const int32_t* slot, int n,
+                    float* logits, void* stream);
+
+/* ---- per-video reduction (K8) -----------------------------------------------------------------
+ * Replaces `pre_process_prediction(pred_sig(y))` (cvit_prediction.py:240,258-281) for many videos:
+ * video v owns logits rows [video_offsets[v], video_offsets[v+1]).  <= 2 frames -> 0.5.
+ * video_offsets is a DEVICE int32 [n_videos+1]; scores a DEVICE fp32 [n_videos].               */
+int ff_video_scores(ff_cvit_t* h, const float* logits, const int32_t* video_offsets, int n_videos,
+                    int mode, float* scores, void* stream);
+
+/* ---- fused predict: forward + reduction --------------------------------------------------------
+ * The model half of `predict()` (cvit_prediction.py:209-242) for n_videos at once.  Crops of
+ * video v are rows [off[v], off[v+1]) of x; slot = (frame index within the video) % 32, i.e.
+ * the reference's [0:32],[32:64],[64:90] chunking.  HOST copy of the offsets is required to
+ * size the pass; `video_offsets_host` and `video_offsets_dev` hold the same n_videos+1 values. */
+int ff_cvit_predict(ff_cvit_t* h, const void* x, int x_layout, const int32_t* video_offsets_host,
+                    const int32_t* video_offsets_dev, int n_videos, int mode, float* logits_out,
+                    float* scores, void* stream);
+
+/* ---- host-buffer convenience (what bench.py's e2e leg and a cgo/JNI caller would use) -----------
+ * x_host: pinned or pageable HOST uint8 [n,224,224,3]; scores_host: HOST fp32 [n_videos].
+ * Copies in, runs ff_cvit_predict, copies the scores back and synchronises the stream.          */
+int ff_cvit_predict_host(ff_cvit_t* h, const uint8_t* x_host, const int32_t* video_offsets_host,
+                         int n_videos, int mode, float* scores_host, void* stream);
+
+/* ---- introspection -------------------------------------------------------------------------------
+ * Kernel launches issued by this handle since creation (bench.py's `gpu_launches`).              */
+int64_t ff_cvit_launch_count(const ff_cvit_t* h);
+/* Debug/test hook: run the forward on n <= max_crops crops and stop after step `stop_after`
+ * (1..17 = conv layer k incl. its pool; 18 = tokens; 19..24 = transformer layer; 25 = logits),
+ * copying that step's activation to out (HOST, fp32, NHWC for conv layers, row-major otherwise).
+ * out_elems is the capacity of `out` in floats; returns the element count written or <0.        */
+int64_t ff_cvit_debug_activation(ff_cvit_t* h, const void* x, int x_layout, const int32_t* slot,
+                                 int n, int stop_after, float* out_host, int64_t out_elems,
+                                 void* stream);
+/* Per-launch timing for bench.py's roofline: when enabled every kernel launch is bracketed by a CUDA event
+ * pair on the launching stream.  ff_cvit_get_profile synchronises and returns accumulated milliseconds and
+ * launch counts per kernel class: 0 = conv1 (CUDA cores), 1 = tcgen05 conv, 2 = tcgen05 GEMM, 3 = small kernels.
+ * ff_cvit_set_profiling resets the accumulators.                                                            */
+int ff_cvit_set_profiling(ff_cvit_t* h, int enable);
+int ff_cvit_get_profile(ff_cvit_t* h, double* ms_by_class /*[4]*/, int64_t* launches_by_class /*[4]*/);
+/* Tunables (0 keeps the current value): crops per stage-1/2 sub-pass (L2 residency).            */
+int ff_cvit_set_tuning(ff_cvit_t* h, int stage12_sub_batch, int use_cuda_graph);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACFAKE_H_ */

@@ -1,0 +1,98 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference here (build container only).
+
+    python oracle/make_golden.py
+
+Imports ``cvit.CViT`` from /root/reference/CViT-main/model (cvit.py:80-179), loads the
+deterministic synthetic state_dicts of ``fac_fake_b200.weights`` and records the
+reference's own outputs on seeded inputs.  /root/reference does not exist on the GPU
+box, so the vectors are committed; the oracle and the CUDA engine are both checked
+against them.  The per-video reduction vectors are produced with the reference's
+``pred_sig`` / ``pre_process_prediction`` source text (cvit_prediction.py:258-281),
+exec'd verbatim from the reference file because that script is not importable
+(missing facenet_pytorch / face_recognition, os.chdir to a Windows path).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference/CViT-main"
+sys.path.insert(0, os.path.join(REF, "model"))
+
+from cvit import CViT  # noqa: E402  (reference class)
+from fac_fake_b200 import weights as W  # noqa: E402
+from oracle import cvit_oracle as O  # noqa: E402
+
+
+def reference_reduction_functions():
+    """exec the reference's pred_sig / pre_process_prediction source lines verbatim."""
+    lines = open(os.path.join(REF, "cvit_prediction.py"), encoding="utf-8").read().splitlines()
+    src = "\n".join(lines[257:260] + [""] + lines[265:282])     # :258-260 and :266-282 (1-based)
+    ns = {"torch": torch}
+    exec(src, ns)
+    return ns["pred_sig"], ns["pre_process_prediction"]
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    torch.set_num_threads(8)
+    for variant in ("default", "bn"):
+        sd = W.make_state_dict(0, variant)
+        model = CViT(image_size=224, patch_size=7, num_classes=2, channels=512,
+                     dim=1024, depth=6, heads=8, mlp_dim=2048).eval()
+        model.load_state_dict(sd, strict=True)
+        crops = W.synthetic_crops(40, seed=1)
+        x = O.normalize_crops(crops)
+        with torch.no_grad():
+            logits_a = model(x[0:32])                  # slots 0..31
+            logits_b = model(x[32:40])                 # slots 0..7 (second chunk of a 40-crop video)
+            # intermediate checkpoints of the first 4 crops
+            feats = {}
+            h = x[0:4]
+            conv_no = 0
+            for idx, mod in enumerate(model.features):
+                h = mod(h)
+                if isinstance(mod, torch.nn.ReLU):
+                    nxt = model.features[idx + 1] if idx + 1 < len(model.features) else None
+                    if not isinstance(nxt, torch.nn.MaxPool2d):
+                        feats[conv_no] = h
+                        conv_no += 1
+                elif isinstance(mod, torch.nn.MaxPool2d):
+                    feats[conv_no] = h
+                    conv_no += 1
+            assert conv_no == 17
+        layer_stats = np.stack([np.array([feats[i].double().mean().item(), feats[i].double().abs().mean().item(),
+                                          feats[i].double().pow(2).mean().sqrt().item()]) for i in range(17)])
+        np.savez_compressed(
+            os.path.join(out_dir, f"cvit_logits_{variant}.npz"),
+            logits=torch.cat([logits_a, logits_b]).numpy(),
+            layer_stats=layer_stats,
+            feat_final=feats[16].numpy().astype(np.float32),        # [4,512,7,7]
+            feat_l2_sample=feats[2][0, :, :8, :8].numpy(),           # crop 0, 32ch, 8x8 corner after pool
+            seed_weights=0, seed_crops=1, n=40,
+        )
+        print(variant, "logits[0:3] =", logits_a[0:3].tolist())
+
+    # --- per-video reduction vectors from the reference's own source text
+    pred_sig, pre_process_prediction = reference_reduction_functions()
+    g = torch.Generator().manual_seed(5)
+    cases, lens, scores = [], [], []
+    for n in (1, 2, 3, 4, 15, 29, 30, 32, 33, 64, 90):
+        for scale, shift in ((1.0, 0.0), (3.0, 1.5), (3.0, -1.5), (0.01, 0.0)):
+            lg = torch.randn((n, 2), generator=g) * scale
+            lg[:, 0] += shift
+            s = pre_process_prediction(pred_sig(lg))
+            cases.append(lg.numpy())
+            lens.append(n)
+            scores.append(float(s.item()))
+    np.savez_compressed(os.path.join(out_dir, "video_reduction.npz"),
+                        logits=np.concatenate(cases, 0), lens=np.array(lens), scores=np.array(scores, dtype=np.float64))
+    print("reduction cases:", len(lens))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,207 @@
+"""GPU (B200): the CUDA path, called through the C-ABI, against the CPU oracle and the golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fac_fake_b200 import weights as W
+from oracle import cvit_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 2e-2      # north_star: per-frame logits within 2e-2 abs (bf16 path)
+FP32_TOL = 1e-4      # north_star: 1e-4 (fp32 path)
+
+
+def _engine(variant="bn", max_crops=64, compute="bf16", seed=0):
+    from fac_fake_b200 import CViTEngine
+    sd = W.make_state_dict(seed, variant)
+    eng = CViTEngine(max_crops=max_crops, compute_dtype=compute).to("cuda:0").load_state_dict(sd)
+    return eng, sd
+
+
+@pytest.fixture(scope="module")
+def eng_bn():
+    return _engine("bn")
+
+
+@pytest.fixture(scope="module")
+def eng_default():
+    return _engine("default")
+
+
+def _oracle_layers(sd, x, upto):
+    acts = {}
+    h = x
+    with torch.no_grad():
+        for li in range(upto):
+            h = O.feature_layer(h, sd, li)
+            acts[li + 1] = h.permute(0, 2, 3, 1).contiguous().flatten()
+    return acts
+
+
+def test_conv_layers_match_oracle(eng_bn):
+    """Every conv layer (conv+BN+ReLU[+pool]) against the fp32 oracle; bf16 activations => relative gate."""
+    eng, sd = eng_bn
+    torch.set_num_threads(os.cpu_count() or 4)
+    crops = W.synthetic_crops(3, seed=21)
+    acts = _oracle_layers(sd, O.normalize_crops(crops), 17)
+    xg = crops.cuda()
+    for step in range(1, 18):
+        got = eng.debug_activation(xg, step)
+        ref = acts[step]
+        assert got.numel() == ref.numel(), step
+        scale = ref.abs().max().item()
+        err = (got - ref).abs().max().item()
+        assert torch.isfinite(got).all(), step
+        # bf16 rounding compounds over layers: 2^-8 per layer budget, never above 3 %
+        assert err <= scale * min(0.03, 0.004 * (step + 1)), f"layer {step}: err {err} scale {scale}"
+
+
+def test_tokens_and_transformer_match_oracle(eng_bn):
+    eng, sd = eng_bn
+    crops = W.synthetic_crops(5, seed=22)
+    x = O.normalize_crops(crops)
+    slots = torch.tensor([3, 0, 31, 7, 7])
+    with torch.no_grad():
+        f = O.features(x, sd)
+        t = O.embed_tokens(f, sd, slots)
+        xg = crops.cuda()
+        got = eng.debug_activation(xg, 18, slots).view(5, 2, 1024)
+        assert (got - t).abs().max().item() <= 3e-2 * max(1.0, t.abs().max().item() / 4)
+        t6 = O.transformer(t, sd)
+        got6 = eng.debug_activation(xg, 24, slots).view(5, 2, 1024)
+        assert (got6 - t6).abs().max().item() <= 5e-2 * max(1.0, t6.abs().max().item() / 4)
+
+
+@pytest.mark.parametrize("variant", ["default", "bn"])
+def test_logits_match_reference_golden(golden_dir, variant, eng_bn, eng_default):
+    """Per-frame logits vs the reference's own outputs (tests/golden), 40 crops = chunks [0:32],[32:40]."""
+    eng, _ = eng_bn if variant == "bn" else eng_default
+    g = np.load(os.path.join(golden_dir, f"cvit_logits_{variant}.npz"))
+    crops = W.synthetic_crops(40, seed=1).cuda()
+    slots = torch.cat([torch.arange(32), torch.arange(8)])
+    got = eng.forward_slots(crops, slots).cpu().numpy()
+    assert np.abs(got - g["logits"]).max() <= BF16_TOL
+    # reference-compatible call: fp32 NCHW normalised input, b <= 32, slot = batch index
+    x = O.normalize_crops(W.synthetic_crops(40, seed=1))[:32].cuda()
+    got2 = eng(x).cpu().numpy()
+    assert np.abs(got2 - g["logits"][:32]).max() <= BF16_TOL
+    with pytest.raises(RuntimeError):
+        eng(torch.zeros((33, 3, 224, 224), device="cuda"))
+
+
+def test_predict_videos_matches_oracle_and_decisions(eng_bn):
+    eng, sd = eng_bn
+    lens = [0, 1, 2, 3, 15, 30, 33]                 # empty / sentinel / ragged / > 32 (second chunk)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).tolist()
+    n = offsets[-1]
+    crops = W.synthetic_crops(n, seed=23)
+    scores, logits = eng.predict_videos(crops.cuda(), offsets, return_logits=True)
+    scores, logits = scores.cpu(), logits.cpu()
+    x = O.normalize_crops(crops)
+    ref_scores, ref_logits = [], []
+    for v, ln in enumerate(lens):
+        s, lg = O.predict_from_crops(crops[offsets[v]:offsets[v + 1]], sd)
+        ref_scores.append(s)
+        ref_logits.append(lg)
+    ref_logits = torch.cat(ref_logits)
+    assert (logits - ref_logits).abs().max().item() <= BF16_TOL
+    for v, ln in enumerate(lens):
+        if ln <= 2:
+            assert scores[v].item() == 0.5
+        else:
+            assert abs(scores[v].item() - ref_scores[v]) <= 1e-2
+            if abs(ref_scores[v] - 0.5) > 2e-2:
+                assert O.real_or_fake(scores[v].item()) == O.real_or_fake(ref_scores[v])
+    # the reduction kernel alone on the oracle's logits is exact to fp32 rounding
+    off_t = torch.tensor(offsets, dtype=torch.int32)
+    s2 = eng.video_scores(ref_logits.cuda(), off_t).cpu()
+    for v in range(len(lens)):
+        assert abs(s2[v].item() - ref_scores[v]) <= 2e-6
+
+
+def test_reduction_golden(golden_dir, eng_bn):
+    eng, _ = eng_bn
+    g = np.load(os.path.join(golden_dir, "video_reduction.npz"))
+    offsets = np.concatenate([[0], np.cumsum(g["lens"])]).astype(np.int32)
+    s = eng.video_scores(torch.from_numpy(g["logits"]).cuda(), torch.from_numpy(offsets)).cpu().numpy()
+    assert np.abs(s - g["scores"]).max() <= 2e-6
+
+
+def test_fp32_path_logits(golden_dir):
+    eng, sd = _engine("bn", max_crops=32, compute="fp32")
+    g = np.load(os.path.join(golden_dir, "cvit_logits_bn.npz"))
+    crops = W.synthetic_crops(40, seed=1)[:6].cuda()
+    got = eng.forward_slots(crops, torch.arange(6)).cpu().numpy()
+    assert np.abs(got - g["logits"][:6]).max() <= FP32_TOL
+
+
+def test_full_size_properties(eng_default):
+    """BASELINE configs[1] size (512 crops): results do not depend on batch composition, only on (crop, slot)."""
+    from fac_fake_b200 import CViTEngine
+    sd = W.make_state_dict(0, "default")
+    eng = CViTEngine(max_crops=512).to("cuda:0").load_state_dict(sd)
+    crops = W.synthetic_crops(512, seed=31).cuda()
+    slots = torch.arange(512) % 32
+    full = eng.forward_slots(crops, slots)
+    assert torch.isfinite(full).all()
+    # (a) a crop's logits are identical whether it is evaluated inside the 512 batch or in a small one
+    idx = torch.tensor([0, 31, 32, 100, 255, 256, 480, 511])
+    sub = eng.forward_slots(crops[idx.cuda()], slots[idx])
+    assert (full[idx.cuda()] - sub).abs().max().item() <= 1e-5
+    # (b) permuting the batch permutes the logits (slot carried along)
+    perm = torch.randperm(512, generator=torch.Generator().manual_seed(0))
+    permd = eng.forward_slots(crops[perm.cuda()], slots[perm])
+    assert (permd - full[perm.cuda()]).abs().max().item() <= 1e-5
+    # (c) oracle spot-check on one reference-sized chunk of the same batch
+    x = O.normalize_crops(crops[64:96].cpu())
+    ref = O.forward(x, sd)
+    assert (full[64:96].cpu() - ref).abs().max().item() <= BF16_TOL
+    # (d) host-buffer entry point gives the same scores as the device one
+    offs = list(range(0, 513, 32))
+    s_dev = eng.predict_videos(crops, offs).cpu()
+    s_host = eng.predict_videos_host(crops.cpu().pin_memory(), offs)
+    assert torch.equal(s_dev, s_host)
+
+
+def test_preprocess_matches_oracle(eng_bn):
+    cv2 = pytest.importorskip("cv2")
+    from oracle import resize_oracle as R
+    eng, _ = eng_bn
+    rng = np.random.default_rng(5)
+    sizes = [(448, 448), (672, 448), (300, 300), (500, 333), (905, 640), (159, 159), (100, 180), (300, 180), (225, 225), (224, 224)]
+    srcs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    out, norm = eng.preprocess_crops([torch.from_numpy(s).cuda() for s in srcs], swap_rb=True, normalized=True)
+    out = out.cpu().numpy()
+    for i, s in enumerate(srcs):
+        ref = cv2.cvtColor(cv2.resize(s, (224, 224), interpolation=cv2.INTER_AREA), cv2.COLOR_RGB2BGR)
+        d = np.abs(out[i].astype(int) - ref.astype(int))
+        assert d.max() <= 1, sizes[i]
+        assert (d > 0).mean() < 1e-3, sizes[i]
+        np.testing.assert_array_equal(R.crop_to_model_input(s), ref)
+    want = O.normalize_crops(torch.from_numpy(out))
+    assert (norm.cpu() - want).abs().max().item() <= 1e-6
+
+
+def test_errors_and_edge_cases(eng_bn):
+    from fac_fake_b200 import CViTEngine, EngineError
+    eng, _ = eng_bn
+    assert eng.forward_slots(torch.zeros((0, 224, 224, 3), dtype=torch.uint8, device="cuda")).shape == (0, 2)
+    with pytest.raises(ValueError):
+        eng.forward_slots(torch.zeros((2, 3, 100, 100), device="cuda"))
+    with pytest.raises(ValueError):
+        eng.forward_slots(torch.zeros((2, 224, 224, 3), dtype=torch.uint8, device="cuda"), torch.tensor([0, 32]))
+    fresh = CViTEngine().to("cuda:0")
+    with pytest.raises(EngineError):
+        fresh.forward_slots(torch.zeros((1, 224, 224, 3), dtype=torch.uint8, device="cuda"))
+    sd = W.make_state_dict(0, "default")
+    bad = dict(sd)
+    bad["features.0.weight"] = torch.zeros((32, 3, 5, 5))
+    with pytest.raises((ValueError, EngineError)):
+        CViTEngine().to("cuda:0").load_state_dict(bad)
+    missing = {k: v for k, v in sd.items() if k != "cls_token"}
+    with pytest.raises((ValueError, EngineError)):
+        CViTEngine().to("cuda:0").load_state_dict(missing)
+    assert eng.launch_count() > 0
