@@ -22,6 +22,7 @@
 #include "ff_pre.cuh"
 #include "ff_small.cuh"
 #include "ff_tc.cuh"
+#include "ff_ws.cuh"
 
 namespace {
 
@@ -39,6 +40,7 @@ const ConvPlan kConv[17] = {
 };
 constexpr int DIM = 1024, DEPTH = 6, MLP = 2048, PATCH = 25088, SLOTS = 32;
 constexpr float BN_EPS = 1e-5f;
+constexpr int EMBED_SPLITS = 8;   // split-K of the 25088-deep patch embedding (392 k-blocks = 8 x 49)
 
 std::string g_create_error;
 
@@ -55,6 +57,8 @@ struct ConvLayerDev {
   CUtensorMap tmA, tmB;
   int rowb = 128, bn = 128;
   int bw = 16, bh = 8, bi = 1;
+  bool ws = false;          // persistent weight-stationary halo kernel (ff_ws.cuh)
+  CUtensorMap tmA_ws, tmW_ws;
 };
 struct LinearDev {
   bf16* w = nullptr;        // [out][in] bf16
@@ -79,6 +83,9 @@ struct ff_cvit {
   int s12_cap = 32;
   int compute = FF_COMPUTE_BF16;
   int variant = 0;         // tile-shape variant (tuning)
+  int use_ws = 1;          // feature layers 2..6 on the weight-stationary halo kernel
+  int ws_ctas_per_sm = 1;
+  int num_sms = 148;
   bool finalized = false;
   std::mutex mu;
   mutable std::string err;
@@ -121,8 +128,8 @@ struct ff_cvit {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   std::vector<int> ev_class;       // class of pair i (events 2i, 2i+1)
-  double prof_ms[4] = {0, 0, 0, 0};
-  int64_t prof_launches[4] = {0, 0, 0, 0};
+  double prof_ms[21] = {0};
+  int64_t prof_launches[21] = {0};
 };
 
 namespace {
@@ -137,7 +144,9 @@ int fail(const ff_cvit* h, int code, const char* fmt, ...) {
   return code;
 }
 
-enum { KC_CONV1 = 0, KC_TC_CONV = 1, KC_TC_GEMM = 2, KC_SMALL = 3 };
+// profile slots: 0 = conv1, 1..16 = tcgen05 conv layer (index li), 17 = embed GEMM, 18 = transformer GEMMs,
+// 19 = head GEMM, 20 = small kernels
+enum { KC_CONV1 = 0, KC_TC_CONV = 1, KC_GEMM_EMBED = 17, KC_GEMM_XF = 18, KC_GEMM_HEAD = 19, KC_SMALL = 20, KC_COUNT = 21 };
 
 void prof_mark(ff_cvit* h, cudaStream_t st, int cls, bool begin) {
   if (!h->profiling) return;
@@ -261,6 +270,35 @@ cudaError_t launch_conv(int rowb, int bn, bool pool, int variant, dim3 grid, cud
   return cudaErrorInvalidValue;
 }
 
+template <int ROWB, int BN, bool POOL, int STAGES>
+cudaError_t launch_ws_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args) {
+  using L = WsSmem<ROWB, BN, STAGES>;
+  auto k = wsconv_kernel<ROWB, BN, POOL, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  k<<<grid, 192, L::TOTAL, st>>>(a, w, args);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ws(int cin, int cout, bool pool, int cps, int grid, cudaStream_t st, const CUtensorMap& a,
+                      const CUtensorMap& w, const TcArgs& args) {
+  if (cps >= 2 && cin == 32) {   // shallower patch ring so that 2-3 CTAs share an SM
+    if (cout == 32)
+      return pool ? launch_ws_t<64, 32, true, 3>(grid, st, a, w, args) : launch_ws_t<64, 32, false, 3>(grid, st, a, w, args);
+    return launch_ws_t<64, 64, false, 3>(grid, st, a, w, args);
+  }
+  if (cin == 32 && cout == 32)
+    return pool ? launch_ws_t<64, 32, true, 8>(grid, st, a, w, args) : launch_ws_t<64, 32, false, 8>(grid, st, a, w, args);
+  if (cin == 32 && cout == 64) return launch_ws_t<64, 64, false, 8>(grid, st, a, w, args);
+  if (cin == 64 && cout == 64)
+    return pool ? launch_ws_t<128, 64, true, 5>(grid, st, a, w, args) : launch_ws_t<128, 64, false, 5>(grid, st, a, w, args);
+  return cudaErrorInvalidValue;
+}
+
 int conv_bn_for(int cout, int variant) {
   const int bn_max = (variant == 1) ? 128 : 256;
   return std::min(cout, bn_max);
@@ -349,6 +387,13 @@ int build_conv_maps(ff_cvit* h) {
     if (rc) return rc;
     rc = tmap_2d(h, &L.tmB, L.w, (uint64_t)9 * p.cin, p.cout, L.rowb / 2, L.bn);
     if (rc) return rc;
+    L.ws = h->use_ws && li <= 5;
+    if (L.ws) {
+      rc = tmap_4d(h, &L.tmA_ws, conv_input_buffer(h, li), p.cin, p.hw, p.hw, ncap, p.cin, 10, 18, 1);
+      if (rc) return rc;
+      rc = tmap_2d(h, &L.tmW_ws, L.w, (uint64_t)9 * p.cin, p.cout, p.cin, p.cout);
+      if (rc) return rc;
+    }
   }
   return FF_OK;
 }
@@ -440,13 +485,14 @@ int launch_gemm(ff_cvit* h, cudaStream_t st, const CUtensorMap& tmA, const Linea
   a.ldo = ldo;
   a.kb_total = L.in_f / 64;
   a.kb_per_split = (a.kb_total + splits - 1) / splits;
-  a.shift = (epi == EPI_ATOMIC_F32) ? nullptr : L.b;
+  a.shift = (splits > 1) ? nullptr : L.b;     // split-K: bias is added by the consumer of the partial slabs
+  a.split_stride = (splits > 1) ? (long long)h->cap * ldo : 0;
   a.out = out;
   a.epi = epi;
   a.act = act;
   const int zs = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
   dim3 grid((M + 127) / 128, L.out_f / L.bn, zs);
-  ProfScope ps(h, st, KC_TC_GEMM);
+  ProfScope ps(h, st, &L == &h->embed ? KC_GEMM_EMBED : (&L == &h->head1 ? KC_GEMM_HEAD : KC_GEMM_XF));
   cudaError_t e = L.bn == 128 ? launch_tc_t<MODE_GEMM, 128, 128, false, 4>(grid, st, tmA, L.tmB, a)
                               : launch_tc_t<MODE_GEMM, 128, 64, false, 6>(grid, st, tmA, L.tmB, a);
   if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of gemm %s failed: %s", what, cudaGetErrorString(e));
@@ -493,8 +539,18 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     a.kb_per_split = a.kb_total;
     a.scale = L.scale; a.shift = L.shift;
     a.out = conv_output_buffer(h, li);
+    ProfScope ps(h, st, KC_TC_CONV + li - 1);
+    if (L.ws) {
+      a.tiles_w = p.hw / 8; a.tiles_h = p.hw / 16;
+      a.lg_bw = 3; a.lg_bh = 4;
+      const int tiles = a.tiles_w * a.tiles_h * n_img;
+      const int g = std::min(tiles, h->num_sms * h->ws_ctas_per_sm);
+      cudaError_t e = launch_ws(p.cin, p.cout, p.pool, h->ws_ctas_per_sm, g, st, L.tmA_ws, L.tmW_ws, a);
+      if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of ws conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
+      ++h->launches;
+      return FF_OK;
+    }
     dim3 grid(a.tiles_w * a.tiles_h * ((n_img + L.bi - 1) / L.bi), p.cout / L.bn, 1);
-    ProfScope ps(h, st, KC_TC_CONV);
     cudaError_t e = launch_conv(L.rowb, L.bn, p.pool, h->variant, grid, st, L.tmA, L.tmB, a);
     if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
     ++h->launches;
@@ -532,10 +588,9 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     if (tap_hit(li + 1, conv_output_buffer(h, li), (int64_t)n * ohw * ohw * p.cout, true)) return FF_OK;
   }
   // ---- patch embedding (split-K, fp32 atomics) + token assembly
-  FF_CUDA(h, cudaMemsetAsync(h->emb, 0, (size_t)n * DIM * sizeof(float), st));
-  int rc = launch_gemm(h, st, h->tm_feat, h->embed, n, h->emb, DIM, EPI_ATOMIC_F32, ACT_NONE, 8, "patch_to_embedding");
+  int rc = launch_gemm(h, st, h->tm_feat, h->embed, n, h->emb, DIM, EPI_STORE_F32, ACT_NONE, EMBED_SPLITS, "patch_to_embedding");
   if (rc) return rc;
-  { ProfScope ps(h, st, KC_SMALL); tokens_kernel<<<n, 256, 0, st>>>(h->emb, h->embed.b, h->cls, h->pos, slot, slot_base, h->x, n); }
+  { ProfScope ps(h, st, KC_SMALL); tokens_kernel<<<n, 256, 0, st>>>(h->emb, EMBED_SPLITS, (long long)h->cap * DIM, h->embed.b, h->cls, h->pos, slot, slot_base, h->x, n); }
   FF_LAUNCH_CHECK(h, "tokens");
   const int rows = 2 * n;
   if (tap_hit(18, h->x, (int64_t)rows * DIM, false)) return FF_OK;
@@ -612,7 +667,7 @@ int forward_fp32(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   };
   int rc;
   if ((rc = lin(featf, h->embed, n, h->emb, 0, 0, "embed_fp32"))) return rc;
-  tokens_kernel<<<n, 256, 0, st>>>(h->emb, nullptr, h->cls, h->pos, slot, slot_base, h->x, n);
+  tokens_kernel<<<n, 256, 0, st>>>(h->emb, 1, 0, nullptr, h->cls, h->pos, slot, slot_base, h->x, n);
   FF_LAUNCH_CHECK(h, "tokens");
   if (tap_hit(18, h->x, (int64_t)rows * DIM)) return FF_OK;
   for (int l = 0; l < DEPTH; ++l) {
@@ -710,12 +765,15 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
   h->s12_cap = 32;
   h->s12 = std::min(16, h->cap);
   if (const char* v = getenv("FF_TC_VARIANT")) h->variant = atoi(v);
+  if (const char* v = getenv("FF_WS")) h->use_ws = atoi(v);
+  if (const char* v = getenv("FF_WS_CPS")) h->ws_ctas_per_sm = std::max(1, atoi(v));
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   if (const char* v = getenv("FF_S12")) h->s12 = std::max(1, std::min(h->s12_cap, atoi(v)));
   int rc = FF_OK;
   const int cap128 = (h->cap + 127) / 128 * 128;
   do {
     if (cudaEventCreateWithFlags(&h->done_ev, cudaEventDisableTiming) != cudaSuccess) { rc = fail(h, FF_ERR_CUDA, "event create failed"); break; }
-    if ((rc = dev_alloc(h, &h->emb, (size_t)h->cap * DIM))) break;
+    if ((rc = dev_alloc(h, &h->emb, (size_t)EMBED_SPLITS * h->cap * DIM))) break;
     if ((rc = dev_alloc(h, &h->x, (size_t)h->rows_cap * DIM))) break;
     if ((rc = dev_alloc(h, &h->qkv, (size_t)h->rows_cap * 3 * DIM))) break;
     if ((rc = dev_alloc(h, &h->hid, (size_t)cap128 * MLP))) break;
@@ -950,7 +1008,7 @@ int ff_cvit_set_profiling(ff_cvit_t* h, int enable) {
   h->profiling = enable != 0;
   h->ev_used = 0;
   h->ev_class.clear();
-  for (int i = 0; i < 4; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
+  for (int i = 0; i < KC_COUNT; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
   return FF_OK;
 }
 
@@ -969,7 +1027,7 @@ int ff_cvit_get_profile(ff_cvit_t* h, double* ms_by_class, int64_t* launches_by_
   }
   h->ev_used = 0;
   h->ev_class.clear();
-  for (int i = 0; i < 4; ++i) { ms_by_class[i] = h->prof_ms[i]; launches_by_class[i] = h->prof_launches[i]; }
+  for (int i = 0; i < KC_COUNT; ++i) { ms_by_class[i] = h->prof_ms[i]; launches_by_class[i] = h->prof_launches[i]; }
   return FF_OK;
 }
 

@@ -146,16 +146,22 @@ attention2_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ out
 }
 
 // Token assembly (cvit.py:171-175): tok0 = cls + pos[slot], tok1 = (patch embedding + bias) + pos[slot].
+// The patch embedding arrives as n_splits split-K partial slabs that are summed here in a fixed order.
 __global__ void __launch_bounds__(256)
-tokens_kernel(const float* __restrict__ emb, const float* __restrict__ bias, const float* __restrict__ cls,
-              const float* __restrict__ pos, const int* __restrict__ slot, int slot_base, float* __restrict__ x, int n) {
+tokens_kernel(const float* __restrict__ emb, int n_splits, long long split_stride, const float* __restrict__ bias,
+              const float* __restrict__ cls, const float* __restrict__ pos, const int* __restrict__ slot, int slot_base,
+              float* __restrict__ x, int n) {
   const int b = blockIdx.x;
   if (b >= n) return;
   const int s = slot ? slot[b] : ((slot_base + b) & 31);
   const int i = threadIdx.x;   // 256 threads x float4 = 1024
   const float4 p = reinterpret_cast<const float4*>(pos + static_cast<size_t>(s) * 1024)[i];
   const float4 c = reinterpret_cast<const float4*>(cls)[i];
-  const float4 e = reinterpret_cast<const float4*>(emb + static_cast<size_t>(b) * 1024)[i];
+  float4 e = reinterpret_cast<const float4*>(emb + static_cast<size_t>(b) * 1024)[i];
+  for (int z = 1; z < n_splits; ++z) {   // split-K partial sums, fixed order => deterministic
+    const float4 t = reinterpret_cast<const float4*>(emb + z * split_stride + static_cast<size_t>(b) * 1024)[i];
+    e.x += t.x; e.y += t.y; e.z += t.z; e.w += t.w;
+  }
   const float4 bb = bias ? reinterpret_cast<const float4*>(bias)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   float4* x0 = reinterpret_cast<float4*>(x + static_cast<size_t>(2 * b) * 1024);
   x0[i] = make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);

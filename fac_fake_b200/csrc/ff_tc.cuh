@@ -44,6 +44,7 @@ struct TcArgs {
   const float* scale;     // conv: per-channel scale (gamma / sqrt(var+eps))
   const float* shift;     // conv: per-channel shift;  gemm: bias or nullptr
   void* out;              // conv: bf16 NHWC;  gemm: see epi
+  long long split_stride; // gemm split-K: element offset of split z's private output slab
   int epi;                // gemm: EPI_*
   int act;                // gemm: ACT_*
 };
@@ -64,6 +65,91 @@ struct TcSmem {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// ---- conv epilogue, phase 1: TMEM accumulator row r (one per thread) -> scale/shift/ReLU -> bf16 -> staging smem.
+// Staging is [128 rows][BN] bf16 with the 16-byte chunk index XOR-swizzled by the row (bank-conflict-free).
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_to_staging(uint32_t taddr, const float* ss, uint8_t* stg, int r) {
+  constexpr int CPR = BN / 8;
+  const int swz = (CPR >= 8) ? (r & 7) : ((r >> 1) & (CPR - 1));
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t p[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = c0 + j * 8 + e * 2;
+        float x0 = fmaf(__uint_as_float(v[j * 8 + e * 2]), ss[c], ss[BN + c]);
+        float x1 = fmaf(__uint_as_float(v[j * 8 + e * 2 + 1]), ss[c + 1], ss[BN + c + 1]);
+        p[e] = pack_bf16x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f));
+      }
+      const int q = (c0 >> 3) + j;
+      *reinterpret_cast<uint4*>(stg + r * (BN * 2) + ((q ^ swz) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+  }
+}
+
+// ---- conv epilogue, phase 2: staging -> global NHWC bf16 with coalesced 16-byte stores (optional 2x2 max-pool).
+template <int BN, bool POOL>
+__device__ __forceinline__ void conv_staging_to_global(const uint8_t* stg, const TcArgs& a, int w0, int h0, int n0,
+                                                       int col0, int te) {
+  constexpr int CPR = BN / 8;
+  const int BW = 1 << a.lg_bw, BH = 1 << a.lg_bh;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
+  if (!POOL) {
+    for (int idx = te; idx < 128 * CPR; idx += 128) {
+      const int row = idx / CPR, q = idx % CPR;
+      const int rs = (CPR >= 8) ? (row & 7) : ((row >> 1) & (CPR - 1));
+      const uint4 val = *reinterpret_cast<const uint4*>(stg + row * (BN * 2) + ((q ^ rs) << 4));
+      const int wl = row & (BW - 1);
+      const int hl = (row >> a.lg_bw) & (BH - 1);
+      const int nl = row >> (a.lg_bw + a.lg_bh);
+      const int n = n0 + nl;
+      if (n < a.n_img) {
+        const size_t pix = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * a.W + (w0 + wl);
+        *reinterpret_cast<uint4*>(out + pix * a.cout + col0 + q * 8) = val;
+      }
+    }
+  } else {
+    const int PW = BW >> 1, PH = BH >> 1;
+    const int Ho = a.H >> 1, Wo = a.W >> 1;
+    for (int idx = te; idx < 32 * CPR; idx += 128) {
+      const int p = idx / CPR, q = idx % CPR;
+      const int pw = p % PW;
+      const int ph = (p / PW) % PH;
+      const int pn = p / (PW * PH);
+      const int r00 = ((pn << a.lg_bh) + 2 * ph) * BW + 2 * pw;
+      uint4 m;
+      {
+        const int rows[4] = {r00, r00 + 1, r00 + BW, r00 + BW + 1};
+        uint4 x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = rows[i];
+          const int rs = (CPR >= 8) ? (row & 7) : ((row >> 1) & (CPR - 1));
+          x[i] = *reinterpret_cast<const uint4*>(stg + row * (BN * 2) + ((q ^ rs) << 4));
+        }
+        auto mx = [](uint32_t a0, uint32_t b0) {
+          __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a0), *reinterpret_cast<__nv_bfloat162*>(&b0));
+          return *reinterpret_cast<uint32_t*>(&r2);
+        };
+        m.x = mx(mx(x[0].x, x[1].x), mx(x[2].x, x[3].x));
+        m.y = mx(mx(x[0].y, x[1].y), mx(x[2].y, x[3].y));
+        m.z = mx(mx(x[0].z, x[1].z), mx(x[2].z, x[3].z));
+        m.w = mx(mx(x[0].w, x[1].w), mx(x[2].w, x[3].w));
+      }
+      const int n = n0 + pn;
+      if (n < a.n_img) {
+        const size_t pix = (static_cast<size_t>(a.img_off_out + n) * Ho + ((h0 >> 1) + ph)) * Wo + ((w0 >> 1) + pw);
+        *reinterpret_cast<uint4*>(out + pix * a.cout + col0 + q * 8) = m;
+      }
+    }
+  }
+}
+
 template <int MODE, int ROWB, int BN, bool POOL, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -71,7 +157,6 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr int BKE = ROWB / 2;        // bf16 elements per k-block row
   constexpr int KSTEPS = ROWB / 32;    // UMMA K=16 steps per k-block
   constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  constexpr int CPR = BN / 8;          // 16-byte chunks per staged row
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
   static_assert(ROWB == 64 || ROWB == 128, "ROWB");
 
@@ -190,78 +275,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
     if (MODE == MODE_CONV) {
       uint8_t* stg = base_ptr;            // pipeline stages are idle now: reuse as staging [128][BN] bf16
-      const int swz = (CPR >= 8) ? (r & 7) : ((r >> 1) & (CPR - 1));
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t p[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = c0 + j * 8 + e * 2;
-            float x0 = fmaf(__uint_as_float(v[j * 8 + e * 2]), ss[c], ss[BN + c]);
-            float x1 = fmaf(__uint_as_float(v[j * 8 + e * 2 + 1]), ss[c + 1], ss[BN + c + 1]);
-            p[e] = pack_bf16x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f));
-          }
-          const int q = (c0 >> 3) + j;
-          *reinterpret_cast<uint4*>(stg + r * (BN * 2) + ((q ^ swz) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
-        }
-      }
+      conv_epilogue_to_staging<BN>(taddr, ss, stg, r);
       named_bar_sync(1, 128);
-      const int BW = 1 << a.lg_bw, BH = 1 << a.lg_bh;
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
-      if (!POOL) {
-        for (int idx = te; idx < 128 * CPR; idx += 128) {
-          const int row = idx / CPR, q = idx % CPR;
-          const int rs = (CPR >= 8) ? (row & 7) : ((row >> 1) & (CPR - 1));
-          const uint4 val = *reinterpret_cast<const uint4*>(stg + row * (BN * 2) + ((q ^ rs) << 4));
-          const int wl = row & (BW - 1);
-          const int hl = (row >> a.lg_bw) & (BH - 1);
-          const int nl = row >> (a.lg_bw + a.lg_bh);
-          const int n = n0 + nl;
-          if (n < a.n_img) {
-            const size_t pix = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * a.W + (w0 + wl);
-            *reinterpret_cast<uint4*>(out + pix * a.cout + col0 + q * 8) = val;
-          }
-        }
-      } else {
-        const int PW = BW >> 1, PH = BH >> 1;
-        const int Ho = a.H >> 1, Wo = a.W >> 1;
-        for (int idx = te; idx < 32 * CPR; idx += 128) {
-          const int p = idx / CPR, q = idx % CPR;
-          const int pw = p % PW;
-          const int ph = (p / PW) % PH;
-          const int pn = p / (PW * PH);
-          const int r00 = ((pn << a.lg_bh) + 2 * ph) * BW + 2 * pw;
-          uint4 m;
-          {
-            const int rows[4] = {r00, r00 + 1, r00 + BW, r00 + BW + 1};
-            uint4 x[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int row = rows[i];
-              const int rs = (CPR >= 8) ? (row & 7) : ((row >> 1) & (CPR - 1));
-              x[i] = *reinterpret_cast<const uint4*>(stg + row * (BN * 2) + ((q ^ rs) << 4));
-            }
-            auto mx = [](uint32_t a0, uint32_t b0) {
-              __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a0), *reinterpret_cast<__nv_bfloat162*>(&b0));
-              return *reinterpret_cast<uint32_t*>(&r2);
-            };
-            m.x = mx(mx(x[0].x, x[1].x), mx(x[2].x, x[3].x));
-            m.y = mx(mx(x[0].y, x[1].y), mx(x[2].y, x[3].y));
-            m.z = mx(mx(x[0].z, x[1].z), mx(x[2].z, x[3].z));
-            m.w = mx(mx(x[0].w, x[1].w), mx(x[2].w, x[3].w));
-          }
-          const int n = n0 + pn;
-          if (n < a.n_img) {
-            const size_t pix = (static_cast<size_t>(a.img_off_out + n) * Ho + ((h0 >> 1) + ph)) * Wo + ((w0 >> 1) + pw);
-            *reinterpret_cast<uint4*>(out + pix * a.cout + col0 + q * 8) = m;
-          }
-        }
-      }
+      conv_staging_to_global<BN, POOL>(stg, a, w0, h0, n0, col0, te);
     } else {
       // ---- GEMM epilogue: direct stores, one accumulator row per thread
       const int m = m0 + r;
@@ -281,7 +297,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             else if (a.act == ACT_GELU) x = gelu_erf(x);
             f[i] = x;
           }
-          const size_t off = static_cast<size_t>(m) * a.ldo + nb;
+          const size_t off = static_cast<size_t>(blockIdx.z) * a.split_stride + static_cast<size_t>(m) * a.ldo + nb;
           if (a.epi == EPI_STORE_F32) {
             float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + off);
 #pragma unroll

@@ -1,0 +1,212 @@
+// ff_ws.cuh — persistent, weight-stationary, halo-patch 3x3 convolution for the wide-and-shallow layers
+// (feature layers 2..6: Cin, Cout in {32, 64} at 224x224 / 112x112; /root/reference/CViT-main/model/cvit.py:91-108).
+//
+// Why a second conv kernel: with K = 9*Cin <= 576 the per-tap implicit GEMM of ff_tc.cuh re-reads every activation
+// 9 times from L2 and pays CTA setup per 128 pixels; measured, those layers were L2->SMEM-bandwidth bound
+// (~6.4 TB/s) at 210-360 TFLOP/s.  Here
+//   * each CTA is persistent (grid = #SMs) and keeps ALL 9 x [Cout][Cin] filter taps resident in shared memory;
+//   * one TMA box {Cin, 10, 18, 1} brings the (8+2) x (16+2) halo patch of a tile of 8 x 16 output pixels ONCE
+//     (1.4x read amplification instead of 9x; out-of-bounds rows/cols are zero-filled = the conv padding);
+//   * the 9 taps are 9 shared-memory descriptors into that one patch: tap (kh,kw) starts (kh*10 + kw) rows into
+//     the patch and uses a stride-byte-offset of 10 rows between the 8-row core groups.  (Measured on B200:
+//     tcgen05 applies the 128B/64B swizzle on absolute smem address bits, so descriptors may start at any row
+//     and use any 16-byte-multiple SBO with base_offset = 0 — tools/umma_shift_test.cu.)
+//   * the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * the epilogue goes straight from registers to global memory (one output pixel = one thread = one contiguous
+//     Cout*2-byte run); the 2x2 max-pool is two warp shuffles (w-neighbour = lane^1, h-neighbour = lane^8).
+#pragma once
+#include "ff_tc.cuh"
+
+namespace ff {
+
+template <int ROWB, int BN, int STAGES>
+struct WsSmem {
+  static constexpr int W_BYTES = 9 * BN * ROWB;                       // all filter taps
+  static constexpr int PATCH_ROWS = 180;                              // 18 x 10 pixels
+  static constexpr int PATCH_BYTES = PATCH_ROWS * ROWB;
+  static constexpr int PATCH_STRIDE = (PATCH_BYTES + 1023) / 1024 * 1024;
+  static constexpr int W_OFF = 0;
+  static constexpr int P_OFF = (W_BYTES + 1023) / 1024 * 1024;
+  static constexpr int SS_OFF = P_OFF + STAGES * PATCH_STRIDE;
+  static constexpr int BAR_OFF = SS_OFF + 2 * BN * 4;                 // w, full[S], empty[S], tfull[2], tempty[2]
+  static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 5) * 8;
+  static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
+};
+
+// K-major descriptor with an explicit stride-byte-offset (bytes between consecutive 8-row groups).
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  constexpr uint64_t layout = (ROWB == 128) ? 2ull : 4ull;
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= 1ull << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= 1ull << 46;
+  d |= layout << 61;
+  return d;
+}
+
+// Epilogue of one 8x16 tile for the thread owning accumulator row r = h_l*8 + w_l (TMEM lane r).
+// `arrive_bar`: mbarrier to arrive on as soon as the accumulator has been read out of TMEM.
+template <int BN, bool POOL>
+__device__ __forceinline__ void ws_epilogue_direct(uint32_t taddr, const float* ss, const TcArgs& a, int w0, int h0, int n,
+                                                   int r, int lane, uint32_t arrive_bar) {
+  uint32_t v[BN];
+#pragma unroll
+  for (int c0 = 0; c0 < BN; c0 += 32) tmem_ld_32x32(taddr + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[c0]));
+  tmem_ld_wait();
+  tcgen05_fence_before();
+  mbar_arrive(arrive_bar);
+  uint32_t p[BN / 2];
+#pragma unroll
+  for (int c = 0; c < BN; c += 2) {
+    const float x0 = fmaf(__uint_as_float(v[c]), ss[c], ss[BN + c]);
+    const float x1 = fmaf(__uint_as_float(v[c + 1]), ss[c + 1], ss[BN + c + 1]);
+    p[c >> 1] = pack_bf16x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f));
+  }
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
+  const int hl = r >> 3, wl = r & 7;
+  if (!POOL) {
+    const size_t pix = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * a.W + (w0 + wl);
+    uint4* o = reinterpret_cast<uint4*>(out + pix * BN);
+#pragma unroll
+    for (int i = 0; i < BN / 8; ++i) o[i] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < BN / 2; ++i) {
+      uint32_t o1 = __shfl_xor_sync(0xffffffffu, p[i], 1);
+      __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&p[i]), *reinterpret_cast<__nv_bfloat162*>(&o1));
+      uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
+      uint32_t o2 = __shfl_xor_sync(0xffffffffu, mu, 8);
+      m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o2));
+      p[i] = *reinterpret_cast<uint32_t*>(&m);
+    }
+    if ((lane & 9) == 0) {
+      const size_t pix = (static_cast<size_t>(a.img_off_out + n) * (a.H >> 1) + ((h0 + hl) >> 1)) * (a.W >> 1) + ((w0 + wl) >> 1);
+      uint4* o = reinterpret_cast<uint4*>(out + pix * BN);
+#pragma unroll
+      for (int i = 0; i < BN / 8; ++i) o[i] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+    }
+  }
+}
+
+// args reuse TcArgs: H, W, tiles_w (= W/8), tiles_h (= H/16), n_img, img_off_out, cout, scale, shift, out.
+template <int ROWB, int BN, bool POOL, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+wsconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs a) {
+  using L = WsSmem<ROWB, BN, STAGES>;
+  constexpr int KSTEPS = ROWB / 32;
+  constexpr int CIN = ROWB / 2;
+  constexpr int TMEM_COLS = 2 * BN;       // double-buffered accumulator (64 or 128 columns)
+  static_assert(BN == 32 || BN == 64, "BN");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  float* ss = reinterpret_cast<float*>(base_ptr + L::SS_OFF);
+  const uint32_t bar_w = base + L::BAR_OFF;
+  const uint32_t bar_full = bar_w + 8;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_tfull = bar_empty + STAGES * 8;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_per_img = a.tiles_w * a.tiles_h;
+  const int num_tiles = tiles_per_img * a.n_img;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tfull + 8, 1);
+    mbar_init(bar_tempty, 128);
+    mbar_init(bar_tempty + 8, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      ss[i] = a.scale[i];
+      ss[BN + i] = a.shift[i];
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- filters: resident for the whole kernel
+      mbar_arrive_expect_tx(bar_w, L::W_BYTES);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(base + L::W_OFF + tap * BN * ROWB, &tmW, bar_w, tap * CIN, 0);
+      // ---- halo patches
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(bar_empty + 8 * s, ((it / STAGES) - 1) & 1);
+        const int n = t / tiles_per_img;
+        const int rem = t - n * tiles_per_img;
+        const int th = rem / a.tiles_w, tw = rem - th * a.tiles_w;
+        mbar_arrive_expect_tx(bar_full + 8 * s, L::PATCH_BYTES);
+        tma_load_4d(base + L::P_OFF + s * L::PATCH_STRIDE, &tmA, bar_full + 8 * s, 0, tw * 8 - 1, th * 16 - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+      mbar_wait(bar_w, 0);
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        const int acc = it & 1;
+        if (it >= 2) mbar_wait(bar_tempty + 8 * acc, ((it >> 1) - 1) & 1);
+        mbar_wait(bar_full + 8 * s, (it / STAGES) & 1);
+        tcgen05_fence_after();
+        const uint32_t patch = base + L::P_OFF + s * L::PATCH_STRIDE;
+        const uint32_t d_tmem = tmem_base + acc * BN;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int kh = tap / 3, kw = tap % 3;
+          const uint64_t adesc = make_kmajor_desc_sbo<ROWB>(patch + (kh * 10 + kw) * ROWB, 10 * ROWB);
+          const uint64_t bdesc = make_kmajor_desc<ROWB>(base + L::W_OFF + tap * BN * ROWB);
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k)
+            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (tap > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * s);
+        umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+  } else {
+    const int g = warp & 3;
+    const int r = g * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int n = t / tiles_per_img;
+      const int rem = t - n * tiles_per_img;
+      const int th = rem / a.tiles_w, tw = rem - th * a.tiles_w;
+      mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
+      tcgen05_fence_after();
+      ws_epilogue_direct<BN, POOL>(tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN, ss, a, tw * 8, th * 16, n, r,
+                                   lane, bar_tempty + 8 * acc);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace ff

@@ -290,13 +290,21 @@ class CViTEngine:
         self._require_ready()
         self._check(self._lib.ff_cvit_set_profiling(self._h, int(bool(enable))), "ff_cvit_set_profiling")
 
-    def get_profile(self):
-        """{class: (milliseconds, launches)} accumulated since set_profiling(True)."""
+    def get_profile(self, per_layer: bool = False):
+        """{class: (milliseconds, launches)} accumulated since set_profiling(True).
+        per_layer=True returns the raw 21 slots (see include/facfake.h)."""
         self._require_ready()
-        ms = (C.c_double * 4)()
-        cnt = (C.c_int64 * 4)()
+        ms = (C.c_double * 21)()
+        cnt = (C.c_int64 * 21)()
         self._check(self._lib.ff_cvit_get_profile(self._h, ms, cnt), "ff_cvit_get_profile")
-        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+        if per_layer:
+            names = ["conv1"] + [f"conv{i + 1}" for i in range(1, 17)] + ["gemm_embed", "gemm_transformer", "gemm_head", "small"]
+            return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(names)}
+        agg = {"conv1_cuda_core": (float(ms[0]), int(cnt[0])),
+               "tcgen05_conv": (float(sum(ms[1:17])), int(sum(cnt[1:17]))),
+               "tcgen05_gemm": (float(sum(ms[17:20])), int(sum(cnt[17:20]))),
+               "small_kernels": (float(ms[20]), int(cnt[20]))}
+        return agg
 
     def debug_activation(self, x: torch.Tensor, stop_after: int, slots: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Activation after step `stop_after` (see include/facfake.h) as a flat fp32 CPU tensor."""

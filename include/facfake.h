@@ -124,10 +124,11 @@ int64_t ff_cvit_debug_activation(ff_cvit_t* h, const void* x, int x_layout, cons
                                  void* stream);
 /* Per-launch timing for bench.py's roofline: when enabled every kernel launch is bracketed by a CUDA event
  * pair on the launching stream.  ff_cvit_get_profile synchronises and returns accumulated milliseconds and
- * launch counts per kernel class: 0 = conv1 (CUDA cores), 1 = tcgen05 conv, 2 = tcgen05 GEMM, 3 = small kernels.
+ * launch counts in 21 slots: 0 = conv1 (CUDA cores), 1..16 = tcgen05 conv of feature layer 2..17,
+ * 17 = patch-embedding GEMM, 18 = transformer GEMMs, 19 = head GEMM, 20 = small kernels.
  * ff_cvit_set_profiling resets the accumulators.                                                            */
 int ff_cvit_set_profiling(ff_cvit_t* h, int enable);
-int ff_cvit_get_profile(ff_cvit_t* h, double* ms_by_class /*[4]*/, int64_t* launches_by_class /*[4]*/);
+int ff_cvit_get_profile(ff_cvit_t* h, double* ms_by_slot /*[21]*/, int64_t* launches_by_slot /*[21]*/);
 /* Tunables (0 keeps the current value): crops per stage-1/2 sub-pass (L2 residency).            */
 int ff_cvit_set_tuning(ff_cvit_t* h, int stage12_sub_batch, int use_cuda_graph);
 
