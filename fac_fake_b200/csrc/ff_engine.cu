@@ -23,6 +23,7 @@
 #include "ff_small.cuh"
 #include "ff_tc.cuh"
 #include "ff_ws.cuh"
+#include "ff_c1.cuh"
 
 namespace {
 
@@ -59,6 +60,7 @@ struct ConvLayerDev {
   int bw = 16, bh = 8, bi = 1;
   bool ws = false;          // persistent weight-stationary halo kernel (ff_ws.cuh)
   CUtensorMap tmA_ws, tmW_ws;
+  WsEpi epi;                // host copy of (scale, shift) passed by value to the ws kernel
 };
 struct LinearDev {
   bf16* w = nullptr;        // [out][in] bf16
@@ -84,7 +86,11 @@ struct ff_cvit {
   int compute = FF_COMPUTE_BF16;
   int variant = 0;         // tile-shape variant (tuning)
   int use_ws = 1;          // feature layers 2..6 on the weight-stationary halo kernel
-  int ws_ctas_per_sm = 1;
+  int ws_ctas_per_sm = 2;   // CTAs per SM for the Cin=32 weight-stationary kernels (Cin=64 always 1: smem)
+  int use_c1_tc = 1;       // feature layer 1 on the tensor cores (ff_c1.cuh) instead of the CUDA-core kernel
+  int c1_ctas_per_sm = 6;
+  bf16* c1_w = nullptr;    // [32][64] bf16, k = kh*16 + kw*4 + cin
+  bf16* c1_lut = nullptr;  // [3][256] bf16 normalisation table
   int num_sms = 148;
   bool finalized = false;
   std::mutex mu;
@@ -271,7 +277,8 @@ cudaError_t launch_conv(int rowb, int bn, bool pool, int variant, dim3 grid, cud
 }
 
 template <int ROWB, int BN, bool POOL, int STAGES>
-cudaError_t launch_ws_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args) {
+cudaError_t launch_ws_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args,
+                        const WsEpi& epi) {
   using L = WsSmem<ROWB, BN, STAGES>;
   auto k = wsconv_kernel<ROWB, BN, POOL, STAGES>;
   static bool attr_done = false;
@@ -280,22 +287,22 @@ cudaError_t launch_ws_t(int grid, cudaStream_t st, const CUtensorMap& a, const C
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  k<<<grid, 192, L::TOTAL, st>>>(a, w, args);
+  k<<<grid, 192, L::TOTAL, st>>>(a, w, args, epi);
   return cudaGetLastError();
 }
 
 cudaError_t launch_ws(int cin, int cout, bool pool, int cps, int grid, cudaStream_t st, const CUtensorMap& a,
-                      const CUtensorMap& w, const TcArgs& args) {
+                      const CUtensorMap& w, const TcArgs& args, const WsEpi& epi) {
   if (cps >= 2 && cin == 32) {   // shallower patch ring so that 2-3 CTAs share an SM
     if (cout == 32)
-      return pool ? launch_ws_t<64, 32, true, 3>(grid, st, a, w, args) : launch_ws_t<64, 32, false, 3>(grid, st, a, w, args);
-    return launch_ws_t<64, 64, false, 3>(grid, st, a, w, args);
+      return pool ? launch_ws_t<64, 32, true, 3>(grid, st, a, w, args, epi) : launch_ws_t<64, 32, false, 3>(grid, st, a, w, args, epi);
+    return launch_ws_t<64, 64, false, 3>(grid, st, a, w, args, epi);
   }
   if (cin == 32 && cout == 32)
-    return pool ? launch_ws_t<64, 32, true, 8>(grid, st, a, w, args) : launch_ws_t<64, 32, false, 8>(grid, st, a, w, args);
-  if (cin == 32 && cout == 64) return launch_ws_t<64, 64, false, 8>(grid, st, a, w, args);
+    return pool ? launch_ws_t<64, 32, true, 8>(grid, st, a, w, args, epi) : launch_ws_t<64, 32, false, 8>(grid, st, a, w, args, epi);
+  if (cin == 32 && cout == 64) return launch_ws_t<64, 64, false, 8>(grid, st, a, w, args, epi);
   if (cin == 64 && cout == 64)
-    return pool ? launch_ws_t<128, 64, true, 5>(grid, st, a, w, args) : launch_ws_t<128, 64, false, 5>(grid, st, a, w, args);
+    return pool ? launch_ws_t<128, 64, true, 5>(grid, st, a, w, args, epi) : launch_ws_t<128, 64, false, 5>(grid, st, a, w, args, epi);
   return cudaErrorInvalidValue;
 }
 
@@ -420,13 +427,29 @@ int finalize(ff_cvit* h) {
         for (int t = 0; t < 9; ++t) wr[((size_t)o * 9 + t) * p.cin + ci] = (*w)[((size_t)o * p.cin + ci) * 9 + t];
     }
     ConvLayerDev& L = h->conv[li];
+    if (p.cout <= 64)
+      for (int o = 0; o < p.cout; ++o) { L.epi.scale[o] = scale[o]; L.epi.shift[o] = shift[o]; }
     if ((rc = dev_upload(h, &L.scale, scale))) return rc;
     if ((rc = dev_upload(h, &L.shift, shift))) return rc;
     if (li == 0) {
+      std::vector<float> w32(32 * 64, 0.0f);     // tensor-core layout: k = kh*16 + kw*4 + cin (ff_c1.cuh)
       for (int o = 0; o < 32; ++o) {
-        for (int k = 0; k < 27; ++k) h->conv1.w[o][k] = wr[(size_t)o * 27 + k];
+        for (int k = 0; k < 27; ++k) {
+          h->conv1.w[o][k] = wr[(size_t)o * 27 + k];
+          const int tap = k / 3, c = k % 3, kh = tap / 3, kw = tap % 3;
+          w32[o * 64 + kh * 16 + kw * 4 + c] = wr[(size_t)o * 27 + k];
+        }
         h->conv1.scale[o] = scale[o];
         h->conv1.shift[o] = shift[o];
+      }
+      if (h->compute == FF_COMPUTE_BF16) {
+        if ((rc = dev_upload(h, &h->c1_w, to_bf16(w32)))) return rc;
+        // lut[c][u] = bf16((u/255 - mean_c)/std_c), the fp32 arithmetic of cvit_prediction.py:41-45,214-215
+        const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+        std::vector<float> lut(3 * 256);
+        for (int c = 0; c < 3; ++c)
+          for (int u = 0; u < 256; ++u) lut[c * 256 + u] = ((float)u / 255.0f - mean[c]) / sd[c];
+        if ((rc = dev_upload(h, &h->c1_lut, to_bf16(lut)))) return rc;
       }
     }
     if (h->compute == FF_COMPUTE_FP32) {
@@ -544,8 +567,8 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
       a.tiles_w = p.hw / 8; a.tiles_h = p.hw / 16;
       a.lg_bw = 3; a.lg_bh = 4;
       const int tiles = a.tiles_w * a.tiles_h * n_img;
-      const int g = std::min(tiles, h->num_sms * h->ws_ctas_per_sm);
-      cudaError_t e = launch_ws(p.cin, p.cout, p.pool, h->ws_ctas_per_sm, g, st, L.tmA_ws, L.tmW_ws, a);
+      const int g = std::min(tiles, h->num_sms * (p.cin == 32 ? h->ws_ctas_per_sm : 1));
+      cudaError_t e = launch_ws(p.cin, p.cout, p.pool, h->ws_ctas_per_sm, g, st, L.tmA_ws, L.tmW_ws, a, L.epi);
       if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of ws conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
       ++h->launches;
       return FF_OK;
@@ -566,7 +589,15 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     dim3 g1(14, 14, ns);
     {
       ProfScope ps(h, st, KC_CONV1);
-      if (layout == FF_X_NHWC_U8) conv1_kernel<2><<<g1, 256, 0, st>>>(xin, h->bufA, ns, h->conv1);
+      if (h->use_c1_tc) {
+        C1Args ca;
+        ca.x = xin; ca.out = h->bufA; ca.w = h->c1_w; ca.lut = h->c1_lut;
+        ca.n_img = ns;
+        for (int o = 0; o < 32; ++o) { ca.scale[o] = h->conv1.scale[o]; ca.shift[o] = h->conv1.shift[o]; }
+        const int grid = std::min(392 * ns, h->num_sms * h->c1_ctas_per_sm);
+        if (layout == FF_X_NHWC_U8) conv1_tc_kernel<2><<<grid, 128, 0, st>>>(ca);
+        else conv1_tc_kernel<0><<<grid, 128, 0, st>>>(ca);
+      } else if (layout == FF_X_NHWC_U8) conv1_kernel<2><<<g1, 256, 0, st>>>(xin, h->bufA, ns, h->conv1);
       else conv1_kernel<0><<<g1, 256, 0, st>>>(xin, h->bufA, ns, h->conv1);
     }
     FF_LAUNCH_CHECK(h, "conv1");
@@ -766,6 +797,8 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
   h->s12 = std::min(16, h->cap);
   if (const char* v = getenv("FF_TC_VARIANT")) h->variant = atoi(v);
   if (const char* v = getenv("FF_WS")) h->use_ws = atoi(v);
+  if (const char* v = getenv("FF_C1_TC")) h->use_c1_tc = atoi(v);
+  if (const char* v = getenv("FF_C1_CPS")) h->c1_ctas_per_sm = std::max(1, atoi(v));
   if (const char* v = getenv("FF_WS_CPS")) h->ws_ctas_per_sm = std::max(1, atoi(v));
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   if (const char* v = getenv("FF_S12")) h->s12 = std::max(1, std::min(h->s12_cap, atoi(v)));

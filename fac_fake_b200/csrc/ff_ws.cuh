@@ -46,10 +46,17 @@ __device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t smem_addr, uin
   return d;
 }
 
+// Folded BN scale / shift passed by value (kernel-parameter constant bank): the epilogue FMAs take them as
+// constant operands instead of shared-memory loads.
+struct WsEpi {
+  float scale[64];
+  float shift[64];
+};
+
 // Epilogue of one 8x16 tile for the thread owning accumulator row r = h_l*8 + w_l (TMEM lane r).
 // `arrive_bar`: mbarrier to arrive on as soon as the accumulator has been read out of TMEM.
 template <int BN, bool POOL>
-__device__ __forceinline__ void ws_epilogue_direct(uint32_t taddr, const float* ss, const TcArgs& a, int w0, int h0, int n,
+__device__ __forceinline__ void ws_epilogue_direct(uint32_t taddr, const WsEpi& ss, const TcArgs& a, int w0, int h0, int n,
                                                    int r, int lane, uint32_t arrive_bar) {
   uint32_t v[BN];
 #pragma unroll
@@ -60,17 +67,16 @@ __device__ __forceinline__ void ws_epilogue_direct(uint32_t taddr, const float* 
   uint32_t p[BN / 2];
 #pragma unroll
   for (int c = 0; c < BN; c += 2) {
-    const float x0 = fmaf(__uint_as_float(v[c]), ss[c], ss[BN + c]);
-    const float x1 = fmaf(__uint_as_float(v[c + 1]), ss[c + 1], ss[BN + c + 1]);
-    p[c >> 1] = pack_bf16x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f));
+    const float x0 = fmaf(__uint_as_float(v[c]), ss.scale[c], ss.shift[c]);
+    const float x1 = fmaf(__uint_as_float(v[c + 1]), ss.scale[c + 1], ss.shift[c + 1]);
+    p[c >> 1] = pack_bf16x2_relu(x0, x1);
   }
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
   const int hl = r >> 3, wl = r & 7;
   if (!POOL) {
     const size_t pix = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * a.W + (w0 + wl);
-    uint4* o = reinterpret_cast<uint4*>(out + pix * BN);
 #pragma unroll
-    for (int i = 0; i < BN / 8; ++i) o[i] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+    for (int i = 0; i < BN / 16; ++i) st_global_v8(out + pix * BN + i * 16, p + 8 * i);
   } else {
 #pragma unroll
     for (int i = 0; i < BN / 2; ++i) {
@@ -83,9 +89,8 @@ __device__ __forceinline__ void ws_epilogue_direct(uint32_t taddr, const float* 
     }
     if ((lane & 9) == 0) {
       const size_t pix = (static_cast<size_t>(a.img_off_out + n) * (a.H >> 1) + ((h0 + hl) >> 1)) * (a.W >> 1) + ((w0 + wl) >> 1);
-      uint4* o = reinterpret_cast<uint4*>(out + pix * BN);
 #pragma unroll
-      for (int i = 0; i < BN / 8; ++i) o[i] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+      for (int i = 0; i < BN / 16; ++i) st_global_v8(out + pix * BN + i * 16, p + 8 * i);
     }
   }
 }
@@ -93,7 +98,8 @@ __device__ __forceinline__ void ws_epilogue_direct(uint32_t taddr, const float* 
 // args reuse TcArgs: H, W, tiles_w (= W/8), tiles_h (= H/16), n_img, img_off_out, cout, scale, shift, out.
 template <int ROWB, int BN, bool POOL, int STAGES>
 __global__ void __launch_bounds__(192, 1)
-wsconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs a) {
+wsconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs a,
+              const __grid_constant__ WsEpi epi) {
   using L = WsSmem<ROWB, BN, STAGES>;
   constexpr int KSTEPS = ROWB / 32;
   constexpr int CIN = ROWB / 2;
@@ -103,7 +109,6 @@ wsconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  float* ss = reinterpret_cast<float*>(base_ptr + L::SS_OFF);
   const uint32_t bar_w = base + L::BAR_OFF;
   const uint32_t bar_full = bar_w + 8;
   const uint32_t bar_empty = bar_full + STAGES * 8;
@@ -131,12 +136,6 @@ wsconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += 128) {
-      ss[i] = a.scale[i];
-      ss[BN + i] = a.shift[i];
-    }
-  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -196,7 +195,7 @@ wsconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const int th = rem / a.tiles_w, tw = rem - th * a.tiles_w;
       mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
       tcgen05_fence_after();
-      ws_epilogue_direct<BN, POOL>(tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN, ss, a, tw * 8, th * 16, n, r,
+      ws_epilogue_direct<BN, POOL>(tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN, epi, a, tw * 8, th * 16, n, r,
                                    lane, bar_tempty + 8 * acc);
     }
   }
