@@ -60,6 +60,8 @@ conv1_tc_kernel(const __grid_constant__ C1Args a) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = s_tmem;
+  if (tid == 0) pdl_trigger();
+  pdl_wait();                      // inputs may come from, and bufA may still be read by, the previous kernel
   const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
   constexpr uint32_t idesc = make_idesc_bf16(128, 32);
 

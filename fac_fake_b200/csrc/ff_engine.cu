@@ -15,6 +15,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/facfake.h"
@@ -61,6 +62,9 @@ struct ConvLayerDev {
   bool ws = false;          // persistent weight-stationary halo kernel (ff_ws.cuh)
   CUtensorMap tmA_ws, tmW_ws;
   WsEpi epi;                // host copy of (scale, shift) passed by value to the ws kernel
+  bool ws2 = false;         // pixel-pair formulation (Cin = 32): N = 2*Cout
+  bf16* w2 = nullptr;       // pair-expanded filter [2*Cout][384]
+  CUtensorMap tmA_ws2, tmW_ws2;
 };
 struct LinearDev {
   bf16* w = nullptr;        // [out][in] bf16
@@ -87,6 +91,7 @@ struct ff_cvit {
   int variant = 0;         // tile-shape variant (tuning)
   int use_ws = 1;          // feature layers 2..6 on the weight-stationary halo kernel
   int ws_ctas_per_sm = 2;   // CTAs per SM for the Cin=32 weight-stationary kernels (Cin=64 always 1: smem)
+  int use_ws2 = 1;         // Cin = 32 layers in the pixel-pair formulation
   int use_c1_tc = 1;       // feature layer 1 on the tensor cores (ff_c1.cuh) instead of the CUDA-core kernel
   int c1_ctas_per_sm = 6;
   bf16* c1_w = nullptr;    // [32][64] bf16, k = kh*16 + kw*4 + cin
@@ -245,6 +250,27 @@ int tmap_4d(ff_cvit* h, CUtensorMap* m, const void* base, int C, int W, int H, i
   return FF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ launch helper
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may start while its predecessor
+// in the stream is still draining; every kernel launched this way executes griddepcontrol.wait before it touches
+// global data produced (or still read) by the predecessor.
+bool g_use_pdl = true;
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && g_use_pdl) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------ tc launch dispatch
 template <int MODE, int ROWB, int BN, bool POOL, int STAGES>
 cudaError_t launch_tc_t(dim3 grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
@@ -256,8 +282,7 @@ cudaError_t launch_tc_t(dim3 grid, cudaStream_t st, const CUtensorMap& a, const 
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  k<<<grid, 192, L::TOTAL, st>>>(a, b, args);
-  return cudaGetLastError();
+  return launch_k(k, grid, dim3(192), L::TOTAL, st, true, a, b, args);
 }
 
 cudaError_t launch_conv(int rowb, int bn, bool pool, int variant, dim3 grid, cudaStream_t st, const CUtensorMap& a,
@@ -287,8 +312,7 @@ cudaError_t launch_ws_t(int grid, cudaStream_t st, const CUtensorMap& a, const C
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  k<<<grid, 192, L::TOTAL, st>>>(a, w, args, epi);
-  return cudaGetLastError();
+  return launch_k(k, dim3(grid), dim3(192), L::TOTAL, st, true, a, w, args, epi);
 }
 
 cudaError_t launch_ws(int cin, int cout, bool pool, int cps, int grid, cudaStream_t st, const CUtensorMap& a,
@@ -304,6 +328,20 @@ cudaError_t launch_ws(int cin, int cout, bool pool, int cps, int grid, cudaStrea
   if (cin == 64 && cout == 64)
     return pool ? launch_ws_t<128, 64, true, 5>(grid, st, a, w, args, epi) : launch_ws_t<128, 64, false, 5>(grid, st, a, w, args, epi);
   return cudaErrorInvalidValue;
+}
+
+template <int BN, bool POOL, int STAGES>
+cudaError_t launch_ws2_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args,
+                         const WsEpi& epi) {
+  using L = Ws2Smem<BN, STAGES>;
+  auto k = ws2conv_kernel<BN, POOL, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  return launch_k(k, dim3(grid), dim3(192), L::TOTAL, st, true, a, w, args, epi);
 }
 
 int conv_bn_for(int cout, int variant) {
@@ -394,6 +432,13 @@ int build_conv_maps(ff_cvit* h) {
     if (rc) return rc;
     rc = tmap_2d(h, &L.tmB, L.w, (uint64_t)9 * p.cin, p.cout, L.rowb / 2, L.bn);
     if (rc) return rc;
+    L.ws2 = h->use_ws && h->use_ws2 && p.cin == 32;
+    if (L.ws2) {
+      rc = tmap_4d(h, &L.tmA_ws2, conv_input_buffer(h, li), 64, p.hw / 2, p.hw, ncap, 64, 10, 18, 1);
+      if (rc) return rc;
+      rc = tmap_2d(h, &L.tmW_ws2, L.w2, 384, (uint64_t)2 * p.cout, 64, 2 * p.cout);
+      if (rc) return rc;
+    }
     L.ws = h->use_ws && li <= 5;
     if (L.ws) {
       rc = tmap_4d(h, &L.tmA_ws, conv_input_buffer(h, li), p.cin, p.hw, p.hw, ncap, p.cin, 10, 18, 1);
@@ -456,6 +501,20 @@ int finalize(ff_cvit* h) {
       if ((rc = dev_upload(h, &L.wf, wr))) return rc;
     } else if (li > 0) {
       if ((rc = dev_upload(h, &L.w, to_bf16(wr)))) return rc;
+      if (p.cin == 32) {
+        // pair-expanded filter: B[(p,co)][(kh,q,ci)] = W[co][kh][q-p][ci], zero unless 0 <= q-p <= 2 (ff_ws.cuh)
+        std::vector<float> w2((size_t)2 * p.cout * 384, 0.0f);
+        for (int pp = 0; pp < 2; ++pp)
+          for (int o = 0; o < p.cout; ++o)
+            for (int kh = 0; kh < 3; ++kh)
+              for (int q = 0; q < 4; ++q) {
+                const int kw = q - pp;
+                if (kw < 0 || kw > 2) continue;
+                for (int ci = 0; ci < 32; ++ci)
+                  w2[((size_t)pp * p.cout + o) * 384 + kh * 128 + q * 32 + ci] = wr[((size_t)o * 9 + kh * 3 + kw) * 32 + ci];
+              }
+        if ((rc = dev_upload(h, &L.w2, to_bf16(w2)))) return rc;
+      }
     }
   }
   // ---- embedding / tokens
@@ -563,6 +622,21 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     a.scale = L.scale; a.shift = L.shift;
     a.out = conv_output_buffer(h, li);
     ProfScope ps(h, st, KC_TC_CONV + li - 1);
+    if (L.ws2) {
+      a.tiles_w = p.hw / 16; a.tiles_h = p.hw / 16;
+      const int tiles = a.tiles_w * a.tiles_h * n_img;
+      cudaError_t e;
+      if (p.cout == 32) {
+        const int g = std::min(tiles, h->num_sms * 2);
+        e = p.pool ? launch_ws2_t<64, true, 2>(g, st, L.tmA_ws2, L.tmW_ws2, a, L.epi)
+                   : launch_ws2_t<64, false, 2>(g, st, L.tmA_ws2, L.tmW_ws2, a, L.epi);
+      } else {
+        e = launch_ws2_t<128, false, 4>(std::min(tiles, h->num_sms), st, L.tmA_ws2, L.tmW_ws2, a, L.epi);
+      }
+      if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of ws2 conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
+      ++h->launches;
+      return FF_OK;
+    }
     if (L.ws) {
       a.tiles_w = p.hw / 8; a.tiles_h = p.hw / 16;
       a.lg_bw = 3; a.lg_bh = 4;
@@ -595,8 +669,8 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
         ca.n_img = ns;
         for (int o = 0; o < 32; ++o) { ca.scale[o] = h->conv1.scale[o]; ca.shift[o] = h->conv1.shift[o]; }
         const int grid = std::min(392 * ns, h->num_sms * h->c1_ctas_per_sm);
-        if (layout == FF_X_NHWC_U8) conv1_tc_kernel<2><<<grid, 128, 0, st>>>(ca);
-        else conv1_tc_kernel<0><<<grid, 128, 0, st>>>(ca);
+        if (layout == FF_X_NHWC_U8) launch_k(conv1_tc_kernel<2>, dim3(grid), dim3(128), 0, st, true, ca);
+        else launch_k(conv1_tc_kernel<0>, dim3(grid), dim3(128), 0, st, true, ca);
       } else if (layout == FF_X_NHWC_U8) conv1_kernel<2><<<g1, 256, 0, st>>>(xin, h->bufA, ns, h->conv1);
       else conv1_kernel<0><<<g1, 256, 0, st>>>(xin, h->bufA, ns, h->conv1);
     }
@@ -797,6 +871,8 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
   h->s12 = std::min(16, h->cap);
   if (const char* v = getenv("FF_TC_VARIANT")) h->variant = atoi(v);
   if (const char* v = getenv("FF_WS")) h->use_ws = atoi(v);
+  if (const char* v = getenv("FF_PDL")) g_use_pdl = atoi(v) != 0;
+  if (const char* v = getenv("FF_WS2")) h->use_ws2 = atoi(v);
   if (const char* v = getenv("FF_C1_TC")) h->use_c1_tc = atoi(v);
   if (const char* v = getenv("FF_C1_CPS")) h->c1_ctas_per_sm = std::max(1, atoi(v));
   if (const char* v = getenv("FF_WS_CPS")) h->ws_ctas_per_sm = std::max(1, atoi(v));

@@ -224,6 +224,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
+      pdl_wait();                  // A (activations) is produced by the previous kernel
       int it = 0, s = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         if (it > 0) mbar_wait(bar_empty + 8 * s, (it - 1) & 1);

@@ -146,6 +146,8 @@ wsconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       // ---- filters: resident for the whole kernel
       mbar_arrive_expect_tx(bar_w, L::W_BYTES);
       for (int tap = 0; tap < 9; ++tap) tma_load_2d(base + L::W_OFF + tap * BN * ROWB, &tmW, bar_w, tap * CIN, 0);
+      pdl_trigger();
+      pdl_wait();                  // activations are produced by the previous kernel (filters are static)
       // ---- halo patches
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -197,6 +199,196 @@ wsconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tcgen05_fence_after();
       ws_epilogue_direct<BN, POOL>(tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN, epi, a, tw * 8, th * 16, n, r,
                                    lane, bar_tempty + 8 * acc);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// =================================================================================================================
+// Pixel-pair formulation for the Cin = 32 layers (feature layers 2, 3, 4).
+//
+// Measured on B200 (tools/umma_rate_test.cu): one tcgen05.mma M=128,K=16 costs >= 64 cycles whatever N <= 128 is
+// (the 128x32-byte A fetch), so with N = Cout = 32 the tensor pipe runs at 25 %.  Two horizontally adjacent pixels
+// of a 32-channel NHWC tensor are one contiguous 128-byte row, so the GEMM is re-shaped as
+//     rows    = pixel PAIRS (2j, 2j+1)                       M = 128 pairs = a 16 x 16 pixel tile
+//     columns = (pixel-in-pair p, cout)                      N = 2*Cout (64 or 128)
+//     K       = (kh, window pixel q in 0..3, cin)            K = 3*4*32 = 384, window = pixels 2j-1 .. 2j+2
+// with the pair-expanded filter  B[(p,co)][(kh,q,ci)] = W[co][kh][q-p][ci]  (zero unless 0 <= q-p <= 2).
+// 24 MMAs per 256 pixels instead of 36: 1.5x fewer tensor cycles at N = 64, 3x fewer at N = 128.
+// A is still the single halo patch: TMA box {64 elems = 1 pair, 10 pairs, 18 rows}; the K window of a row starts
+// 64 bytes into pair j and runs 256 bytes, i.e. descriptor start = patch + kh*10 rows + 64 + 32*kstep bytes.
+// The output row (pair, N values) is 2*Cout contiguous bf16 in NHWC.
+template <int BN, int STAGES>
+struct Ws2Smem {
+  static constexpr int W_TILE = BN * 128;                             // one 64-element k-block of the filter
+  static constexpr int W_BYTES = 6 * W_TILE;                          // 3 kh x 2 k-blocks
+  static constexpr int PATCH_BYTES = 180 * 128;
+  static constexpr int PATCH_STRIDE = (PATCH_BYTES + 1023) / 1024 * 1024;
+  static constexpr int W_OFF = 0;
+  static constexpr int P_OFF = W_BYTES;
+  static constexpr int BAR_OFF = P_OFF + STAGES * PATCH_STRIDE;       // w, full[S], empty[S], tfull[2], tempty[2]
+  static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 5) * 8;
+  static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
+};
+
+// Epilogue for one accumulator row = one pixel pair.  COUT = BN/2.  Processes the pair one pixel (COUT columns) at
+// a time to bound registers.  POOL: horizontal max = the two pixels of the pair, vertical max = lane ^ 8.
+template <int BN, bool POOL>
+__device__ __forceinline__ void ws2_epilogue(uint32_t taddr, const WsEpi& ss, const TcArgs& a, int pw0, int h0, int n, int r,
+                                             int lane, uint32_t arrive_bar) {
+  constexpr int COUT = BN / 2;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
+  const int hl = r >> 3, jl = r & 7;
+  const int Wp = a.W >> 1;                                            // pairs per image row
+  uint32_t pk[2][COUT / 2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    uint32_t v[COUT];
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 32) tmem_ld_32x32(taddr + p * COUT + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[c0]));
+    tmem_ld_wait();
+    if (p == 1) {
+      tcgen05_fence_before();
+      mbar_arrive(arrive_bar);
+    }
+#pragma unroll
+    for (int c = 0; c < COUT; c += 2) {
+      const float x0 = fmaf(__uint_as_float(v[c]), ss.scale[c], ss.shift[c]);
+      const float x1 = fmaf(__uint_as_float(v[c + 1]), ss.scale[c + 1], ss.shift[c + 1]);
+      pk[p][c >> 1] = pack_bf16x2_relu(x0, x1);
+    }
+    if (!POOL) {
+      const size_t pair = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * Wp + (pw0 + jl);
+      __nv_bfloat16* o = out + pair * BN + p * COUT;
+#pragma unroll
+      for (int i = 0; i < COUT / 16; ++i) st_global_v8(o + i * 16, &pk[p][8 * i]);
+    }
+  }
+  if (POOL) {
+#pragma unroll
+    for (int i = 0; i < COUT / 2; ++i) {
+      __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[0][i]), *reinterpret_cast<__nv_bfloat162*>(&pk[1][i]));
+      uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
+      uint32_t o2 = __shfl_xor_sync(0xffffffffu, mu, 8);
+      m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o2));
+      pk[0][i] = *reinterpret_cast<uint32_t*>(&m);
+    }
+    if ((lane & 8) == 0) {
+      const size_t pix = (static_cast<size_t>(a.img_off_out + n) * (a.H >> 1) + ((h0 + hl) >> 1)) * Wp + (pw0 + jl);
+      __nv_bfloat16* o = out + pix * COUT;
+#pragma unroll
+      for (int i = 0; i < COUT / 16; ++i) st_global_v8(o + i * 16, &pk[0][8 * i]);
+    }
+  }
+}
+
+// TcArgs: H, W, tiles_w (= W/16), tiles_h (= H/16), n_img, img_off_out, out.  epi.scale/shift indexed by cout.
+template <int BN, bool POOL, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs a,
+               const __grid_constant__ WsEpi epi) {
+  using L = Ws2Smem<BN, STAGES>;
+  constexpr int TMEM_COLS = 2 * BN;       // double-buffered accumulator (128 or 256 columns)
+  static_assert(BN == 64 || BN == 128, "BN");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_w = base + L::BAR_OFF;
+  const uint32_t bar_full = bar_w + 8;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_tfull = bar_empty + STAGES * 8;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_per_img = a.tiles_w * a.tiles_h;
+  const int num_tiles = tiles_per_img * a.n_img;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tfull + 8, 1);
+    mbar_init(bar_tempty, 128);
+    mbar_init(bar_tempty + 8, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w, L::W_BYTES);
+      for (int kb = 0; kb < 6; ++kb) tma_load_2d(base + L::W_OFF + kb * L::W_TILE, &tmW, bar_w, kb * 64, 0);
+      pdl_trigger();
+      pdl_wait();                  // activations are produced by the previous kernel (filters are static)
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(bar_empty + 8 * s, ((it / STAGES) - 1) & 1);
+        const int n = t / tiles_per_img;
+        const int rem = t - n * tiles_per_img;
+        const int th = rem / a.tiles_w, tw = rem - th * a.tiles_w;
+        mbar_arrive_expect_tx(bar_full + 8 * s, L::PATCH_BYTES);
+        tma_load_4d(base + L::P_OFF + s * L::PATCH_STRIDE, &tmA, bar_full + 8 * s, 0, tw * 8 - 1, th * 16 - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+      mbar_wait(bar_w, 0);
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        const int acc = it & 1;
+        if (it >= 2) mbar_wait(bar_tempty + 8 * acc, ((it >> 1) - 1) & 1);
+        mbar_wait(bar_full + 8 * s, (it / STAGES) & 1);
+        tcgen05_fence_after();
+        const uint32_t patch = base + L::P_OFF + s * L::PATCH_STRIDE;
+        const uint32_t d_tmem = tmem_base + acc * BN;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            // A: window starts 64 bytes (one pixel) into pair j of patch row (h_l + kh); 32 bytes per k-step
+            const uint64_t adesc = make_kmajor_desc_sbo<128>(patch + kh * 10 * 128 + 64 + 32 * c, 10 * 128);
+            const uint64_t bdesc = make_kmajor_desc<128>(base + L::W_OFF + (kh * 2 + (c >> 2)) * L::W_TILE) + 2 * (c & 3);
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kh > 0 || c > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar_empty + 8 * s);
+        umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+  } else {
+    const int g = warp & 3;
+    const int r = g * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int n = t / tiles_per_img;
+      const int rem = t - n * tiles_per_img;
+      const int th = rem / a.tiles_w, tw = rem - th * a.tiles_w;
+      mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
+      tcgen05_fence_after();
+      ws2_epilogue<BN, POOL>(tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN, epi, a, tw * 8, th * 16, n, r, lane,
+                             bar_tempty + 8 * acc);
     }
   }
 
