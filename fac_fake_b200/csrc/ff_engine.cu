@@ -85,7 +85,7 @@ struct ff_cvit {
   int device = 0;
   int cap = 0;             // crops per pass (multiple of 32)
   int rows_cap = 0;        // token rows capacity (multiple of 128)
-  int s12 = 16;            // crops per stage-1/2 sub-pass
+  int s12 = 32;            // crops per stage-1/2 sub-pass
   int s12_cap = 32;
   int compute = FF_COMPUTE_BF16;
   int variant = 0;         // tile-shape variant (tuning)
@@ -868,7 +868,7 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
   h->cap = (max_crops + 31) / 32 * 32;
   h->rows_cap = (2 * h->cap + 127) / 128 * 128;
   h->s12_cap = 32;
-  h->s12 = std::min(16, h->cap);
+  h->s12 = std::min(32, h->cap);
   if (const char* v = getenv("FF_TC_VARIANT")) h->variant = atoi(v);
   if (const char* v = getenv("FF_WS")) h->use_ws = atoi(v);
   if (const char* v = getenv("FF_PDL")) g_use_pdl = atoi(v) != 0;

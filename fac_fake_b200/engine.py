@@ -284,7 +284,7 @@ class CViTEngine:
         self._require_ready()
         self._check(self._lib.ff_cvit_set_tuning(self._h, stage12_sub_batch, use_cuda_graph), "ff_cvit_set_tuning")
 
-    KERNEL_CLASSES = ("conv1_cuda_core", "tcgen05_conv", "tcgen05_gemm", "small_kernels")
+    KERNEL_CLASSES = ("conv1", "tcgen05_conv", "tcgen05_gemm", "small_kernels")
 
     def set_profiling(self, enable: bool):
         self._require_ready()
@@ -300,7 +300,7 @@ class CViTEngine:
         if per_layer:
             names = ["conv1"] + [f"conv{i + 1}" for i in range(1, 17)] + ["gemm_embed", "gemm_transformer", "gemm_head", "small"]
             return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(names)}
-        agg = {"conv1_cuda_core": (float(ms[0]), int(cnt[0])),
+        agg = {"conv1": (float(ms[0]), int(cnt[0])),
                "tcgen05_conv": (float(sum(ms[1:17])), int(sum(cnt[1:17]))),
                "tcgen05_gemm": (float(sum(ms[17:20])), int(sum(cnt[17:20]))),
                "small_kernels": (float(ms[20]), int(cnt[20]))}
