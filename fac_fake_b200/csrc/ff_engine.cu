@@ -134,6 +134,12 @@ struct ff_cvit {
   int32_t* off_buf = nullptr; size_t off_cap = 0;
   float* score_buf = nullptr; size_t score_cap = 0;
   std::vector<void*> allocs;
+  // pipelined host->device input copy (ff_cvit_predict_host): chunk j of `h2d_chunk` crops is copied on
+  // copy_stream and published with h2d_ready[j]; the forward waits on it right before it first reads the chunk
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> h2d_ready;
+  int h2d_chunks_pending = 0;   // > 0 while a predict_host call is in flight
+  int h2d_chunk = 0;
   // optional per-launch timing (bench.py roofline): event pairs tagged with a kernel class
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -660,6 +666,11 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   for (int s0 = 0; s0 < n; s0 += sub) {
     const int ns = std::min(sub, n - s0);
     const uint8_t* xin = reinterpret_cast<const uint8_t*>(x) + (size_t)s0 * crop_in_bytes;
+    if (h->h2d_chunks_pending > 0) {   // input still streaming in: wait for the chunks covering [g0, g0+ns)
+      const int g0 = slot_base + s0;   // slot_base == offset of this pass inside the whole batch
+      const int c1 = std::min(h->h2d_chunks_pending - 1, (g0 + ns - 1) / h->h2d_chunk);
+      FF_CUDA(h, cudaStreamWaitEvent(st, h->h2d_ready[c1], 0));
+    }
     dim3 g1(14, 14, ns);
     {
       ProfScope ps(h, st, KC_CONV1);
@@ -732,6 +743,7 @@ int forward_fp32(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     if (stop == step) { tap->ptr = p; tap->elems = elems; tap->is_bf16 = false; tap->hit = true; return true; }
     return false;
   };
+  if (h->h2d_chunks_pending > 0) FF_CUDA(h, cudaStreamWaitEvent(st, h->h2d_ready[h->h2d_chunks_pending - 1], 0));
   // conv stack, NHWC fp32, ping-pong fA/fB; processed `chunk` crops at a time to bound the workspace
   const int chunk = h->s12_cap;
   const size_t crop_in_bytes = layout == FF_X_NHWC_U8 ? (size_t)224 * 224 * 3 : (size_t)224 * 224 * 3 * 4;
@@ -930,6 +942,8 @@ void ff_cvit_destroy(ff_cvit_t* h) {
   if (h->score_buf) cudaFree(h->score_buf);
   if (h->done_ev) cudaEventDestroy(h->done_ev);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->h2d_ready) cudaEventDestroy(e);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
 }
 
@@ -1026,10 +1040,32 @@ int ff_cvit_predict_host(ff_cvit_t* h, const uint8_t* x_host, const int32_t* off
     if ((rc = grow(h, &h->off_buf, &h->off_cap, (size_t)n_videos + 1))) return rc;
     if ((rc = grow(h, &h->score_buf, &h->score_cap, (size_t)n_videos))) return rc;
     FF_CUDA(h, cudaStreamWaitEvent(st, h->done_ev, 0));
-    if (n > 0) FF_CUDA(h, cudaMemcpyAsync(h->xin_buf, x_host, (size_t)n * 224 * 224 * 3, cudaMemcpyHostToDevice, st));
     FF_CUDA(h, cudaMemcpyAsync(h->off_buf, off_host, ((size_t)n_videos + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // crops stream in on a second stream, one stage-1/2 sub-pass at a time, overlapping the forward of earlier chunks
+    if (!h->copy_stream) FF_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    h->h2d_chunk = h->s12;
+    const int chunks = (n + h->h2d_chunk - 1) / h->h2d_chunk;
+    while ((int)h->h2d_ready.size() < chunks) {
+      cudaEvent_t e;
+      FF_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->h2d_ready.push_back(e);
+    }
+    FF_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->done_ev, 0));   // previous call has finished reading xin_buf
+    const size_t crop_bytes = (size_t)224 * 224 * 3;
+    for (int c = 0; c < chunks; ++c) {
+      const int c0 = c * h->h2d_chunk, cn = std::min(h->h2d_chunk, n - c0);
+      FF_CUDA(h, cudaMemcpyAsync(h->xin_buf + c0 * crop_bytes, x_host + c0 * crop_bytes, cn * crop_bytes, cudaMemcpyHostToDevice,
+                                 h->copy_stream));
+      FF_CUDA(h, cudaEventRecord(h->h2d_ready[c], h->copy_stream));
+    }
+    h->h2d_chunks_pending = chunks;
   }
-  if ((rc = ff_cvit_predict(h, h->xin_buf, FF_X_NHWC_U8, off_host, h->off_buf, n_videos, mode, nullptr, h->score_buf, stream))) return rc;
+  rc = ff_cvit_predict(h, h->xin_buf, FF_X_NHWC_U8, off_host, h->off_buf, n_videos, mode, nullptr, h->score_buf, stream);
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->h2d_chunks_pending = 0;
+  }
+  if (rc) return rc;
   FF_CUDA(h, cudaMemcpyAsync(scores_host, h->score_buf, (size_t)n_videos * sizeof(float), cudaMemcpyDeviceToHost, st));
   FF_CUDA(h, cudaStreamSynchronize(st));
   return FF_OK;
