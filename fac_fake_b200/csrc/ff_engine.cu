@@ -85,12 +85,13 @@ struct ff_cvit {
   int device = 0;
   int cap = 0;             // crops per pass (multiple of 32)
   int rows_cap = 0;        // token rows capacity (multiple of 128)
-  int s12 = 32;            // crops per stage-1/2 sub-pass
-  int s12_cap = 32;
+  int s12 = 64;            // crops per stage-1/2 sub-pass
+  int s12_cap = 256;
   int compute = FF_COMPUTE_BF16;
   int variant = 0;         // tile-shape variant (tuning)
   int use_ws = 1;          // feature layers 2..6 on the weight-stationary halo kernel
   int ws_ctas_per_sm = 2;   // CTAs per SM for the Cin=32 weight-stationary kernels (Cin=64 always 1: smem)
+  int use_ptc = 1;         // feature layers 7..17 on the persistent implicit-GEMM kernel
   int use_ws2 = 1;         // Cin = 32 layers in the pixel-pair formulation
   int use_c1_tc = 1;       // feature layer 1 on the tensor cores (ff_c1.cuh) instead of the CUDA-core kernel
   int c1_ctas_per_sm = 6;
@@ -348,6 +349,19 @@ cudaError_t launch_ws2_t(int grid, cudaStream_t st, const CUtensorMap& a, const 
     attr_done = true;
   }
   return launch_k(k, dim3(grid), dim3(192), L::TOTAL, st, true, a, w, args, epi);
+}
+
+template <int BN, int MSUB, bool POOL, int STAGES>
+cudaError_t launch_ptc_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
+  using L = PtcSmem<BN, MSUB, STAGES>;
+  auto k = ptc_conv_kernel<BN, MSUB, POOL, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  return launch_k(k, dim3(grid), dim3(192), L::TOTAL, st, true, a, b, args);
 }
 
 int conv_bn_for(int cout, int variant) {
@@ -653,6 +667,18 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
       ++h->launches;
       return FF_OK;
     }
+    if (h->use_ptc && L.rowb == 128 && (L.bn == 128 || L.bn == 256)) {
+      const int msub = L.bn == 128 ? 2 : 1;
+      const int m_tiles = a.tiles_w * a.tiles_h * ((n_img + L.bi - 1) / L.bi);
+      const int tiles = ((m_tiles + msub - 1) / msub) * (p.cout / L.bn);
+      const int g = std::min(tiles, h->num_sms);
+      cudaError_t e;
+      if (L.bn == 128) e = p.pool ? launch_ptc_t<128, 2, true, 4>(g, st, L.tmA, L.tmB, a) : launch_ptc_t<128, 2, false, 4>(g, st, L.tmA, L.tmB, a);
+      else e = p.pool ? launch_ptc_t<256, 1, true, 4>(g, st, L.tmA, L.tmB, a) : launch_ptc_t<256, 1, false, 4>(g, st, L.tmA, L.tmB, a);
+      if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of persistent conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
+      ++h->launches;
+      return FF_OK;
+    }
     dim3 grid(a.tiles_w * a.tiles_h * ((n_img + L.bi - 1) / L.bi), p.cout / L.bn, 1);
     cudaError_t e = launch_conv(L.rowb, L.bn, p.pool, h->variant, grid, st, L.tmA, L.tmB, a);
     if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
@@ -879,11 +905,12 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
   h->compute = compute_dtype;
   h->cap = (max_crops + 31) / 32 * 32;
   h->rows_cap = (2 * h->cap + 127) / 128 * 128;
-  h->s12_cap = 32;
-  h->s12 = std::min(32, h->cap);
+  h->s12_cap = 256;
+  h->s12 = std::min(64, h->cap);
   if (const char* v = getenv("FF_TC_VARIANT")) h->variant = atoi(v);
   if (const char* v = getenv("FF_WS")) h->use_ws = atoi(v);
   if (const char* v = getenv("FF_PDL")) g_use_pdl = atoi(v) != 0;
+  if (const char* v = getenv("FF_PTC")) h->use_ptc = atoi(v);
   if (const char* v = getenv("FF_WS2")) h->use_ws2 = atoi(v);
   if (const char* v = getenv("FF_C1_TC")) h->use_c1_tc = atoi(v);
   if (const char* v = getenv("FF_C1_CPS")) h->c1_ctas_per_sm = std::max(1, atoi(v));
@@ -1043,7 +1070,7 @@ int ff_cvit_predict_host(ff_cvit_t* h, const uint8_t* x_host, const int32_t* off
     FF_CUDA(h, cudaMemcpyAsync(h->off_buf, off_host, ((size_t)n_videos + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     // crops stream in on a second stream, one stage-1/2 sub-pass at a time, overlapping the forward of earlier chunks
     if (!h->copy_stream) FF_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    h->h2d_chunk = h->s12;
+    h->h2d_chunk = std::min(h->s12, 32);
     const int chunks = (n + h->h2d_chunk - 1) / h->h2d_chunk;
     while ((int)h->h2d_ready.size() < chunks) {
       cudaEvent_t e;
