@@ -166,3 +166,159 @@ conv1_tc_kernel(const __grid_constant__ C1Args a) {
 }
 
 }  // namespace ff
+
+namespace ff {
+
+// -----------------------------------------------------------------------------------------------------------------
+// uint8 fast path of feature layer 1: same math as conv1_tc_kernel<2>, but the raw patch arrives by TMA
+// (3-D map over the uint8 [n][224][672] view) through a 3-deep ring.  TMA needs a 16-byte aligned inner
+// coordinate (measured: tools/tma_u8_test.cu), and the 30-byte row segment of an 8-pixel-wide tile starts at byte
+// 24*tw-3, so the box is 48 bytes wide starting at 24*tw-16 (tw even) / 24*tw-8 (tw odd); out-of-image bytes are
+// zero-filled by TMA and masked to 0 AFTER normalisation by the conversion step.
+struct C1TmaArgs {
+  __nv_bfloat16* out;
+  const __nv_bfloat16* w;        // [32][64] bf16, k = kh*16 + kw*4 + cin
+  int n_img;
+  float na[3], nb[3];            // normalisation as one FMA: bf16(u*na[c] + nb[c]) == bf16((u/255 - mean_c)/std_c)
+                                 // for all 256 codes (checked on the host at finalize)
+  float scale[32];
+  float shift[32];
+};
+
+__global__ void __launch_bounds__(128, 8)
+conv1_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C1TmaArgs a) {
+  constexpr int HW = 224, TW = 8, TH = 16, PW = TW + 2, PH = TH + 2;
+  constexpr int TILES_W = HW / TW, TILES_H = HW / TH, TILES = TILES_W * TILES_H;
+  constexpr int RING = 3, ROW_WORDS = 12, RAW_BYTES = PH * ROW_WORDS * 4;
+  __shared__ __align__(1024) uint8_t sA[128 * 128];
+  __shared__ __align__(1024) uint8_t sB[32 * 128];
+  __shared__ __align__(128) uint8_t s_raw[RING][896];   // 864 B used per slot; TMA destinations must be 128-B aligned
+  __shared__ __align__(16) __nv_bfloat16 s_in[PH * PW * 4];
+  __shared__ __align__(8) uint64_t s_bar[1 + RING];
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar_mma = smem_u32(&s_bar[0]);
+  const uint32_t bar_raw = smem_u32(&s_bar[1]);
+  for (int i = tid; i < 32 * 8; i += 128) {
+    const int row = i >> 3, ch = i & 7;
+    *reinterpret_cast<uint4*>(sB + row * 128 + ((ch ^ (row & 7)) << 4)) = reinterpret_cast<const uint4*>(a.w)[i];
+  }
+  for (int i = tid; i < PH * PW * 4 / 8; i += 128) reinterpret_cast<uint4*>(s_in)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 128 * 8; i += 128) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    mbar_init(bar_mma, 1);
+    for (int s = 0; s < RING; ++s) mbar_init(bar_raw + 8 * s, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<32>(smem_u32(&s_tmem));
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (tid == 0) pdl_trigger();
+  pdl_wait();
+  const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+  constexpr uint32_t idesc = make_idesc_bf16(128, 32);
+  const int num_tiles = TILES * a.n_img;
+  const int hl = tid >> 3, wl = tid & 7;
+
+  // conversion job of this thread: patch pixels tid and tid + 128 (180 pixels, 3 raw bytes -> 4 bf16 each)
+  int job_py[2], job_px[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int pi = tid + j * 128;
+    job_py[j] = pi / PW;
+    job_px[j] = pi - job_py[j] * PW;
+  }
+  auto issue = [&](int t, int slot) {
+    const int n = t / TILES;
+    const int rem = t - n * TILES;
+    const int th = rem / TILES_W, tw = rem - th * TILES_W;
+    mbar_arrive_expect_tx(bar_raw + 8 * slot, RAW_BYTES);
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(&s_raw[slot][0])),
+        "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar_raw + 8 * slot), "r"(24 * tw - ((tw & 1) ? 8 : 16)), "r"(th * TH - 1), "r"(n)
+        : "memory");
+  };
+  if (tid == 0) {
+    for (int s = 0; s < RING - 1; ++s) {
+      const int t = blockIdx.x + s * gridDim.x;
+      if (t < num_tiles) issue(t, s);
+    }
+  }
+  int it = 0;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    const int n = t / TILES;
+    const int rem = t - n * TILES;
+    const int th = rem / TILES_W, tw = rem - th * TILES_W;
+    const int h0 = th * TH, w0 = tw * TW;
+    const int slot = it % RING;
+    // ---- 1. raw uint8 window -> normalised bf16 patch (0 outside the image)
+    mbar_wait(bar_raw + 8 * slot, (it / RING) & 1);
+    const int off = (tw & 1) ? 5 : 13;            // first segment byte inside the 48-byte window
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int pi = tid + j * 128;
+      if (pi < PH * PW) {
+        const uint8_t* rp = &s_raw[slot][job_py[j] * (ROW_WORDS * 4) + off + 3 * job_px[j]];
+        const int gy = h0 - 1 + job_py[j], gx = w0 - 1 + job_px[j];
+        const bool ok = gy >= 0 && gy < HW && gx >= 0 && gx < HW;
+        const float v0 = ok ? fmaf(static_cast<float>(rp[0]), a.na[0], a.nb[0]) : 0.0f;
+        const float v1 = ok ? fmaf(static_cast<float>(rp[1]), a.na[1], a.nb[1]) : 0.0f;
+        const float v2 = ok ? fmaf(static_cast<float>(rp[2]), a.na[2], a.nb[2]) : 0.0f;
+        *reinterpret_cast<uint2*>(s_in + pi * 4) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, 0.0f));
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {                       // the slot two tiles ahead is free: its consumer (tile it-1) has passed the barrier
+      const int tn = t + (RING - 1) * gridDim.x;
+      if (tn < num_tiles) issue(tn, (it + RING - 1) % RING);
+    }
+    // ---- 2. this thread's K-major row
+    {
+      const int sw = tid & 7;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const uint2* src = reinterpret_cast<const uint2*>(s_in + ((hl + kh) * PW + wl) * 4);
+        const uint2 p0 = src[0], p1 = src[1], p2 = src[2];
+        *reinterpret_cast<uint4*>(sA + tid * 128 + (((2 * kh) ^ sw) << 4)) = make_uint4(p0.x, p0.y, p1.x, p1.y);
+        *reinterpret_cast<uint4*>(sA + tid * 128 + (((2 * kh + 1) ^ sw) << 4)) = make_uint4(p2.x, p2.y, 0u, 0u);
+      }
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tcgen05_fence_after();
+      const uint64_t ad = make_kmajor_desc<128>(sA_addr), bd = make_kmajor_desc<128>(sB_addr);
+      umma_bf16_ss(tmem, ad, bd, idesc, 0u);
+      umma_bf16_ss(tmem, ad + 2, bd + 2, idesc, 1u);
+      umma_bf16_ss(tmem, ad + 4, bd + 4, idesc, 1u);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, it & 1);
+    tcgen05_fence_after();
+    uint32_t v[32];
+    tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16), v);
+    tmem_ld_wait();
+    uint32_t p[16];
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      const float x0 = fmaf(__uint_as_float(v[c]), a.scale[c], a.shift[c]);
+      const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale[c + 1], a.shift[c + 1]);
+      p[c >> 1] = pack_bf16x2_relu(x0, x1);
+    }
+    __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * HW + (h0 + hl)) * HW + (w0 + wl)) * 32;
+    st_global_v8(o, p);
+    st_global_v8(o + 16, p + 8);
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<32>(tmem); }
+}
+
+}  // namespace ff

@@ -93,10 +93,11 @@ struct ff_cvit {
   int ws_ctas_per_sm = 2;   // CTAs per SM for the Cin=32 weight-stationary kernels (Cin=64 always 1: smem)
   int use_ptc = 1;         // feature layers 7..17 on the persistent implicit-GEMM kernel
   int use_ws2 = 1;         // Cin = 32 layers in the pixel-pair formulation
-  int use_c1_tc = 1;       // feature layer 1 on the tensor cores (ff_c1.cuh) instead of the CUDA-core kernel
-  int c1_ctas_per_sm = 6;
+  int use_c1_tc = 2;       // feature layer 1: 2 = tensor cores + TMA-fed uint8 patch, 1 = tensor cores, 0 = CUDA cores
+  int c1_ctas_per_sm = 8;
   bf16* c1_w = nullptr;    // [32][64] bf16, k = kh*16 + kw*4 + cin
   bf16* c1_lut = nullptr;  // [3][256] bf16 normalisation table
+  float c1_na[3] = {0, 0, 0}, c1_nb[3] = {0, 0, 0};   // FMA form of the table (valid iff it reproduces all 768 entries)
   int num_sms = 148;
   bool finalized = false;
   std::mutex mu;
@@ -120,7 +121,8 @@ struct ff_cvit {
   float* emb = nullptr;                    // [cap][1024]
   float* x = nullptr;                      // [rows_cap][1024] residual stream
   bf16* xn = nullptr;                      // [rows_cap][1024]
-  float* qkv = nullptr;                    // [rows_cap][3072]
+  float* qkv = nullptr;                    // [rows_cap][3072] (fp32 path)
+  bf16* qkvb = nullptr;                    // [rows_cap][3072] (bf16 path)
   bf16* att = nullptr;                     // [rows_cap][1024]
   bf16* ffh = nullptr;                     // [rows_cap][2048]
   bf16* clsb = nullptr;                    // [cap128][1024]
@@ -143,6 +145,7 @@ struct ff_cvit {
   int h2d_chunk = 0;
   // optional per-launch timing (bench.py roofline): event pairs tagged with a kernel class
   bool profiling = false;
+  bool prof_coarse = false;   // true: only 3 phase boundaries per pass are timed (slots 0/1/2), launches stay PDL-chained
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   std::vector<int> ev_class;       // class of pair i (events 2i, 2i+1)
@@ -166,8 +169,8 @@ int fail(const ff_cvit* h, int code, const char* fmt, ...) {
 // 19 = head GEMM, 20 = small kernels
 enum { KC_CONV1 = 0, KC_TC_CONV = 1, KC_GEMM_EMBED = 17, KC_GEMM_XF = 18, KC_GEMM_HEAD = 19, KC_SMALL = 20, KC_COUNT = 21 };
 
-void prof_mark(ff_cvit* h, cudaStream_t st, int cls, bool begin) {
-  if (!h->profiling) return;
+void prof_mark(ff_cvit* h, cudaStream_t st, int cls, bool begin, bool coarse = false) {
+  if (!h->profiling || (h->prof_coarse != coarse)) return;
   if (h->ev_used >= h->ev_pool.size()) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
@@ -515,6 +518,18 @@ int finalize(ff_cvit* h) {
         for (int c = 0; c < 3; ++c)
           for (int u = 0; u < 256; ++u) lut[c * 256 + u] = ((float)u / 255.0f - mean[c]) / sd[c];
         if ((rc = dev_upload(h, &h->c1_lut, to_bf16(lut)))) return rc;
+        // single-FMA form used by the TMA-fed kernel; keep it only if it reproduces the table bit for bit
+        bool fma_ok = true;
+        for (int c = 0; c < 3; ++c) {
+          h->c1_na[c] = 1.0f / (255.0f * sd[c]);
+          h->c1_nb[c] = -mean[c] / sd[c];
+          for (int u = 0; u < 256; ++u) {
+            const float f = std::fmaf((float)u, h->c1_na[c], h->c1_nb[c]);
+            const bf16 x = __float2bfloat16(f), y = __float2bfloat16(lut[c * 256 + u]);
+            if (memcmp(&x, &y, sizeof(bf16)) != 0) fma_ok = false;
+          }
+        }
+        if (!fma_ok && h->use_c1_tc == 2) h->use_c1_tc = 1;
       }
     }
     if (h->compute == FF_COMPUTE_FP32) {
@@ -554,9 +569,9 @@ int finalize(ff_cvit* h) {
     if ((rc = upload_vec(h, &X.ln1_b, p + ".0.fn.norm.bias", DIM))) return rc;
     if ((rc = upload_vec(h, &X.ln2_g, p + ".1.fn.norm.weight", DIM))) return rc;
     if ((rc = upload_vec(h, &X.ln2_b, p + ".1.fn.norm.bias", DIM))) return rc;
-    if ((rc = upload_linear(h, &X.qkv, p + ".0.fn.fn.to_qkv", 3 * DIM, DIM, false, 128))) return rc;
+    if ((rc = upload_linear(h, &X.qkv, p + ".0.fn.fn.to_qkv", 3 * DIM, DIM, false, 64))) return rc;
     if ((rc = upload_linear(h, &X.out, p + ".0.fn.fn.to_out", DIM, DIM, true, 64))) return rc;
-    if ((rc = upload_linear(h, &X.ff1, p + ".1.fn.fn.net.0", MLP, DIM, true, 128))) return rc;
+    if ((rc = upload_linear(h, &X.ff1, p + ".1.fn.fn.net.0", MLP, DIM, true, 64))) return rc;
     if ((rc = upload_linear(h, &X.ff2, p + ".1.fn.fn.net.2", DIM, MLP, true, 64))) return rc;
   }
   if ((rc = upload_linear(h, &h->head1, "mlp_head.0", MLP, DIM, true, 64))) return rc;
@@ -596,7 +611,7 @@ int launch_gemm(ff_cvit* h, cudaStream_t st, const CUtensorMap& tmA, const Linea
   dim3 grid((M + 127) / 128, L.out_f / L.bn, zs);
   ProfScope ps(h, st, &L == &h->embed ? KC_GEMM_EMBED : (&L == &h->head1 ? KC_GEMM_HEAD : KC_GEMM_XF));
   cudaError_t e = L.bn == 128 ? launch_tc_t<MODE_GEMM, 128, 128, false, 4>(grid, st, tmA, L.tmB, a)
-                              : launch_tc_t<MODE_GEMM, 128, 64, false, 6>(grid, st, tmA, L.tmB, a);
+                              : launch_tc_t<MODE_GEMM, 128, 64, false, 4>(grid, st, tmA, L.tmB, a);
   if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of gemm %s failed: %s", what, cudaGetErrorString(e));
   ++h->launches;
   return FF_OK;
@@ -687,6 +702,7 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   };
 
   // ---- stages 1-2 in sub-passes of s12 crops (activations of 3.2 MB/crop stay L2-resident between layers)
+  prof_mark(h, st, 0, true, true);
   const int sub = stop ? std::min(n, h->s12_cap) : h->s12;
   if (stop && n > h->s12_cap) return fail(h, FF_ERR_BAD_ARG, "debug tap needs n <= %d", h->s12_cap);
   for (int s0 = 0; s0 < n; s0 += sub) {
@@ -700,7 +716,24 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     dim3 g1(14, 14, ns);
     {
       ProfScope ps(h, st, KC_CONV1);
-      if (h->use_c1_tc) {
+      if (h->use_c1_tc == 2 && layout == FF_X_NHWC_U8) {
+        // TMA-fed uint8 path: per-launch 3-D map over the caller's uint8 crops viewed as [ns][224][672]
+        CUtensorMap tmX;
+        cuuint64_t dims[3] = {672, 224, (cuuint64_t)ns};
+        cuuint64_t strides[2] = {672, (cuuint64_t)224 * 672};
+        cuuint32_t box[3] = {48, 18, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = g_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(xin), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(uint8 crops) failed: %d (is the input 16-byte aligned?)", (int)r);
+        C1TmaArgs ca;
+        ca.out = h->bufA; ca.w = h->c1_w; ca.n_img = ns;
+        for (int c = 0; c < 3; ++c) { ca.na[c] = h->c1_na[c]; ca.nb[c] = h->c1_nb[c]; }
+        for (int o = 0; o < 32; ++o) { ca.scale[o] = h->conv1.scale[o]; ca.shift[o] = h->conv1.shift[o]; }
+        const int grid = std::min(392 * ns, h->num_sms * h->c1_ctas_per_sm);
+        launch_k(conv1_tma_kernel, dim3(grid), dim3(128), 0, st, true, tmX, ca);
+      } else if (h->use_c1_tc) {
         C1Args ca;
         ca.x = xin; ca.out = h->bufA; ca.w = h->c1_w; ca.lut = h->c1_lut;
         ca.n_img = ns;
@@ -721,6 +754,8 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
       if (tap_hit(li + 1, conv_output_buffer(h, li), (int64_t)ns * ohw * ohw * p.cout, true)) return FF_OK;
     }
   }
+  prof_mark(h, st, 0, false, true);
+  prof_mark(h, st, 1, true, true);
   // ---- stages 3-5 on the whole pass
   for (int li = 6; li < 17; ++li) {
     int rc = run_conv(li, n, 0);
@@ -729,34 +764,37 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     const int ohw = p.pool ? p.hw / 2 : p.hw;
     if (tap_hit(li + 1, conv_output_buffer(h, li), (int64_t)n * ohw * ohw * p.cout, true)) return FF_OK;
   }
+  prof_mark(h, st, 1, false, true);
+  prof_mark(h, st, 2, true, true);
   // ---- patch embedding (split-K, fp32 atomics) + token assembly
   int rc = launch_gemm(h, st, h->tm_feat, h->embed, n, h->emb, DIM, EPI_STORE_F32, ACT_NONE, EMBED_SPLITS, "patch_to_embedding");
   if (rc) return rc;
-  { ProfScope ps(h, st, KC_SMALL); tokens_kernel<<<n, 256, 0, st>>>(h->emb, EMBED_SPLITS, (long long)h->cap * DIM, h->embed.b, h->cls, h->pos, slot, slot_base, h->x, n); }
+  { ProfScope ps(h, st, KC_SMALL); launch_k(tokens_kernel, dim3(n), dim3(256), 0, st, true, (const float*)h->emb, (int)EMBED_SPLITS, (long long)h->cap * DIM, (const float*)h->embed.b, (const float*)h->cls, (const float*)h->pos, slot, slot_base, h->x, n); }
   FF_LAUNCH_CHECK(h, "tokens");
   const int rows = 2 * n;
   if (tap_hit(18, h->x, (int64_t)rows * DIM, false)) return FF_OK;
   // ---- transformer
   for (int l = 0; l < DEPTH; ++l) {
     const XfLayerDev& X = h->xf[l];
-    { ProfScope ps(h, st, KC_SMALL); layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(h->x, X.ln1_g, X.ln1_b, h->xn, rows); }
+    { ProfScope ps(h, st, KC_SMALL); launch_k(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, true, (const float*)h->x, (const float*)X.ln1_g, (const float*)X.ln1_b, h->xn, rows); }
     FF_LAUNCH_CHECK(h, "layernorm1");
-    if ((rc = launch_gemm(h, st, h->tm_xn, X.qkv, rows, h->qkv, 3 * DIM, EPI_STORE_F32, ACT_NONE, 1, "to_qkv"))) return rc;
-    { ProfScope ps(h, st, KC_SMALL); attention2_kernel<<<(n * 8 + 7) / 8, 256, 0, st>>>(h->qkv, h->att, n); }
+    if ((rc = launch_gemm(h, st, h->tm_xn, X.qkv, rows, h->qkvb, 3 * DIM, EPI_STORE_BF16, ACT_NONE, 1, "to_qkv"))) return rc;
+    { ProfScope ps(h, st, KC_SMALL); launch_k(attention2_kernel, dim3((n * 8 + 7) / 8), dim3(256), 0, st, true, (const bf16*)h->qkvb, h->att, n); }
     FF_LAUNCH_CHECK(h, "attention2");
     if ((rc = launch_gemm(h, st, h->tm_att, X.out, rows, h->x, DIM, EPI_RESID_F32, ACT_NONE, 1, "to_out"))) return rc;
-    { ProfScope ps(h, st, KC_SMALL); layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(h->x, X.ln2_g, X.ln2_b, h->xn, rows); }
+    { ProfScope ps(h, st, KC_SMALL); launch_k(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, true, (const float*)h->x, (const float*)X.ln2_g, (const float*)X.ln2_b, h->xn, rows); }
     FF_LAUNCH_CHECK(h, "layernorm2");
     if ((rc = launch_gemm(h, st, h->tm_xn, X.ff1, rows, h->ffh, MLP, EPI_STORE_BF16, ACT_GELU, 1, "ff1"))) return rc;
     if ((rc = launch_gemm(h, st, h->tm_ffh, X.ff2, rows, h->x, DIM, EPI_RESID_F32, ACT_NONE, 1, "ff2"))) return rc;
     if (tap_hit(19 + l, h->x, (int64_t)rows * DIM, false)) return FF_OK;
   }
   // ---- head
-  { ProfScope ps(h, st, KC_SMALL); cls_gather_kernel<<<n, 256, 0, st>>>(h->x, h->clsb, n); }
+  { ProfScope ps(h, st, KC_SMALL); launch_k(cls_gather_kernel, dim3(n), dim3(256), 0, st, true, (const float*)h->x, h->clsb, n); }
   FF_LAUNCH_CHECK(h, "cls_gather");
   if ((rc = launch_gemm(h, st, h->tm_cls, h->head1, n, h->hid, MLP, EPI_STORE_F32, ACT_RELU, 1, "mlp_head.0"))) return rc;
-  { ProfScope ps(h, st, KC_SMALL); head2_kernel<<<(n + 7) / 8, 256, 0, st>>>(h->hid, h->head2.wf, h->head2.b, logits, n); }
+  { ProfScope ps(h, st, KC_SMALL); launch_k(head2_kernel, dim3((n + 7) / 8), dim3(256), 0, st, true, (const float*)h->hid, (const float*)h->head2.wf, (const float*)h->head2.b, logits, n); }
   FF_LAUNCH_CHECK(h, "head2");
+  prof_mark(h, st, 2, false, true);
   if (tap_hit(25, logits, (int64_t)n * 2, false)) return FF_OK;
   return FF_OK;
 }
@@ -934,6 +972,7 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
       if ((rc = dev_alloc(h, &h->xn, (size_t)h->rows_cap * DIM))) break;
       if ((rc = dev_alloc(h, &h->att, (size_t)h->rows_cap * DIM))) break;
       if ((rc = dev_alloc(h, &h->ffh, (size_t)h->rows_cap * MLP))) break;
+      if ((rc = dev_alloc(h, &h->qkvb, (size_t)h->rows_cap * 3 * DIM))) break;
       if ((rc = dev_alloc(h, &h->clsb, (size_t)cap128 * DIM))) break;
       // rows beyond the valid ones are read by TMA (results masked): keep them finite
       cudaMemset(h->feat, 0, (size_t)cap128 * PATCH * 2);
@@ -1178,6 +1217,7 @@ int ff_cvit_set_profiling(ff_cvit_t* h, int enable) {
   if (!h) return FF_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   h->profiling = enable != 0;
+  h->prof_coarse = enable == 2;
   h->ev_used = 0;
   h->ev_class.clear();
   for (int i = 0; i < KC_COUNT; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }

@@ -84,6 +84,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ y, int rows) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -120,16 +122,24 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 // 2-token attention (cvit.py:43-60): one warp per (crop, head).  qkv fp32 [2n][3072] with feature index
 // which*1024 + head*128 + d (cvit.py:46); scale = dim**-0.5 = 1/32 (cvit.py:38); out bf16 [2n][1024] '(h d)'.
 __global__ void __launch_bounds__(256)
-attention2_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_crops) {
+attention2_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_crops) {
+  pdl_trigger();
+  pdl_wait();
   const int wid = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (wid >= n_crops * 8) return;
   const int b = wid >> 3, h = wid & 7;
-  const float* r0 = qkv + static_cast<size_t>(2 * b) * 3072 + h * 128 + lane * 4;
-  const float* r1 = r0 + 3072;
-  const float4 q0 = *reinterpret_cast<const float4*>(r0), q1 = *reinterpret_cast<const float4*>(r1);
-  const float4 k0 = *reinterpret_cast<const float4*>(r0 + 1024), k1 = *reinterpret_cast<const float4*>(r1 + 1024);
-  const float4 v0 = *reinterpret_cast<const float4*>(r0 + 2048), v1 = *reinterpret_cast<const float4*>(r1 + 2048);
+  const __nv_bfloat16* r0 = qkv + static_cast<size_t>(2 * b) * 3072 + h * 128 + lane * 4;
+  const __nv_bfloat16* r1 = r0 + 3072;
+  auto ld4 = [](const __nv_bfloat16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, c.x, c.y);
+  };
+  const float4 q0 = ld4(r0), q1 = ld4(r1);
+  const float4 k0 = ld4(r0 + 1024), k1 = ld4(r1 + 1024);
+  const float4 v0 = ld4(r0 + 2048), v1 = ld4(r1 + 2048);
   auto dot = [](const float4& a, const float4& c) { return (a.x * c.x + a.y * c.y) + (a.z * c.z + a.w * c.w); };
   const float s = 0.03125f;
   const float d00 = warp_sum(dot(q0, k0)) * s, d01 = warp_sum(dot(q0, k1)) * s;
@@ -151,6 +161,8 @@ __global__ void __launch_bounds__(256)
 tokens_kernel(const float* __restrict__ emb, int n_splits, long long split_stride, const float* __restrict__ bias,
               const float* __restrict__ cls, const float* __restrict__ pos, const int* __restrict__ slot, int slot_base,
               float* __restrict__ x, int n) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   if (b >= n) return;
   const int s = slot ? slot[b] : ((slot_base + b) & 31);
@@ -171,6 +183,8 @@ tokens_kernel(const float* __restrict__ emb, int n_splits, long long split_strid
 // cls select (cvit.py:177): bf16 copy of token 0 of every crop -> A operand of mlp_head.0.
 __global__ void __launch_bounds__(256)
 cls_gather_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int n) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   if (b >= n) return;
   const float4 v = reinterpret_cast<const float4*>(x + static_cast<size_t>(2 * b) * 1024)[threadIdx.x];
@@ -182,6 +196,8 @@ cls_gather_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, 
 __global__ void __launch_bounds__(256)
 head2_kernel(const float* __restrict__ hid, const float* __restrict__ w, const float* __restrict__ bias,
              float* __restrict__ logits, int n) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= n) return;
@@ -209,6 +225,8 @@ head2_kernel(const float* __restrict__ hid, const float* __restrict__ w, const f
 __global__ void __launch_bounds__(256)
 video_reduce_kernel(const float* __restrict__ logits, const int* __restrict__ off, int n_videos, int mode,
                     float* __restrict__ scores) {
+  pdl_trigger();
+  pdl_wait();
   const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (v >= n_videos) return;

@@ -191,6 +191,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   // ---- one-time setup
   if (warp == 0 && lane == 0) {
+    if (MODE == MODE_GEMM) pdl_trigger();   // <= 2 waves of CTAs: let the next (small) kernel pre-stage
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
@@ -300,22 +301,27 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           const size_t off = static_cast<size_t>(blockIdx.z) * a.split_stride + static_cast<size_t>(m) * a.ldo + nb;
           if (a.epi == EPI_STORE_F32) {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + off);
+            float* o = reinterpret_cast<float*>(a.out) + off;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) st_global_v8(o + 8 * i, reinterpret_cast<const uint32_t*>(&f[8 * i]));
           } else if (a.epi == EPI_STORE_BF16) {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + off);
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + off;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
-                                pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+            for (int i = 0; i < 2; ++i) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(f[16 * i + 2 * e], f[16 * i + 2 * e + 1]);
+              st_global_v8(o + 16 * i, pk);
+            }
           } else if (a.epi == EPI_RESID_F32) {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + off);
+            float* o = reinterpret_cast<float*>(a.out) + off;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 t = o[i];
-              t.x += f[4 * i]; t.y += f[4 * i + 1]; t.z += f[4 * i + 2]; t.w += f[4 * i + 3];
-              o[i] = t;
+            for (int i = 0; i < 4; ++i) {
+              uint32_t t[8];
+              ld_global_v8(o + 8 * i, t);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t[e] = __float_as_uint(__uint_as_float(t[e]) + f[8 * i + e]);
+              st_global_v8(o + 8 * i, t);
             }
           } else {
             float* o = reinterpret_cast<float*>(a.out) + off;

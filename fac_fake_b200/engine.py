@@ -286,9 +286,10 @@ class CViTEngine:
 
     KERNEL_CLASSES = ("conv1", "tcgen05_conv", "tcgen05_gemm", "small_kernels")
 
-    def set_profiling(self, enable: bool):
+    def set_profiling(self, enable):
+        """False/0 off, True/1 per-launch event pairs, 2 coarse (three phases per pass, launches stay PDL-chained)."""
         self._require_ready()
-        self._check(self._lib.ff_cvit_set_profiling(self._h, int(bool(enable))), "ff_cvit_set_profiling")
+        self._check(self._lib.ff_cvit_set_profiling(self._h, int(enable)), "ff_cvit_set_profiling")
 
     def get_profile(self, per_layer: bool = False):
         """{class: (milliseconds, launches)} accumulated since set_profiling(True).

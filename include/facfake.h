@@ -126,6 +126,8 @@ int64_t ff_cvit_debug_activation(ff_cvit_t* h, const void* x, int x_layout, cons
  * pair on the launching stream.  ff_cvit_get_profile synchronises and returns accumulated milliseconds and
  * launch counts in 21 slots: 0 = conv1 (CUDA cores), 1..16 = tcgen05 conv of feature layer 2..17,
  * 17 = patch-embedding GEMM, 18 = transformer GEMMs, 19 = head GEMM, 20 = small kernels.
+ * enable == 2 selects a coarse mode that only times three phases per pass (slot 0 = feature layers 1-6,
+ * slot 1 = feature layers 7-17, slot 2 = embedding + transformer + head) and leaves the launches PDL-chained.
  * ff_cvit_set_profiling resets the accumulators.                                                            */
 int ff_cvit_set_profiling(ff_cvit_t* h, int enable);
 int ff_cvit_get_profile(ff_cvit_t* h, double* ms_by_slot /*[21]*/, int64_t* launches_by_slot /*[21]*/);

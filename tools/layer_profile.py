@@ -40,6 +40,14 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     plain_ms = e0.elapsed_time(e1) / args.steps
+    eng.set_profiling(2)
+    for i in range(args.steps):
+        eng.predict_videos(crops[i % 2], offs)
+    torch.cuda.synchronize()
+    coarse = eng.get_profile(per_layer=True)
+    names = list(coarse.keys())
+    ph = [coarse[names[i]][0] / args.steps for i in range(3)]
+    print(f"coarse phases (PDL intact): layers1-6 {ph[0]:.3f} ms | layers7-17 {ph[1]:.3f} ms | embed+transformer+head {ph[2]:.3f} ms")
     eng.set_profiling(True)
     e0.record()
     for i in range(args.steps):
