@@ -291,7 +291,13 @@ def main():
             "achieved": tc_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tc_tflops / peak,
             "peak_source": f"bf16_tflops_sustained, {peaks['source']} (kernel timed inside a long step)",
             "frac_of_burst_peak": tc_tflops / peaks["bf16_burst"],
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel
+            # ff::ptc_conv_kernel<256,1,false,4> (feature layer 11/12: 256->256 @28x28, 512 crops) from the
+            # `ncu --set full` capture in profiles/r01_ncu_ptc_conv_raw.csv: 107.5 MB read + 68.1 MB written,
+            # below the layer's algorithmic 411 MB (205 MB in + 205 MB out + 1.2 MB weights) because the previous
+            # layer's output is still L2-resident.
+            "traffic": 175.6e6,
+            "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum), kernel ff::ptc_conv_kernel<256,1,0,4>",
             "algorithmic_flops_per_crop": TC_CONV_FLOPS,
             "kernel_ms_per_step": conv_ms / steps, "kernel_launches_per_step": conv_launches / steps,
             "step_share": conv_ms / ms_instr if ms_instr > 0 else None,
