@@ -62,6 +62,9 @@ struct ConvLayerDev {
   bool ws = false;          // persistent weight-stationary halo kernel (ff_ws.cuh)
   CUtensorMap tmA_ws, tmW_ws;
   WsEpi epi;                // host copy of (scale, shift) passed by value to the ws kernel
+  bool ws2x = false;        // pixel-pair formulation on a CTA pair (Cin = 64): N = 128, cta_group::2
+  bf16* w2x = nullptr;      // pair-expanded filter [128][768]
+  CUtensorMap tmA_ws2x, tmW_ws2x;
   bool ws2 = false;         // pixel-pair formulation (Cin = 32): N = 2*Cout
   bf16* w2 = nullptr;       // pair-expanded filter [2*Cout][384]
   CUtensorMap tmA_ws2, tmW_ws2;
@@ -93,6 +96,7 @@ struct ff_cvit {
   int ws_ctas_per_sm = 2;   // CTAs per SM for the Cin=32 weight-stationary kernels (Cin=64 always 1: smem)
   int use_ptc = 1;         // feature layers 7..17 on the persistent implicit-GEMM kernel
   int use_ws2 = 1;         // Cin = 32 layers in the pixel-pair formulation
+  int use_ws2x = 1;        // Cin = 64 layers (5, 6) in the pixel-pair formulation on CTA pairs (needs use_ws2)
   int use_c1_tc = 2;       // feature layer 1: 2 = tensor cores + TMA-fed uint8 patch, 1 = tensor cores, 0 = CUDA cores
   int c1_ctas_per_sm = 8;
   bf16* c1_w = nullptr;    // [32][64] bf16, k = kh*16 + kw*4 + cin
@@ -367,6 +371,19 @@ cudaError_t launch_ptc_t(int grid, cudaStream_t st, const CUtensorMap& a, const 
   return launch_k(k, dim3(grid), dim3(192), L::TOTAL, st, true, a, b, args);
 }
 
+template <bool POOL>
+cudaError_t launch_ws2x_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args,
+                          const WsEpi& epi) {
+  auto k = ws2x_conv_kernel<POOL>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Ws2xSmem::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  return launch_k(k, dim3(grid), dim3(192), Ws2xSmem::TOTAL, st, true, a, w, args, epi);
+}
+
 int conv_bn_for(int cout, int variant) {
   const int bn_max = (variant == 1) ? 128 : 256;
   return std::min(cout, bn_max);
@@ -455,6 +472,13 @@ int build_conv_maps(ff_cvit* h) {
     if (rc) return rc;
     rc = tmap_2d(h, &L.tmB, L.w, (uint64_t)9 * p.cin, p.cout, L.rowb / 2, L.bn);
     if (rc) return rc;
+    L.ws2x = h->use_ws && h->use_ws2 && h->use_ws2x && p.cin == 64 && p.cout == 64 && li <= 5;
+    if (L.ws2x) {
+      rc = tmap_4d(h, &L.tmA_ws2x, conv_input_buffer(h, li), 64, p.hw / 2, p.hw, 2 * ncap, 64, 10, 18, 1);
+      if (rc) return rc;
+      rc = tmap_2d(h, &L.tmW_ws2x, L.w2x, 768, 128, 64, 64);
+      if (rc) return rc;
+    }
     L.ws2 = h->use_ws && h->use_ws2 && p.cin == 32;
     if (L.ws2) {
       rc = tmap_4d(h, &L.tmA_ws2, conv_input_buffer(h, li), 64, p.hw / 2, p.hw, ncap, 64, 10, 18, 1);
@@ -550,6 +574,21 @@ int finalize(ff_cvit* h) {
               }
         if ((rc = dev_upload(h, &L.w2, to_bf16(w2)))) return rc;
       }
+      if (p.cin == 64 && p.cout == 64) {
+        // CTA-pair variant: B[(pp,co)][(cb,kh,q,ci)] = W[co][kh][q-pp][cb*32+ci]
+        std::vector<float> w2((size_t)128 * 768, 0.0f);
+        for (int pp = 0; pp < 2; ++pp)
+          for (int o = 0; o < 64; ++o)
+            for (int cb = 0; cb < 2; ++cb)
+              for (int kh = 0; kh < 3; ++kh)
+                for (int q = 0; q < 4; ++q) {
+                  const int kw = q - pp;
+                  if (kw < 0 || kw > 2) continue;
+                  for (int ci = 0; ci < 32; ++ci)
+                    w2[((size_t)pp * 64 + o) * 768 + cb * 384 + kh * 128 + q * 32 + ci] = wr[((size_t)o * 9 + kh * 3 + kw) * 64 + cb * 32 + ci];
+                }
+        if ((rc = dev_upload(h, &L.w2x, to_bf16(w2)))) return rc;
+      }
     }
   }
   // ---- embedding / tokens
@@ -618,6 +657,7 @@ int launch_gemm(ff_cvit* h, cudaStream_t st, const CUtensorMap& tmA, const Linea
 }
 
 struct DebugTap {
+  int blocked_hw = 0;       // != 0: activation is channel-blocked [n][2][hw][hw][32] bf16
   int stop_after = 0;       // 0 = run everything
   const void* ptr = nullptr;
   int64_t elems = 0;
@@ -657,7 +697,19 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     a.scale = L.scale; a.shift = L.shift;
     a.out = conv_output_buffer(h, li);
     ProfScope ps(h, st, KC_TC_CONV + li - 1);
+    if (L.ws2x) {
+      a.tiles_w = p.hw / 16; a.tiles_h = p.hw / 16;
+      a.out_blocked = (li == 4) ? 1 : 0;          // layer 5 feeds layer 6 (also a pair kernel); layer 6 writes plain NHWC
+      const int tiles = a.tiles_w * a.tiles_h * n_img;
+      const int g = std::min(2 * ((tiles + 1) / 2), h->num_sms & ~1);
+      cudaError_t e = p.pool ? launch_ws2x_t<true>(g, st, L.tmA_ws2x, L.tmW_ws2x, a, L.epi)
+                             : launch_ws2x_t<false>(g, st, L.tmA_ws2x, L.tmW_ws2x, a, L.epi);
+      if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of ws2x conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
+      ++h->launches;
+      return FF_OK;
+    }
     if (L.ws2) {
+      a.out_blocked = (li == 3 && h->conv[4].ws2x) ? 1 : 0;   // layer 4 feeds the CTA-pair kernel of layer 5
       a.tiles_w = p.hw / 16; a.tiles_h = p.hw / 16;
       const int tiles = a.tiles_w * a.tiles_h * n_img;
       cudaError_t e;
@@ -751,7 +803,10 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
       if (rc) return rc;
       const ConvPlan& p = kConv[li];
       const int ohw = p.pool ? p.hw / 2 : p.hw;
-      if (tap_hit(li + 1, conv_output_buffer(h, li), (int64_t)ns * ohw * ohw * p.cout, true)) return FF_OK;
+      if (tap_hit(li + 1, conv_output_buffer(h, li), (int64_t)ns * ohw * ohw * p.cout, true)) {
+        if ((li == 3 || li == 4) && h->conv[4].ws2x) tap->blocked_hw = ohw;
+        return FF_OK;
+      }
     }
   }
   prof_mark(h, st, 0, false, true);
@@ -903,6 +958,17 @@ __global__ void slots_from_offsets_kernel(const int* __restrict__ off, int n_vid
   const int a = off[v], e = off[v + 1];
   for (int i = a + threadIdx.x; i < e; i += blockDim.x) slot[i] = (i - a) & 31;
 }
+// channel-blocked [n][2][hw][hw][32] bf16 -> NHWC fp32 [n][hw][hw][64] (debug tap of layers 4, 5)
+__global__ void unblock_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int n, int hw) {
+  const size_t total = (size_t)n * hw * hw * 64;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % 64);
+  const size_t pix = i / 64;
+  const size_t per = (size_t)hw * hw;
+  const size_t img = pix / per, rem = pix % per;
+  out[i] = __bfloat162float(in[((img * 2 + c / 32) * per + rem) * 32 + (c % 32)]);
+}
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = __bfloat162float(in[i]);
@@ -950,6 +1016,7 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
   if (const char* v = getenv("FF_PDL")) g_use_pdl = atoi(v) != 0;
   if (const char* v = getenv("FF_PTC")) h->use_ptc = atoi(v);
   if (const char* v = getenv("FF_WS2")) h->use_ws2 = atoi(v);
+  if (const char* v = getenv("FF_WS2X")) h->use_ws2x = atoi(v);
   if (const char* v = getenv("FF_C1_TC")) h->use_c1_tc = atoi(v);
   if (const char* v = getenv("FF_C1_CPS")) h->c1_ctas_per_sm = std::max(1, atoi(v));
   if (const char* v = getenv("FF_WS_CPS")) h->ws_ctas_per_sm = std::max(1, atoi(v));
@@ -1196,7 +1263,10 @@ int64_t ff_cvit_debug_activation(ff_cvit_t* h, const void* x, int x_layout, cons
         float* tmp = nullptr;
         e = cudaMalloc(&tmp, (size_t)tap.elems * sizeof(float));
         if (e == cudaSuccess) {
-          bf16_to_f32_kernel<<<(unsigned)((tap.elems + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(tap.ptr), tmp, (size_t)tap.elems);
+          if (tap.blocked_hw)
+            unblock_bf16_to_f32_kernel<<<(unsigned)((tap.elems + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(tap.ptr), tmp, n, tap.blocked_hw);
+          else
+            bf16_to_f32_kernel<<<(unsigned)((tap.elems + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(tap.ptr), tmp, (size_t)tap.elems);
           e = cudaMemcpyAsync(out_host, tmp, (size_t)tap.elems * sizeof(float), cudaMemcpyDeviceToHost, st);
           if (e == cudaSuccess) e = cudaStreamSynchronize(st);
           cudaFree(tmp);

@@ -32,6 +32,7 @@ struct TcArgs {
   int n_img;              // valid images in this launch
   int img_off_out;        // image offset added on output (placement inside a larger buffer)
   int cout;               // total output channels (row pitch of the NHWC output)
+  int out_blocked;        // pair kernels: write the output channel-blocked [n][C/32][H][W][32] (feeds ws2x)
   int kb_per_tap;         // Cin / (channels per k-block)
   int cin;                // input channels
   // ---- gemm geometry

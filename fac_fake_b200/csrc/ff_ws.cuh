@@ -239,7 +239,7 @@ struct Ws2Smem {
 
 // Epilogue for one accumulator row = one pixel pair.  COUT = BN/2.  Processes the pair one pixel (COUT columns) at
 // a time to bound registers.  POOL: horizontal max = the two pixels of the pair, vertical max = lane ^ 8.
-template <int BN, bool POOL>
+template <int BN, bool POOL, bool ARRIVE_ON_LEADER = false>
 __device__ __forceinline__ void ws2_epilogue(uint32_t taddr, const WsEpi& ss, const TcArgs& a, int pw0, int h0, int n, int r,
                                              int lane, uint32_t arrive_bar) {
   constexpr int COUT = BN / 2;
@@ -255,7 +255,8 @@ __device__ __forceinline__ void ws2_epilogue(uint32_t taddr, const WsEpi& ss, co
     tmem_ld_wait();
     if (p == 1) {
       tcgen05_fence_before();
-      mbar_arrive(arrive_bar);
+      if (ARRIVE_ON_LEADER) mbar_arrive_cluster(arrive_bar, 0);   // CTA pair: the leader (rank 0) issues the MMAs
+      else mbar_arrive(arrive_bar);
     }
 #pragma unroll
     for (int c = 0; c < COUT; c += 2) {
@@ -263,11 +264,22 @@ __device__ __forceinline__ void ws2_epilogue(uint32_t taddr, const WsEpi& ss, co
       const float x1 = fmaf(__uint_as_float(v[c + 1]), ss.scale[c + 1], ss.shift[c + 1]);
       pk[p][c >> 1] = pack_bf16x2_relu(x0, x1);
     }
-    if (!POOL) {
-      const size_t pair = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * Wp + (pw0 + jl);
-      __nv_bfloat16* o = out + pair * BN + p * COUT;
+    if (!POOL && n < a.n_img) {
+      if (COUT == 64 && a.out_blocked) {
+        // channel-blocked [n][2][H][W][32]: each 32-channel half of this pixel is one 64-byte run
 #pragma unroll
-      for (int i = 0; i < COUT / 16; ++i) st_global_v8(o + i * 16, &pk[p][8 * i]);
+        for (int b = 0; b < COUT / 32; ++b) {
+          const size_t pix = (static_cast<size_t>((a.img_off_out + n) * 2 + b) * a.H + (h0 + hl)) * a.W + (2 * (pw0 + jl) + p);
+          __nv_bfloat16* o = out + pix * 32;
+          st_global_v8(o, &pk[p][16 * b]);
+          st_global_v8(o + 16, &pk[p][16 * b + 8]);
+        }
+      } else {
+        const size_t pair = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * Wp + (pw0 + jl);
+        __nv_bfloat16* o = out + pair * BN + p * COUT;
+#pragma unroll
+        for (int i = 0; i < COUT / 16; ++i) st_global_v8(o + i * 16, &pk[p][8 * i]);
+      }
     }
   }
   if (POOL) {
@@ -279,7 +291,7 @@ __device__ __forceinline__ void ws2_epilogue(uint32_t taddr, const WsEpi& ss, co
       m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o2));
       pk[0][i] = *reinterpret_cast<uint32_t*>(&m);
     }
-    if ((lane & 8) == 0) {
+    if ((lane & 8) == 0 && n < a.n_img) {
       const size_t pix = (static_cast<size_t>(a.img_off_out + n) * (a.H >> 1) + ((h0 + hl) >> 1)) * Wp + (pw0 + jl);
       __nv_bfloat16* o = out + pix * COUT;
 #pragma unroll
@@ -397,6 +409,162 @@ ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+
+// =================================================================================================================
+// Pixel-pair formulation for Cin = 64 (feature layers 5, 6) on a CTA PAIR (cta_group::2).
+//
+// With 64 input channels the pair-expanded filter is [N = 2*64 = 128][K = 2 blocks * 3 * 4 * 32 = 768] = 196 KB and
+// no longer fits one SM next to the activation patches.  Two CTAs of a cluster each keep HALF of it (64 of the 128
+// (pixel, cout) rows, 96 KB) and issue tcgen05.mma.cta_group::2 with M = 256: each SM multiplies its own 128 pixel
+// pairs against the full N = 128 (reading the peer's filter half through the pair datapath), so the MMAs run at
+// N = 128 = full tensor rate instead of N = 64.  The input is channel-blocked [n][2][H][W][32] (written that way
+// by the producer layer) so that a pixel pair of one 32-channel block is one contiguous 128-byte row.
+//   * both CTAs issue their own TMA patch loads (2 blocks x 23 KB) whose bytes are credited to the leader's barrier;
+//   * only the leader's thread issues the 48 MMAs per tile pair; tcgen05.commit multicasts stage-free / accumulator-
+//     ready to both CTAs; both epilogues report "TMEM drained" to the leader's barrier (256 arrivals).
+struct Ws2xSmem {
+  static constexpr int W_TILE = 64 * 128;                             // this CTA's 64 filter rows of one k-block
+  static constexpr int W_BYTES = 12 * W_TILE;                         // (block, kh, half) k-blocks
+  static constexpr int PATCH_ONE = 23552;                             // 180 rows x 128 B, 1024-aligned
+  static constexpr int PATCH_BYTES = 2 * 23040;                       // bytes actually transferred per stage
+  static constexpr int PATCH_STRIDE = 2 * PATCH_ONE;
+  static constexpr int STAGES = 2;
+  static constexpr int W_OFF = 0;
+  static constexpr int P_OFF = W_BYTES;
+  static constexpr int BAR_OFF = P_OFF + STAGES * PATCH_STRIDE;       // w, full[2], empty[2], tfull[2], tempty[2]
+  static constexpr int SLOT_OFF = BAR_OFF + 9 * 8;
+  static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
+};
+
+template <bool POOL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs a,
+                 const __grid_constant__ WsEpi epi) {
+  using L = Ws2xSmem;
+  constexpr int BN = 128, STAGES = L::STAGES;
+  constexpr int TMEM_COLS = 2 * BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_w = base + L::BAR_OFF;
+  const uint32_t bar_full = bar_w + 8;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_tfull = bar_empty + STAGES * 8;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int tiles_per_img = a.tiles_w * a.tiles_h;
+  const int num_tiles = tiles_per_img * a.n_img;
+  const int num_pairs = (num_tiles + 1) >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tfull + 8, 1);
+    mbar_init(bar_tempty, 256);        // both CTAs' epilogue threads (only the leader's copy is used)
+    mbar_init(bar_tempty + 8, 256);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (warp == 0 && lane == 0) {
+    // this CTA's half of the pair-expanded filter: rows [64*rank, 64*rank + 64) of every k-block
+    mbar_arrive_expect_tx(bar_w, L::W_BYTES);
+    for (int kb = 0; kb < 12; ++kb) tma_load_2d(base + L::W_OFF + kb * L::W_TILE, &tmW, bar_w, kb * 64, 64 * rank);
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                  // barrier inits + TMEM allocation visible to the peer
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  mbar_wait(bar_w, 0);
+  cluster_sync_all();                  // both filter halves have landed before the leader issues any MMA
+
+  auto tile_of = [&](int pair_idx, int* n, int* th, int* tw) {
+    const int t = 2 * pair_idx + static_cast<int>(rank);
+    *n = t / tiles_per_img;            // t >= num_tiles -> n >= n_img: TMA reads past the valid images, stores are masked
+    const int rem = t - *n * tiles_per_img;
+    *th = rem / a.tiles_w;
+    *tw = rem - *th * a.tiles_w;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_trigger();
+      pdl_wait();
+      int it = 0;
+      for (int pi = cluster_id; pi < num_pairs; pi += num_clusters, ++it) {
+        const int s = it & 1;
+        if (it >= STAGES) mbar_wait(bar_empty + 8 * s, ((it >> 1) - 1) & 1);
+        int n, th, tw;
+        tile_of(pi, &n, &th, &tw);
+        if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, 2 * L::PATCH_BYTES);    // own + peer's bytes
+        const uint32_t dst = base + L::P_OFF + s * L::PATCH_STRIDE;
+        tma_load_4d_2cta(dst, &tmA, bar_full + 8 * s, 0, tw * 8 - 1, th * 16 - 1, 2 * n);
+        tma_load_4d_2cta(dst + L::PATCH_ONE, &tmA, bar_full + 8 * s, 0, tw * 8 - 1, th * 16 - 1, 2 * n + 1);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      int it = 0;
+      for (int pi = cluster_id; pi < num_pairs; pi += num_clusters, ++it) {
+        const int s = it & 1;
+        const int acc = it & 1;
+        if (it >= 2) mbar_wait(bar_tempty + 8 * acc, ((it >> 1) - 1) & 1);
+        mbar_wait(bar_full + 8 * s, (it >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t patch = base + L::P_OFF + s * L::PATCH_STRIDE;
+        const uint32_t d_tmem = tmem_base + acc * BN;
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint64_t adesc = make_kmajor_desc_sbo<128>(patch + cb * L::PATCH_ONE + kh * 10 * 128 + 64 + 32 * c, 10 * 128);
+              const uint64_t bdesc = make_kmajor_desc<128>(base + L::W_OFF + (cb * 6 + kh * 2 + (c >> 2)) * L::W_TILE) + 2 * (c & 3);
+              umma_bf16_ss_2cta(d_tmem, adesc, bdesc, idesc, (cb > 0 || kh > 0 || c > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit_2cta(bar_empty + 8 * s, 0x3);
+        umma_commit_2cta(bar_tfull + 8 * acc, 0x3);
+      }
+    }
+  } else {
+    const int g = warp & 3;
+    const int r = g * 32 + lane;
+    int it = 0;
+    for (int pi = cluster_id; pi < num_pairs; pi += num_clusters, ++it) {
+      const int acc = it & 1;
+      int n, th, tw;
+      tile_of(pi, &n, &th, &tw);
+      mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
+      tcgen05_fence_after();
+      ws2_epilogue<BN, POOL, true>(tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN, epi, a, tw * 8, th * 16, n, r, lane,
+                                   bar_tempty + 8 * acc);
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();                  // the peer's smem / TMEM stay alive until the leader's last MMA has retired
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
   }
 }
 
