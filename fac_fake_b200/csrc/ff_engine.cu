@@ -140,6 +140,7 @@ struct ff_cvit {
   float* logit_buf = nullptr; size_t logit_cap = 0;
   int32_t* off_buf = nullptr; size_t off_cap = 0;
   float* score_buf = nullptr; size_t score_cap = 0;
+  CropDesc* crop_desc = nullptr; size_t crop_desc_cap = 0;
   std::vector<void*> allocs;
   // pipelined host->device input copy (ff_cvit_predict_host): chunk j of `h2d_chunk` crops is copied on
   // copy_stream and published with h2d_ready[j]; the forward waits on it right before it first reads the chunk
@@ -1073,6 +1074,7 @@ void ff_cvit_destroy(ff_cvit_t* h) {
   if (h->logit_buf) cudaFree(h->logit_buf);
   if (h->off_buf) cudaFree(h->off_buf);
   if (h->score_buf) cudaFree(h->score_buf);
+  if (h->crop_desc) cudaFree(h->crop_desc);
   if (h->done_ev) cudaEventDestroy(h->done_ev);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->h2d_ready) cudaEventDestroy(e);
@@ -1226,17 +1228,13 @@ int ff_preprocess_crops(ff_cvit_t* h, const uint8_t* const* crop_ptrs, const int
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaSetDevice(h->device);
-  CropDesc* dd = nullptr;
-  FF_CUDA(h, cudaMalloc(&dd, sizeof(CropDesc) * n));
-  cudaError_t e = cudaMemcpyAsync(dd, d.data(), sizeof(CropDesc) * n, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) {
-    preprocess_kernel<<<dim3((224 * 224 + 255) / 256, n), 256, 0, st>>>(dd, n, swap_rb, out_u8, out_norm_nchw);
-    e = cudaGetLastError();
-    ++h->launches;
-  }
-  cudaError_t e2 = cudaStreamSynchronize(st);   // descriptors are stack-lifetime host memory
-  cudaFree(dd);
-  if (e != cudaSuccess || e2 != cudaSuccess) return fail(h, FF_ERR_CUDA, "preprocess failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+  int rc;
+  if ((rc = grow(h, &h->crop_desc, &h->crop_desc_cap, (size_t)n))) return rc;
+  // pageable-host source: cudaMemcpyAsync stages the descriptors before returning, so `d` may die with this call;
+  // the descriptor buffer is reused by the next call only after the stream-ordered kernel below has been enqueued
+  FF_CUDA(h, cudaMemcpyAsync(h->crop_desc, d.data(), sizeof(CropDesc) * n, cudaMemcpyHostToDevice, st));
+  preprocess_kernel<<<dim3((224 * 224 / 4 + 255) / 256, n), 256, 0, st>>>(h->crop_desc, n, swap_rb, out_u8, out_norm_nchw);
+  FF_LAUNCH_CHECK(h, "preprocess");
   return FF_OK;
 }
 

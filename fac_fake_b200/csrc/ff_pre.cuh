@@ -79,16 +79,10 @@ __device__ __forceinline__ void linear_tap(int d, int ssize, int dsize, int* sx,
 
 __device__ __forceinline__ uint8_t sat_u8_rn(float v) { return static_cast<uint8_t>(max(0, min(255, __float2int_rn(v)))); }
 
-__global__ void __launch_bounds__(256)
-preprocess_kernel(const CropDesc* __restrict__ crops, int n, int swap_rb, uint8_t* __restrict__ out_u8,
-                  float* __restrict__ out_norm) {
+// One thread produces 4 consecutive output pixels of one row (12 output bytes = three aligned 32-bit stores);
+// a warp therefore covers 128 consecutive output pixels and reads, per source row, one contiguous byte range.
+__device__ __forceinline__ void preprocess_pixel(const CropDesc& c, int dy, int dx, int res[3]) {
   constexpr int D = 224;
-  const int i = blockIdx.y;
-  const int pix = blockIdx.x * 256 + threadIdx.x;
-  if (i >= n || pix >= D * D) return;
-  const int dy = pix / D, dx = pix % D;
-  const CropDesc c = crops[i];
-  int res[3];
   if (c.mode == PRE_FAST) {
     int sum[3] = {0, 0, 0};
     for (int sy = 0; sy < c.isy; ++sy) {
@@ -141,16 +135,39 @@ preprocess_kernel(const CropDesc* __restrict__ crops, int n, int swap_rb, uint8_
       res[k] = max(0, min(255, v));
     }
   }
-  if (swap_rb) { const int t = res[0]; res[0] = res[2]; res[2] = t; }
-  if (out_u8) {
-    uint8_t* o = out_u8 + (static_cast<size_t>(i) * D * D + pix) * 3;
-    o[0] = static_cast<uint8_t>(res[0]); o[1] = static_cast<uint8_t>(res[1]); o[2] = static_cast<uint8_t>(res[2]);
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_kernel(const CropDesc* __restrict__ crops, int n, int swap_rb, uint8_t* __restrict__ out_u8,
+                  float* __restrict__ out_norm) {
+  constexpr int D = 224;
+  const int i = blockIdx.y;
+  const int quad = blockIdx.x * 256 + threadIdx.x;      // group of 4 output pixels
+  if (i >= n || quad >= D * D / 4) return;
+  const int pix0 = quad * 4;
+  const int dy = pix0 / D, dx0 = pix0 % D;               // D % 4 == 0: the 4 pixels share a row
+  const CropDesc c = crops[i];
+  uint32_t packed[3] = {0u, 0u, 0u};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int res[3];
+    preprocess_pixel(c, dy, dx0 + j, res);
+    if (swap_rb) { const int t = res[0]; res[0] = res[2]; res[2] = t; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int byte = j * 3 + k;
+      packed[byte >> 2] |= static_cast<uint32_t>(res[k]) << (8 * (byte & 3));
+    }
+    if (out_norm) {
+      const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+      for (int k = 0; k < 3; ++k)
+        out_norm[(static_cast<size_t>(i) * 3 + k) * D * D + pix0 + j] =
+            __fdiv_rn(__fdiv_rn(static_cast<float>(res[k]), 255.0f) - mean[k], sd[k]);
+    }
   }
-  if (out_norm) {
-    const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
-    for (int k = 0; k < 3; ++k)
-      out_norm[(static_cast<size_t>(i) * 3 + k) * D * D + pix] =
-          __fdiv_rn(__fdiv_rn(static_cast<float>(res[k]), 255.0f) - mean[k], sd[k]);
+  if (out_u8) {
+    uint32_t* o = reinterpret_cast<uint32_t*>(out_u8 + (static_cast<size_t>(i) * D * D + pix0) * 3);   // 12-byte aligned
+    o[0] = packed[0]; o[1] = packed[1]; o[2] = packed[2];
   }
 }
 

@@ -205,3 +205,29 @@ def test_errors_and_edge_cases(eng_bn):
     with pytest.raises((ValueError, EngineError)):
         CViTEngine().to("cuda:0").load_state_dict(missing)
     assert eng.launch_count() > 0
+
+
+def test_multi_pass_and_ragged_batches():
+    """n > max_crops (several internal passes), n not a multiple of any tile/sub-pass size, n = 1."""
+    from fac_fake_b200 import CViTEngine
+    sd = W.make_state_dict(0, "bn")
+    small = CViTEngine(max_crops=32).to("cuda:0").load_state_dict(sd)     # forces 3 passes for 71 crops
+    big = CViTEngine(max_crops=128).to("cuda:0").load_state_dict(sd)
+    crops = W.synthetic_crops(71, seed=41).cuda()
+    slots = (torch.arange(71) * 7) % 32
+    a = small.forward_slots(crops, slots)
+    b = big.forward_slots(crops, slots)
+    assert torch.isfinite(a).all()
+    assert (a - b).abs().max().item() <= 1e-5          # pass structure does not change results
+    one = big.forward_slots(crops[5:6], slots[5:6])
+    assert (one - b[5:6]).abs().max().item() <= 1e-5
+    x = O.normalize_crops(crops[:9].cpu())
+    ref = O.forward_slots(x, sd, slots[:9])
+    assert (b[:9].cpu() - ref).abs().max().item() <= BF16_TOL
+    # ragged videos through the fused entry point, crossing the internal pass boundary
+    lens = [3, 30, 0, 17, 21]
+    offs = np.concatenate([[0], np.cumsum(lens)]).tolist()
+    s_small = small.predict_videos(crops, offs).cpu()
+    s_big = big.predict_videos(crops, offs).cpu()
+    assert torch.equal(s_small, s_big)
+    assert s_big[2].item() == 0.5
