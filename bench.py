@@ -185,6 +185,9 @@ def main():
         run_reference(args)
         return
 
+    # keep stdout to the single JSON line: NCCL's version banner goes to stdout when NCCL_DEBUG=VERSION/INFO
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "") and not os.environ.get("FF_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     from fac_fake_b200 import CViTEngine, weights as W
