@@ -97,10 +97,12 @@ struct ff_cvit {
   int use_ptc = 1;         // feature layers 7..17 on the persistent implicit-GEMM kernel
   int use_ws2 = 1;         // Cin = 32 layers in the pixel-pair formulation
   int use_ws2x = 1;        // Cin = 64 layers (5, 6) in the pixel-pair formulation on CTA pairs (needs use_ws2)
-  int use_c1_tc = 2;       // feature layer 1: 2 = tensor cores + TMA-fed uint8 patch, 1 = tensor cores, 0 = CUDA cores
+  int use_c1_tc = 3;       // feature layer 1: 3 = pixel-pair GEMM out of the patch (no im2col), 2 = TMA-fed im2col rows,
+                           // 1 = register-prefetched im2col rows, 0 = CUDA cores
   int c1_ctas_per_sm = 8;
   bf16* c1_w = nullptr;    // [32][64] bf16, k = kh*16 + kw*4 + cin
   bf16* c1_lut = nullptr;  // [3][256] bf16 normalisation table
+  bf16* c1_wp = nullptr;   // [3][64][16] pair-expanded conv1 filter (conv1_pair_kernel)
   float c1_na[3] = {0, 0, 0}, c1_nb[3] = {0, 0, 0};   // FMA form of the table (valid iff it reproduces all 768 entries)
   int num_sms = 148;
   bool finalized = false;
@@ -537,6 +539,19 @@ int finalize(ff_cvit* h) {
       }
       if (h->compute == FF_COMPUTE_BF16) {
         if ((rc = dev_upload(h, &h->c1_w, to_bf16(w32)))) return rc;
+        {
+          // pair-expanded filter: B[kh][(p,co)][(q,c)] = W[co][kh][q-p][c], zero unless 0 <= q-p <= 2 and c < 3
+          std::vector<float> wp(3 * 64 * 16, 0.0f);
+          for (int kh = 0; kh < 3; ++kh)
+            for (int pp = 0; pp < 2; ++pp)
+              for (int o = 0; o < 32; ++o)
+                for (int q = 0; q < 4; ++q) {
+                  const int kw = q - pp;
+                  if (kw < 0 || kw > 2) continue;
+                  for (int c = 0; c < 3; ++c) wp[(kh * 64 + pp * 32 + o) * 16 + q * 4 + c] = wr[(size_t)o * 27 + (kh * 3 + kw) * 3 + c];
+                }
+          if ((rc = dev_upload(h, &h->c1_wp, to_bf16(wp)))) return rc;
+        }
         // lut[c][u] = bf16((u/255 - mean_c)/std_c), the fp32 arithmetic of cvit_prediction.py:41-45,214-215
         const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
         std::vector<float> lut(3 * 256);
@@ -554,7 +569,7 @@ int finalize(ff_cvit* h) {
             if (memcmp(&x, &y, sizeof(bf16)) != 0) fma_ok = false;
           }
         }
-        if (!fma_ok && h->use_c1_tc == 2) h->use_c1_tc = 1;
+        if (!fma_ok && h->use_c1_tc >= 2) h->use_c1_tc = 1;
       }
     }
     if (h->compute == FF_COMPUTE_FP32) {
@@ -769,7 +784,23 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     dim3 g1(14, 14, ns);
     {
       ProfScope ps(h, st, KC_CONV1);
-      if (h->use_c1_tc == 2 && layout == FF_X_NHWC_U8) {
+      if (h->use_c1_tc == 3 && layout == FF_X_NHWC_U8) {
+        CUtensorMap tmX;
+        cuuint64_t dims[3] = {672, 224, (cuuint64_t)ns};
+        cuuint64_t strides[2] = {672, (cuuint64_t)224 * 672};
+        cuuint32_t box[3] = {80, 18, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = g_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(xin), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(uint8 crops) failed: %d (is the input 16-byte aligned?)", (int)r);
+        C1PairArgs ca;
+        ca.out = h->bufA; ca.w = h->c1_wp; ca.n_img = ns;
+        for (int c = 0; c < 3; ++c) { ca.na[c] = h->c1_na[c]; ca.nb[c] = h->c1_nb[c]; }
+        for (int o = 0; o < 32; ++o) { ca.scale[o] = h->conv1.scale[o]; ca.shift[o] = h->conv1.shift[o]; }
+        const int grid = std::min(196 * ns, h->num_sms * h->c1_ctas_per_sm);
+        launch_k(conv1_pair_kernel, dim3(grid), dim3(128), 0, st, true, tmX, ca);
+      } else if (h->use_c1_tc >= 2 && layout == FF_X_NHWC_U8) {
         // TMA-fed uint8 path: per-launch 3-D map over the caller's uint8 crops viewed as [ns][224][672]
         CUtensorMap tmX;
         cuuint64_t dims[3] = {672, 224, (cuuint64_t)ns};
