@@ -116,12 +116,17 @@ struct ff_cvit {
 
   Conv1Params conv1;
   ConvLayerDev conv[17];
+  ConvLayerDev conv_alt[6];   // layers 1..6 with TMA descriptors over the second ping-pong set
   LinearDev embed, head1, head2;
   XfLayerDev xf[DEPTH];
   float *pos = nullptr, *cls = nullptr;
 
   // workspace
   bf16 *bufA = nullptr, *bufB = nullptr;   // stage 1/2 ping-pong, s12_cap crops
+  bf16 *bufA2 = nullptr, *bufB2 = nullptr; // second ping-pong set: odd sub-passes run on aux_stream (dual-stream overlap)
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int use_dual = 1;        // overlap consecutive stage-1/2 sub-passes on two streams (hides launch tails/prologues)
   bf16 *P = nullptr, *Q = nullptr;         // stage 3..5 ping-pong, cap crops
   bf16* feat = nullptr;                    // [cap_rows128][25088]
   float* emb = nullptr;                    // [cap][1024]
@@ -443,18 +448,22 @@ void conv_tile_geometry(int hw, int* bw, int* bh, int* bi) {
 int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 // Which buffer conv layer li (1..16; layer 0 is conv1) reads, per the ping-pong schedule in forward_pass().
-const bf16* conv_input_buffer(const ff_cvit* h, int li) {
+const bf16* conv_input_buffer(const ff_cvit* h, int li, int set = 0) {
+  const bf16* A = set ? h->bufA2 : h->bufA;
+  const bf16* B = set ? h->bufB2 : h->bufB;
   switch (li) {
-    case 1: return h->bufA; case 2: return h->bufB; case 3: return h->bufA; case 4: return h->bufB; case 5: return h->bufA;
+    case 1: return A; case 2: return B; case 3: return A; case 4: return B; case 5: return A;
     case 6: return h->P; case 7: return h->Q; case 8: return h->P;
     case 9: return h->Q; case 10: return h->P; case 11: return h->Q; case 12: return h->P;
     case 13: return h->Q; case 14: return h->P; case 15: return h->Q; case 16: return h->P;
   }
   return nullptr;
 }
-bf16* conv_output_buffer(const ff_cvit* h, int li) {
+bf16* conv_output_buffer(const ff_cvit* h, int li, int set = 0) {
+  bf16* A = set ? h->bufA2 : h->bufA;
+  bf16* B = set ? h->bufB2 : h->bufB;
   switch (li) {
-    case 0: return h->bufA; case 1: return h->bufB; case 2: return h->bufA; case 3: return h->bufB; case 4: return h->bufA;
+    case 0: return A; case 1: return B; case 2: return A; case 3: return B; case 4: return A;
     case 5: return h->P;
     case 6: return h->Q; case 7: return h->P; case 8: return h->Q;
     case 9: return h->P; case 10: return h->Q; case 11: return h->P; case 12: return h->Q;
@@ -464,34 +473,37 @@ bf16* conv_output_buffer(const ff_cvit* h, int li) {
 }
 
 int build_conv_maps(ff_cvit* h) {
-  for (int li = 1; li < 17; ++li) {
+  for (int pass = 0; pass < 2; ++pass)
+  for (int li = 1; li < (pass == 0 ? 17 : 6); ++li) {
     const ConvPlan& p = kConv[li];
-    ConvLayerDev& L = h->conv[li];
+    if (pass == 1) h->conv_alt[li] = h->conv[li];
+    ConvLayerDev& L = pass == 0 ? h->conv[li] : h->conv_alt[li];
+    const int set = pass;
     L.rowb = p.cin == 32 ? 64 : 128;
     L.bn = conv_bn_for(p.cout, h->variant);
     conv_tile_geometry(p.hw, &L.bw, &L.bh, &L.bi);
     const int ncap = li <= 5 ? h->s12_cap : h->cap;
-    int rc = tmap_4d(h, &L.tmA, conv_input_buffer(h, li), p.cin, p.hw, p.hw, ncap, L.rowb / 2, L.bw, L.bh, L.bi);
+    int rc = tmap_4d(h, &L.tmA, conv_input_buffer(h, li, set), p.cin, p.hw, p.hw, ncap, L.rowb / 2, L.bw, L.bh, L.bi);
     if (rc) return rc;
     rc = tmap_2d(h, &L.tmB, L.w, (uint64_t)9 * p.cin, p.cout, L.rowb / 2, L.bn);
     if (rc) return rc;
     L.ws2x = h->use_ws && h->use_ws2 && h->use_ws2x && p.cin == 64 && p.cout == 64 && li <= 5;
     if (L.ws2x) {
-      rc = tmap_4d(h, &L.tmA_ws2x, conv_input_buffer(h, li), 64, p.hw / 2, p.hw, 2 * ncap, 64, 10, 18, 1);
+      rc = tmap_4d(h, &L.tmA_ws2x, conv_input_buffer(h, li, set), 64, p.hw / 2, p.hw, 2 * ncap, 64, 10, 18, 1);
       if (rc) return rc;
       rc = tmap_2d(h, &L.tmW_ws2x, L.w2x, 768, 128, 64, 64);
       if (rc) return rc;
     }
     L.ws2 = h->use_ws && h->use_ws2 && p.cin == 32;
     if (L.ws2) {
-      rc = tmap_4d(h, &L.tmA_ws2, conv_input_buffer(h, li), 64, p.hw / 2, p.hw, ncap, 64, 10, 18, 1);
+      rc = tmap_4d(h, &L.tmA_ws2, conv_input_buffer(h, li, set), 64, p.hw / 2, p.hw, ncap, 64, 10, 18, 1);
       if (rc) return rc;
       rc = tmap_2d(h, &L.tmW_ws2, L.w2, 384, (uint64_t)2 * p.cout, 64, 2 * p.cout);
       if (rc) return rc;
     }
     L.ws = h->use_ws && li <= 5;
     if (L.ws) {
-      rc = tmap_4d(h, &L.tmA_ws, conv_input_buffer(h, li), p.cin, p.hw, p.hw, ncap, p.cin, 10, 18, 1);
+      rc = tmap_4d(h, &L.tmA_ws, conv_input_buffer(h, li, set), p.cin, p.hw, p.hw, ncap, p.cin, 10, 18, 1);
       if (rc) return rc;
       rc = tmap_2d(h, &L.tmW_ws, L.w, (uint64_t)9 * p.cin, p.cout, p.cin, p.cout);
       if (rc) return rc;
@@ -695,9 +707,9 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   };
   const size_t crop_in_bytes = layout == FF_X_NHWC_U8 ? (size_t)224 * 224 * 3 : (size_t)224 * 224 * 3 * 4;
 
-  auto run_conv = [&](int li, int n_img, int img_off_out) -> int {
+  auto run_conv = [&](int li, int n_img, int img_off_out, int set, cudaStream_t st) -> int {
     const ConvPlan& p = kConv[li];
-    const ConvLayerDev& L = h->conv[li];
+    const ConvLayerDev& L = (set && li <= 5) ? h->conv_alt[li] : h->conv[li];
     TcArgs a;
     memset(&a, 0, sizeof(a));
     a.H = p.hw; a.W = p.hw;
@@ -711,7 +723,7 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     a.kb_total = 9 * a.kb_per_tap;
     a.kb_per_split = a.kb_total;
     a.scale = L.scale; a.shift = L.shift;
-    a.out = conv_output_buffer(h, li);
+    a.out = conv_output_buffer(h, li, set);
     ProfScope ps(h, st, KC_TC_CONV + li - 1);
     if (L.ws2x) {
       a.tiles_w = p.hw / 16; a.tiles_h = p.hw / 16;
@@ -773,7 +785,19 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   prof_mark(h, st, 0, true, true);
   const int sub = stop ? std::min(n, h->s12_cap) : h->s12;
   if (stop && n > h->s12_cap) return fail(h, FF_ERR_BAD_ARG, "debug tap needs n <= %d", h->s12_cap);
-  for (int s0 = 0; s0 < n; s0 += sub) {
+  // consecutive sub-passes alternate between the caller's stream and aux_stream (own ping-pong buffers), so the
+  // launch tail / prologue of one chain is filled by the other chain's kernels
+  const bool dual = h->use_dual && !stop && (!h->profiling || h->prof_coarse) && n > sub;
+  cudaStream_t st_main = st;
+  if (dual) {
+    FF_CUDA(h, cudaEventRecord(h->ev_fork, st_main));
+    FF_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+  }
+  int sub_idx = 0;
+  for (int s0 = 0; s0 < n; s0 += sub, ++sub_idx) {
+    const int set = dual ? (sub_idx & 1) : 0;
+    cudaStream_t st = set ? h->aux_stream : st_main;
+    bf16* bufA = set ? h->bufA2 : h->bufA;
     const int ns = std::min(sub, n - s0);
     const uint8_t* xin = reinterpret_cast<const uint8_t*>(x) + (size_t)s0 * crop_in_bytes;
     if (h->h2d_chunks_pending > 0) {   // input still streaming in: wait for the chunks covering [g0, g0+ns)
@@ -795,7 +819,7 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(uint8 crops) failed: %d (is the input 16-byte aligned?)", (int)r);
         C1PairArgs ca;
-        ca.out = h->bufA; ca.w = h->c1_wp; ca.n_img = ns;
+        ca.out = bufA; ca.w = h->c1_wp; ca.n_img = ns;
         for (int c = 0; c < 3; ++c) { ca.na[c] = h->c1_na[c]; ca.nb[c] = h->c1_nb[c]; }
         for (int o = 0; o < 32; ++o) { ca.scale[o] = h->conv1.scale[o]; ca.shift[o] = h->conv1.shift[o]; }
         const int grid = std::min(196 * ns, h->num_sms * h->c1_ctas_per_sm);
@@ -812,40 +836,44 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(uint8 crops) failed: %d (is the input 16-byte aligned?)", (int)r);
         C1TmaArgs ca;
-        ca.out = h->bufA; ca.w = h->c1_w; ca.n_img = ns;
+        ca.out = bufA; ca.w = h->c1_w; ca.n_img = ns;
         for (int c = 0; c < 3; ++c) { ca.na[c] = h->c1_na[c]; ca.nb[c] = h->c1_nb[c]; }
         for (int o = 0; o < 32; ++o) { ca.scale[o] = h->conv1.scale[o]; ca.shift[o] = h->conv1.shift[o]; }
         const int grid = std::min(392 * ns, h->num_sms * h->c1_ctas_per_sm);
         launch_k(conv1_tma_kernel, dim3(grid), dim3(128), 0, st, true, tmX, ca);
       } else if (h->use_c1_tc) {
         C1Args ca;
-        ca.x = xin; ca.out = h->bufA; ca.w = h->c1_w; ca.lut = h->c1_lut;
+        ca.x = xin; ca.out = bufA; ca.w = h->c1_w; ca.lut = h->c1_lut;
         ca.n_img = ns;
         for (int o = 0; o < 32; ++o) { ca.scale[o] = h->conv1.scale[o]; ca.shift[o] = h->conv1.shift[o]; }
         const int grid = std::min(392 * ns, h->num_sms * h->c1_ctas_per_sm);
         if (layout == FF_X_NHWC_U8) launch_k(conv1_tc_kernel<2>, dim3(grid), dim3(128), 0, st, true, ca);
         else launch_k(conv1_tc_kernel<0>, dim3(grid), dim3(128), 0, st, true, ca);
-      } else if (layout == FF_X_NHWC_U8) conv1_kernel<2><<<g1, 256, 0, st>>>(xin, h->bufA, ns, h->conv1);
-      else conv1_kernel<0><<<g1, 256, 0, st>>>(xin, h->bufA, ns, h->conv1);
+      } else if (layout == FF_X_NHWC_U8) conv1_kernel<2><<<g1, 256, 0, st>>>(xin, bufA, ns, h->conv1);
+      else conv1_kernel<0><<<g1, 256, 0, st>>>(xin, bufA, ns, h->conv1);
     }
     FF_LAUNCH_CHECK(h, "conv1");
-    if (tap_hit(1, h->bufA, (int64_t)ns * 224 * 224 * 32, true)) return FF_OK;
+    if (tap_hit(1, bufA, (int64_t)ns * 224 * 224 * 32, true)) return FF_OK;
     for (int li = 1; li <= 5; ++li) {
-      int rc = run_conv(li, ns, li == 5 ? s0 : 0);
+      int rc = run_conv(li, ns, li == 5 ? s0 : 0, set, st);
       if (rc) return rc;
       const ConvPlan& p = kConv[li];
       const int ohw = p.pool ? p.hw / 2 : p.hw;
-      if (tap_hit(li + 1, conv_output_buffer(h, li), (int64_t)ns * ohw * ohw * p.cout, true)) {
+      if (tap_hit(li + 1, conv_output_buffer(h, li, set), (int64_t)ns * ohw * ohw * p.cout, true)) {
         if ((li == 3 || li == 4) && h->conv[4].ws2x) tap->blocked_hw = ohw;
         return FF_OK;
       }
     }
   }
+  if (dual) {
+    FF_CUDA(h, cudaEventRecord(h->ev_join, h->aux_stream));
+    FF_CUDA(h, cudaStreamWaitEvent(st_main, h->ev_join, 0));
+  }
   prof_mark(h, st, 0, false, true);
   prof_mark(h, st, 1, true, true);
   // ---- stages 3-5 on the whole pass
   for (int li = 6; li < 17; ++li) {
-    int rc = run_conv(li, n, 0);
+    int rc = run_conv(li, n, 0, 0, st);
     if (rc) return rc;
     const ConvPlan& p = kConv[li];
     const int ohw = p.pool ? p.hw / 2 : p.hw;
@@ -1046,6 +1074,7 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
   if (const char* v = getenv("FF_TC_VARIANT")) h->variant = atoi(v);
   if (const char* v = getenv("FF_WS")) h->use_ws = atoi(v);
   if (const char* v = getenv("FF_PDL")) g_use_pdl = atoi(v) != 0;
+  if (const char* v = getenv("FF_DUAL")) h->use_dual = atoi(v);
   if (const char* v = getenv("FF_PTC")) h->use_ptc = atoi(v);
   if (const char* v = getenv("FF_WS2")) h->use_ws2 = atoi(v);
   if (const char* v = getenv("FF_WS2X")) h->use_ws2x = atoi(v);
@@ -1065,6 +1094,11 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
     if (compute_dtype == FF_COMPUTE_BF16) {
       if ((rc = dev_alloc(h, &h->bufA, (size_t)h->s12_cap * 224 * 224 * 32))) break;
       if ((rc = dev_alloc(h, &h->bufB, (size_t)h->s12_cap * 224 * 224 * 32))) break;
+      if ((rc = dev_alloc(h, &h->bufA2, (size_t)h->s12_cap * 224 * 224 * 32))) break;
+      if ((rc = dev_alloc(h, &h->bufB2, (size_t)h->s12_cap * 224 * 224 * 32))) break;
+      if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { rc = fail(h, FF_ERR_CUDA, "aux stream/event create failed"); break; }
       if ((rc = dev_alloc(h, &h->P, (size_t)h->cap * 56 * 56 * 128))) break;
       if ((rc = dev_alloc(h, &h->Q, (size_t)h->cap * 56 * 56 * 128))) break;
       if ((rc = dev_alloc(h, &h->feat, (size_t)cap128 * PATCH))) break;
@@ -1110,6 +1144,9 @@ void ff_cvit_destroy(ff_cvit_t* h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->h2d_ready) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 
