@@ -1301,7 +1301,10 @@ int ff_preprocess_crops(ff_cvit_t* h, const uint8_t* const* crop_ptrs, const int
   // pageable-host source: cudaMemcpyAsync stages the descriptors before returning, so `d` may die with this call;
   // the descriptor buffer is reused by the next call only after the stream-ordered kernel below has been enqueued
   FF_CUDA(h, cudaMemcpyAsync(h->crop_desc, d.data(), sizeof(CropDesc) * n, cudaMemcpyHostToDevice, st));
-  preprocess_kernel<<<dim3((224 * 224 / 4 + 255) / 256, n), 256, 0, st>>>(h->crop_desc, n, swap_rb, out_u8, out_norm_nchw);
+  {
+    ProfScope ps(h, st, KC_SMALL);
+    preprocess_kernel<<<dim3(224 / 4, n), 256, 0, st>>>(h->crop_desc, n, swap_rb, out_u8, out_norm_nchw);
+  }
   FF_LAUNCH_CHECK(h, "preprocess");
   return FF_OK;
 }

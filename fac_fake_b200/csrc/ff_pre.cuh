@@ -79,79 +79,117 @@ __device__ __forceinline__ void linear_tap(int d, int ssize, int dsize, int* sx,
 
 __device__ __forceinline__ uint8_t sat_u8_rn(float v) { return static_cast<uint8_t>(max(0, min(255, __float2int_rn(v)))); }
 
-// One thread produces 4 consecutive output pixels of one row (12 output bytes = three aligned 32-bit stores);
-// a warp therefore covers 128 consecutive output pixels and reads, per source row, one contiguous byte range.
-__device__ __forceinline__ void preprocess_pixel(const CropDesc& c, int dy, int dx, int res[3]) {
-  constexpr int D = 224;
-  if (c.mode == PRE_FAST) {
-    int sum[3] = {0, 0, 0};
-    for (int sy = 0; sy < c.isy; ++sy) {
-      const uint8_t* row = c.ptr + static_cast<size_t>(dy * c.isy + sy) * c.pitch + static_cast<size_t>(dx) * c.isx * 3;
-      for (int sx = 0; sx < c.isx; ++sx) {
-        sum[0] += row[sx * 3]; sum[1] += row[sx * 3 + 1]; sum[2] += row[sx * 3 + 2];
-      }
-    }
-    if (c.isx == 2 && c.isy == 2) {
-      for (int k = 0; k < 3; ++k) res[k] = (sum[k] + 2) >> 2;
-    } else {
-      const float scale = 1.0f / static_cast<float>(c.isx * c.isy);
-      for (int k = 0; k < 3; ++k) res[k] = sat_u8_rn(__fmul_rn(static_cast<float>(sum[k]), scale));
-    }
-  } else if (c.mode == PRE_FRAC) {
-    const AreaSpan xs = area_span(dx, static_cast<double>(c.w) / D, c.w);
-    const AreaSpan ys = area_span(dy, static_cast<double>(c.h) / D, c.h);
-    float sum[3] = {0.f, 0.f, 0.f};
-    for (int ey = 0; ey < ys.n; ++ey) {
-      int sy; float beta;
-      area_entry(ys, ey, &sy, &beta);
-      const uint8_t* row = c.ptr + static_cast<size_t>(sy) * c.pitch;
-      float buf[3] = {0.f, 0.f, 0.f};
-      for (int ex = 0; ex < xs.n; ++ex) {
-        int sx; float alpha;
-        area_entry(xs, ex, &sx, &alpha);
-        const uint8_t* p = row + static_cast<size_t>(sx) * 3;
-        for (int k = 0; k < 3; ++k) buf[k] = __fadd_rn(buf[k], __fmul_rn(static_cast<float>(p[k]), alpha));
-      }
-      for (int k = 0; k < 3; ++k)
-        sum[k] = (ey == 0) ? __fmul_rn(beta, buf[k]) : __fadd_rn(sum[k], __fmul_rn(beta, buf[k]));
-    }
-    for (int k = 0; k < 3; ++k) res[k] = sat_u8_rn(sum[k]);
-  } else {
-    int sx, a0, a1, sy, b0, b1;
-    bool ex, ey;
-    linear_tap(dx, c.w, D, &sx, &a0, &a1, &ex);
-    linear_tap(dy, c.h, D, &sy, &b0, &b1, &ey);
-    const int sx1 = min(sx + 1, c.w - 1), sy1 = min(sy + 1, c.h - 1);
-    const uint8_t* r0 = c.ptr + static_cast<size_t>(sy) * c.pitch;
-    const uint8_t* r1 = c.ptr + static_cast<size_t>(sy1) * c.pitch;
-    for (int k = 0; k < 3; ++k) {
-      int h0, h1;
-      if (ex) { h0 = r0[sx * 3 + k] * 2048; h1 = r1[sx * 3 + k] * 2048; }
-      else {
-        h0 = r0[sx * 3 + k] * a0 + r0[sx1 * 3 + k] * a1;
-        h1 = r1[sx * 3 + k] * a0 + r1[sx1 * 3 + k] * a1;
-      }
-      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-      res[k] = max(0, min(255, v));
-    }
-  }
+// Per-destination-index tables (what OpenCV keeps in xtab/ytab / xofs+ialpha): computed once per block in fp64
+// exactly as before, then shared by the block's 896 output pixels.
+struct AreaTabEntry {          // FRAC: entries of one destination index, in OpenCV's table order
+  int first;                   // source index of entry 0
+  int n;                       // number of entries
+  float a_first, a_mid, a_last;
+};
+struct LinTabEntry { int s, a0, a1, edge; };
+
+__device__ __forceinline__ AreaTabEntry make_area_tab(int d, double scale, int ssize) {
+  const AreaSpan sp = area_span(d, scale, ssize);
+  AreaTabEntry t;
+  t.n = sp.n;
+  t.first = sp.head ? sp.sx1 - 1 : sp.sx1;
+  int si;
+  float al = 0.f;
+  t.a_first = t.a_mid = t.a_last = 0.f;
+  if (sp.n > 0) { area_entry(sp, 0, &si, &al); t.a_first = al; }
+  if (sp.n > 1) { area_entry(sp, sp.n - 1, &si, &al); t.a_last = al; }
+  t.a_mid = static_cast<float>(1.0 / sp.cell);
+  // entry e (0 < e < n-1) is always a full source pixel with weight 1/cell; entry 0 is the head (or a full pixel,
+  // for which a_first == a_mid) and entry n-1 the tail (or a full pixel)
+  return t;
+}
+__device__ __forceinline__ float area_alpha(const AreaTabEntry& t, int e) {
+  return e == 0 ? t.a_first : (e == t.n - 1 ? t.a_last : t.a_mid);
 }
 
+// Block = 4 output rows of one crop (896 pixels); one thread produces 4 consecutive output pixels of one row
+// (12 output bytes = three aligned 32-bit stores), so a warp covers 128 consecutive output pixels.
 __global__ void __launch_bounds__(256)
 preprocess_kernel(const CropDesc* __restrict__ crops, int n, int swap_rb, uint8_t* __restrict__ out_u8,
                   float* __restrict__ out_norm) {
-  constexpr int D = 224;
+  constexpr int D = 224, ROWS = 4;
+  __shared__ AreaTabEntry s_ax[D];
+  __shared__ AreaTabEntry s_ay[ROWS];
+  __shared__ LinTabEntry s_lx[D];
+  __shared__ LinTabEntry s_ly[ROWS];
   const int i = blockIdx.y;
-  const int quad = blockIdx.x * 256 + threadIdx.x;      // group of 4 output pixels
-  if (i >= n || quad >= D * D / 4) return;
-  const int pix0 = quad * 4;
-  const int dy = pix0 / D, dx0 = pix0 % D;               // D % 4 == 0: the 4 pixels share a row
+  if (i >= n) return;
   const CropDesc c = crops[i];
+  const int row0 = blockIdx.x * ROWS;
+  const int tid = threadIdx.x;
+  if (c.mode == PRE_FRAC) {
+    if (tid < D) s_ax[tid] = make_area_tab(tid, static_cast<double>(c.w) / D, c.w);
+    else if (tid < D + ROWS) s_ay[tid - D] = make_area_tab(row0 + tid - D, static_cast<double>(c.h) / D, c.h);
+  } else if (c.mode == PRE_LINEAR) {
+    if (tid < D + ROWS) {
+      const bool isx = tid < D;
+      LinTabEntry e;
+      bool edge;
+      linear_tap(isx ? tid : row0 + tid - D, isx ? c.w : c.h, D, &e.s, &e.a0, &e.a1, &edge);
+      e.edge = edge ? 1 : 0;
+      if (isx) s_lx[tid] = e; else s_ly[tid - D] = e;
+    }
+  }
+  __syncthreads();
+  if (tid >= ROWS * D / 4) return;
+  const int rl = tid / (D / 4);
+  const int dy = row0 + rl, dx0 = (tid - rl * (D / 4)) * 4;
+  const int pix0 = dy * D + dx0;
   uint32_t packed[3] = {0u, 0u, 0u};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
+    const int dx = dx0 + j;
     int res[3];
-    preprocess_pixel(c, dy, dx0 + j, res);
+    if (c.mode == PRE_FAST) {
+      int sum[3] = {0, 0, 0};
+      for (int sy = 0; sy < c.isy; ++sy) {
+        const uint8_t* row = c.ptr + static_cast<size_t>(dy * c.isy + sy) * c.pitch + static_cast<size_t>(dx) * c.isx * 3;
+        for (int sx = 0; sx < c.isx; ++sx) {
+          sum[0] += row[sx * 3]; sum[1] += row[sx * 3 + 1]; sum[2] += row[sx * 3 + 2];
+        }
+      }
+      if (c.isx == 2 && c.isy == 2) {
+        for (int k = 0; k < 3; ++k) res[k] = (sum[k] + 2) >> 2;
+      } else {
+        const float scale = 1.0f / static_cast<float>(c.isx * c.isy);
+        for (int k = 0; k < 3; ++k) res[k] = sat_u8_rn(__fmul_rn(static_cast<float>(sum[k]), scale));
+      }
+    } else if (c.mode == PRE_FRAC) {
+      const AreaTabEntry tx = s_ax[dx], ty = s_ay[rl];
+      float sum[3] = {0.f, 0.f, 0.f};
+      for (int ey = 0; ey < ty.n; ++ey) {
+        const float beta = area_alpha(ty, ey);
+        const uint8_t* p = c.ptr + static_cast<size_t>(ty.first + ey) * c.pitch + static_cast<size_t>(tx.first) * 3;
+        float buf[3] = {0.f, 0.f, 0.f};
+        for (int ex = 0; ex < tx.n; ++ex, p += 3) {
+          const float alpha = area_alpha(tx, ex);
+          for (int k = 0; k < 3; ++k) buf[k] = __fadd_rn(buf[k], __fmul_rn(static_cast<float>(p[k]), alpha));
+        }
+        for (int k = 0; k < 3; ++k)
+          sum[k] = (ey == 0) ? __fmul_rn(beta, buf[k]) : __fadd_rn(sum[k], __fmul_rn(beta, buf[k]));
+      }
+      for (int k = 0; k < 3; ++k) res[k] = sat_u8_rn(sum[k]);
+    } else {
+      const LinTabEntry ex = s_lx[dx], ey = s_ly[rl];
+      const int sx1 = min(ex.s + 1, c.w - 1), sy1 = min(ey.s + 1, c.h - 1);
+      const uint8_t* r0 = c.ptr + static_cast<size_t>(ey.s) * c.pitch;
+      const uint8_t* r1 = c.ptr + static_cast<size_t>(sy1) * c.pitch;
+      for (int k = 0; k < 3; ++k) {
+        int h0, h1;
+        if (ex.edge) { h0 = r0[ex.s * 3 + k] * 2048; h1 = r1[ex.s * 3 + k] * 2048; }
+        else {
+          h0 = r0[ex.s * 3 + k] * ex.a0 + r0[sx1 * 3 + k] * ex.a1;
+          h1 = r1[ex.s * 3 + k] * ex.a0 + r1[sx1 * 3 + k] * ex.a1;
+        }
+        const int v = (((ey.a0 * (h0 >> 4)) >> 16) + ((ey.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        res[k] = max(0, min(255, v));
+      }
+    }
     if (swap_rb) { const int t = res[0]; res[0] = res[2]; res[2] = t; }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
