@@ -126,6 +126,7 @@ struct ff_cvit {
   bf16 *bufA2 = nullptr, *bufB2 = nullptr; // second ping-pong set: odd sub-passes run on aux_stream (dual-stream overlap)
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int gemm_bn_wide = 64;   // N tile of the wide transformer linears (qkv, ff1): 64 or 128
   int use_dual = 1;        // overlap consecutive stage-1/2 sub-passes on two streams (hides launch tails/prologues)
   bf16 *P = nullptr, *Q = nullptr;         // stage 3..5 ping-pong, cap crops
   bf16* feat = nullptr;                    // [cap_rows128][25088]
@@ -636,9 +637,9 @@ int finalize(ff_cvit* h) {
     if ((rc = upload_vec(h, &X.ln1_b, p + ".0.fn.norm.bias", DIM))) return rc;
     if ((rc = upload_vec(h, &X.ln2_g, p + ".1.fn.norm.weight", DIM))) return rc;
     if ((rc = upload_vec(h, &X.ln2_b, p + ".1.fn.norm.bias", DIM))) return rc;
-    if ((rc = upload_linear(h, &X.qkv, p + ".0.fn.fn.to_qkv", 3 * DIM, DIM, false, 64))) return rc;
+    if ((rc = upload_linear(h, &X.qkv, p + ".0.fn.fn.to_qkv", 3 * DIM, DIM, false, h->gemm_bn_wide))) return rc;
     if ((rc = upload_linear(h, &X.out, p + ".0.fn.fn.to_out", DIM, DIM, true, 64))) return rc;
-    if ((rc = upload_linear(h, &X.ff1, p + ".1.fn.fn.net.0", MLP, DIM, true, 64))) return rc;
+    if ((rc = upload_linear(h, &X.ff1, p + ".1.fn.fn.net.0", MLP, DIM, true, h->gemm_bn_wide))) return rc;
     if ((rc = upload_linear(h, &X.ff2, p + ".1.fn.fn.net.2", DIM, MLP, true, 64))) return rc;
   }
   if ((rc = upload_linear(h, &h->head1, "mlp_head.0", MLP, DIM, true, 64))) return rc;
@@ -1075,6 +1076,7 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
   if (const char* v = getenv("FF_WS")) h->use_ws = atoi(v);
   if (const char* v = getenv("FF_PDL")) g_use_pdl = atoi(v) != 0;
   if (const char* v = getenv("FF_DUAL")) h->use_dual = atoi(v);
+  if (const char* v = getenv("FF_GEMM_BN")) h->gemm_bn_wide = atoi(v) == 128 ? 128 : 64;
   if (const char* v = getenv("FF_PTC")) h->use_ptc = atoi(v);
   if (const char* v = getenv("FF_WS2")) h->use_ws2 = atoi(v);
   if (const char* v = getenv("FF_WS2X")) h->use_ws2x = atoi(v);
