@@ -231,3 +231,59 @@ def test_multi_pass_and_ragged_batches():
     s_big = big.predict_videos(crops, offs).cpu()
     assert torch.equal(s_small, s_big)
     assert s_big[2].item() == 0.5
+
+
+def test_softmax_mean_mode(eng_bn):
+    eng, _ = eng_bn
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn((50, 2), generator=g) * 2
+    offs = torch.tensor([0, 7, 7, 30, 50], dtype=torch.int32)
+    s = eng.video_scores(logits.cuda(), offs, mode=1).cpu()
+    p = torch.softmax(logits, dim=1)[:, 0]
+    want = [p[0:7].mean().item(), 0.5, p[7:30].mean().item(), p[30:50].mean().item()]
+    for a, b in zip(s.tolist(), want):
+        assert abs(a - b) <= 2e-6
+
+
+def test_prediction_api_mirror_end_to_end(tmp_path, eng_bn):
+    """fac_fake_b200.cvit_prediction.predict(): video file in -> score out, same sampling/chunking as the reference
+    (cvit_prediction.py:153-242), with an injected face extractor; checked against the oracle on the same crops."""
+    cv2 = pytest.importorskip("cv2")
+    import fac_fake_b200.cvit_prediction as cp
+    eng, sd = eng_bn
+    path = str(tmp_path / "clip.avi")
+    rng = np.random.default_rng(7)
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 25.0, (320, 240))
+    if not vw.isOpened():
+        pytest.skip("no MJPG encoder in this OpenCV build")
+    base = rng.integers(0, 256, (240, 320, 3), dtype=np.uint8)
+    for i in range(120):
+        vw.write(np.roll(base, 3 * i, axis=1))
+    vw.release()
+    seen = []
+
+    def extractor(frame, _unused=None):
+        # two "faces" per frame: fixed boxes, resized exactly like cvit_prediction.py:113-115
+        crops = []
+        for (t, r, b, l) in ((20, 200, 180, 40), (60, 300, 220, 140)):
+            c = cv2.resize(frame[t:b, l:r], (224, 224), interpolation=cv2.INTER_AREA)
+            crops.append(cv2.cvtColor(c, cv2.COLOR_RGB2BGR))
+        out = np.stack(crops)
+        seen.append(out)
+        return out, len(crops)
+
+    cp.configure(model_=eng, face_extractor=extractor, sample_dir=str(tmp_path))
+    score = cp.predict_on_video(["clip.avi"], num_workers=1)[0]
+    # the reference loop: int(0.1 * n_frames) iterations, 2 crops each, capped at 29 crops
+    assert len(seen) == 12
+    crops = np.concatenate(seen)[:29]
+    ref_score, _ = O.predict_from_crops(torch.from_numpy(crops), sd)
+    assert abs(score - ref_score) <= 1e-2
+    assert cp.real_or_fake(score) in ("REAL", "FAKE")
+    # sentinel: no faces -> 0.5 (cvit_prediction.py:218-219)
+    cp.configure(face_extractor=lambda frame, _u=None: ([], 0))
+    assert cp.predict_on_video(["clip.avi"], num_workers=1)[0] == 0.5
+    # helper parity with the reference's reduction helpers
+    lg = torch.randn((9, 2), generator=torch.Generator().manual_seed(1))
+    got = cp.pre_process_prediction(cp.pred_sig(lg)).item()
+    assert abs(got - O.video_score(lg)) <= 1e-5
