@@ -101,3 +101,84 @@ def synthetic_crops(n: int, seed: int = 0) -> torch.Tensor:
     gen = torch.Generator(device="cpu")
     gen.manual_seed(7919 * seed + 3)
     return torch.randint(0, 256, (n, 224, 224, 3), generator=gen, dtype=torch.uint8)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# ResVitKan (/root/reference/CViT-main/ResVitKan/ResVitKan.py:284-329, kan.py:18-206)
+RESNET_LAYERS = ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2))     # (planes, blocks, stride of the first block)
+
+
+def _bn(gen, sd, name, c, variant):
+    if variant == "bn":
+        sd[name + ".weight"] = torch.rand((c,), generator=gen) * 0.5 + 0.5
+        sd[name + ".bias"] = torch.randn((c,), generator=gen) * 0.1
+        sd[name + ".running_mean"] = torch.randn((c,), generator=gen) * 0.1
+        sd[name + ".running_var"] = torch.rand((c,), generator=gen) + 0.5
+    else:
+        sd[name + ".weight"] = torch.ones(c)
+        sd[name + ".bias"] = torch.zeros(c)
+        sd[name + ".running_mean"] = torch.zeros(c)
+        sd[name + ".running_var"] = torch.ones(c)
+    sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+
+def _conv_normal(gen, shape):
+    # ResNet.__init__ (ResVitKan.py:202-209): normal(0, sqrt(2 / (k*k*out_channels)))
+    out_c, _, kh, kw = shape
+    return torch.randn(shape, generator=gen) * math.sqrt(2.0 / (kh * kw * out_c))
+
+
+def make_resvitkan_state_dict(seed: int = 0, variant: str = "default") -> "OrderedDict[str, torch.Tensor]":
+    """state_dict of the reference ResVitKan `CViT` (ResNet-50 features + ViT + KAN head), key names as in the reference."""
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(7000003 * seed + 29)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    sd["pos_embedding"] = torch.randn((MAX_SLOTS, 1, DIM), generator=gen)
+    sd["cls_token"] = torch.randn((1, 1, DIM), generator=gen)
+    sd["features.conv1.weight"] = _conv_normal(gen, (64, 3, 7, 7))
+    _bn(gen, sd, "features.bn1", 64, variant)
+    inplanes = 64
+    for li, (planes, blocks, stride) in enumerate(RESNET_LAYERS, start=1):
+        for b in range(blocks):
+            p = f"features.layer{li}.{b}"
+            sd[p + ".conv1.weight"] = _conv_normal(gen, (planes, inplanes, 1, 1))
+            _bn(gen, sd, p + ".bn1", planes, variant)
+            sd[p + ".conv2.weight"] = _conv_normal(gen, (planes, planes, 3, 3))
+            _bn(gen, sd, p + ".bn2", planes, variant)
+            sd[p + ".conv3.weight"] = _conv_normal(gen, (planes * 4, planes, 1, 1))
+            _bn(gen, sd, p + ".bn3", planes * 4, variant)
+            if b == 0:
+                sd[p + ".downsample.0.weight"] = _conv_normal(gen, (planes * 4, inplanes, 1, 1))
+                _bn(gen, sd, p + ".downsample.1", planes * 4, variant)
+            inplanes = planes * 4
+    sd["features.channel.weight"] = _conv_normal(gen, (512, 2048, 1, 1))
+    _bn(gen, sd, "features.bn2", 512, variant)
+    _linear(gen, sd, "patch_to_embedding", DIM, PATCH_DIM)
+    for layer in range(DEPTH):
+        p = f"transformer.layers.{layer}"
+        for blk in (0, 1):
+            if variant == "bn":
+                sd[f"{p}.{blk}.fn.norm.weight"] = torch.rand((DIM,), generator=gen) + 0.5
+                sd[f"{p}.{blk}.fn.norm.bias"] = torch.randn((DIM,), generator=gen) * 0.1
+            else:
+                sd[f"{p}.{blk}.fn.norm.weight"] = torch.ones(DIM)
+                sd[f"{p}.{blk}.fn.norm.bias"] = torch.zeros(DIM)
+            if blk == 0:
+                _linear(gen, sd, f"{p}.0.fn.fn.to_qkv", 3 * DIM, DIM, bias=False)
+                _linear(gen, sd, f"{p}.0.fn.fn.to_out", DIM, DIM)
+            else:
+                _linear(gen, sd, f"{p}.1.fn.fn.net.0", MLP_DIM, DIM)
+                _linear(gen, sd, f"{p}.1.fn.fn.net.2", DIM, MLP_DIM)
+    _linear(gen, sd, "kan_head.0", MLP_DIM, DIM)
+    for i, (fin, fout) in enumerate(((MLP_DIM, 64), (64, NUM_CLASSES))):
+        q = f"kan_head.3.layers.{i}"
+        b = 1.0 / math.sqrt(fin)
+        sd[q + ".base_weight"] = _uniform(gen, (fout, fin), b)
+        sd[q + ".spline_weight"] = torch.randn((fout, fin, 8), generator=gen) * 0.1
+        sd[q + ".spline_scaler"] = _uniform(gen, (fout, fin), b)
+        h = 2.0 / 5
+        sd[q + ".grid"] = (torch.arange(-3, 5 + 3 + 1) * h - 1.0).expand(fin, -1).contiguous()
+    # mlp_head exists in the reference module but is not used by forward(); keep the keys so load_state_dict(strict) works
+    _linear(gen, sd, "mlp_head.0", MLP_DIM, DIM)
+    _linear(gen, sd, "mlp_head.3", NUM_CLASSES, MLP_DIM)
+    return sd

@@ -96,3 +96,37 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def main_resvitkan():
+    """tests/golden/resvitkan_{default,bn}.npz from the reference ResVitKan class (ResVitKan/ResVitKan.py:284-329)."""
+    sys.path.insert(0, os.path.join(REF, "ResVitKan"))
+    from ResVitKan import CViT as RVK  # noqa: E402  (reference class; imports kan.KAN from its own directory)
+    from oracle import resvitkan_oracle as R  # noqa: E402
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    for variant in ("default", "bn"):
+        sd = W.make_resvitkan_state_dict(0, variant)
+        model = RVK().eval()
+        model.load_state_dict(sd, strict=True)
+        crops = W.synthetic_crops(8, seed=2)
+        x = O.normalize_crops(crops)
+        with torch.no_grad():
+            logits = model(x)
+            f = model.features
+            h = f.maxpool(f.relu(f.bn1(f.conv1(x[:2]))))
+            stats = [h]
+            for layer in (f.layer1, f.layer2, f.layer3, f.layer4):
+                h = layer(h)
+                stats.append(h)
+            h = f.bn2(f.channel(h))
+            stats.append(h)
+        layer_stats = np.stack([np.array([s.double().mean().item(), s.double().abs().mean().item(),
+                                          s.double().pow(2).mean().sqrt().item()]) for s in stats])
+        np.savez_compressed(os.path.join(out_dir, f"resvitkan_{variant}.npz"), logits=logits.numpy(), layer_stats=layer_stats,
+                            feat_final=stats[-1].numpy().astype(np.float32), stem_sample=stats[0][0, :, :6, :6].numpy(),
+                            seed_weights=0, seed_crops=2, n=8)
+        print("resvitkan", variant, "logits[0:2] =", logits[0:2].tolist())
+
+
+if __name__ == "__main__" and os.environ.get("FF_GOLDEN_RESVITKAN", "1") == "1":
+    main_resvitkan()
