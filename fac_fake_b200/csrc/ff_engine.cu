@@ -25,6 +25,7 @@
 #include "ff_tc.cuh"
 #include "ff_ws.cuh"
 #include "ff_c1.cuh"
+#include "ff_rvk.cuh"
 
 namespace {
 
@@ -126,6 +127,28 @@ struct ff_cvit {
   bf16 *bufA2 = nullptr, *bufB2 = nullptr; // second ping-pong set: odd sub-passes run on aux_stream (dual-stream overlap)
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // ---- ResVitKan (kind == 1): ResNet-50 features + the same ViT + KAN head
+  int kind = 0;
+  struct RvkOp {
+    int type = 0;            // 0 = 1x1 stride-1 conv as GEMM, 1 = implicit-GEMM conv (3x3 any stride, or 1x1 stride 2)
+    int cin = 0, cout = 0, taps = 9, stride = 1, in_hw = 0, out_hw = 0;
+    int act = 0;             // 1 = ReLU after BN
+    int resid = -1;          // buffer index of the residual (conv3) or -1
+    int in_buf = 0, out_buf = 0;
+    int bn = 64, bw = 8, bh = 8, bi = 2;
+    bf16* w = nullptr;
+    float *scale = nullptr, *shift = nullptr;
+    CUtensorMap tmA, tmB;
+    std::string name;
+  };
+  std::vector<RvkOp> rvk_ops;
+  int rvk_layer_end[4] = {0, 0, 0, 0};   // index of the last op of layer1..4 (debug taps)
+  bf16* rvk_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bf16* rvk_x4 = nullptr;                // normalised bf16 NHWC4 input
+  bf16* rvk_stem_w = nullptr;
+  float rvk_stem_scale[64], rvk_stem_shift[64];
+  CUtensorMap rvk_tm_x4;
+  float *kan_w0 = nullptr, *kan_w1 = nullptr, *kan_g0 = nullptr, *kan_g1 = nullptr;
   int gemm_bn_wide = 64;   // N tile of the wide transformer linears (qkv, ff1): 64 or 128
   int use_dual = 1;        // overlap consecutive stage-1/2 sub-passes on two streams (hides launch tails/prologues)
   bf16 *P = nullptr, *Q = nullptr;         // stage 3..5 ping-pong, cap crops
@@ -260,11 +283,13 @@ int tmap_2d(ff_cvit* h, CUtensorMap* m, const void* base, uint64_t inner, uint64
                                      (unsigned long long)inner, (unsigned long long)rows, (int)r);
   return FF_OK;
 }
-int tmap_4d(ff_cvit* h, CUtensorMap* m, const void* base, int C, int W, int H, int N, int boxC, int bw, int bh, int bi) {
+int tmap_4d(ff_cvit* h, CUtensorMap* m, const void* base, int C, int W, int H, int N, int boxC, int bw, int bh, int bi,
+            int estride = 1) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bi};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // with element strides the box is given in input-space extents: ceil(box/stride) elements are loaded per dim
+  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), (cuuint32_t)bi};
+  cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
   CUtensorMapSwizzle sw = boxC * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -513,8 +538,151 @@ int build_conv_maps(ff_cvit* h) {
   return FF_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ ResVitKan features
+// ResNet-50 plan (ResVitKan.py:185-240): the stem is its own kernel (ff_rvk.cuh); every bottleneck convolution is
+// one launch of tc_kernel: 1x1 stride-1 convs as GEMMs over pixels, 3x3 / strided convs as implicit GEMMs whose TMA
+// descriptor carries the stride.  Eval-mode BN is folded into (scale, shift) of the producing launch.
+constexpr int kRvkPlanes[4] = {64, 128, 256, 512}, kRvkBlocks[4] = {3, 4, 6, 3}, kRvkStride[4] = {1, 2, 2, 2};
+constexpr size_t kRvkActElems = (size_t)112 * 112 * 64;      // largest activation per crop (stem / layer1 output)
+
+void rvk_tile_geometry(int out_hw, int* bw, int* bh, int* bi) {
+  if (out_hw == 56) { *bw = 8; *bh = 8; *bi = 2; }
+  else if (out_hw == 28) { *bw = 4; *bh = 4; *bi = 8; }
+  else if (out_hw == 14) { *bw = 2; *bh = 2; *bi = 32; }
+  else { *bw = 8; *bh = 8; *bi = 2; }                         // 7x7: one masked 8x8 box per image
+}
+
+int rvk_fold_bn(ff_cvit* h, const std::string& bn, int c, std::vector<float>* scale, std::vector<float>* shift) {
+  const auto* g = get_w(h, bn + ".weight", {c});
+  const auto* be = get_w(h, bn + ".bias", {c});
+  const auto* mu = get_w(h, bn + ".running_mean", {c});
+  const auto* var = get_w(h, bn + ".running_var", {c});
+  if (!g || !be || !mu || !var) return h->err.find("shape") != std::string::npos ? FF_ERR_SHAPE : FF_ERR_STATE;
+  scale->resize(c);
+  shift->resize(c);
+  for (int o = 0; o < c; ++o) {
+    const float s = (*g)[o] / std::sqrt((*var)[o] + BN_EPS);
+    (*scale)[o] = s;
+    (*shift)[o] = (*be)[o] - (*mu)[o] * s;                    // the ResNet convolutions have no bias (ResVitKan.py:191,198)
+  }
+  return FF_OK;
+}
+
+int rvk_add_op(ff_cvit* h, const std::string& conv, const std::string& bn, int cin, int cout, int k, int stride, int in_hw,
+               int act, int in_buf, int out_buf, int resid, bf16* out_override = nullptr) {
+  ff_cvit::RvkOp op;
+  op.name = conv;
+  op.cin = cin; op.cout = cout; op.taps = k * k; op.stride = stride; op.in_hw = in_hw; op.out_hw = in_hw / stride;
+  op.type = (k == 1 && stride == 1) ? 0 : 1;
+  op.act = act; op.resid = resid; op.in_buf = in_buf; op.out_buf = out_buf;
+  op.bn = std::min(cout, 128);
+  const auto* w = get_w(h, conv + ".weight", {cout, cin, k, k});
+  if (!w) return h->err.find("shape") != std::string::npos ? FF_ERR_SHAPE : FF_ERR_STATE;
+  std::vector<float> scale, shift, wr((size_t)cout * k * k * cin);
+  int rc = rvk_fold_bn(h, bn, cout, &scale, &shift);
+  if (rc) return rc;
+  for (int o = 0; o < cout; ++o)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < k * k; ++t) wr[((size_t)o * k * k + t) * cin + ci] = (*w)[((size_t)o * cin + ci) * k * k + t];
+  if ((rc = dev_upload(h, &op.w, to_bf16(wr)))) return rc;
+  if ((rc = dev_upload(h, &op.scale, scale))) return rc;
+  if ((rc = dev_upload(h, &op.shift, shift))) return rc;
+  if ((rc = tmap_2d(h, &op.tmB, op.w, (uint64_t)k * k * cin, cout, 64, op.bn))) return rc;
+  const bf16* in = h->rvk_buf[in_buf];
+  if (op.type == 0) {
+    rc = tmap_2d(h, &op.tmA, in, cin, (uint64_t)h->cap * in_hw * in_hw, 64, 128);
+  } else {
+    rvk_tile_geometry(op.out_hw, &op.bw, &op.bh, &op.bi);
+    rc = tmap_4d(h, &op.tmA, in, cin, in_hw, in_hw, h->cap, 64, op.bw, op.bh, op.bi, stride);
+  }
+  if (rc) return rc;
+  (void)out_override;
+  h->rvk_ops.push_back(op);
+  return FF_OK;
+}
+
+int finalize_rvk_features(ff_cvit* h) {
+  int rc;
+  // ---- stem: [64][3][7][7] -> [kh][cout][8 px][4 ch] with kw = px - 1 (ff_rvk.cuh)
+  {
+    const auto* w = get_w(h, "features.conv1.weight", {64, 3, 7, 7});
+    if (!w) return h->err.find("shape") != std::string::npos ? FF_ERR_SHAPE : FF_ERR_STATE;
+    std::vector<float> ws((size_t)7 * 64 * 32, 0.0f), scale, shift;
+    for (int kh = 0; kh < 7; ++kh)
+      for (int o = 0; o < 64; ++o)
+        for (int kw = 0; kw < 7; ++kw)
+          for (int c = 0; c < 3; ++c) ws[((size_t)kh * 64 + o) * 32 + (kw + 1) * 4 + c] = (*w)[(((size_t)o * 3 + c) * 7 + kh) * 7 + kw];
+    if ((rc = dev_upload(h, &h->rvk_stem_w, to_bf16(ws)))) return rc;
+    if ((rc = rvk_fold_bn(h, "features.bn1", 64, &scale, &shift))) return rc;
+    for (int o = 0; o < 64; ++o) { h->rvk_stem_scale[o] = scale[o]; h->rvk_stem_shift[o] = shift[o]; }
+    cuuint64_t dims[3] = {896, 224, (cuuint64_t)h->cap};
+    cuuint64_t strides[2] = {896 * 2, (cuuint64_t)224 * 896 * 2};
+    cuuint32_t box[3] = {96, 37, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(&h->rvk_tm_x4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, h->rvk_x4, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(stem input) failed: %d", (int)r);
+  }
+  // ---- bottlenecks.  Buffers: X in {0,1} (block input / output, alternating), 2 = conv1 out, 3 = conv2 out, 4 = downsample
+  h->rvk_ops.clear();
+  int inplanes = 64, hw = 56, xb = 1;           // the max-pool writes buffer 1
+  for (int li = 0; li < 4; ++li) {
+    const int planes = kRvkPlanes[li];
+    for (int b = 0; b < kRvkBlocks[li]; ++b) {
+      const std::string p = "features.layer" + std::to_string(li + 1) + "." + std::to_string(b);
+      const int stride = b == 0 ? kRvkStride[li] : 1;
+      const int yb = xb ^ 1;
+      if ((rc = rvk_add_op(h, p + ".conv1", p + ".bn1", inplanes, planes, 1, 1, hw, 1, xb, 2, -1))) return rc;
+      if ((rc = rvk_add_op(h, p + ".conv2", p + ".bn2", planes, planes, 3, stride, hw, 1, 2, 3, -1))) return rc;
+      int resid = xb;
+      if (b == 0) {
+        if ((rc = rvk_add_op(h, p + ".downsample.0", p + ".downsample.1", inplanes, planes * 4, 1, stride, hw, 0, xb, 4, -1))) return rc;
+        resid = 4;
+      }
+      hw /= stride;
+      // conv3 + bn3 + ReLU, + residual, + ReLU (ResVitKan.py:169-176: both ReLUs are in the reference)
+      if ((rc = rvk_add_op(h, p + ".conv3", p + ".bn3", planes, planes * 4, 1, 1, hw, 1, 3, yb, resid))) return rc;
+      inplanes = planes * 4;
+      xb = yb;
+    }
+    h->rvk_layer_end[li] = (int)h->rvk_ops.size() - 1;
+  }
+  // features.channel + bn2 (no activation) writes the [n][49][512] patch vector the embedding GEMM reads
+  if ((rc = rvk_add_op(h, "features.channel", "features.bn2", 2048, 512, 1, 1, 7, 0, xb, -1, -1))) return rc;
+  // ---- KAN([2048, 64, 2])
+  const int kin[2] = {MLP, 64}, kout[2] = {64, 2};
+  for (int l = 0; l < 2; ++l) {
+    const std::string q = "kan_head.3.layers." + std::to_string(l);
+    const auto* bw = get_w(h, q + ".base_weight", {kout[l], kin[l]});
+    const auto* sw = get_w(h, q + ".spline_weight", {kout[l], kin[l], 8});
+    const auto* gr = get_w(h, q + ".grid", {kin[l], 12});
+    if (!bw || !sw || !gr) return h->err.find("shape") != std::string::npos ? FF_ERR_SHAPE : FF_ERR_STATE;
+    // enable_standalone_scale_spline=True is the KANLinear default (kan.py:19); accept checkpoints without the scaler
+    const std::vector<float>* sc = nullptr;
+    if (h->host_w.count(q + ".spline_scaler")) {
+      sc = get_w(h, q + ".spline_scaler", {kout[l], kin[l]});
+      if (!sc) return FF_ERR_SHAPE;
+    }
+    std::vector<float> pk((size_t)kin[l] * 9 * kout[l]);
+    for (int i = 0; i < kin[l]; ++i)
+      for (int o = 0; o < kout[l]; ++o) {
+        pk[((size_t)i * 9) * kout[l] + o] = (*bw)[(size_t)o * kin[l] + i];
+        const float s = sc ? (*sc)[(size_t)o * kin[l] + i] : 1.0f;
+        for (int k = 0; k < 8; ++k) pk[((size_t)i * 9 + 1 + k) * kout[l] + o] = (*sw)[((size_t)o * kin[l] + i) * 8 + k] * s;
+      }
+    if ((rc = dev_upload(h, l == 0 ? &h->kan_w0 : &h->kan_w1, pk))) return rc;
+    if ((rc = dev_upload(h, l == 0 ? &h->kan_g0 : &h->kan_g1, *gr))) return rc;
+  }
+  return FF_OK;
+}
+
 int finalize(ff_cvit* h) {
   int rc;
+  if (h->kind == 1) {
+    if ((rc = finalize_rvk_features(h))) return rc;
+  } else
   // ---- conv stack: fold bias + eval BN into (scale, shift); weights -> [cout][kh][kw][cin]
   for (int li = 0; li < 17; ++li) {
     const ConvPlan& p = kConv[li];
@@ -642,11 +810,15 @@ int finalize(ff_cvit* h) {
     if ((rc = upload_linear(h, &X.ff1, p + ".1.fn.fn.net.0", MLP, DIM, true, h->gemm_bn_wide))) return rc;
     if ((rc = upload_linear(h, &X.ff2, p + ".1.fn.fn.net.2", DIM, MLP, true, 64))) return rc;
   }
-  if ((rc = upload_linear(h, &h->head1, "mlp_head.0", MLP, DIM, true, 64))) return rc;
-  if ((rc = upload_linear(h, &h->head2, "mlp_head.2", 2, MLP, true, 64))) return rc;
+  if (h->kind == 1) {     // kan_head = Linear, Dropout, ReLU, KAN (ResVitKan.py:302-307); mlp_head is not on the forward path
+    if ((rc = upload_linear(h, &h->head1, "kan_head.0", MLP, DIM, true, 64))) return rc;
+  } else {
+    if ((rc = upload_linear(h, &h->head1, "mlp_head.0", MLP, DIM, true, 64))) return rc;
+    if ((rc = upload_linear(h, &h->head2, "mlp_head.2", 2, MLP, true, 64))) return rc;
+  }
 
   if (h->compute == FF_COMPUTE_BF16) {
-    if ((rc = build_conv_maps(h))) return rc;
+    if (h->kind == 0 && (rc = build_conv_maps(h))) return rc;
     const int cap128 = (h->cap + 127) / 128 * 128;
     if ((rc = tmap_2d(h, &h->tm_feat, h->feat, PATCH, cap128, 64, 128))) return rc;
     if ((rc = tmap_2d(h, &h->tm_xn, h->xn, DIM, h->rows_cap, 64, 128))) return rc;
@@ -696,6 +868,98 @@ struct DebugTap {
 
 int forward_fp32(ff_cvit* h, const void* x, int layout, const int32_t* slot, int slot_base, int n, float* logits,
                  cudaStream_t st, DebugTap* tap);
+
+
+// ---- ResVitKan feature extractor: input conversion, stem, max-pool, 16 bottlenecks, channel conv -> h->feat
+int rvk_launch_op(ff_cvit* h, const ff_cvit::RvkOp& op, int n, cudaStream_t st, int prof_cls) {
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.scale = op.scale; a.shift = op.shift;
+  a.out = op.out_buf < 0 ? h->feat : h->rvk_buf[op.out_buf];
+  a.kb_per_tap = op.cin / 64;
+  a.kb_total = op.taps * a.kb_per_tap;
+  a.kb_per_split = a.kb_total;
+  a.cin = op.cin;
+  a.cout = op.cout;
+  ProfScope ps(h, st, prof_cls);
+  cudaError_t e;
+  if (op.type == 0) {
+    a.M = n * op.out_hw * op.out_hw;
+    a.N = op.cout;
+    a.ldo = op.cout;
+    a.epi = EPI_BN_BF16;
+    a.act = op.act ? ACT_RELU : ACT_NONE;
+    a.resid = op.resid >= 0 ? h->rvk_buf[op.resid] : nullptr;
+    a.act2 = op.resid >= 0 ? ACT_RELU : ACT_NONE;
+    dim3 grid((a.M + 127) / 128, op.cout / op.bn, 1);
+    e = op.bn == 128 ? launch_tc_t<MODE_GEMM, 128, 128, false, 4>(grid, st, op.tmA, op.tmB, a)
+                     : launch_tc_t<MODE_GEMM, 128, 64, false, 4>(grid, st, op.tmA, op.tmB, a);
+  } else {
+    a.H = op.out_hw; a.W = op.out_hw;
+    a.tiles_w = (op.out_hw + op.bw - 1) / op.bw; a.tiles_h = (op.out_hw + op.bh - 1) / op.bh;
+    a.lg_bw = ilog2(op.bw); a.lg_bh = ilog2(op.bh);
+    a.n_img = n;
+    a.taps = op.taps; a.stride = op.stride;
+    a.conv_act = op.act ? 0 : 1;
+    dim3 grid(a.tiles_w * a.tiles_h * ((n + op.bi - 1) / op.bi), op.cout / op.bn, 1);
+    e = launch_conv(128, op.bn, false, h->variant, grid, st, op.tmA, op.tmB, a);
+  }
+  if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of %s failed: %s", op.name.c_str(), cudaGetErrorString(e));
+  ++h->launches;
+  return FF_OK;
+}
+
+int rvk_features(ff_cvit* h, const void* x, int layout, int slot_base, int n, cudaStream_t st, DebugTap* tap) {
+  const int stop = tap ? tap->stop_after : 0;
+  auto tap_hit = [&](int step, const void* p, int64_t elems) {
+    if (stop == step) { tap->ptr = p; tap->elems = elems; tap->is_bf16 = true; tap->hit = true; return true; }
+    return false;
+  };
+  if (h->h2d_chunks_pending > 0) {     // host-buffer entry point: wait for the chunks covering this pass
+    const int c1 = std::min(h->h2d_chunks_pending - 1, (slot_base + n - 1) / h->h2d_chunk);
+    FF_CUDA(h, cudaStreamWaitEvent(st, h->h2d_ready[c1], 0));
+  }
+  {
+    ProfScope ps(h, st, KC_CONV1);
+    const unsigned blocks = (unsigned)(((size_t)n * 224 * 224 + 255) / 256);
+    if (layout == FF_X_NHWC_U8) {
+      // (u/255 - mean)/std as one fp32 FMA per channel (cvit_prediction.py:41-45 convention)
+      const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+      rvk_convert_kernel<2><<<blocks, 256, 0, st>>>(x, h->rvk_x4, n, 1.0f / (255.0f * sd[0]), -mean[0] / sd[0],
+                                                    1.0f / (255.0f * sd[1]), -mean[1] / sd[1], 1.0f / (255.0f * sd[2]), -mean[2] / sd[2]);
+    } else {
+      rvk_convert_kernel<0><<<blocks, 256, 0, st>>>(x, h->rvk_x4, n, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f);
+    }
+    FF_LAUNCH_CHECK(h, "rvk_convert");
+    static bool stem_attr = false;
+    if (!stem_attr) {
+      FF_CUDA(h, cudaFuncSetAttribute(rvk_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RVK_STEM_SMEM));
+      stem_attr = true;
+    }
+    RvkStemArgs sa;
+    sa.out = h->rvk_buf[0]; sa.w = h->rvk_stem_w; sa.n_img = n;
+    for (int o = 0; o < 64; ++o) { sa.scale[o] = h->rvk_stem_scale[o]; sa.shift[o] = h->rvk_stem_shift[o]; }
+    const int tiles = 14 * 7 * n;
+    cudaError_t e = launch_k(rvk_stem_kernel, dim3(std::min(tiles, h->num_sms * 4)), dim3(128), RVK_STEM_SMEM, st, false, h->rvk_tm_x4, sa);
+    if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of the stem failed: %s", cudaGetErrorString(e));
+    ++h->launches;
+    rvk_maxpool_kernel<<<(unsigned)(((size_t)n * 56 * 56 * 8 + 255) / 256), 256, 0, st>>>(h->rvk_buf[0], h->rvk_buf[1], n);
+    FF_LAUNCH_CHECK(h, "rvk_maxpool");
+  }
+  if (tap_hit(1, h->rvk_buf[1], (int64_t)n * 56 * 56 * 64)) return FF_OK;
+  int layer = 0;
+  for (size_t i = 0; i < h->rvk_ops.size(); ++i) {
+    const ff_cvit::RvkOp& op = h->rvk_ops[i];
+    int rc = rvk_launch_op(h, op, n, st, KC_TC_CONV + std::min(layer, 4));
+    if (rc) return rc;
+    if (layer < 4 && (int)i == h->rvk_layer_end[layer]) {
+      ++layer;
+      if (tap_hit(1 + layer, h->rvk_buf[op.out_buf], (int64_t)n * op.out_hw * op.out_hw * op.cout)) return FF_OK;
+    }
+  }
+  if (tap_hit(6, h->feat, (int64_t)n * PATCH)) return FF_OK;
+  return FF_OK;
+}
 
 // One pass over n <= cap crops.  x points at the first crop of the pass.
 int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int slot_base, int n, float* logits,
@@ -782,6 +1046,10 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     return FF_OK;
   };
 
+  if (h->kind == 1) {
+    int rc = rvk_features(h, x, layout, slot_base, n, st, tap);
+    if (rc || (tap && tap->hit)) return rc;
+  } else {
   // ---- stages 1-2 in sub-passes of s12 crops (activations of 3.2 MB/crop stay L2-resident between layers)
   prof_mark(h, st, 0, true, true);
   const int sub = stop ? std::min(n, h->s12_cap) : h->s12;
@@ -881,6 +1149,7 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     if (tap_hit(li + 1, conv_output_buffer(h, li), (int64_t)n * ohw * ohw * p.cout, true)) return FF_OK;
   }
   prof_mark(h, st, 1, false, true);
+  }   // kind == 0
   prof_mark(h, st, 2, true, true);
   // ---- patch embedding (split-K, fp32 atomics) + token assembly
   int rc = launch_gemm(h, st, h->tm_feat, h->embed, n, h->emb, DIM, EPI_STORE_F32, ACT_NONE, EMBED_SPLITS, "patch_to_embedding");
@@ -907,9 +1176,15 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   // ---- head
   { ProfScope ps(h, st, KC_SMALL); launch_k(cls_gather_kernel, dim3(n), dim3(256), 0, st, true, (const float*)h->x, h->clsb, n); }
   FF_LAUNCH_CHECK(h, "cls_gather");
-  if ((rc = launch_gemm(h, st, h->tm_cls, h->head1, n, h->hid, MLP, EPI_STORE_F32, ACT_RELU, 1, "mlp_head.0"))) return rc;
-  { ProfScope ps(h, st, KC_SMALL); launch_k(head2_kernel, dim3((n + 7) / 8), dim3(256), 0, st, true, (const float*)h->hid, (const float*)h->head2.wf, (const float*)h->head2.b, logits, n); }
-  FF_LAUNCH_CHECK(h, "head2");
+  if ((rc = launch_gemm(h, st, h->tm_cls, h->head1, n, h->hid, MLP, EPI_STORE_F32, ACT_RELU, 1, "head.0"))) return rc;
+  if (h->kind == 1) {
+    ProfScope ps(h, st, KC_SMALL);
+    kan_head_kernel<<<n, 256, 0, st>>>(h->hid, h->kan_w0, h->kan_g0, h->kan_w1, h->kan_g1, logits, n);
+    FF_LAUNCH_CHECK(h, "kan_head");
+  } else {
+    { ProfScope ps(h, st, KC_SMALL); launch_k(head2_kernel, dim3((n + 7) / 8), dim3(256), 0, st, true, (const float*)h->hid, (const float*)h->head2.wf, (const float*)h->head2.b, logits, n); }
+    FF_LAUNCH_CHECK(h, "head2");
+  }
   prof_mark(h, st, 2, false, true);
   if (tap_hit(25, logits, (int64_t)n * 2, false)) return FF_OK;
   return FF_OK;
@@ -1042,10 +1317,13 @@ extern "C" {
 
 const char* ff_last_error(const ff_cvit_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype) {
+namespace {
+int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, int kind) {
   if (!out || max_crops <= 0) return fail(nullptr, FF_ERR_BAD_ARG, "ff_cvit_create: bad arguments");
   if (compute_dtype != FF_COMPUTE_BF16 && compute_dtype != FF_COMPUTE_FP32)
     return fail(nullptr, FF_ERR_BAD_ARG, "ff_cvit_create: unknown compute_dtype %d", compute_dtype);
+  if (kind == 1 && compute_dtype != FF_COMPUTE_BF16)
+    return fail(nullptr, FF_ERR_BAD_ARG, "ff_resvitkan_create: only FF_COMPUTE_BF16 is implemented for ResVitKan");
   *out = nullptr;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1068,6 +1346,7 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
   ff_cvit* h = new ff_cvit();
   h->device = device;
   h->compute = compute_dtype;
+  h->kind = kind;
   h->cap = (max_crops + 31) / 32 * 32;
   h->rows_cap = (2 * h->cap + 127) / 128 * 128;
   h->s12_cap = 256;
@@ -1093,7 +1372,12 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
     if ((rc = dev_alloc(h, &h->x, (size_t)h->rows_cap * DIM))) break;
     if ((rc = dev_alloc(h, &h->qkv, (size_t)h->rows_cap * 3 * DIM))) break;
     if ((rc = dev_alloc(h, &h->hid, (size_t)cap128 * MLP))) break;
-    if (compute_dtype == FF_COMPUTE_BF16) {
+    if (kind == 1) {
+      for (int i = 0; i < 5 && rc == FF_OK; ++i) rc = dev_alloc(h, &h->rvk_buf[i], (size_t)h->cap * kRvkActElems);
+      if (rc) break;
+      if ((rc = dev_alloc(h, &h->rvk_x4, (size_t)h->cap * 224 * 224 * 4))) break;
+    }
+    if (compute_dtype == FF_COMPUTE_BF16 && kind == 0) {
       if ((rc = dev_alloc(h, &h->bufA, (size_t)h->s12_cap * 224 * 224 * 32))) break;
       if ((rc = dev_alloc(h, &h->bufB, (size_t)h->s12_cap * 224 * 224 * 32))) break;
       if ((rc = dev_alloc(h, &h->bufA2, (size_t)h->s12_cap * 224 * 224 * 32))) break;
@@ -1103,6 +1387,8 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
           cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) { rc = fail(h, FF_ERR_CUDA, "aux stream/event create failed"); break; }
       if ((rc = dev_alloc(h, &h->P, (size_t)h->cap * 56 * 56 * 128))) break;
       if ((rc = dev_alloc(h, &h->Q, (size_t)h->cap * 56 * 56 * 128))) break;
+    }
+    if (compute_dtype == FF_COMPUTE_BF16) {
       if ((rc = dev_alloc(h, &h->feat, (size_t)cap128 * PATCH))) break;
       if ((rc = dev_alloc(h, &h->xn, (size_t)h->rows_cap * DIM))) break;
       if ((rc = dev_alloc(h, &h->att, (size_t)h->rows_cap * DIM))) break;
@@ -1129,6 +1415,14 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
   }
   *out = h;
   return FF_OK;
+}
+}  // namespace
+
+int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype) {
+  return create_impl(out, device, max_crops, compute_dtype, 0);
+}
+int ff_resvitkan_create(ff_cvit_t** out, int device, int max_crops) {
+  return create_impl(out, device, max_crops, FF_COMPUTE_BF16, 1);
 }
 
 void ff_cvit_destroy(ff_cvit_t* h) {

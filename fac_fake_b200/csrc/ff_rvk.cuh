@@ -1,0 +1,261 @@
+// ff_rvk.cuh — kernels specific to ResVitKan inference (SURVEY.md §8f-1;
+// /root/reference/CViT-main/ResVitKan/ResVitKan.py:185-240,284-329 and kan.py:90-206).
+// The bottleneck convolutions reuse ff_tc.cuh (1x1 convs = GEMM over pixels with a folded-BN / residual epilogue,
+// 3x3 and strided convs = the implicit-GEMM kernel with elementStrides in the TMA descriptor); this file adds the
+// stem (7x7 stride 2), the 3x3 stride-2 max-pool, the input conversion and the KAN head.
+#pragma once
+#include "ff_c1.cuh"
+
+namespace ff {
+
+// ---- input -> normalised bf16 NHWC4 [n,224,224,4] (channel 3 = 0), 8 bytes per pixel.
+// IN_KIND 2: uint8 NHWC with (x/255-mean)/std (cvit_prediction.py:41-45 convention); IN_KIND 0: fp32 NCHW as given.
+template <int IN_KIND>
+__global__ void __launch_bounds__(256)
+rvk_convert_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int n_img, float a0, float b0, float a1, float b1,
+                   float a2, float b2) {
+  const size_t total = static_cast<size_t>(n_img) * 224 * 224;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  float v0, v1, v2;
+  if (IN_KIND == 2) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(x) + i * 3;
+    v0 = fmaf(static_cast<float>(p[0]), a0, b0);
+    v1 = fmaf(static_cast<float>(p[1]), a1, b1);
+    v2 = fmaf(static_cast<float>(p[2]), a2, b2);
+  } else {
+    const size_t img = i / (224 * 224), pix = i % (224 * 224);
+    const float* p = reinterpret_cast<const float*>(x) + img * 3 * 224 * 224 + pix;
+    v0 = p[0]; v1 = p[224 * 224]; v2 = p[2 * 224 * 224];
+  }
+  reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, 0.0f));
+}
+
+// ---- stem: Conv2d(3,64,7,stride 2,pad 3) + BN + ReLU (ResVitKan.py:191-193,229-231) with NO im2col.
+// Output pixel w needs input pixels 2w-3..2w+3.  The NHWC4 patch (24 pixels x 37 rows, TMA, zero-filled borders) is
+// read by non-swizzled K-major descriptors: row = output pixel (16 bytes = 2 input pixels apart), K window = the 8
+// input pixels 2w-4..2w+3 (64 contiguous bytes = two K=16 steps; the first pixel meets zero weights), filter row kh
+// = patch row 2*h_l + kh.  Tile = 8 x 16 output pixels, 14 tcgen05.mma (M=128, N=64) per tile.
+struct RvkStemArgs {
+  __nv_bfloat16* out;            // [n,112,112,64] bf16
+  const __nv_bfloat16* w;        // [7 kh][64 cout][32 = 8 px x 4 ch] bf16 (px 0 and ch 3 are zero)
+  int n_img;
+  float scale[64];
+  float shift[64];
+};
+
+constexpr int RVK_STEM_RING = 3, RVK_STEM_PSLOT = 7168;
+constexpr int RVK_STEM_SMEM = RVK_STEM_RING * RVK_STEM_PSLOT + 7 * 4096 + 128;
+__global__ void __launch_bounds__(128, 4)
+rvk_stem_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ RvkStemArgs a) {
+  constexpr int OW = 112, TW = 8, TH = 16, TILES_W = OW / TW, TILES_H = OW / TH, TILES = TILES_W * TILES_H;
+  constexpr int RING = RVK_STEM_RING, PROW = 192, PROWS = 37, PBYTES = PROWS * PROW, PSLOT = RVK_STEM_PSLOT;
+  extern __shared__ uint8_t rvk_smem_raw[];
+  uint8_t* sm = rvk_smem_raw + ((128u - (smem_u32(rvk_smem_raw) & 127u)) & 127u);
+  uint8_t (*s_patch)[PSLOT] = reinterpret_cast<uint8_t (*)[PSLOT]>(sm);
+  uint8_t* sB = sm + RING * PSLOT;
+  __shared__ __align__(8) uint64_t s_bar[1 + RING];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar_mma = smem_u32(&s_bar[0]);
+  const uint32_t bar_raw = smem_u32(&s_bar[1]);
+  // filter -> core-matrix layout: (n, 16-byte chunk c) at ((n/8)*4 + c)*128 + (n%8)*16
+  for (int i = tid; i < 7 * 64 * 4; i += 128) {
+    const int kh = i / 256, rem = i % 256, n = rem >> 2, c = rem & 3;
+    *reinterpret_cast<uint4*>(sB + kh * 4096 + ((n >> 3) * 4 + c) * 128 + (n & 7) * 16) = reinterpret_cast<const uint4*>(a.w)[i];
+  }
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    mbar_init(bar_mma, 1);
+    for (int s = 0; s < RING; ++s) mbar_init(bar_raw + 8 * s, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<64>(smem_u32(&s_tmem));
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (tid == 0) pdl_trigger();
+  pdl_wait();
+  const uint32_t sB_addr = smem_u32(sB);
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+  const int num_tiles = TILES * a.n_img;
+  const int hl = tid >> 3, wl = tid & 7;
+  auto issue = [&](int t, int slot) {
+    const int n = t / TILES;
+    const int rem = t - n * TILES;
+    const int th = rem / TILES_W, tw = rem - th * TILES_W;
+    mbar_arrive_expect_tx(bar_raw + 8 * slot, PBYTES);
+    // patch = input pixels 2*w0-4 .. 2*w0+19 (96 bf16 = 192 B, 16-byte aligned start), rows 2*h0-3 .. 2*h0+33
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(&s_patch[slot][0])),
+        "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar_raw + 8 * slot), "r"((2 * tw * TW - 4) * 4), "r"(2 * th * TH - 3), "r"(n)
+        : "memory");
+  };
+  if (tid == 0)
+    for (int s = 0; s < RING - 1; ++s) {
+      const int t = blockIdx.x + s * gridDim.x;
+      if (t < num_tiles) issue(t, s);
+    }
+  int it = 0;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    const int n = t / TILES;
+    const int rem = t - n * TILES;
+    const int th = rem / TILES_W, tw = rem - th * TILES_W;
+    const int slot = it % RING;
+    if (tid == 0) {
+      const int tn = t + (RING - 1) * gridDim.x;        // slot (it+2)%3 was consumed by tile it-1 (all threads passed bar_mma)
+      if (tn < num_tiles) issue(tn, (it + RING - 1) % RING);
+      mbar_wait(bar_raw + 8 * slot, (it / RING) & 1);
+      tcgen05_fence_after();
+      const uint32_t patch = smem_u32(&s_patch[slot][0]);
+#pragma unroll
+      for (int kh = 0; kh < 7; ++kh) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          // A: row (h_l, w_l) at patch + (2*h_l + kh)*192 + w_l*16; K chunks 16 B apart; groups (h_l) 2 patch rows apart
+          const uint64_t ad = make_kmajor_desc_noswz(patch + kh * PROW + 32 * j, 16, 2 * PROW);
+          const uint64_t bd = make_kmajor_desc_noswz(sB_addr + kh * 4096 + 2 * j * 128, 128, 512);
+          umma_bf16_ss(tmem, ad, bd, idesc, (kh > 0 || j > 0) ? 1u : 0u);
+        }
+      }
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, it & 1);
+    tcgen05_fence_after();
+    __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * OW + (th * TH + hl)) * OW + (tw * TW + wl)) * 64;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + p * 32, v);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        const float x0 = fmaf(__uint_as_float(v[c]), a.scale[p * 32 + c], a.shift[p * 32 + c]);
+        const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale[p * 32 + c + 1], a.shift[p * 32 + c + 1]);
+        pk[c >> 1] = pack_bf16x2_relu(x0, x1);
+      }
+      st_global_v8(o + p * 32, pk);
+      st_global_v8(o + p * 32 + 16, pk + 8);
+    }
+    tcgen05_fence_before();
+    __syncthreads();               // every thread has read TMEM and passed bar_mma before the next tile's MMAs / TMA reuse
+  }
+  __syncthreads();
+  if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<64>(tmem); }
+}
+
+// ---- MaxPool2d(kernel 3, stride 2, pad 1) on NHWC bf16 with C = 64 (ResVitKan.py:194,232): [n,112,112,64] -> [n,56,56,64]
+__global__ void __launch_bounds__(256)
+rvk_maxpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n_img) {
+  constexpr int IW = 112, OW = 56, C8 = 8;     // 8 chunks of 8 channels
+  const size_t total = static_cast<size_t>(n_img) * OW * OW * C8;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int q = static_cast<int>(i % C8);
+  size_t t = i / C8;
+  const int ow = static_cast<int>(t % OW); t /= OW;
+  const int oh = static_cast<int>(t % OW);
+  const size_t n = t / OW;
+  uint4 m = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // bf16 -inf pairs
+  auto mx = [](uint32_t a0, uint32_t b0) {
+    __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a0), *reinterpret_cast<__nv_bfloat162*>(&b0));
+    return *reinterpret_cast<uint32_t*>(&r2);
+  };
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int ih = 2 * oh + dy;
+    if (ih < 0 || ih >= IW) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int iw = 2 * ow + dx;
+      if (iw < 0 || iw >= IW) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(in + ((n * IW + ih) * IW + iw) * 64 + q * 8);
+      m.x = mx(m.x, v.x); m.y = mx(m.y, v.y); m.z = mx(m.z, v.z); m.w = mx(m.w, v.w);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + ((n * OW + oh) * OW + ow) * 64 + q * 8) = m;
+}
+
+// ---- KAN head: KAN([2048, 64, 2]) on the ReLU'd hidden vector (ResVitKan.py:302-307, kan.py:189-206).
+// KANLinear(x) = silu(x) W_base^T + Bspline(x) W_spline_scaled^T, cubic B-splines on each input feature's 12 knots
+// (g0[2048][12], g1[64][12]) with half-open intervals (kan.py:115), Cox-de Boor recursion in the reference's order
+// (kan.py:116-126).  Weights are pre-packed on the host as w0[in=2048][9][64] and w1[in=64][9][2]
+// (slot 0 = base_weight, 1..8 = spline_weight * spline_scaler).
+__device__ __forceinline__ void kan_bases(float x, const float* __restrict__ grid, float b[8]) {
+  float g[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) g[i] = grid[i];     // this input feature's knots (kan.py:44-52; update_grid may move them)
+  float t[11];
+#pragma unroll
+  for (int i = 0; i < 11; ++i) t[i] = (x >= g[i] && x < g[i + 1]) ? 1.0f : 0.0f;
+#pragma unroll
+  for (int k = 1; k <= 3; ++k) {
+#pragma unroll
+    for (int i = 0; i < 11 - k; ++i)
+      t[i] = (x - g[i]) / (g[i + k] - g[i]) * t[i] + (g[i + k + 1] - x) / (g[i + k + 1] - g[i + 1]) * t[i + 1];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = t[i];
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(256)
+kan_head_kernel(const float* __restrict__ hid, const float* __restrict__ w0, const float* __restrict__ g0,
+                const float* __restrict__ w1, const float* __restrict__ g1, float* __restrict__ logits, int n) {
+  __shared__ float s_part[8][64];
+  __shared__ float s_h[64];
+  const int b = blockIdx.x;
+  if (b >= n) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // layer 0: each thread owns 8 of the 2048 inputs and two of the 64 outputs per warp pass
+  float acc0 = 0.0f, acc1 = 0.0f;              // outputs (lane) and (lane + 32), partial over this warp's inputs
+  for (int ii = 0; ii < 2048 / 8; ++ii) {      // warp w handles inputs i = w + 8*ii
+    const int i = warp + 8 * ii;
+    const float x = hid[static_cast<size_t>(b) * 2048 + i];
+    float f[9];
+    f[0] = silu_f(x);
+    kan_bases(x, g0 + i * 12, f + 1);
+    const float* w = w0 + static_cast<size_t>(i) * 9 * 64;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      acc0 = fmaf(f[k], w[k * 64 + lane], acc0);
+      acc1 = fmaf(f[k], w[k * 64 + 32 + lane], acc1);
+    }
+  }
+  s_part[warp][lane] = acc0;
+  s_part[warp][lane + 32] = acc1;
+  __syncthreads();
+  if (tid < 64) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_part[w][tid];
+    s_h[tid] = s;
+  }
+  __syncthreads();
+  // layer 1: 64 -> 2, warp 0
+  if (warp == 0) {
+    float o0 = 0.0f, o1 = 0.0f;
+    for (int i = lane; i < 64; i += 32) {
+      const float x = s_h[i];
+      float f[9];
+      f[0] = silu_f(x);
+      kan_bases(x, g1 + i * 12, f + 1);
+      const float* w = w1 + i * 9 * 2;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        o0 = fmaf(f[k], w[k * 2], o0);
+        o1 = fmaf(f[k], w[k * 2 + 1], o1);
+      }
+    }
+    o0 = warp_sum(o0);
+    o1 = warp_sum(o1);
+    if (lane == 0) {
+      logits[2 * b] = o0;
+      logits[2 * b + 1] = o1;
+    }
+  }
+}
+
+}  // namespace ff

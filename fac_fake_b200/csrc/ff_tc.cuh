@@ -21,7 +21,7 @@
 namespace ff {
 
 enum { MODE_CONV = 0, MODE_GEMM = 1 };
-enum { EPI_STORE_F32 = 0, EPI_STORE_BF16 = 1, EPI_RESID_F32 = 2, EPI_ATOMIC_F32 = 3 };
+enum { EPI_STORE_F32 = 0, EPI_STORE_BF16 = 1, EPI_RESID_F32 = 2, EPI_ATOMIC_F32 = 3, EPI_BN_BF16 = 4 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
 struct TcArgs {
@@ -33,6 +33,11 @@ struct TcArgs {
   int img_off_out;        // image offset added on output (placement inside a larger buffer)
   int cout;               // total output channels (row pitch of the NHWC output)
   int out_blocked;        // pair kernels: write the output channel-blocked [n][C/32][H][W][32] (feeds ws2x)
+  int taps;               // conv: 0/9 = 3x3 (pad 1), 1 = 1x1 (pad 0)
+  int stride;             // conv: 0/1 = stride 1, 2 = stride 2 (the tensor map carries elementStrides = 2)
+  int conv_act;           // conv epilogue: 0 = ReLU (CViT layers), 1 = none (ResNet downsample / channel conv)
+  const void* resid;      // gemm EPI_BN_BF16: optional bf16 residual [M][ldo] added after the first activation
+  int act2;               // gemm EPI_BN_BF16: activation after the residual add (ACT_*)
   int kb_per_tap;         // Cin / (channels per k-block)
   int cin;                // input channels
   // ---- gemm geometry
@@ -69,7 +74,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // ---- conv epilogue, phase 1: TMEM accumulator row r (one per thread) -> scale/shift/ReLU -> bf16 -> staging smem.
 // Staging is [128 rows][BN] bf16 with the 16-byte chunk index XOR-swizzled by the row (bank-conflict-free).
 template <int BN>
-__device__ __forceinline__ void conv_epilogue_to_staging(uint32_t taddr, const float* ss, uint8_t* stg, int r) {
+__device__ __forceinline__ void conv_epilogue_to_staging(uint32_t taddr, const float* ss, uint8_t* stg, int r, bool relu = true) {
   constexpr int CPR = BN / 8;
   const int swz = (CPR >= 8) ? (r & 7) : ((r >> 1) & (CPR - 1));
 #pragma unroll 1
@@ -85,7 +90,8 @@ __device__ __forceinline__ void conv_epilogue_to_staging(uint32_t taddr, const f
         const int c = c0 + j * 8 + e * 2;
         float x0 = fmaf(__uint_as_float(v[j * 8 + e * 2]), ss[c], ss[BN + c]);
         float x1 = fmaf(__uint_as_float(v[j * 8 + e * 2 + 1]), ss[c + 1], ss[BN + c + 1]);
-        p[e] = pack_bf16x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f));
+        if (relu) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
+        p[e] = pack_bf16x2(x0, x1);
       }
       const int q = (c0 >> 3) + j;
       *reinterpret_cast<uint4*>(stg + r * (BN * 2) + ((q ^ swz) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
@@ -109,7 +115,7 @@ __device__ __forceinline__ void conv_staging_to_global(const uint8_t* stg, const
       const int hl = (row >> a.lg_bw) & (BH - 1);
       const int nl = row >> (a.lg_bw + a.lg_bh);
       const int n = n0 + nl;
-      if (n < a.n_img) {
+      if (n < a.n_img && (w0 + wl) < a.W && (h0 + hl) < a.H) {   // W/H bounds matter for 7x7 maps tiled by 8x8 boxes
         const size_t pix = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * a.W + (w0 + wl);
         *reinterpret_cast<uint4*>(out + pix * a.cout + col0 + q * 8) = val;
       }
@@ -213,7 +219,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         ss[i] = a.scale[c];
         ss[BN + i] = a.shift[c];
       } else {
-        ss[i] = 1.0f;
+        ss[i] = (a.epi == EPI_BN_BF16 && c < a.N) ? a.scale[c] : 1.0f;
         ss[BN + i] = (a.shift != nullptr && c < a.N) ? a.shift[c] : 0.0f;
       }
     }
@@ -237,8 +243,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (MODE == MODE_CONV) {
           const int tap = kb / a.kb_per_tap;
           const int cc = kb - tap * a.kb_per_tap;
-          const int kh = tap / 3, kw = tap - kh * 3;
-          tma_load_4d(sa, &tmA, bar, cc * BKE, w0 + kw - 1, h0 + kh - 1, n0);
+          const int sd = a.stride == 2 ? 2 : 1;
+          if (a.taps == 1) {          // 1x1 (possibly strided) conv: one tap, no padding
+            tma_load_4d(sa, &tmA, bar, cc * BKE, sd * w0, sd * h0, n0);
+          } else {
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d(sa, &tmA, bar, cc * BKE, sd * w0 + kw - 1, sd * h0 + kh - 1, n0);
+          }
         } else {
           tma_load_2d(sa, &tmA, bar, kb * BKE, m0);
         }
@@ -278,7 +289,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
     if (MODE == MODE_CONV) {
       uint8_t* stg = base_ptr;            // pipeline stages are idle now: reuse as staging [128][BN] bf16
-      conv_epilogue_to_staging<BN>(taddr, ss, stg, r);
+      conv_epilogue_to_staging<BN>(taddr, ss, stg, r, a.conv_act == 0);
       named_bar_sync(1, 128);
       conv_staging_to_global<BN, POOL>(stg, a, w0, h0, n0, col0, te);
     } else {
@@ -295,12 +306,41 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(v[i]) + ss[BN + c0 + i];
+            float x = fmaf(__uint_as_float(v[i]), ss[c0 + i], ss[BN + c0 + i]);    // scale is 1 except for EPI_BN_BF16
             if (a.act == ACT_RELU) x = fmaxf(x, 0.0f);
             else if (a.act == ACT_GELU) x = gelu_erf(x);
             f[i] = x;
           }
           const size_t off = static_cast<size_t>(blockIdx.z) * a.split_stride + static_cast<size_t>(m) * a.ldo + nb;
+          if (a.epi == EPI_BN_BF16) {
+            // 1x1 conv + folded BN (+ReLU) [+ bf16 residual, + ReLU]  (ResNet bottleneck, ResVitKan.py:150-177)
+            if (a.resid != nullptr) {
+              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.resid) + off;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                uint32_t rr[8];
+                ld_global_v8(rp + 16 * i, rr);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float2 rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[e]));
+                  f[16 * i + 2 * e] += rf.x;
+                  f[16 * i + 2 * e + 1] += rf.y;
+                }
+              }
+            }
+            if (a.act2 == ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+            }
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + off;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(f[16 * i + 2 * e], f[16 * i + 2 * e + 1]);
+              st_global_v8(o + 16 * i, pk);
+            }
+          } else
           if (a.epi == EPI_STORE_F32) {
             float* o = reinterpret_cast<float*>(a.out) + off;
 #pragma unroll

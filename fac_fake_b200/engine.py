@@ -93,11 +93,14 @@ class CViTEngine:
         if self._device is None:
             self.to("cuda")
         h = C.c_void_p()
-        rc = self._lib.ff_cvit_create(C.byref(h), self._device.index, self._max_crops, self._compute)
+        rc = self._create(h)
         if rc != L.FF_OK:
             msg = self._lib.ff_last_error(None)
-            raise EngineError(f"ff_cvit_create failed: {msg.decode() if msg else ''} (code {rc})")
+            raise EngineError(f"engine create failed: {msg.decode() if msg else ''} (code {rc})")
         self._h = h
+
+    def _create(self, h) -> int:
+        return self._lib.ff_cvit_create(C.byref(h), self._device.index, self._max_crops, self._compute)
 
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
         """Accepts a bare CViT state_dict or ``{'state_dict': ...}`` (cvit_prediction.py:66-69)."""
@@ -324,3 +327,21 @@ class CViTEngine:
         if cnt < 0:
             self._check(int(cnt), "ff_cvit_debug_activation")
         return out[:cnt]
+
+
+class ResVitKanEngine(CViTEngine):
+    """Drop-in for the ResVitKan ``CViT`` at inference time
+    (/root/reference/CViT-main/ResVitKan/ResVitKan.py:284-329: ResNet-50 features + ViT + KAN head).
+
+    Same surface as ``CViTEngine`` (``.to()``, ``.load_state_dict()``, ``.eval()``, ``model(x)``,
+    ``forward_slots``, ``predict_videos``...); the state_dict keys are the reference module's.
+    Only the bf16 tensor-core path exists for this variant.
+    """
+
+    def __init__(self, image_size=224, patch_size=7, num_classes=2, channels=512, dim=1024, depth=6, heads=8,
+                 mlp_dim=2048, *, max_crops: int = 256):
+        super().__init__(image_size, patch_size, num_classes, channels, dim, depth, heads, mlp_dim,
+                         max_crops=max_crops, compute_dtype="bf16")
+
+    def _create(self, h) -> int:
+        return self._lib.ff_resvitkan_create(C.byref(h), self._device.index, self._max_crops)

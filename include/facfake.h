@@ -57,6 +57,14 @@ enum {
  * crops one internal pass holds (workspace is allocated here; none on the forward path);
  * larger batches are processed in several passes.                                          */
 int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype);
+/* Same handle type for the ResVitKan variant: replaces `CViT(...)` of
+ * ResVitKan/ResVitKan.py:284-329 — ResNet-50 `features` (:185-240), the same patch embedding and
+ * 6-layer ViT, and `kan_head` = Linear, Dropout, ReLU, KAN([2048,64,2]) (kan.py:90-206).  Weight keys are
+ * that module's state_dict names (`features.layer{L}.{b}.conv{1,2,3}.weight`, `kan_head.3.layers.{0,1}.*`, …;
+ * `mlp_head.*` and `num_batches_tracked` are accepted and ignored).  bf16 tensor-core path only.  Every
+ * other entry point below works unchanged on such a handle; ff_cvit_debug_activation steps are
+ * 1 = stem + max-pool, 2..5 = layer1..layer4, 6 = channel conv + bn2, 18..25 as for CViT.            */
+int ff_resvitkan_create(ff_cvit_t** out, int device, int max_crops);
 void ff_cvit_destroy(ff_cvit_t* h);
 const char* ff_last_error(const ff_cvit_t* h); /* h may be NULL: last create() error */
 
