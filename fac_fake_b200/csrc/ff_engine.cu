@@ -139,9 +139,11 @@ struct ff_cvit {
     bf16* w = nullptr;
     float *scale = nullptr, *shift = nullptr;
     CUtensorMap tmA, tmB;
+    CUtensorMap tmA_flat;    // 1x1 stride-1 ops for the persistent kernel: [1][1][pixels][cin], boxes of 128 pixels
     std::string name;
   };
   std::vector<RvkOp> rvk_ops;
+  int rvk_persist = 1;                   // 1 = rvk_conv_kernel (persistent), 0 = one tc_kernel CTA per tile
   int rvk_layer_end[4] = {0, 0, 0, 0};   // index of the last op of layer1..4 (debug taps)
   bf16* rvk_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bf16* rvk_x4 = nullptr;                // normalised bf16 NHWC4 input
@@ -592,6 +594,7 @@ int rvk_add_op(ff_cvit* h, const std::string& conv, const std::string& bn, int c
   const bf16* in = h->rvk_buf[in_buf];
   if (op.type == 0) {
     rc = tmap_2d(h, &op.tmA, in, cin, (uint64_t)h->cap * in_hw * in_hw, 64, 128);
+    if (!rc) rc = tmap_4d(h, &op.tmA_flat, in, cin, h->cap * in_hw * in_hw, 1, 1, 64, 128, 1, 1);
   } else {
     rvk_tile_geometry(op.out_hw, &op.bw, &op.bh, &op.bi);
     rc = tmap_4d(h, &op.tmA, in, cin, in_hw, in_hw, h->cap, 64, op.bw, op.bh, op.bi, stride);
@@ -909,6 +912,56 @@ int rvk_launch_op(ff_cvit* h, const ff_cvit::RvkOp& op, int n, cudaStream_t st, 
   return FF_OK;
 }
 
+template <int BN>
+cudaError_t launch_rvk_conv_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
+  using L = RvkSmem<BN, 2, 4>;
+  auto k = rvk_conv_kernel<BN, 2, 4>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  return launch_k(k, dim3(grid), dim3(320), L::TOTAL, st, true, a, b, args);
+}
+
+int rvk_launch_op_persistent(ff_cvit* h, const ff_cvit::RvkOp& op, int n, cudaStream_t st, int prof_cls) {
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.scale = op.scale; a.shift = op.shift;
+  a.out = op.out_buf < 0 ? h->feat : h->rvk_buf[op.out_buf];
+  a.kb_per_tap = op.cin / 64;
+  a.kb_total = op.taps * a.kb_per_tap;
+  a.kb_per_split = a.kb_total;
+  a.cin = op.cin;
+  a.cout = op.cout;
+  a.taps = op.taps; a.stride = op.stride;
+  a.conv_act = op.act ? 0 : 1;
+  a.resid = op.resid >= 0 ? h->rvk_buf[op.resid] : nullptr;
+  int bi = 1;
+  if (op.type == 0) {           // flat: W = every pixel of the pass
+    a.H = 1; a.W = n * op.out_hw * op.out_hw;
+    a.tiles_w = (a.W + 127) / 128; a.tiles_h = 1;
+    a.lg_bw = 7; a.lg_bh = 0;
+    a.n_img = 1;
+  } else {
+    a.H = op.out_hw; a.W = op.out_hw;
+    a.tiles_w = (op.out_hw + op.bw - 1) / op.bw; a.tiles_h = (op.out_hw + op.bh - 1) / op.bh;
+    a.lg_bw = ilog2(op.bw); a.lg_bh = ilog2(op.bh);
+    a.n_img = n;
+    bi = op.bi;
+  }
+  const int m_tiles = a.tiles_w * a.tiles_h * ((a.n_img + bi - 1) / bi);
+  const int tiles = ((m_tiles + 1) / 2) * (op.cout / op.bn);
+  const int grid = std::min(tiles, h->num_sms);
+  ProfScope ps(h, st, prof_cls);
+  const CUtensorMap& tmA = op.type == 0 ? op.tmA_flat : op.tmA;
+  cudaError_t e = op.bn == 128 ? launch_rvk_conv_t<128>(grid, st, tmA, op.tmB, a) : launch_rvk_conv_t<64>(grid, st, tmA, op.tmB, a);
+  if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of %s failed: %s", op.name.c_str(), cudaGetErrorString(e));
+  ++h->launches;
+  return FF_OK;
+}
+
 int rvk_features(ff_cvit* h, const void* x, int layout, int slot_base, int n, cudaStream_t st, DebugTap* tap) {
   const int stop = tap ? tap->stop_after : 0;
   auto tap_hit = [&](int step, const void* p, int64_t elems) {
@@ -950,7 +1003,8 @@ int rvk_features(ff_cvit* h, const void* x, int layout, int slot_base, int n, cu
   int layer = 0;
   for (size_t i = 0; i < h->rvk_ops.size(); ++i) {
     const ff_cvit::RvkOp& op = h->rvk_ops[i];
-    int rc = rvk_launch_op(h, op, n, st, KC_TC_CONV + std::min(layer, 4));
+    int rc = h->rvk_persist ? rvk_launch_op_persistent(h, op, n, st, KC_TC_CONV + std::min(layer, 4))
+                            : rvk_launch_op(h, op, n, st, KC_TC_CONV + std::min(layer, 4));
     if (rc) return rc;
     if (layer < 4 && (int)i == h->rvk_layer_end[layer]) {
       ++layer;
@@ -1353,6 +1407,7 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
   h->s12 = std::min(64, h->cap);
   if (const char* v = getenv("FF_TC_VARIANT")) h->variant = atoi(v);
   if (const char* v = getenv("FF_WS")) h->use_ws = atoi(v);
+  if (const char* v = getenv("FF_RVK_PERSIST")) h->rvk_persist = atoi(v);
   if (const char* v = getenv("FF_PDL")) g_use_pdl = atoi(v) != 0;
   if (const char* v = getenv("FF_DUAL")) h->use_dual = atoi(v);
   if (const char* v = getenv("FF_GEMM_BN")) h->gemm_bn_wide = atoi(v) == 128 ? 128 : 64;
