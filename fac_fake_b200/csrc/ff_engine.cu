@@ -151,6 +151,7 @@ struct ff_cvit {
   float rvk_stem_scale[64], rvk_stem_shift[64];
   CUtensorMap rvk_tm_x4;
   float *kan_w0 = nullptr, *kan_w1 = nullptr, *kan_g0 = nullptr, *kan_g1 = nullptr;
+  float* kan_part = nullptr;             // layer-0 split-K slabs [KAN_CHUNKS][cap][64]
   int gemm_bn_wide = 64;   // N tile of the wide transformer linears (qkv, ff1): 64 or 128
   int use_dual = 1;        // overlap consecutive stage-1/2 sub-passes on two streams (hides launch tails/prologues)
   bf16 *P = nullptr, *Q = nullptr;         // stage 3..5 ping-pong, cap crops
@@ -1233,8 +1234,10 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   if ((rc = launch_gemm(h, st, h->tm_cls, h->head1, n, h->hid, MLP, EPI_STORE_F32, ACT_RELU, 1, "head.0"))) return rc;
   if (h->kind == 1) {
     ProfScope ps(h, st, KC_SMALL);
-    kan_head_kernel<<<n, 256, 0, st>>>(h->hid, h->kan_w0, h->kan_g0, h->kan_w1, h->kan_g1, logits, n);
-    FF_LAUNCH_CHECK(h, "kan_head");
+    kan_l0_kernel<<<dim3(KAN_CHUNKS, (n + KAN_SG - 1) / KAN_SG), 256, 0, st>>>(h->hid, h->kan_w0, h->kan_g0, h->kan_part, n, h->cap);
+    FF_LAUNCH_CHECK(h, "kan_l0");
+    kan_l1_kernel<<<(n + 7) / 8, 256, 0, st>>>(h->kan_part, h->kan_w1, h->kan_g1, logits, n, h->cap);
+    FF_LAUNCH_CHECK(h, "kan_l1");
   } else {
     { ProfScope ps(h, st, KC_SMALL); launch_k(head2_kernel, dim3((n + 7) / 8), dim3(256), 0, st, true, (const float*)h->hid, (const float*)h->head2.wf, (const float*)h->head2.b, logits, n); }
     FF_LAUNCH_CHECK(h, "head2");
@@ -1431,6 +1434,7 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
       for (int i = 0; i < 5 && rc == FF_OK; ++i) rc = dev_alloc(h, &h->rvk_buf[i], (size_t)h->cap * kRvkActElems);
       if (rc) break;
       if ((rc = dev_alloc(h, &h->rvk_x4, (size_t)h->cap * 224 * 224 * 4))) break;
+      if ((rc = dev_alloc(h, &h->kan_part, (size_t)KAN_CHUNKS * h->cap * 64))) break;
     }
     if (compute_dtype == FF_COMPUTE_BF16 && kind == 0) {
       if ((rc = dev_alloc(h, &h->bufA, (size_t)h->s12_cap * 224 * 224 * 32))) break;

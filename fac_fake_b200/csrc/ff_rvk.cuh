@@ -421,60 +421,80 @@ __device__ __forceinline__ void kan_bases(float x, const float* __restrict__ gri
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
+// Layer 0 (2048 -> 64) as a split-K product of the [n][2048*9] feature matrix (silu + 8 bases per input, built on
+// the fly in shared memory) with w0: block = 64 inputs x 32 samples, so w0 is streamed once per 32 samples instead
+// of once per sample; the 32 K-chunks write private slabs part[chunk][n_cap][64] that layer 1 sums in a fixed order.
+constexpr int KAN_KC = 64, KAN_SUB = 16, KAN_SG = 32, KAN_CHUNKS = 2048 / KAN_KC;
 __global__ void __launch_bounds__(256)
-kan_head_kernel(const float* __restrict__ hid, const float* __restrict__ w0, const float* __restrict__ g0,
-                const float* __restrict__ w1, const float* __restrict__ g1, float* __restrict__ logits, int n) {
-  __shared__ float s_part[8][64];
-  __shared__ float s_h[64];
-  const int b = blockIdx.x;
-  if (b >= n) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // layer 0: each thread owns 8 of the 2048 inputs and two of the 64 outputs per warp pass
-  float acc0 = 0.0f, acc1 = 0.0f;              // outputs (lane) and (lane + 32), partial over this warp's inputs
-  for (int ii = 0; ii < 2048 / 8; ++ii) {      // warp w handles inputs i = w + 8*ii
-    const int i = warp + 8 * ii;
-    const float x = hid[static_cast<size_t>(b) * 2048 + i];
-    float f[9];
-    f[0] = silu_f(x);
-    kan_bases(x, g0 + i * 12, f + 1);
-    const float* w = w0 + static_cast<size_t>(i) * 9 * 64;
+kan_l0_kernel(const float* __restrict__ hid, const float* __restrict__ w0, const float* __restrict__ g0,
+              float* __restrict__ part, int n, int n_cap) {
+  __shared__ float s_feat[KAN_SG][KAN_SUB * 9 + 1];
+  const int tid = threadIdx.x;
+  const int i_base = blockIdx.x * KAN_KC, s_base = blockIdx.y * KAN_SG;
+  const int o = tid & 63, q = tid >> 6;
+  float acc[8];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      acc0 = fmaf(f[k], w[k * 64 + lane], acc0);
-      acc1 = fmaf(f[k], w[k * 64 + 32 + lane], acc1);
-    }
-  }
-  s_part[warp][lane] = acc0;
-  s_part[warp][lane + 32] = acc1;
-  __syncthreads();
-  if (tid < 64) {
-    float s = 0.0f;
+  for (int s = 0; s < 8; ++s) acc[s] = 0.0f;
+  for (int sub = 0; sub < KAN_KC / KAN_SUB; ++sub) {
+    const int i0 = i_base + sub * KAN_SUB;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += s_part[w][tid];
-    s_h[tid] = s;
-  }
-  __syncthreads();
-  // layer 1: 64 -> 2, warp 0
-  if (warp == 0) {
-    float o0 = 0.0f, o1 = 0.0f;
-    for (int i = lane; i < 64; i += 32) {
-      const float x = s_h[i];
+    for (int rep = 0; rep < KAN_SG * KAN_SUB / 256; ++rep) {
+      const int idx = tid + rep * 256;
+      const int s = idx / KAN_SUB, ii = idx % KAN_SUB;
+      const int smp = s_base + s;
+      const float x = smp < n ? hid[static_cast<size_t>(smp) * 2048 + i0 + ii] : 0.0f;
       float f[9];
       f[0] = silu_f(x);
-      kan_bases(x, g1 + i * 12, f + 1);
-      const float* w = w1 + i * 9 * 2;
+      kan_bases(x, g0 + (i0 + ii) * 12, f + 1);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        o0 = fmaf(f[k], w[k * 2], o0);
-        o1 = fmaf(f[k], w[k * 2 + 1], o1);
-      }
+      for (int k = 0; k < 9; ++k) s_feat[s][ii * 9 + k] = f[k];
     }
-    o0 = warp_sum(o0);
-    o1 = warp_sum(o1);
-    if (lane == 0) {
-      logits[2 * b] = o0;
-      logits[2 * b + 1] = o1;
+    __syncthreads();
+    const float* w = w0 + static_cast<size_t>(i0) * 9 * 64 + o;
+#pragma unroll 4
+    for (int kk = 0; kk < KAN_SUB * 9; ++kk) {
+      const float wv = w[kk * 64];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) acc[s] = fmaf(s_feat[q * 8 + s][kk], wv, acc[s]);
     }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int smp = s_base + q * 8 + s;
+    if (smp < n) part[(static_cast<size_t>(blockIdx.x) * n_cap + smp) * 64 + o] = acc[s];
+  }
+}
+
+// Layer 1 (64 -> 2): one warp per sample; sums the K-chunk slabs of layer 0, then silu / B-spline features of the 64
+// hidden values against w1.
+__global__ void __launch_bounds__(256)
+kan_l1_kernel(const float* __restrict__ part, const float* __restrict__ w1, const float* __restrict__ g1,
+              float* __restrict__ logits, int n, int n_cap) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= n) return;
+  float o0 = 0.0f, o1 = 0.0f;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int i = lane + 32 * half;
+    float x = 0.0f;
+    for (int c = 0; c < KAN_CHUNKS; ++c) x += part[(static_cast<size_t>(c) * n_cap + b) * 64 + i];
+    float f[9];
+    f[0] = silu_f(x);
+    kan_bases(x, g1 + i * 12, f + 1);
+    const float* w = w1 + i * 9 * 2;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      o0 = fmaf(f[k], w[k * 2], o0);
+      o1 = fmaf(f[k], w[k * 2 + 1], o1);
+    }
+  }
+  o0 = warp_sum(o0);
+  o1 = warp_sum(o1);
+  if (lane == 0) {
+    logits[2 * b] = o0;
+    logits[2 * b + 1] = o1;
   }
 }
 

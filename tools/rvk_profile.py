@@ -64,8 +64,8 @@ def main():
         ms, cnt = prof[i]
         ms /= args.steps
         print(f"  {name:>8s}: {ms:8.3f} ms  {cnt / args.steps:4.0f} launches  {fl[name] * n / ms / 1e9:8.1f} TFLOP/s")
-    rest = sum(p[0] for p in prof[6:]) / args.steps
-    print(f"  embed + transformer + KAN head: {rest:8.3f} ms")
+    for name, i in (("embed GEMM", 17), ("transformer GEMMs", 18), ("head Linear", 19), ("small kernels + KAN", 20)):
+        print(f"  {name:>20s}: {prof[i][0] / args.steps:8.3f} ms  {prof[i][1] / args.steps:4.0f} launches")
 
 
 if __name__ == "__main__":
