@@ -40,6 +40,38 @@ METRIC = "CViT face-crops/sec"
 UNIT = "crops/s"
 
 
+def resvitkan_trunk_work():
+    """(2*MAC flops, unfused bf16 activation bytes) per crop of the ResNet-50 trunk as the reference defines it
+    (ResVitKan.py:185-240): every convolution reads its input once and writes its output once, conv3 also reads
+    the residual; the stem path is uint8 crop -> bf16 NHWC4 -> conv -> max-pool."""
+    fl = 2 * 112 * 112 * 64 * 3 * 49
+    by = 224 * 224 * 3 + 2 * 224 * 224 * 8 + 2 * 112 * 112 * 64 * 2 + 56 * 56 * 64 * 2
+    inpl, hw = 64, 56
+    for planes, blocks, stride in ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)):
+        for b in range(blocks):
+            s = stride if b == 0 else 1
+            oh = hw // s
+            fl += 2 * hw * hw * inpl * planes + 2 * oh * oh * planes * planes * 9 + 2 * oh * oh * planes * planes * 4
+            by += 2 * (hw * hw * inpl + hw * hw * planes)                 # conv1
+            by += 2 * (hw * hw * planes + oh * oh * planes)               # conv2 (reads every input pixel)
+            by += 2 * (oh * oh * planes + 2 * oh * oh * planes * 4)       # conv3: in + residual + out
+            if b == 0:
+                fl += 2 * oh * oh * inpl * planes * 4
+                by += 2 * (oh * oh * inpl + oh * oh * planes * 4)         # strided 1x1 reads only the sampled pixels
+            inpl, hw = planes * 4, oh
+    fl += 2 * 49 * 2048 * 512
+    by += 2 * (49 * 2048 + 49 * 512)
+    return fl, by
+
+
+MODELS = {
+    "cvit": {"metric": METRIC, "flops_per_crop": FLOPS_PER_CROP, "max_crops": 512,
+             "name": "CViT", "baseline_config": "configs[1]"},
+    "resvitkan": {"metric": "ResVitKan face-crops/sec", "flops_per_crop": None, "max_crops": 512,
+                  "name": "ResVitKan (ResNet-50 + ViT + KAN head)", "baseline_config": "configs[3]"},
+}
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -99,14 +131,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(sample_crops: int, repeats: int):
+def cpu_baseline(sample_crops: int, repeats: int, model: str = "cvit"):
     """The CPU oracle port (torch fp32, all host threads) on `sample_crops` crops of the same workload."""
     import torch
     from fac_fake_b200 import weights as W
     from oracle import cvit_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = W.make_state_dict(0, "default")
+    if model == "resvitkan":
+        from oracle import resvitkan_oracle as R
+        sd = W.make_resvitkan_state_dict(0, "default")
+        fwd = lambda x: torch.cat([R.forward(x[i:i + 32], sd) for i in range(0, x.shape[0], 32)])   # noqa: E731
+    else:
+        sd = W.make_state_dict(0, "default")
+        fwd = lambda x: O.forward_chunked(x, sd, chunk=32)                                          # noqa: E731
     crops = W.synthetic_crops(sample_crops, seed=11)
     offs = list(range(0, sample_crops + 1, CROPS_PER_VIDEO))
     if offs[-1] != sample_crops:
@@ -114,7 +152,7 @@ def cpu_baseline(sample_crops: int, repeats: int):
 
     def one():
         x = O.normalize_crops(crops)
-        lg = O.forward_chunked(x, sd, chunk=32)
+        lg = fwd(x)
         return O.video_scores(lg, offs)
 
     one()                                         # warm-up
@@ -178,6 +216,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--crops", type=int, default=CROPS_PER_STEP)
+    ap.add_argument("--model", default="cvit", choices=sorted(MODELS),
+                    help="cvit = the north-star path (default, what the driver runs); resvitkan = SURVEY 8f-1 / BASELINE configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: same as --steps")
     args = ap.parse_args()
@@ -190,8 +230,10 @@ def main():
         os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
-    from fac_fake_b200 import CViTEngine, weights as W
+    from fac_fake_b200 import CViTEngine, ResVitKanEngine, weights as W
     from fac_fake_b200.sharding import gather_scores
+    model = MODELS[args.model]
+    rvk = args.model == "resvitkan"
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -207,8 +249,11 @@ def main():
     n = args.crops
     peaks = read_peaks()
 
-    sd = W.make_state_dict(0, "default")
-    eng = CViTEngine(max_crops=min(512, (n + 31) // 32 * 32)).to(dev).load_state_dict(sd)
+    cap = min(model["max_crops"], (n + 31) // 32 * 32)
+    if rvk:
+        eng = ResVitKanEngine(max_crops=cap).to(dev).load_state_dict(W.make_resvitkan_state_dict(0, "default"))
+    else:
+        eng = CViTEngine(max_crops=cap).to(dev).load_state_dict(W.make_state_dict(0, "default"))
     offsets = list(range(0, n + 1, CROPS_PER_VIDEO))
     if offsets[-1] != n:
         offsets.append(n)
@@ -285,7 +330,42 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / (float(t.item()) * 1e-3)
 
-    if rank == 0:
+    if rank == 0 and rvk:
+        fl, by = resvitkan_trunk_work()
+        conv_ms, conv_launches = prof["tcgen05_conv"]
+        stem_ms = prof["conv1"][0]
+        trunk_ms = conv_ms + stem_ms
+        gbs = by * n * steps / (trunk_ms * 1e-3) / 1e9 if trunk_ms > 0 else 0.0
+        out = {
+            "metric": model["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"ResVitKan bf16 inference, synthetic batch of {n} uint8 face crops 224x224 per GPU "
+                                   f"(BASELINE {model['baseline_config']}; {n_videos} videos x {CROPS_PER_VIDEO} crops, passes of {cap}), random-init weights",
+                       "crops_per_step_per_gpu": n, "parallelism": f"video-sharded x{world} (no data-path collective)",
+                       "l2": "inputs rotate over 4 distinct batches; > 10 GB of activations per step sweep L2",
+                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 224 * 224 * 3 + 4 * (n_videos + 1),
+                    "d2h_bytes_per_step": 4 * n_videos, "steps": e2e_steps,
+                    "api": "ff_cvit_predict_host on an ff_resvitkan_create handle (ResVitKanEngine.predict_videos_host)"},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "bound": "hbm", "kernel": "ResNet-50 trunk: ff::rvk_conv_kernel (52 bottleneck convolutions + channel conv) + stem kernels",
+                "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                "peak_source": f"hbm_gbs, {peaks['source']}", "traffic": None,
+                "algorithmic_bytes_per_crop": by, "algorithmic_flops_per_crop": fl,
+                "trunk_tflops": fl * n * steps / (trunk_ms * 1e-3) / 1e12 if trunk_ms > 0 else 0.0,
+                "kernel_ms_per_step": trunk_ms / steps, "kernel_launches_per_step": (conv_launches + prof["conv1"][1]) / steps,
+                "step_share": trunk_ms / ms_instr if ms_instr > 0 else None,
+                "how": "second pass of the same K steps with a CUDA-event pair around every launch; unfused per-layer bf16 activation bytes (each conv reads its input and writes its output once)",
+                "by_class_ms_per_step": {k: v[0] / steps for k, v in prof.items()},
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(32, 2, "resvitkan")
+        print(json.dumps(out), flush=True)
+    elif rank == 0:
         conv_ms, conv_launches = prof["tcgen05_conv"]
         tc_tflops = (TC_CONV_FLOPS * n * steps) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         peak = peaks["bf16_sustained"]
