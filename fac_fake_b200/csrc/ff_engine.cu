@@ -139,11 +139,12 @@ struct ff_cvit {
     bf16* w = nullptr;
     float *scale = nullptr, *shift = nullptr;
     CUtensorMap tmA, tmB;
+    CUtensorMap tmO, tmR;    // TMA-store epilogue: output / residual tiles in the output geometry
     CUtensorMap tmA_flat;    // 1x1 stride-1 ops for the persistent kernel: [1][1][pixels][cin], boxes of 128 pixels
     std::string name;
   };
   std::vector<RvkOp> rvk_ops;
-  int rvk_persist = 1;                   // 1 = rvk_conv_kernel (persistent), 0 = one tc_kernel CTA per tile
+  int rvk_persist = 2;                   // 2 = rvk_conv2_kernel (persistent, TMA epilogue), 1 = rvk_conv_kernel, 0 = tc_kernel per tile
   int rvk_layer_end[4] = {0, 0, 0, 0};   // index of the last op of layer1..4 (debug taps)
   bf16* rvk_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bf16* rvk_x4 = nullptr;                // normalised bf16 NHWC4 input
@@ -602,6 +603,17 @@ int rvk_add_op(ff_cvit* h, const std::string& conv, const std::string& bn, int c
   }
   if (rc) return rc;
   (void)out_override;
+  {
+    const bf16* outp = out_buf < 0 ? h->feat : h->rvk_buf[out_buf];
+    const int ohw = op.out_hw;
+    for (int k = 0; k < 2; ++k) {
+      const bf16* base = k == 0 ? outp : (resid >= 0 ? h->rvk_buf[resid] : outp);
+      CUtensorMap* m = k == 0 ? &op.tmO : &op.tmR;
+      if (op.type == 0) rc = tmap_4d(h, m, base, cout, h->cap * ohw * ohw, 1, 1, 64, 128, 1, 1);
+      else rc = tmap_4d(h, m, base, cout, ohw, ohw, h->cap, 64, op.bw, op.bh, op.bi);
+      if (rc) return rc;
+    }
+  }
   h->rvk_ops.push_back(op);
   return FF_OK;
 }
@@ -926,6 +938,20 @@ cudaError_t launch_rvk_conv_t(int grid, cudaStream_t st, const CUtensorMap& a, c
   return launch_k(k, dim3(grid), dim3(320), L::TOTAL, st, true, a, b, args);
 }
 
+template <int BN, int STAGES, bool RESID>
+cudaError_t launch_rvk_conv2_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o,
+                               const CUtensorMap& r, const TcArgs& args) {
+  using L = Rvk2Smem<BN, STAGES, RESID>;
+  auto k = rvk_conv2_kernel<BN, STAGES, RESID>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  return launch_k(k, dim3(grid), dim3(320), L::TOTAL, st, true, a, b, o, r, args);
+}
+
 int rvk_launch_op_persistent(ff_cvit* h, const ff_cvit::RvkOp& op, int n, cudaStream_t st, int prof_cls) {
   TcArgs a;
   memset(&a, 0, sizeof(a));
@@ -957,7 +983,15 @@ int rvk_launch_op_persistent(ff_cvit* h, const ff_cvit::RvkOp& op, int n, cudaSt
   const int grid = std::min(tiles, h->num_sms);
   ProfScope ps(h, st, prof_cls);
   const CUtensorMap& tmA = op.type == 0 ? op.tmA_flat : op.tmA;
-  cudaError_t e = op.bn == 128 ? launch_rvk_conv_t<128>(grid, st, tmA, op.tmB, a) : launch_rvk_conv_t<64>(grid, st, tmA, op.tmB, a);
+  cudaError_t e;
+  if (h->rvk_persist == 2) {
+    if (op.resid >= 0 && op.bn == 128) e = launch_rvk_conv2_t<128, 2, true>(grid, st, tmA, op.tmB, op.tmO, op.tmR, a);
+    else if (op.resid >= 0) return fail(h, FF_ERR_STATE, "%s: residual epilogue needs cout >= 128", op.name.c_str());
+    else if (op.bn == 128) e = launch_rvk_conv2_t<128, 3, false>(grid, st, tmA, op.tmB, op.tmO, op.tmO, a);
+    else e = launch_rvk_conv2_t<64, 4, false>(grid, st, tmA, op.tmB, op.tmO, op.tmO, a);
+  } else {
+    e = op.bn == 128 ? launch_rvk_conv_t<128>(grid, st, tmA, op.tmB, a) : launch_rvk_conv_t<64>(grid, st, tmA, op.tmB, a);
+  }
   if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of %s failed: %s", op.name.c_str(), cudaGetErrorString(e));
   ++h->launches;
   return FF_OK;

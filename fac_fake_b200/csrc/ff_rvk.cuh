@@ -368,6 +368,246 @@ rvk_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// ---- the same persistent kernel with ALL global traffic on TMA ------------------------------------------------------
+// ncu on rvk_conv_kernel (profiles/r01_ncu_rvk_conv.txt): the per-thread 32-byte residual loads / output stores run
+// at 32 sectors per request and hold the LSU at 71 % while DRAM sits at 50 %.  Here the epilogue converts a sub-tile
+// in a swizzled shared-memory panel ([128 pixels][64 channels] bf16, the TMA SW128 layout) and one elected thread
+// stores it with cp.async.bulk.tensor; the residual arrives in the same panel by TMA (LA sub-tiles ahead) and is
+// overwritten in place.  NSTG panels-sets rotate; set b is owned by elected thread E_b, which is the only one that
+// stores from it and loads into it, so "my previous store has finished reading" is a plain bulk-group wait.
+template <int BN, int STAGES, bool RESID>
+struct Rvk2Smem {
+  static constexpr int A_BYTES = 2 * 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NSTG = RESID ? 3 : 2;
+  static constexpr int STG_BYTES = 128 * BN * 2;                      // one 128-pixel sub-tile: BN/64 panels of 16 KB
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr int SS_OFF = STG_OFF + NSTG * STG_BYTES;           // scale/shift floats [2][2048]
+  static constexpr int BAR_OFF = SS_OFF + 2 * 2048 * 4;               // full[S], empty[S], tfull[2], tempty[2], res_full[3]
+  static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 4 + 3) * 8;
+  static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
+  static_assert(TOTAL <= 232448, "shared memory budget");
+};
+
+template <int BN, int STAGES, bool RESID>
+__global__ void __launch_bounds__(320, 1)
+rvk_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const TcArgs a) {
+  using L = Rvk2Smem<BN, STAGES, RESID>;
+  constexpr int MSUB = 2, BKE = 64, NSTG = L::NSTG, LA = NSTG - 1;
+  constexpr int TMEM_COLS = 2 * MSUB * BN;
+  constexpr int HALF = BN / 2, NCH = HALF / 32;
+  constexpr int PANELS = BN / 64;
+  static_assert(BN == 64 || BN == 128, "BN");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  float* ss = reinterpret_cast<float*>(base_ptr + L::SS_OFF);
+  const uint32_t bar_full = base + L::BAR_OFF;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_tfull = bar_empty + STAGES * 8;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  const uint32_t bar_res = bar_tempty + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = a.cout / BN;
+  const int lg_bi = 7 - a.lg_bw - a.lg_bh;
+  const int m_tiles = a.tiles_w * a.tiles_h * ((a.n_img + (1 << lg_bi) - 1) >> lg_bi);
+  const int num_tiles = ((m_tiles + MSUB - 1) / MSUB) * n_tiles;
+  const int kb_total = a.kb_total;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    if (RESID) tma_prefetch_desc(&tmR);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tfull + 8, 1);
+    mbar_init(bar_tempty, 256);
+    mbar_init(bar_tempty + 8, 256);
+    for (int b = 0; b < 3; ++b) mbar_init(bar_res + 8 * b, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (warp >= 2)
+    for (int i = threadIdx.x - 64; i < a.cout; i += 256) {
+      ss[i] = a.scale[i];
+      ss[2048 + i] = a.shift[i];
+    }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
+
+  auto tile_coords = [&](int t, int j, int* w0, int* h0, int* n0, int* col0) {
+    const int nt = t % n_tiles, mt = (t / n_tiles) * MSUB + j;
+    const int tw = mt % a.tiles_w;
+    const int th = (mt / a.tiles_w) % a.tiles_h;
+    const int nb = mt / (a.tiles_w * a.tiles_h);
+    *w0 = tw << a.lg_bw;
+    *h0 = th << a.lg_bh;
+    *n0 = nb << lg_bi;
+    *col0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int sd = a.stride == 2 ? 2 : 1;
+      int s = 0, ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int w0[MSUB], h0[MSUB], n0[MSUB], col0;
+#pragma unroll
+        for (int j = 0; j < MSUB; ++j) tile_coords(t, j, &w0[j], &h0[j], &n0[j], &col0);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t sa = base + s * L::STAGE_BYTES;
+          const uint32_t bar = bar_full + 8 * s;
+          mbar_arrive_expect_tx(bar, L::STAGE_BYTES);
+          const int tap = kb / a.kb_per_tap;
+          const int cc = kb - tap * a.kb_per_tap;
+          int dx = 0, dy = 0;
+          if (a.taps == 9) { const int kh = tap / 3; dy = kh - 1; dx = tap - kh * 3 - 1; }
+#pragma unroll
+          for (int j = 0; j < MSUB; ++j) tma_load_4d(sa + j * 128 * 128, &tmA, bar, cc * BKE, sd * w0[j] + dx, sd * h0[j] + dy, n0[j]);
+          tma_load_2d(sa + L::A_BYTES, &tmB, bar, kb * BKE, col0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+      int s = 0, ph = 0, it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        if (it >= 2) mbar_wait(bar_tempty + 8 * acc, ((it >> 1) - 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * MSUB * BN;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tcgen05_fence_after();
+          const uint32_t sa = base + s * L::STAGE_BYTES;
+          const uint64_t bdesc = make_kmajor_desc<128>(sa + L::A_BYTES);
+#pragma unroll
+          for (int j = 0; j < MSUB; ++j) {
+            const uint64_t adesc = make_kmajor_desc<128>(sa + j * 128 * 128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(d_tmem + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * s);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+  } else {
+    const int g = warp & 3;
+    const int cb = ((warp - 2) >> 2) * HALF;     // this thread's first column inside the BN tile
+    const int r = g * 32 + lane;                 // accumulator row == TMEM lane == pixel of the sub-tile
+    const int et = threadIdx.x - 64;             // 0..255
+    const int my_set = (et & 31) == 0 && (et >> 5) < NSTG ? (et >> 5) : -1;   // E_b = first lane of epilogue warp b
+    const bool relu1 = a.conv_act == 0;
+    const int total_q = ((num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * MSUB;   // sub-tiles of this CTA
+    // panel holding this thread's columns, and the byte offset of its row inside a panel
+    const int panel = cb / 64, chunk0 = (cb % 64) / 8;      // 16-byte chunk index of the first column
+    const uint32_t row_off = r * 128;
+    const int rsw = r & 7;
+    auto issue_resid = [&](int q) {              // by E_{q % NSTG}: residual of sub-tile q -> staging set q % NSTG
+      if (q >= total_q) return;
+      const int t = blockIdx.x + (q >> 1) * gridDim.x;
+      int w0, h0, n0, col0;
+      tile_coords(t, q & 1, &w0, &h0, &n0, &col0);
+      const uint32_t dst = base + L::STG_OFF + (q % NSTG) * L::STG_BYTES;
+      const uint32_t bar = bar_res + 8 * (q % NSTG);
+      mbar_arrive_expect_tx(bar, L::STG_BYTES);
+#pragma unroll
+      for (int p = 0; p < PANELS; ++p) tma_load_4d(dst + p * 16384, &tmR, bar, col0 + p * 64, w0, h0, n0);
+    };
+    if (RESID && my_set >= 0 && my_set < LA) issue_resid(my_set);
+    int it = 0, q = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < MSUB; ++j, ++q) {
+        int w0, h0, n0, col0;
+        tile_coords(t, j, &w0, &h0, &n0, &col0);
+        const int set = q % NSTG;
+        uint8_t* stg = base_ptr + L::STG_OFF + set * L::STG_BYTES + panel * 16384 + row_off;
+        if (RESID) mbar_wait(bar_res + 8 * set, (q / NSTG) & 1);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + (acc * MSUB + j) * BN + cb;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + ch * 32, v);
+          tmem_ld_wait();
+          if (j == MSUB - 1 && ch == NCH - 1) {
+            tcgen05_fence_before();
+            mbar_arrive(bar_tempty + 8 * acc);
+          }
+          const float* sc = ss + col0 + cb + ch * 32;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {       // four 16-byte chunks = 32 columns
+            const int cidx = chunk0 + ch * 4 + k4;
+            uint4* sp = reinterpret_cast<uint4*>(stg + ((cidx ^ rsw) << 4));
+            uint32_t rr[4] = {0u, 0u, 0u, 0u};
+            if (RESID) { const uint4 rv = *sp; rr[0] = rv.x; rr[1] = rv.y; rr[2] = rv.z; rr[3] = rv.w; }
+            uint32_t p[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = k4 * 8 + e * 2;
+              float x0 = fmaf(__uint_as_float(v[c]), sc[c], sc[2048 + c]);
+              float x1 = fmaf(__uint_as_float(v[c + 1]), sc[c + 1], sc[2048 + c + 1]);
+              if (relu1) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
+              if (RESID) {
+                const float2 rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[e]));
+                x0 = fmaxf(x0 + rf.x, 0.0f);
+                x1 = fmaxf(x1 + rf.y, 0.0f);
+              }
+              p[e] = pack_bf16x2(x0, x1);
+            }
+            *sp = make_uint4(p[0], p[1], p[2], p[3]);
+          }
+        }
+        fence_proxy_async_smem();                // generic-proxy writes of this thread -> visible to the TMA store
+        // E of the set that sub-tile q+LA will use: its last store (sub-tile q+LA-NSTG = q-1) was issued one sub-tile
+        // ago; once it has finished reading, the set is free (for the next residual load / for direct writes)
+        if (my_set == (q + LA) % NSTG) {
+          bulk_wait_group_read<0>();
+          if (RESID) issue_resid(q + LA);
+        }
+        named_bar_sync(1, 256);
+        if (my_set == set) {
+          const uint32_t src = base + L::STG_OFF + set * L::STG_BYTES;
+#pragma unroll
+          for (int p = 0; p < PANELS; ++p) tma_store_4d(&tmO, src + p * 16384, col0 + p * 64, w0, h0, n0);
+          bulk_commit_group();
+        }
+      }
+    }
+    if (my_set >= 0) bulk_wait_group<0>();       // stores performed before the CTA retires
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
 // ---- MaxPool2d(kernel 3, stride 2, pad 1) on NHWC bf16 with C = 64 (ResVitKan.py:194,232): [n,112,112,64] -> [n,56,56,64]
 __global__ void __launch_bounds__(256)
 rvk_maxpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n_img) {
