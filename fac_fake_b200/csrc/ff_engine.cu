@@ -866,6 +866,7 @@ int launch_gemm(ff_cvit* h, cudaStream_t st, const CUtensorMap& tmA, const Linea
   const int zs = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
   dim3 grid((M + 127) / 128, L.out_f / L.bn, zs);
   ProfScope ps(h, st, &L == &h->embed ? KC_GEMM_EMBED : (&L == &h->head1 ? KC_GEMM_HEAD : KC_GEMM_XF));
+  // (a deeper TMA ring - 8 stages - was measured slower: 192 KB of smem leaves one CTA per SM instead of two)
   cudaError_t e = L.bn == 128 ? launch_tc_t<MODE_GEMM, 128, 128, false, 4>(grid, st, tmA, L.tmB, a)
                               : launch_tc_t<MODE_GEMM, 128, 64, false, 4>(grid, st, tmA, L.tmB, a);
   if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of gemm %s failed: %s", what, cudaGetErrorString(e));
@@ -1036,10 +1037,16 @@ int rvk_features(ff_cvit* h, const void* x, int layout, int slot_base, int n, cu
   }
   if (tap_hit(1, h->rvk_buf[1], (int64_t)n * 56 * 56 * 64)) return FF_OK;
   int layer = 0;
+  // FF_RVK_PROF_LAYER=L (tools/rvk_profile.py --ops L): profile slots 1..16 = the first 16 ops of layer L, rest -> small
+  static const int prof_layer = getenv("FF_RVK_PROF_LAYER") ? atoi(getenv("FF_RVK_PROF_LAYER")) : 0;
+  int op_in_layer = 0;
   for (size_t i = 0; i < h->rvk_ops.size(); ++i) {
     const ff_cvit::RvkOp& op = h->rvk_ops[i];
-    int rc = h->rvk_persist ? rvk_launch_op_persistent(h, op, n, st, KC_TC_CONV + std::min(layer, 4))
-                            : rvk_launch_op(h, op, n, st, KC_TC_CONV + std::min(layer, 4));
+    int cls = KC_TC_CONV + std::min(layer, 4);
+    if (prof_layer) cls = (layer + 1 == prof_layer && op_in_layer < 16) ? KC_TC_CONV + op_in_layer : KC_SMALL;
+    ++op_in_layer;
+    if (layer < 4 && (int)i == h->rvk_layer_end[layer]) op_in_layer = 0;
+    int rc = h->rvk_persist ? rvk_launch_op_persistent(h, op, n, st, cls) : rvk_launch_op(h, op, n, st, cls);
     if (rc) return rc;
     if (layer < 4 && (int)i == h->rvk_layer_end[layer]) {
       ++layer;
