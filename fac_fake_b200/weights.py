@@ -182,3 +182,76 @@ def make_resvitkan_state_dict(seed: int = 0, variant: str = "default") -> "Order
     _linear(gen, sd, "mlp_head.0", MLP_DIM, DIM)
     _linear(gen, sd, "mlp_head.3", NUM_CLASSES, MLP_DIM)
     return sd
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# cvit_GGCA_ADD_DEConv_RepBn8 (/root/reference/CViT-main/model/cvit_GGCA_ADD_DEConv_RepBn8.py:353-455)
+# (sequential, conv index, kind, bn index or None, cin, cout)
+GGCA_PLAN = (
+    ("features1", 0, "conv", 1, 3, 32), ("features1", 3, "de", 4, 32, 32), ("features1", 6, "de", 7, 32, 32),
+    ("features1", 10, "conv", 11, 32, 64), ("features1", 13, "de", 14, 64, 64), ("features1", 16, "de", 17, 64, 64),
+    ("features1", 20, "conv", 21, 64, 128), ("features1", 23, "de", 24, 128, 128),
+    ("features1", 26, "conv", None, 128, 128), ("features1", 27, "de", None, 128, 128),
+    ("features1", 30, "conv", 31, 128, 256), ("features1", 33, "de", 34, 256, 256), ("features1", 36, "de", 37, 256, 256),
+    ("features1", 39, "de", 40, 256, 256),
+    ("features2", 0, "conv", 1, 256, 512), ("features2", 3, "de", 4, 512, 512), ("features2", 6, "de", 7, 512, 512),
+    ("features2", 9, "de", 10, 512, 512),
+)
+
+
+def _deconv(gen, sd, p, dim, std):
+    """The five branches of a DEConv (:329-335): 2-D convs for cd / ad / plain, Conv1d weights for hd / vd."""
+    b = 1.0 / math.sqrt(dim * 9)
+    for name, shape in (("conv1_1.conv", (dim, dim, 3, 3)), ("conv1_2.conv", (dim, dim, 3)), ("conv1_3.conv", (dim, dim, 3)),
+                        ("conv1_4.conv", (dim, dim, 3, 3)), ("conv1_5", (dim, dim, 3, 3))):
+        sd[f"{p}.{name}.weight"] = torch.randn(shape, generator=gen) * std
+        sd[f"{p}.{name}.bias"] = _uniform(gen, (dim,), b * 0.2)
+
+
+def make_ggca_state_dict(seed: int = 0, variant: str = "default") -> "OrderedDict[str, torch.Tensor]":
+    """state_dict of the reference `cvit_GGCA_ADD_DEConv_RepBn8.CViT`, key names as in the reference."""
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(9000011 * seed + 41)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    sd["pos_embedding"] = torch.randn((MAX_SLOTS, 1, DIM), generator=gen)
+    sd["cls_token"] = torch.randn((1, 1, DIM), generator=gen)
+    gain = 1.3 if variant == "bn" else 1.15      # "bn": the random BN scales (mean 0.75) shrink every layer
+    for seq, ci, kind, bi, cin, cout in GGCA_PLAN:
+        p = f"{seq}.{ci}"
+        if kind == "de":
+            # the folded kernel is a sum of five terms (6.0x the variance of one, measured); He gain x `gain` keeps the
+            # activations O(1) through the 18 layers so that the conv features reach the logits
+            _deconv(gen, sd, p, cout, gain * math.sqrt(2.0 / (9 * cin * 6.0)))
+        else:
+            sd[p + ".weight"] = torch.randn((cout, cin, 3, 3), generator=gen) * gain * math.sqrt((1.0 if bi is None else 2.0) / (9 * cin))
+            sd[p + ".bias"] = _uniform(gen, (cout,), 0.2 / math.sqrt(cin * 9))
+        if bi is not None:
+            _bn(gen, sd, f"{seq}.{bi}", cout, variant)
+    # GGCA(512, 7, 7): shared 1x1 convs 128 -> 8 -> 128 with a BN in between (:159-166)
+    sd["ggca.shared_conv.0.weight"] = _uniform(gen, (8, 128, 1, 1), 1.0 / math.sqrt(128))
+    sd["ggca.shared_conv.0.bias"] = _uniform(gen, (8,), 1.0 / math.sqrt(128))
+    _bn(gen, sd, "ggca.shared_conv.1", 8, variant)
+    sd["ggca.shared_conv.3.weight"] = _uniform(gen, (128, 8, 1, 1), 1.0 / math.sqrt(8))
+    sd["ggca.shared_conv.3.bias"] = _uniform(gen, (128,), 1.0 / math.sqrt(8))
+    _deconv(gen, sd, "Deconv", 256, 0.01)                    # constructed by the reference (:431) but unused in forward
+    _linear(gen, sd, "patch_to_embedding", DIM, PATCH_DIM)
+    for layer in range(DEPTH):
+        p = f"transformer.layers.{layer}"
+        rand = variant == "bn"
+        sd[f"{p}.0.fn.norm.weight"] = torch.rand((DIM,), generator=gen) + 0.5 if rand else torch.ones(DIM)
+        sd[f"{p}.0.fn.norm.bias"] = torch.randn((DIM,), generator=gen) * 0.1 if rand else torch.zeros(DIM)
+        _linear(gen, sd, f"{p}.0.fn.fn.to_qkv", 3 * DIM, DIM, bias=False)
+        _linear(gen, sd, f"{p}.0.fn.fn.to_out", DIM, DIM)
+        q = f"{p}.1.fn.norm"                                 # LinearNorm (:22-47): eval() uses norm1 only
+        sd[q + ".warm"] = torch.tensor(0)
+        sd[q + ".iter"] = torch.tensor(300000)
+        sd[q + ".total_step"] = torch.tensor(300000)
+        sd[q + ".norm1.weight"] = torch.rand((DIM,), generator=gen) + 0.5 if rand else torch.ones(DIM)
+        sd[q + ".norm1.bias"] = torch.randn((DIM,), generator=gen) * 0.1 if rand else torch.zeros(DIM)
+        sd[q + ".norm2.alpha"] = torch.ones(1)
+        _bn(gen, sd, q + ".norm2.bn", DIM, variant)
+        _linear(gen, sd, f"{p}.1.fn.fn.net.0", MLP_DIM, DIM)
+        _linear(gen, sd, f"{p}.1.fn.fn.net.2", DIM, MLP_DIM)
+    _linear(gen, sd, "mlp_head.0", MLP_DIM, DIM)
+    _linear(gen, sd, "mlp_head.2", NUM_CLASSES, MLP_DIM)
+    return sd

@@ -130,3 +130,53 @@ def main_resvitkan():
 
 if __name__ == "__main__" and os.environ.get("FF_GOLDEN_RESVITKAN", "1") == "1":
     main_resvitkan()
+
+
+def load_reference_ggca_class():
+    """Import `cvit_GGCA_ADD_DEConv_RepBn8.CViT` on a CPU-only host.
+
+    The reference file is CUDA-only in three places that do not change the arithmetic: DEConv's ``get_weight`` builds
+    its folded kernels with ``torch.cuda.FloatTensor(...)`` (:227,297,318), ``Conv2d_vd.__init__`` calls
+    ``self.conv.cuda()`` (:313), and the module imports ``torchsummary`` (:7).  Shims: ``torch.cuda.FloatTensor`` ->
+    ``torch.FloatTensor``, ``nn.Module.cuda`` -> identity, an empty ``torchsummary`` module.  A fourth, layout-only
+    shim is applied per instance by ``make_ggca_model``: on this CPU build the conv stack returns a channels_last
+    tensor, on which GGCA's ``x.view(b*groups, ...)`` (:181) raises; a forward pre-hook makes it contiguous (on CUDA
+    the reference gets a contiguous NCHW tensor and needs no hook).  Everything else is the reference's own code.
+    """
+    import types
+    sys.modules.setdefault("torchsummary", types.SimpleNamespace(summary=lambda *a, **k: None))
+    torch.cuda.FloatTensor = torch.FloatTensor
+    torch.nn.Module.cuda = lambda self, device=None: self
+    sys.path.insert(0, os.path.join(REF, "model"))
+    import importlib
+    return importlib.import_module("cvit_GGCA_ADD_DEConv_RepBn8").CViT
+
+
+def make_ggca_model(sd):
+    model = load_reference_ggca_class()().eval()
+    model.load_state_dict(sd, strict=True)
+    model.ggca.register_forward_pre_hook(lambda mod, args: (args[0].contiguous(),))
+    return model
+
+
+def main_ggca():
+    """tests/golden/ggca_{default,bn}.npz from the reference class (model/cvit_GGCA_ADD_DEConv_RepBn8.py:353-455)."""
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    for variant in ("default", "bn"):
+        sd = W.make_ggca_state_dict(0, variant)
+        model = make_ggca_model(sd)
+        crops = W.synthetic_crops(8, seed=3)
+        x = O.normalize_crops(crops)
+        with torch.no_grad():
+            logits = model(x)
+            f = model.features2(model.features1(x[:2]))
+            g = f * model.ggca(f)
+        stats = np.stack([np.array([s.double().mean().item(), s.double().abs().mean().item(), s.double().pow(2).mean().sqrt().item()])
+                          for s in (f, g)])
+        np.savez_compressed(os.path.join(out_dir, f"ggca_{variant}.npz"), logits=logits.numpy(), feat_stats=stats,
+                            gated_sample=g[0, :16].numpy().astype(np.float32), seed_weights=0, seed_crops=3, n=8)
+        print("ggca", variant, "logits[0:2] =", logits[0:2].tolist(), "feat stats", stats.tolist())
+
+
+if __name__ == "__main__" and os.environ.get("FF_GOLDEN_GGCA", "1") == "1":
+    main_ggca()
