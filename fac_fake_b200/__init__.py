@@ -4,7 +4,7 @@ Host side of the drop-in: a ctypes binding of ``libfacfake.so`` (C-ABI in ``incl
 plus mirrors of the reference's Python seam (``CViT`` module call, ``cvit_prediction`` helpers).
 There is no CPU / PyTorch fallback: without the CUDA library the package raises.
 """
-from .engine import CViTEngine, EngineError, ResVitKanEngine  # noqa: F401
+from .engine import CViTEngine, CViTGGCAEngine, EngineError, ResVitKanEngine  # noqa: F401
 from . import weights  # noqa: F401
 
-__all__ = ["CViTEngine", "ResVitKanEngine", "EngineError", "weights"]
+__all__ = ["CViTEngine", "CViTGGCAEngine", "ResVitKanEngine", "EngineError", "weights"]

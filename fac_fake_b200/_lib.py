@@ -17,6 +17,7 @@ _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 SYMBOLS = [
     ("ff_cvit_create", _i, [C.POINTER(_vp), _i, _i, _i]),
     ("ff_resvitkan_create", _i, [C.POINTER(_vp), _i, _i]),
+    ("ff_cvit_ggca_create", _i, [C.POINTER(_vp), _i, _i]),
     ("ff_cvit_destroy", None, [_vp]),
     ("ff_last_error", C.c_char_p, [_vp]),
     ("ff_cvit_load_weight", _i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i]),

@@ -127,6 +127,10 @@ struct ff_cvit {
   bf16 *bufA2 = nullptr, *bufB2 = nullptr; // second ping-pong set: odd sub-passes run on aux_stream (dual-stream overlap)
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // ---- GGCA / DEConv / RepBN variant (kind == 2): the CViT plan + one BN-less linear conv + the gate
+  bf16* bufR = nullptr;                  // output of the extra Conv2d(128,128) (features1.26), read by layer 9
+  float *ggca_w1 = nullptr, *ggca_b1 = nullptr, *ggca_w2 = nullptr, *ggca_b2 = nullptr;
+  float ln2_eps = 1e-5f;                 // eps of the MLP-branch LayerNorm (1e-6 for LinearNorm.norm1)
   // ---- ResVitKan (kind == 1): ResNet-50 features + the same ViT + KAN head
   int kind = 0;
   struct RvkOp {
@@ -137,13 +141,14 @@ struct ff_cvit {
     int in_buf = 0, out_buf = 0;
     int bn = 64, bw = 8, bh = 8, bi = 2;
     bf16* w = nullptr;
+    bf16* out_ptr = nullptr;   // explicit output (kind 2); otherwise rvk_buf[out_buf] / feat
     float *scale = nullptr, *shift = nullptr;
     CUtensorMap tmA, tmB;
     CUtensorMap tmO, tmR;    // TMA-store epilogue: output / residual tiles in the output geometry
     CUtensorMap tmA_flat;    // 1x1 stride-1 ops for the persistent kernel: [1][1][pixels][cin], boxes of 128 pixels
     std::string name;
   };
-  std::vector<RvkOp> rvk_ops;
+  std::vector<RvkOp> rvk_ops;            // kind 2 keeps its single extra conv (features1.26) here
   int rvk_persist = 2;                   // 2 = rvk_conv2_kernel (persistent, TMA epilogue), 1 = rvk_conv_kernel, 0 = tc_kernel per tile
   int rvk_layer_end[4] = {0, 0, 0, 0};   // index of the last op of layer1..4 (debug taps)
   bf16* rvk_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -483,7 +488,7 @@ const bf16* conv_input_buffer(const ff_cvit* h, int li, int set = 0) {
   const bf16* B = set ? h->bufB2 : h->bufB;
   switch (li) {
     case 1: return A; case 2: return B; case 3: return A; case 4: return B; case 5: return A;
-    case 6: return h->P; case 7: return h->Q; case 8: return h->P;
+    case 6: return h->P; case 7: return h->Q; case 8: return h->kind == 2 ? h->bufR : h->P;
     case 9: return h->Q; case 10: return h->P; case 11: return h->Q; case 12: return h->P;
     case 13: return h->Q; case 14: return h->P; case 15: return h->Q; case 16: return h->P;
   }
@@ -542,6 +547,72 @@ int build_conv_maps(ff_cvit* h) {
   return FF_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ GGCA variant weights
+// cvit_GGCA_ADD_DEConv_RepBn8.py:361-423: (sequential, conv index, is DEConv, BN index or -1).  Entry 8 is the extra
+// Conv2d(128,128) without BN / activation (features1.26); entry 9 the BN-less DEConv(128) + ReLU + pool (features1.27).
+struct GgcaPlan { const char* seq; int conv_idx; bool de; int bn_idx; };
+const GgcaPlan kGgcaPlan[18] = {
+    {"features1", 0, false, 1},  {"features1", 3, true, 4},   {"features1", 6, true, 7},   {"features1", 10, false, 11},
+    {"features1", 13, true, 14}, {"features1", 16, true, 17}, {"features1", 20, false, 21}, {"features1", 23, true, 24},
+    {"features1", 26, false, -1}, {"features1", 27, true, -1}, {"features1", 30, false, 31}, {"features1", 33, true, 34},
+    {"features1", 36, true, 37}, {"features1", 39, true, 40}, {"features2", 0, false, 1},  {"features2", 3, true, 4},
+    {"features2", 6, true, 7},   {"features2", 9, true, 10},
+};
+
+// [cout][cin][3][3] kernel and bias of a plan entry.  A DEConv (:329-351) is folded exactly as its forward does:
+// central difference (centre tap minus the tap sum, :218-235), horizontal / vertical difference built from Conv1d
+// weights (:290-326), angular difference w - w[perm] (:238-255, theta = 1) and a plain 3x3 kernel; biases add.
+int ggca_conv_weights(ff_cvit* h, const GgcaPlan& gp, int cin, int cout, std::vector<float>* w_out, std::vector<float>* b_out) {
+  const std::string p = std::string(gp.seq) + "." + std::to_string(gp.conv_idx);
+  auto bad = [&]() { return h->err.find("shape") != std::string::npos ? FF_ERR_SHAPE : FF_ERR_STATE; };
+  if (!gp.de) {
+    const auto* w = get_w(h, p + ".weight", {cout, cin, 3, 3});
+    const auto* b = get_w(h, p + ".bias", {cout});
+    if (!w || !b) return bad();
+    *w_out = *w;
+    *b_out = *b;
+    return FF_OK;
+  }
+  const auto* w1 = get_w(h, p + ".conv1_1.conv.weight", {cout, cin, 3, 3});
+  const auto* w2 = get_w(h, p + ".conv1_2.conv.weight", {cout, cin, 3});
+  const auto* w3 = get_w(h, p + ".conv1_3.conv.weight", {cout, cin, 3});
+  const auto* w4 = get_w(h, p + ".conv1_4.conv.weight", {cout, cin, 3, 3});
+  const auto* w5 = get_w(h, p + ".conv1_5.weight", {cout, cin, 3, 3});
+  const auto* b1 = get_w(h, p + ".conv1_1.conv.bias", {cout});
+  const auto* b2 = get_w(h, p + ".conv1_2.conv.bias", {cout});
+  const auto* b3 = get_w(h, p + ".conv1_3.conv.bias", {cout});
+  const auto* b4 = get_w(h, p + ".conv1_4.conv.bias", {cout});
+  const auto* b5 = get_w(h, p + ".conv1_5.bias", {cout});
+  if (!w1 || !w2 || !w3 || !w4 || !w5 || !b1 || !b2 || !b3 || !b4 || !b5) return bad();
+  static const int perm[9] = {3, 0, 1, 6, 4, 2, 7, 8, 5};
+  w_out->assign((size_t)cout * cin * 9, 0.0f);
+  b_out->resize(cout);
+  for (size_t oi = 0; oi < (size_t)cout * cin; ++oi) {
+    const float* a1 = &(*w1)[oi * 9];
+    const float* a2 = &(*w2)[oi * 3];
+    const float* a3 = &(*w3)[oi * 3];
+    const float* a4 = &(*w4)[oi * 9];
+    const float* a5 = &(*w5)[oi * 9];
+    float sum1 = 0.0f;
+    for (int t = 0; t < 9; ++t) sum1 += a1[t];
+    float f[9];
+    for (int t = 0; t < 9; ++t) {
+      float cd = a1[t];
+      if (t == 4) cd = a1[4] - sum1;
+      float hd = 0.0f, vd = 0.0f;
+      if (t % 3 == 0) hd = a2[t / 3];                 // taps 0,3,6 = +w, taps 2,5,8 = -w
+      else if (t % 3 == 2) hd = -a2[t / 3];
+      if (t < 3) vd = a3[t];                          // taps 0,1,2 = +w, taps 6,7,8 = -w
+      else if (t >= 6) vd = -a3[t - 6];
+      const float ad = a4[t] - a4[perm[t]];
+      f[t] = (((cd + hd) + vd) + ad) + a5[t];         // the reference's summation order: w1 + w2 + w3 + w4 + w5
+    }
+    for (int t = 0; t < 9; ++t) (*w_out)[oi * 9 + t] = f[t];
+  }
+  for (int o = 0; o < cout; ++o) (*b_out)[o] = ((((*b1)[o] + (*b2)[o]) + (*b3)[o]) + (*b4)[o]) + (*b5)[o];
+  return FF_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ ResVitKan features
 // ResNet-50 plan (ResVitKan.py:185-240): the stem is its own kernel (ff_rvk.cuh); every bottleneck convolution is
@@ -694,6 +765,53 @@ int finalize_rvk_features(ff_cvit* h) {
   return FF_OK;
 }
 
+// kind 2: the BN-less, activation-less Conv2d(128,128) of features1.26 (P -> bufR) as one rvk_conv2_kernel op, and the
+// GGCA shared convs with their BatchNorm2d(8) folded into the first one.
+int finalize_ggca_extras(ff_cvit* h) {
+  int rc;
+  std::vector<float> wsrc, bias;
+  if ((rc = ggca_conv_weights(h, kGgcaPlan[8], 128, 128, &wsrc, &bias))) return rc;
+  ff_cvit::RvkOp op;
+  op.name = "features1.26";
+  op.type = 1; op.cin = 128; op.cout = 128; op.taps = 9; op.stride = 1; op.in_hw = 56; op.out_hw = 56;
+  op.act = 0; op.resid = -1; op.bn = 128; op.bw = 8; op.bh = 8; op.bi = 2;
+  op.out_ptr = h->bufR;
+  std::vector<float> wr((size_t)128 * 9 * 128), ones(128, 1.0f);
+  for (int o = 0; o < 128; ++o)
+    for (int ci = 0; ci < 128; ++ci)
+      for (int t = 0; t < 9; ++t) wr[((size_t)o * 9 + t) * 128 + ci] = wsrc[((size_t)o * 128 + ci) * 9 + t];
+  if ((rc = dev_upload(h, &op.w, to_bf16(wr)))) return rc;
+  if ((rc = dev_upload(h, &op.scale, ones))) return rc;
+  if ((rc = dev_upload(h, &op.shift, bias))) return rc;
+  if ((rc = tmap_2d(h, &op.tmB, op.w, 9 * 128, 128, 64, 128))) return rc;
+  if ((rc = tmap_4d(h, &op.tmA, conv_output_buffer(h, 7), 128, 56, 56, h->cap, 64, 8, 8, 2))) return rc;
+  if ((rc = tmap_4d(h, &op.tmO, h->bufR, 128, 56, 56, h->cap, 64, 8, 8, 2))) return rc;
+  op.tmR = op.tmO;
+  h->rvk_ops.clear();
+  h->rvk_ops.push_back(op);
+  // GGCA(512,7,7).shared_conv: Conv2d(128,8,1) + BatchNorm2d(8) + ReLU + Conv2d(8,128,1)  (:159-166)
+  const auto* w1 = get_w(h, "ggca.shared_conv.0.weight", {8, 128, 1, 1});
+  const auto* b1 = get_w(h, "ggca.shared_conv.0.bias", {8});
+  const auto* g = get_w(h, "ggca.shared_conv.1.weight", {8});
+  const auto* be = get_w(h, "ggca.shared_conv.1.bias", {8});
+  const auto* mu = get_w(h, "ggca.shared_conv.1.running_mean", {8});
+  const auto* var = get_w(h, "ggca.shared_conv.1.running_var", {8});
+  const auto* w2 = get_w(h, "ggca.shared_conv.3.weight", {128, 8, 1, 1});
+  const auto* b2 = get_w(h, "ggca.shared_conv.3.bias", {128});
+  if (!w1 || !b1 || !g || !be || !mu || !var || !w2 || !b2) return h->err.find("shape") != std::string::npos ? FF_ERR_SHAPE : FF_ERR_STATE;
+  std::vector<float> fw1(8 * 128), fb1(8);
+  for (int u = 0; u < 8; ++u) {
+    const float s = (*g)[u] / std::sqrt((*var)[u] + BN_EPS);
+    for (int k = 0; k < 128; ++k) fw1[u * 128 + k] = (*w1)[u * 128 + k] * s;
+    fb1[u] = ((*b1)[u] - (*mu)[u]) * s + (*be)[u];
+  }
+  if ((rc = dev_upload(h, &h->ggca_w1, fw1))) return rc;
+  if ((rc = dev_upload(h, &h->ggca_b1, fb1))) return rc;
+  if ((rc = dev_upload(h, &h->ggca_w2, *w2))) return rc;
+  if ((rc = dev_upload(h, &h->ggca_b2, *b2))) return rc;
+  return FF_OK;
+}
+
 int finalize(ff_cvit* h) {
   int rc;
   if (h->kind == 1) {
@@ -702,22 +820,39 @@ int finalize(ff_cvit* h) {
   // ---- conv stack: fold bias + eval BN into (scale, shift); weights -> [cout][kh][kw][cin]
   for (int li = 0; li < 17; ++li) {
     const ConvPlan& p = kConv[li];
-    const std::string c = "features." + std::to_string(p.conv_idx), b = "features." + std::to_string(p.conv_idx + 1);
-    const auto* w = get_w(h, c + ".weight", {p.cout, p.cin, 3, 3});
-    const auto* bias = get_w(h, c + ".bias", {p.cout});
-    const auto* g = get_w(h, b + ".weight", {p.cout});
-    const auto* be = get_w(h, b + ".bias", {p.cout});
-    const auto* mu = get_w(h, b + ".running_mean", {p.cout});
-    const auto* var = get_w(h, b + ".running_var", {p.cout});
-    if (!w || !bias || !g || !be || !mu || !var) return h->err.find("shape") != std::string::npos ? FF_ERR_SHAPE : FF_ERR_STATE;
-    std::vector<float> scale(p.cout), shift(p.cout), wr((size_t)p.cout * 9 * p.cin);
-    for (int o = 0; o < p.cout; ++o) {
-      const float s = (*g)[o] / std::sqrt((*var)[o] + BN_EPS);
-      scale[o] = s;
-      shift[o] = ((*bias)[o] - (*mu)[o]) * s + (*be)[o];
-      for (int ci = 0; ci < p.cin; ++ci)
-        for (int t = 0; t < 9; ++t) wr[((size_t)o * 9 + t) * p.cin + ci] = (*w)[((size_t)o * p.cin + ci) * 9 + t];
+    std::vector<float> wsrc, bias_v, scale(p.cout), shift(p.cout), wr((size_t)p.cout * 9 * p.cin);
+    std::string bn_key;
+    if (h->kind == 2) {
+      // plan entry of layer li: the extra BN-less conv (entry 8) sits between layers 8 and 9 (0-based li 7 and 8)
+      const GgcaPlan& gp = kGgcaPlan[li < 8 ? li : li + 1];
+      if ((rc = ggca_conv_weights(h, gp, p.cin, p.cout, &wsrc, &bias_v))) return rc;
+      if (gp.bn_idx >= 0) bn_key = std::string(gp.seq) + "." + std::to_string(gp.bn_idx);
+    } else {
+      const std::string c = "features." + std::to_string(p.conv_idx);
+      bn_key = "features." + std::to_string(p.conv_idx + 1);
+      const auto* w = get_w(h, c + ".weight", {p.cout, p.cin, 3, 3});
+      const auto* bias = get_w(h, c + ".bias", {p.cout});
+      if (!w || !bias) return h->err.find("shape") != std::string::npos ? FF_ERR_SHAPE : FF_ERR_STATE;
+      wsrc = *w;
+      bias_v = *bias;
     }
+    if (!bn_key.empty()) {
+      const auto* g = get_w(h, bn_key + ".weight", {p.cout});
+      const auto* be = get_w(h, bn_key + ".bias", {p.cout});
+      const auto* mu = get_w(h, bn_key + ".running_mean", {p.cout});
+      const auto* var = get_w(h, bn_key + ".running_var", {p.cout});
+      if (!g || !be || !mu || !var) return h->err.find("shape") != std::string::npos ? FF_ERR_SHAPE : FF_ERR_STATE;
+      for (int o = 0; o < p.cout; ++o) {
+        const float s = (*g)[o] / std::sqrt((*var)[o] + BN_EPS);
+        scale[o] = s;
+        shift[o] = (bias_v[o] - (*mu)[o]) * s + (*be)[o];
+      }
+    } else {
+      for (int o = 0; o < p.cout; ++o) { scale[o] = 1.0f; shift[o] = bias_v[o]; }     // BN-less DEConv (features1.27)
+    }
+    for (int o = 0; o < p.cout; ++o)
+      for (int ci = 0; ci < p.cin; ++ci)
+        for (int t = 0; t < 9; ++t) wr[((size_t)o * 9 + t) * p.cin + ci] = wsrc[((size_t)o * p.cin + ci) * 9 + t];
     ConvLayerDev& L = h->conv[li];
     if (p.cout <= 64)
       for (int o = 0; o < p.cout; ++o) { L.epi.scale[o] = scale[o]; L.epi.shift[o] = shift[o]; }
@@ -819,8 +954,11 @@ int finalize(ff_cvit* h) {
     XfLayerDev& X = h->xf[l];
     if ((rc = upload_vec(h, &X.ln1_g, p + ".0.fn.norm.weight", DIM))) return rc;
     if ((rc = upload_vec(h, &X.ln1_b, p + ".0.fn.norm.bias", DIM))) return rc;
-    if ((rc = upload_vec(h, &X.ln2_g, p + ".1.fn.norm.weight", DIM))) return rc;
-    if ((rc = upload_vec(h, &X.ln2_b, p + ".1.fn.norm.bias", DIM))) return rc;
+    // kind 2: the MLP branch is pre-normed by LinearNorm, which in eval() is its norm1 = LayerNorm(eps 1e-6)
+    // (cvit_GGCA_ADD_DEConv_RepBn8.py:22-60); its RepBN / schedule buffers are not on the inference path
+    const std::string ln2 = h->kind == 2 ? p + ".1.fn.norm.norm1" : p + ".1.fn.norm";
+    if ((rc = upload_vec(h, &X.ln2_g, ln2 + ".weight", DIM))) return rc;
+    if ((rc = upload_vec(h, &X.ln2_b, ln2 + ".bias", DIM))) return rc;
     if ((rc = upload_linear(h, &X.qkv, p + ".0.fn.fn.to_qkv", 3 * DIM, DIM, false, h->gemm_bn_wide))) return rc;
     if ((rc = upload_linear(h, &X.out, p + ".0.fn.fn.to_out", DIM, DIM, true, 64))) return rc;
     if ((rc = upload_linear(h, &X.ff1, p + ".1.fn.fn.net.0", MLP, DIM, true, h->gemm_bn_wide))) return rc;
@@ -834,7 +972,8 @@ int finalize(ff_cvit* h) {
   }
 
   if (h->compute == FF_COMPUTE_BF16) {
-    if (h->kind == 0 && (rc = build_conv_maps(h))) return rc;
+    if (h->kind != 1 && (rc = build_conv_maps(h))) return rc;
+    if (h->kind == 2 && (rc = finalize_ggca_extras(h))) return rc;
     const int cap128 = (h->cap + 127) / 128 * 128;
     if ((rc = tmap_2d(h, &h->tm_feat, h->feat, PATCH, cap128, 64, 128))) return rc;
     if ((rc = tmap_2d(h, &h->tm_xn, h->xn, DIM, h->rows_cap, 64, 128))) return rc;
@@ -957,7 +1096,7 @@ int rvk_launch_op_persistent(ff_cvit* h, const ff_cvit::RvkOp& op, int n, cudaSt
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.scale = op.scale; a.shift = op.shift;
-  a.out = op.out_buf < 0 ? h->feat : h->rvk_buf[op.out_buf];
+  a.out = op.out_ptr ? op.out_ptr : (op.out_buf < 0 ? h->feat : h->rvk_buf[op.out_buf]);
   a.kb_per_tap = op.cin / 64;
   a.kb_total = op.taps * a.kb_per_tap;
   a.kb_per_split = a.kb_total;
@@ -1243,6 +1382,16 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
     const ConvPlan& p = kConv[li];
     const int ohw = p.pool ? p.hw / 2 : p.hw;
     if (tap_hit(li + 1, conv_output_buffer(h, li), (int64_t)n * ohw * ohw * p.cout, true)) return FF_OK;
+    if (h->kind == 2 && li == 7) {   // features1.26: Conv2d(128,128), no BN, no activation -> bufR (input of layer 9)
+      if ((rc = rvk_launch_op_persistent(h, h->rvk_ops[0], n, st, KC_SMALL))) return rc;
+      if (tap_hit(26, h->bufR, (int64_t)n * 56 * 56 * 128, true)) return FF_OK;
+    }
+  }
+  if (h->kind == 2) {                // x = x * ggca(x)  (cvit_GGCA_ADD_DEConv_RepBn8.py:447-448), in place on feat
+    ProfScope ps(h, st, KC_SMALL);
+    ggca_gate_kernel<<<n, 512, 0, st>>>(h->feat, h->ggca_w1, h->ggca_b1, h->ggca_w2, h->ggca_b2, n);
+    FF_LAUNCH_CHECK(h, "ggca_gate");
+    if (tap_hit(27, h->feat, (int64_t)n * PATCH, true)) return FF_OK;
   }
   prof_mark(h, st, 1, false, true);
   }   // kind == 0
@@ -1257,13 +1406,13 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   // ---- transformer
   for (int l = 0; l < DEPTH; ++l) {
     const XfLayerDev& X = h->xf[l];
-    { ProfScope ps(h, st, KC_SMALL); launch_k(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, true, (const float*)h->x, (const float*)X.ln1_g, (const float*)X.ln1_b, h->xn, rows); }
+    { ProfScope ps(h, st, KC_SMALL); launch_k(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, true, (const float*)h->x, (const float*)X.ln1_g, (const float*)X.ln1_b, h->xn, rows, 1e-5f); }
     FF_LAUNCH_CHECK(h, "layernorm1");
     if ((rc = launch_gemm(h, st, h->tm_xn, X.qkv, rows, h->qkvb, 3 * DIM, EPI_STORE_BF16, ACT_NONE, 1, "to_qkv"))) return rc;
     { ProfScope ps(h, st, KC_SMALL); launch_k(attention2_kernel, dim3((n * 8 + 7) / 8), dim3(256), 0, st, true, (const bf16*)h->qkvb, h->att, n); }
     FF_LAUNCH_CHECK(h, "attention2");
     if ((rc = launch_gemm(h, st, h->tm_att, X.out, rows, h->x, DIM, EPI_RESID_F32, ACT_NONE, 1, "to_out"))) return rc;
-    { ProfScope ps(h, st, KC_SMALL); launch_k(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, true, (const float*)h->x, (const float*)X.ln2_g, (const float*)X.ln2_b, h->xn, rows); }
+    { ProfScope ps(h, st, KC_SMALL); launch_k(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, true, (const float*)h->x, (const float*)X.ln2_g, (const float*)X.ln2_b, h->xn, rows, h->ln2_eps); }
     FF_LAUNCH_CHECK(h, "layernorm2");
     if ((rc = launch_gemm(h, st, h->tm_xn, X.ff1, rows, h->ffh, MLP, EPI_STORE_BF16, ACT_GELU, 1, "ff1"))) return rc;
     if ((rc = launch_gemm(h, st, h->tm_ffh, X.ff2, rows, h->x, DIM, EPI_RESID_F32, ACT_NONE, 1, "ff2"))) return rc;
@@ -1420,8 +1569,8 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
   if (!out || max_crops <= 0) return fail(nullptr, FF_ERR_BAD_ARG, "ff_cvit_create: bad arguments");
   if (compute_dtype != FF_COMPUTE_BF16 && compute_dtype != FF_COMPUTE_FP32)
     return fail(nullptr, FF_ERR_BAD_ARG, "ff_cvit_create: unknown compute_dtype %d", compute_dtype);
-  if (kind == 1 && compute_dtype != FF_COMPUTE_BF16)
-    return fail(nullptr, FF_ERR_BAD_ARG, "ff_resvitkan_create: only FF_COMPUTE_BF16 is implemented for ResVitKan");
+  if (kind != 0 && compute_dtype != FF_COMPUTE_BF16)
+    return fail(nullptr, FF_ERR_BAD_ARG, "only FF_COMPUTE_BF16 is implemented for the ResVitKan / GGCA variants");
   *out = nullptr;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1445,6 +1594,7 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
   h->device = device;
   h->compute = compute_dtype;
   h->kind = kind;
+  h->ln2_eps = kind == 2 ? 1e-6f : 1e-5f;
   h->cap = (max_crops + 31) / 32 * 32;
   h->rows_cap = (2 * h->cap + 127) / 128 * 128;
   h->s12_cap = 256;
@@ -1477,7 +1627,8 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
       if ((rc = dev_alloc(h, &h->rvk_x4, (size_t)h->cap * 224 * 224 * 4))) break;
       if ((rc = dev_alloc(h, &h->kan_part, (size_t)KAN_CHUNKS * h->cap * 64))) break;
     }
-    if (compute_dtype == FF_COMPUTE_BF16 && kind == 0) {
+    if (kind == 2 && (rc = dev_alloc(h, &h->bufR, (size_t)h->cap * 56 * 56 * 128))) break;
+    if (compute_dtype == FF_COMPUTE_BF16 && kind != 1) {
       if ((rc = dev_alloc(h, &h->bufA, (size_t)h->s12_cap * 224 * 224 * 32))) break;
       if ((rc = dev_alloc(h, &h->bufB, (size_t)h->s12_cap * 224 * 224 * 32))) break;
       if ((rc = dev_alloc(h, &h->bufA2, (size_t)h->s12_cap * 224 * 224 * 32))) break;
@@ -1523,6 +1674,9 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
 }
 int ff_resvitkan_create(ff_cvit_t** out, int device, int max_crops) {
   return create_impl(out, device, max_crops, FF_COMPUTE_BF16, 1);
+}
+int ff_cvit_ggca_create(ff_cvit_t** out, int device, int max_crops) {
+  return create_impl(out, device, max_crops, FF_COMPUTE_BF16, 2);
 }
 
 void ff_cvit_destroy(ff_cvit_t* h) {
@@ -1711,7 +1865,7 @@ int64_t ff_cvit_debug_activation(ff_cvit_t* h, const void* x, int x_layout, cons
                                  float* out_host, int64_t out_elems, void* stream) {
   if (!h) return FF_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
-  if (stop_after < 1 || stop_after > 25 || !out_host || n <= 0 || n > h->cap) return fail(h, FF_ERR_BAD_ARG, "ff_cvit_debug_activation: bad arguments");
+  if (stop_after < 1 || stop_after > 27 || !out_host || n <= 0 || n > h->cap) return fail(h, FF_ERR_BAD_ARG, "ff_cvit_debug_activation: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DebugTap tap;
   tap.stop_after = stop_after;

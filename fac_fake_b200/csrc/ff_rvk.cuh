@@ -738,4 +738,73 @@ kan_l1_kernel(const float* __restrict__ part, const float* __restrict__ w1, cons
   }
 }
 
+// ---- GGCA(512, 7, 7) gate of the cvit_GGCA_ADD_DEConv_RepBn8 variant (SURVEY.md §8f-4;
+// /root/reference/CViT-main/model/cvit_GGCA_ADD_DEConv_RepBn8.py:143-213 and forward :447-448):
+//   att_h[c][h] = sigmoid(S(mean_w x) + S(max_w x)),  att_w[c][w] likewise over h,  S = shared 1x1 convs per group of
+//   128 channels: 128 -> 8 (+BN, folded on the host) -> ReLU -> 128;  out = x * (x * att_h * att_w).
+// One block per crop, one thread per channel; the 7x7 map of the thread's channel lives in registers, the pooled
+// vectors and the hidden units go through shared memory.  In place on the bf16 NHWC feature map [n][7][7][512].
+__global__ void __launch_bounds__(512)
+ggca_gate_kernel(__nv_bfloat16* __restrict__ feat, const float* __restrict__ w1, const float* __restrict__ b1,
+                 const float* __restrict__ w2, const float* __restrict__ b2, int n) {
+  __shared__ float s_pool[7][512];             // pooled vectors of one type: [pos][channel]
+  __shared__ float s_hid[28][4][8];            // [type*7 + pos][group][hidden unit]; type 0 = h_avg, 1 = h_max, 2 = w_avg, 3 = w_max
+  const int b = blockIdx.x;
+  if (b >= n) return;
+  const int c = threadIdx.x, grp = c >> 7, cg = c & 127;
+  __nv_bfloat16* f = feat + static_cast<size_t>(b) * 49 * 512 + c;
+  float x[49];
+#pragma unroll
+  for (int i = 0; i < 49; ++i) x[i] = __bfloat162float(f[i * 512]);
+#pragma unroll
+  for (int type = 0; type < 4; ++type) {
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      float sum = 0.f, mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const float v = type < 2 ? x[r * 7 + k] : x[k * 7 + r];   // types 0/1: row r pooled over w; 2/3: column r over h
+        sum += v;
+        mx = fmaxf(mx, v);
+      }
+      s_pool[r][c] = (type & 1) ? mx : sum / 7.0f;
+    }
+    __syncthreads();
+    // hidden units of this type: 7 positions x 4 groups x 8 units = 224 dot products of length 128
+    if (threadIdx.x < 224) {
+      const int u = threadIdx.x & 7, g = (threadIdx.x >> 3) & 3, pos = threadIdx.x >> 5;
+      const float* pv = &s_pool[pos][g * 128];
+      const float* pw = w1 + u * 128;
+      float acc = b1[u];
+      for (int k = 0; k < 128; ++k) acc = fmaf(pw[k], pv[k], acc);
+      s_hid[type * 7 + pos][g][u] = fmaxf(acc, 0.0f);
+    }
+    __syncthreads();
+  }
+  float att[14];                               // att_h[0..6], att_w[0..6] of this channel
+  float wv[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) wv[u] = w2[cg * 8 + u];
+  const float bb = b2[cg];
+#pragma unroll
+  for (int d = 0; d < 2; ++d)
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      float ya = bb, ym = bb;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        ya = fmaf(wv[u], s_hid[d * 14 + r][grp][u], ya);
+        ym = fmaf(wv[u], s_hid[d * 14 + 7 + r][grp][u], ym);
+      }
+      att[d * 7 + r] = 1.0f / (1.0f + expf(-(ya + ym)));
+    }
+#pragma unroll
+  for (int hh = 0; hh < 7; ++hh)
+#pragma unroll
+    for (int ww = 0; ww < 7; ++ww) {
+      const float v = x[hh * 7 + ww];
+      f[(hh * 7 + ww) * 512] = __float2bfloat16(v * (v * att[hh] * att[7 + ww]));
+    }
+}
+
 }  // namespace ff

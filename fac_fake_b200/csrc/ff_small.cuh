@@ -80,10 +80,11 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// LayerNorm(1024), eps 1e-5, affine (cvit.py:16,20).  One warp per row; fp32 in, bf16 out (next GEMM's A operand).
+// LayerNorm(1024), affine (cvit.py:16,20: eps 1e-5; the LinearNorm of the GGCA variant uses 1e-6).  One warp per row;
+// fp32 in, bf16 out (next GEMM's A operand).
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 __nv_bfloat16* __restrict__ y, int rows) {
+                 __nv_bfloat16* __restrict__ y, int rows, float eps) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -104,7 +105,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
     const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
     q += (a * a + b * b) + (c * c + d * d);
   }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / 1024.0f) + 1e-5f);
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / 1024.0f) + eps);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
   uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * 1024);

@@ -345,3 +345,19 @@ class ResVitKanEngine(CViTEngine):
 
     def _create(self, h) -> int:
         return self._lib.ff_resvitkan_create(C.byref(h), self._device.index, self._max_crops)
+
+
+class CViTGGCAEngine(CViTEngine):
+    """Drop-in for ``cvit_GGCA_ADD_DEConv_RepBn8.CViT`` at inference time
+    (/root/reference/CViT-main/model/cvit_GGCA_ADD_DEConv_RepBn8.py:353-455): the CViT conv plan with DEConv blocks
+    (folded to plain 3x3 kernels at load), one BN-less conv pair, the GGCA gate on the 7x7x512 map and
+    LinearNorm (= LayerNorm eps 1e-6 in eval) in the MLP branches.  Same surface as ``CViTEngine``; bf16 path only.
+    """
+
+    def __init__(self, image_size=224, patch_size=7, num_classes=2, channels=512, dim=1024, depth=6, heads=8,
+                 mlp_dim=2048, *, max_crops: int = 512):
+        super().__init__(image_size, patch_size, num_classes, channels, dim, depth, heads, mlp_dim,
+                         max_crops=max_crops, compute_dtype="bf16")
+
+    def _create(self, h) -> int:
+        return self._lib.ff_cvit_ggca_create(C.byref(h), self._device.index, self._max_crops)

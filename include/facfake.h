@@ -65,6 +65,15 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
  * other entry point below works unchanged on such a handle; ff_cvit_debug_activation steps are
  * 1 = stem + max-pool, 2..5 = layer1..layer4, 6 = channel conv + bn2, 18..25 as for CViT.            */
 int ff_resvitkan_create(ff_cvit_t** out, int device, int max_crops);
+/* The `cvit_GGCA_ADD_DEConv_RepBn8` variant: replaces `CViT(...)` of
+ * model/cvit_GGCA_ADD_DEConv_RepBn8.py:353-455.  Weight keys are that module's state_dict names
+ * (`features1.N.*`, `features2.N.*`, DEConv branches `….conv1_{1..4}.conv.*` / `….conv1_5.*`,
+ * `ggca.shared_conv.*`, `transformer.layers.L.1.fn.norm.norm1.*`; RepBN / schedule buffers and the unused
+ * `Deconv.*` are accepted and ignored).  Every DEConv is folded into one 3x3 kernel at finalize (:337-351),
+ * LinearNorm is its eval() form LayerNorm(eps 1e-6) (:22-47), the gate is x * GGCA(x) (:143-213,447-448).
+ * bf16 path only.  Debug steps: 1..17 = the 17 pooled-plan conv layers (step 9 = features1.27), 26 = the extra
+ * BN-less Conv2d(128,128) features1.26 (between steps 8 and 9), 27 = gated feature map, 18..25 as for CViT. */
+int ff_cvit_ggca_create(ff_cvit_t** out, int device, int max_crops);
 void ff_cvit_destroy(ff_cvit_t* h);
 const char* ff_last_error(const ff_cvit_t* h); /* h may be NULL: last create() error */
 
