@@ -67,6 +67,8 @@ def resvitkan_trunk_work():
 MODELS = {
     "cvit": {"metric": METRIC, "flops_per_crop": FLOPS_PER_CROP, "max_crops": 512,
              "name": "CViT", "baseline_config": "configs[1]"},
+    "ggca": {"metric": "CViT-GGCA-DEConv face-crops/sec", "flops_per_crop": FLOPS_PER_CROP + 2 * 9 * 128 * 128 * 56 * 56,
+             "max_crops": 512, "name": "cvit_GGCA_ADD_DEConv_RepBn8", "baseline_config": "SURVEY 8f-4 (no BASELINE config)"},
     "resvitkan": {"metric": "ResVitKan face-crops/sec", "flops_per_crop": None, "max_crops": 512,
                   "name": "ResVitKan (ResNet-50 + ViT + KAN head)", "baseline_config": "configs[3]"},
 }
@@ -142,6 +144,10 @@ def cpu_baseline(sample_crops: int, repeats: int, model: str = "cvit"):
         from oracle import resvitkan_oracle as R
         sd = W.make_resvitkan_state_dict(0, "default")
         fwd = lambda x: torch.cat([R.forward(x[i:i + 32], sd) for i in range(0, x.shape[0], 32)])   # noqa: E731
+    elif model == "ggca":
+        from oracle import ggca_oracle as G
+        sd = W.make_ggca_state_dict(0, "default")
+        fwd = lambda x: torch.cat([G.forward(x[i:i + 32], sd) for i in range(0, x.shape[0], 32)])   # noqa: E731
     else:
         sd = W.make_state_dict(0, "default")
         fwd = lambda x: O.forward_chunked(x, sd, chunk=32)                                          # noqa: E731
@@ -230,7 +236,7 @@ def main():
         os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
-    from fac_fake_b200 import CViTEngine, ResVitKanEngine, weights as W
+    from fac_fake_b200 import CViTEngine, CViTGGCAEngine, ResVitKanEngine, weights as W
     from fac_fake_b200.sharding import gather_scores
     model = MODELS[args.model]
     rvk = args.model == "resvitkan"
@@ -252,6 +258,8 @@ def main():
     cap = min(model["max_crops"], (n + 31) // 32 * 32)
     if rvk:
         eng = ResVitKanEngine(max_crops=cap).to(dev).load_state_dict(W.make_resvitkan_state_dict(0, "default"))
+    elif args.model == "ggca":
+        eng = CViTGGCAEngine(max_crops=cap).to(dev).load_state_dict(W.make_ggca_state_dict(0, "default"))
     else:
         eng = CViTEngine(max_crops=cap).to(dev).load_state_dict(W.make_state_dict(0, "default"))
     offsets = list(range(0, n + 1, CROPS_PER_VIDEO))
@@ -367,6 +375,7 @@ def main():
         print(json.dumps(out), flush=True)
     elif rank == 0:
         conv_ms, conv_launches = prof["tcgen05_conv"]
+        flops_per_crop = model["flops_per_crop"]
         tc_tflops = (TC_CONV_FLOPS * n * steps) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         peak = peaks["bf16_sustained"]
         roofline = {
@@ -386,15 +395,15 @@ def main():
             "step_share": conv_ms / ms_instr if ms_instr > 0 else None,
             "instrumented_ms_per_step": ms_instr / steps,
             "how": "second pass of the same K steps with a CUDA-event pair around every launch; value/ms_per_step come from the uninstrumented pass",
-            "whole_step_tflops": value / world * FLOPS_PER_CROP / 1e12,
-            "whole_step_frac_of_burst": value / world * FLOPS_PER_CROP / 1e12 / peaks["bf16_burst"],
+            "whole_step_tflops": value / world * flops_per_crop / 1e12,
+            "whole_step_frac_of_burst": value / world * flops_per_crop / 1e12 / peaks["bf16_burst"],
             "by_class_ms_per_step": {k: v[0] / steps for k, v in prof.items()},
         }
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "metric": model["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"CViT bf16 inference, synthetic batch of {n} uint8 face crops 224x224 per GPU "
+            "config": {"workload": f"{model['name']} bf16 inference, synthetic batch of {n} uint8 face crops 224x224 per GPU "
                                    f"({n_videos} videos x {CROPS_PER_VIDEO} crops, slot = i % 32), random-init weights",
                        "crops_per_step_per_gpu": n, "videos_per_step_per_gpu": n_videos,
                        "videos_per_s_30f": value / 30.0, "parallelism": f"video-sharded x{world} (no data-path collective)",
@@ -408,7 +417,7 @@ def main():
             "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(32, 3)
+            out["cpu_baseline"] = cpu_baseline(32, 3, args.model)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
