@@ -180,3 +180,51 @@ def main_ggca():
 
 if __name__ == "__main__" and os.environ.get("FF_GOLDEN_GGCA", "1") == "1":
     main_ggca()
+
+
+def main_blazeface():
+    """tests/golden/blazeface_{weights,golden}.npz: the reference's shipped detector weights / anchors
+    (helpers/blazeface.pth, helpers/anchors.npy) and outputs of the reference BlazeFace class (helpers/blazeface.py) on
+    tiles cut from the reference's sample videos exactly as FaceExtractor._tile_frames does
+    (helpers/helpers_face_extract_1.py:139-204: three min(H,W) windows per landscape frame, cv2 INTER_AREA to 128x128)."""
+    import cv2
+    helpers = os.path.join(REF, "helpers")
+    sys.path.insert(0, helpers)
+    from blazeface import BlazeFace  # noqa: E402  (reference class)
+    net = BlazeFace()
+    net.load_weights(os.path.join(helpers, "blazeface.pth"))
+    net.load_anchors(os.path.join(helpers, "anchors.npy"))
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    sd = {k: v.numpy() for k, v in net.state_dict().items()}
+    np.savez_compressed(os.path.join(out_dir, "blazeface_weights.npz"), anchors=net.anchors.numpy(), **sd)
+    tiles = []
+    for name, frame_ids in (("aajsqyyjni.mp4", (0, 40)), ("sample_2.mp4", (10,)), ("0017_fake.mp4.mp4", (5,))):
+        cap = cv2.VideoCapture(os.path.join(REF, "sample__prediction_data", name))
+        for fid in frame_ids:
+            cap.set(cv2.CAP_PROP_POS_FRAMES, fid)
+            ok, frame = cap.read()
+            if not ok:
+                continue
+            frame = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+            H, W, _ = frame.shape
+            split = min(H, W)
+            x_step = (W - split) // 2
+            for t in range(3 if W > H else 1):
+                crop = frame[0:split, t * x_step:t * x_step + split, :]
+                tiles.append(cv2.resize(crop, (128, 128), interpolation=cv2.INTER_AREA))
+        cap.release()
+    tiles = np.stack(tiles)
+    with torch.no_grad():
+        x = net._preprocess(torch.from_numpy(tiles).permute(0, 3, 1, 2))
+        r, c = net(x)
+    det = net.predict_on_batch(tiles, apply_nms=False)
+    faces = net.nms(det)
+    counts = np.array([len(d) for d in det]), np.array([len(f) for f in faces])
+    np.savez_compressed(os.path.join(out_dir, "blazeface_golden.npz"), tiles=tiles, raw_scores=c.numpy()[..., 0],
+                        raw_boxes=r.numpy().astype(np.float32), det_counts=counts[0], face_counts=counts[1],
+                        faces=np.concatenate([f.numpy() for f in faces]) if sum(counts[1]) else np.zeros((0, 17), np.float32))
+    print("blazeface: tiles", tiles.shape, "detections per tile", counts[0].tolist(), "faces per tile", counts[1].tolist())
+
+
+if __name__ == "__main__" and os.environ.get("FF_GOLDEN_BLAZEFACE", "1") == "1":
+    main_blazeface()
