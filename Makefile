@@ -2,7 +2,7 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
-SRC := fac_fake_b200/csrc/ff_engine.cu
+SRC := fac_fake_b200/csrc/ff_engine.cu fac_fake_b200/csrc/ff_blaze.cu
 HDR := $(wildcard fac_fake_b200/csrc/*.cuh) include/facfake.h
 LIB := fac_fake_b200/libfacfake.so
 

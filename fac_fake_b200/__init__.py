@@ -5,6 +5,7 @@ plus mirrors of the reference's Python seam (``CViT`` module call, ``cvit_predic
 There is no CPU / PyTorch fallback: without the CUDA library the package raises.
 """
 from .engine import CViTEngine, CViTGGCAEngine, EngineError, ResVitKanEngine  # noqa: F401
+from .blazeface import BlazeFaceEngine  # noqa: F401
 from . import weights  # noqa: F401
 
-__all__ = ["CViTEngine", "CViTGGCAEngine", "ResVitKanEngine", "EngineError", "weights"]
+__all__ = ["CViTEngine", "CViTGGCAEngine", "ResVitKanEngine", "BlazeFaceEngine", "EngineError", "weights"]

@@ -32,6 +32,13 @@ SYMBOLS = [
     ("ff_cvit_set_tuning", _i, [_vp, _i, _i]),
     ("ff_cvit_set_profiling", _i, [_vp, _i]),
     ("ff_cvit_get_profile", _i, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
+    ("ff_blazeface_create", _i, [C.POINTER(_vp), _i, _i]),
+    ("ff_blazeface_destroy", None, [_vp]),
+    ("ff_blazeface_last_error", C.c_char_p, [_vp]),
+    ("ff_blazeface_load_weight", _i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i]),
+    ("ff_blazeface_finalize", _i, [_vp]),
+    ("ff_blazeface_predict", _i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    ("ff_blazeface_launch_count", _i64, [_vp]),
 ]
 
 _lib = None

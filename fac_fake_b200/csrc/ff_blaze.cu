@@ -1,0 +1,416 @@
+// ff_blaze.cu — BlazeFace face detector on the GPU: the network and the box decoding of
+// /root/reference/CViT-main/helpers/blazeface.py (:8-43 BlazeBlock, :80-148 forward, :236-303 decode) behind the
+// `ff_blazeface_*` entry points of include/facfake.h.  The blending NMS (:305-358) is data dependent and stays on the
+// host in the mirror class, exactly where the reference runs it.
+//
+// The detector is 30 MFLOP per 128x128 tile and its detections are thresholded (score >= 0.75, IoU > 0.3), so the
+// whole path is fp32 on the CUDA cores with the reference's operation order; the cost that matters is launches:
+// 1 (5x5 stride-2 stem) + 16 (one fused kernel per BlazeBlock: depthwise 3x3 -> pointwise 1x1 -> + max-pooled /
+// channel-padded residual -> ReLU) + 1 (four 1x1 heads, anchor-major) + 1 (decode + sigmoid) per batch of tiles.
+// Activations are NHWC fp32; no tensor cores: K is 24..96 and the tiles are tiny, HBM/L2 traffic and launch count
+// bound it.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/facfake.h"
+
+namespace {
+
+struct BlockPlan { int cin, cout, stride, hw_in; };
+// backbone1.2..12 and backbone2.0..4 (blazeface.py:86-107); hw_in = input spatial size
+const BlockPlan kBlocks[16] = {
+    {24, 24, 1, 64}, {24, 28, 1, 64}, {28, 32, 2, 64}, {32, 36, 1, 32}, {36, 42, 1, 32}, {42, 48, 2, 32},
+    {48, 56, 1, 16}, {56, 64, 1, 16}, {64, 72, 1, 16}, {72, 80, 1, 16}, {80, 88, 1, 16},
+    {88, 96, 2, 16}, {96, 96, 1, 8},  {96, 96, 1, 8},  {96, 96, 1, 8},  {96, 96, 1, 8},
+};
+constexpr int NUM_ANCHORS = 896;
+constexpr size_t ACT_ELEMS = (size_t)64 * 64 * 28;   // largest activation per tile
+
+std::string g_blaze_create_error;
+
+}  // namespace
+
+struct ff_blazeface {
+  int device = 0;
+  int cap = 0;
+  bool finalized = false;
+  std::string err;
+  std::mutex mu;
+  std::map<std::string, std::vector<float>> host_w;
+  std::map<std::string, std::vector<int64_t>> host_shape;
+  std::vector<void*> allocs;
+  float *stem_w = nullptr, *stem_b = nullptr;             // [5][5][3][24] (tap-major, cout fastest), [24]
+  float *dw_w[16] = {}, *dw_b[16] = {};                   // [9][cin], [cin]
+  float *pw_w[16] = {}, *pw_b[16] = {};                   // [cin][cout] (transposed: coalesced over cout), [cout]
+  float *head8_w = nullptr, *head8_b = nullptr;           // [88][34]: 2 classifier + 32 regressor outputs per cell
+  float *head16_w = nullptr, *head16_b = nullptr;         // [96][102]: 6 + 96
+  float* anchors = nullptr;                               // [896][4]
+  float *act_a = nullptr, *act_b = nullptr, *feat8 = nullptr;   // ping-pong activations; 16x16x88 map kept for the heads
+  float *raw_boxes = nullptr, *raw_scores = nullptr;      // [cap][896][16], [cap][896]
+  int64_t launches = 0;
+};
+
+namespace {
+
+int bfail(ff_blazeface* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_blaze_create_error = buf;
+  return code;
+}
+
+#define BZ_CUDA(h, call)                                                                                          \
+  do {                                                                                                            \
+    cudaError_t e_ = (call);                                                                                      \
+    if (e_ != cudaSuccess) return bfail(h, FF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));          \
+  } while (0)
+
+// ---- stem: x/127.5 - 1, zero pad (1,2,1,2) of the PREPROCESSED image, Conv2d(3,24,5,stride 2) + ReLU (:113-116,162-164)
+__global__ void __launch_bounds__(256)
+blaze_stem_kernel(const uint8_t* __restrict__ tiles, const float* __restrict__ w, const float* __restrict__ b,
+                  float* __restrict__ out, int n) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;     // (tile, oy, ox, co), co fastest
+  if (idx >= (size_t)n * 64 * 64 * 24) return;
+  const int co = (int)(idx % 24);
+  size_t t = idx / 24;
+  const int ox = (int)(t % 64); t /= 64;
+  const int oy = (int)(t % 64);
+  const size_t img = t / 64;
+  const uint8_t* src = tiles + img * 128 * 128 * 3;
+  float acc = b[co];
+  for (int kh = 0; kh < 5; ++kh) {
+    const int iy = 2 * oy + kh - 1;
+    if (iy < 0 || iy >= 128) continue;
+    for (int kw = 0; kw < 5; ++kw) {
+      const int ix = 2 * ox + kw - 1;
+      if (ix < 0 || ix >= 128) continue;
+      const uint8_t* px = src + ((size_t)iy * 128 + ix) * 3;
+      const float* wp = w + ((kh * 5 + kw) * 3) * 24 + co;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc = fmaf(__fdiv_rn((float)px[c], 127.5f) - 1.0f, wp[c * 24], acc);
+    }
+  }
+  out[idx] = fmaxf(acc, 0.0f);
+}
+
+// ---- one BlazeBlock (:8-43).  CTA = PIX output pixels of one tile x all channels.
+//   phase 1: depthwise 3x3 (stride 1: pad 1; stride 2: zero pad right/bottom by 2, no other padding) -> smem [PIX][cin]
+//   phase 2: pointwise 1x1 + bias + residual (stride 2: 2x2 max-pool of x; channels >= cin see zeros) -> ReLU
+constexpr int BLAZE_PIX = 32;
+__global__ void __launch_bounds__(256)
+blaze_block_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ dw_w,
+                   const float* __restrict__ dw_b, const float* __restrict__ pw_w, const float* __restrict__ pw_b,
+                   int cin, int cout, int stride, int hw_in) {
+  __shared__ float s_dw[BLAZE_PIX][96 + 1];
+  const int hw_out = hw_in / stride;
+  const int pix0 = blockIdx.x * BLAZE_PIX;
+  const size_t img = blockIdx.y;
+  const float* xin = x + img * (size_t)hw_in * hw_in * cin;
+  for (int i = threadIdx.x; i < BLAZE_PIX * cin; i += blockDim.x) {
+    const int p = i / cin, c = i - p * cin;
+    const int pix = pix0 + p;
+    if (pix >= hw_out * hw_out) continue;
+    const int oy = pix / hw_out, ox = pix - oy * hw_out;
+    float acc = dw_b[c];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int iy = stride == 2 ? 2 * oy + kh : oy + kh - 1;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ix = stride == 2 ? 2 * ox + kw : ox + kw - 1;
+        if (iy >= 0 && iy < hw_in && ix >= 0 && ix < hw_in)
+          acc = fmaf(xin[((size_t)iy * hw_in + ix) * cin + c], dw_w[(kh * 3 + kw) * cin + c], acc);
+      }
+    }
+    s_dw[p][c] = acc;
+  }
+  __syncthreads();
+  float* o = out + img * (size_t)hw_out * hw_out * cout;
+  for (int i = threadIdx.x; i < BLAZE_PIX * cout; i += blockDim.x) {
+    const int p = i / cout, co = i - p * cout;
+    const int pix = pix0 + p;
+    if (pix >= hw_out * hw_out) continue;
+    float acc = pw_b[co];
+    for (int c = 0; c < cin; ++c) acc = fmaf(s_dw[p][c], pw_w[c * cout + co], acc);
+    float res = 0.0f;
+    if (co < cin) {
+      const int oy = pix / hw_out, ox = pix - oy * hw_out;
+      if (stride == 2) {
+        const float* q = xin + ((size_t)(2 * oy) * hw_in + 2 * ox) * cin + co;
+        res = fmaxf(fmaxf(q[0], q[cin]), fmaxf(q[(size_t)hw_in * cin], q[(size_t)hw_in * cin + cin]));
+      } else {
+        res = xin[((size_t)oy * hw_in + ox) * cin + co];
+      }
+    }
+    o[(size_t)pix * cout + co] = fmaxf(acc + res, 0.0f);
+  }
+}
+
+// ---- heads (:118-148): classifier_8 / regressor_8 on the 16x16x88 map, classifier_16 / regressor_16 on 8x8x96,
+// written anchor-major: anchor = cell * A + a (A = 2 resp. 6, the second grid after the first 512 anchors).
+__global__ void __launch_bounds__(256)
+blaze_heads_kernel(const float* __restrict__ f8, const float* __restrict__ f16, const float* __restrict__ w8,
+                   const float* __restrict__ b8, const float* __restrict__ w16, const float* __restrict__ b16,
+                   float* __restrict__ raw_boxes, float* __restrict__ raw_scores) {
+  const size_t img = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int N8 = 256 * 34, N16 = 64 * 102;
+  if (idx >= N8 + N16) return;
+  const bool first = idx < N8;
+  const int j = first ? idx : idx - N8;
+  const int nout = first ? 34 : 102, cin = first ? 88 : 96, na = first ? 2 : 6;
+  const int cell = j / nout, o = j - cell * nout;
+  const float* f = (first ? f8 + img * 256 * 88 : f16 + img * 64 * 96) + (size_t)cell * cin;
+  const float* w = (first ? w8 : w16) + o;
+  float acc = (first ? b8 : b16)[o];
+  for (int c = 0; c < cin; ++c) acc = fmaf(f[c], w[c * nout], acc);
+  const int anchor0 = (first ? 0 : 512) + cell * na;
+  if (o < na) raw_scores[img * NUM_ANCHORS + anchor0 + o] = acc;
+  else {
+    const int r = o - na;                       // regressor channel = a * 16 + k
+    raw_boxes[(img * NUM_ANCHORS + anchor0 + r / 16) * 16 + (r & 15)] = acc;
+  }
+}
+
+// ---- _decode_boxes + clamp / sigmoid (:262-303): one thread per anchor -> [n][896][17]
+__global__ void __launch_bounds__(256)
+blaze_decode_kernel(const float* __restrict__ raw_boxes, const float* __restrict__ raw_scores,
+                    const float* __restrict__ anchors, float* __restrict__ det, int n) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * NUM_ANCHORS) return;
+  const int a = (int)(idx % NUM_ANCHORS);
+  const float ax = anchors[a * 4], ay = anchors[a * 4 + 1], aw = anchors[a * 4 + 2], ah = anchors[a * 4 + 3];
+  const float* r = raw_boxes + idx * 16;
+  float* d = det + idx * 17;
+  const float xc = __fadd_rn(__fmul_rn(__fdiv_rn(r[0], 128.0f), aw), ax);
+  const float yc = __fadd_rn(__fmul_rn(__fdiv_rn(r[1], 128.0f), ah), ay);
+  const float w = __fmul_rn(__fdiv_rn(r[2], 128.0f), aw);
+  const float hh = __fmul_rn(__fdiv_rn(r[3], 128.0f), ah);
+  d[0] = __fsub_rn(yc, __fdiv_rn(hh, 2.0f));
+  d[1] = __fsub_rn(xc, __fdiv_rn(w, 2.0f));
+  d[2] = __fadd_rn(yc, __fdiv_rn(hh, 2.0f));
+  d[3] = __fadd_rn(xc, __fdiv_rn(w, 2.0f));
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    d[4 + 2 * k] = __fadd_rn(__fmul_rn(__fdiv_rn(r[4 + 2 * k], 128.0f), aw), ax);
+    d[5 + 2 * k] = __fadd_rn(__fmul_rn(__fdiv_rn(r[5 + 2 * k], 128.0f), ah), ay);
+  }
+  const float s = fminf(fmaxf(raw_scores[idx], -100.0f), 100.0f);
+  d[16] = 1.0f / (1.0f + expf(-s));
+}
+
+template <typename T>
+int balloc(ff_blazeface* h, T** p, size_t count) {
+  void* q = nullptr;
+  BZ_CUDA(h, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return FF_OK;
+}
+int bupload(ff_blazeface* h, float** p, const std::vector<float>& v) {
+  int rc = balloc(h, p, v.size());
+  if (rc) return rc;
+  BZ_CUDA(h, cudaMemcpy(*p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return FF_OK;
+}
+const std::vector<float>* bget(ff_blazeface* h, const std::string& key, std::initializer_list<int64_t> shape) {
+  auto it = h->host_w.find(key);
+  if (it == h->host_w.end()) { bfail(h, FF_ERR_STATE, "missing weight '%s'", key.c_str()); return nullptr; }
+  const auto& s = h->host_shape[key];
+  if (s.size() != shape.size() || !std::equal(s.begin(), s.end(), shape.begin())) {
+    bfail(h, FF_ERR_SHAPE, "weight '%s' has the wrong shape", key.c_str());
+    return nullptr;
+  }
+  return &it->second;
+}
+
+int bfinalize(ff_blazeface* h) {
+  auto bad = [&]() { return h->err.find("shape") != std::string::npos ? FF_ERR_SHAPE : FF_ERR_STATE; };
+  int rc;
+  {
+    const auto* w = bget(h, "backbone1.0.weight", {24, 3, 5, 5});
+    const auto* b = bget(h, "backbone1.0.bias", {24});
+    if (!w || !b) return bad();
+    std::vector<float> wt(5 * 5 * 3 * 24);
+    for (int co = 0; co < 24; ++co)
+      for (int c = 0; c < 3; ++c)
+        for (int t = 0; t < 25; ++t) wt[(t * 3 + c) * 24 + co] = (*w)[(co * 3 + c) * 25 + t];
+    if ((rc = bupload(h, &h->stem_w, wt))) return rc;
+    if ((rc = bupload(h, &h->stem_b, *b))) return rc;
+  }
+  for (int i = 0; i < 16; ++i) {
+    const BlockPlan& p = kBlocks[i];
+    const std::string key = i < 11 ? "backbone1." + std::to_string(i + 2) : "backbone2." + std::to_string(i - 11);
+    const auto* dw = bget(h, key + ".convs.0.weight", {p.cin, 1, 3, 3});
+    const auto* db = bget(h, key + ".convs.0.bias", {p.cin});
+    const auto* pw = bget(h, key + ".convs.1.weight", {p.cout, p.cin, 1, 1});
+    const auto* pb = bget(h, key + ".convs.1.bias", {p.cout});
+    if (!dw || !db || !pw || !pb) return bad();
+    std::vector<float> dwt(9 * p.cin), pwt((size_t)p.cin * p.cout);
+    for (int c = 0; c < p.cin; ++c)
+      for (int t = 0; t < 9; ++t) dwt[t * p.cin + c] = (*dw)[c * 9 + t];
+    for (int co = 0; co < p.cout; ++co)
+      for (int c = 0; c < p.cin; ++c) pwt[(size_t)c * p.cout + co] = (*pw)[(size_t)co * p.cin + c];
+    if ((rc = bupload(h, &h->dw_w[i], dwt))) return rc;
+    if ((rc = bupload(h, &h->dw_b[i], *db))) return rc;
+    if ((rc = bupload(h, &h->pw_w[i], pwt))) return rc;
+    if ((rc = bupload(h, &h->pw_b[i], *pb))) return rc;
+  }
+  for (int g = 0; g < 2; ++g) {
+    const int cin = g == 0 ? 88 : 96, na = g == 0 ? 2 : 6, nout = na * 17;
+    const std::string sfx = g == 0 ? "_8" : "_16";
+    const auto* cw = bget(h, "classifier" + sfx + ".weight", {na, cin, 1, 1});
+    const auto* cb = bget(h, "classifier" + sfx + ".bias", {na});
+    const auto* rw = bget(h, "regressor" + sfx + ".weight", {na * 16, cin, 1, 1});
+    const auto* rb = bget(h, "regressor" + sfx + ".bias", {na * 16});
+    if (!cw || !cb || !rw || !rb) return bad();
+    std::vector<float> wt((size_t)cin * nout), bt(nout);
+    for (int o = 0; o < nout; ++o) {
+      const bool cls = o < na;
+      bt[o] = cls ? (*cb)[o] : (*rb)[o - na];
+      for (int c = 0; c < cin; ++c) wt[(size_t)c * nout + o] = cls ? (*cw)[(size_t)o * cin + c] : (*rw)[(size_t)(o - na) * cin + c];
+    }
+    if ((rc = bupload(h, g == 0 ? &h->head8_w : &h->head16_w, wt))) return rc;
+    if ((rc = bupload(h, g == 0 ? &h->head8_b : &h->head16_b, bt))) return rc;
+  }
+  {
+    const auto* a = bget(h, "anchors", {NUM_ANCHORS, 4});
+    if (!a) return bad();
+    if ((rc = bupload(h, &h->anchors, *a))) return rc;
+  }
+  h->host_w.clear();
+  h->host_shape.clear();
+  h->finalized = true;
+  return FF_OK;
+}
+
+int bforward(ff_blazeface* h, const uint8_t* tiles, int n, float* det, cudaStream_t st) {
+  {
+    const size_t total = (size_t)n * 64 * 64 * 24;
+    blaze_stem_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tiles, h->stem_w, h->stem_b, h->act_a, n);
+    BZ_CUDA(h, cudaGetLastError());
+    ++h->launches;
+  }
+  float* cur = h->act_a;
+  float* nxt = h->act_b;
+  for (int i = 0; i < 16; ++i) {
+    const BlockPlan& p = kBlocks[i];
+    const int hw_out = p.hw_in / p.stride;
+    float* dst = (i == 10) ? h->feat8 : nxt;          // backbone1 output (16x16x88) feeds both backbone2 and the heads
+    dim3 grid((hw_out * hw_out + BLAZE_PIX - 1) / BLAZE_PIX, n);
+    blaze_block_kernel<<<grid, 256, 0, st>>>(cur, dst, h->dw_w[i], h->dw_b[i], h->pw_w[i], h->pw_b[i], p.cin, p.cout, p.stride, p.hw_in);
+    BZ_CUDA(h, cudaGetLastError());
+    ++h->launches;
+    if (i == 10) cur = h->feat8;
+    else { cur = dst; nxt = (dst == h->act_a) ? h->act_b : h->act_a; }
+  }
+  {
+    dim3 grid((256 * 34 + 64 * 102 + 255) / 256, n);
+    blaze_heads_kernel<<<grid, 256, 0, st>>>(h->feat8, cur, h->head8_w, h->head8_b, h->head16_w, h->head16_b, h->raw_boxes, h->raw_scores);
+    BZ_CUDA(h, cudaGetLastError());
+    const size_t total = (size_t)n * NUM_ANCHORS;
+    blaze_decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->raw_boxes, h->raw_scores, h->anchors, det, n);
+    BZ_CUDA(h, cudaGetLastError());
+    h->launches += 2;
+  }
+  return FF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ff_blazeface_create(ff_blazeface_t** out, int device, int max_tiles) {
+  if (!out || max_tiles <= 0) return bfail(nullptr, FF_ERR_BAD_ARG, "ff_blazeface_create: bad arguments");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return bfail(nullptr, FF_ERR_CUDA, "no CUDA device (%s): libfacfake has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return bfail(nullptr, FF_ERR_BAD_ARG, "device %d out of range (%d devices)", device, ndev);
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bfail(nullptr, FF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  ff_blazeface* h = new ff_blazeface();
+  h->device = device;
+  h->cap = max_tiles;
+  int rc = FF_OK;
+  do {
+    if ((rc = balloc(h, &h->act_a, (size_t)h->cap * ACT_ELEMS))) break;
+    if ((rc = balloc(h, &h->act_b, (size_t)h->cap * ACT_ELEMS))) break;
+    if ((rc = balloc(h, &h->feat8, (size_t)h->cap * 16 * 16 * 88))) break;
+    if ((rc = balloc(h, &h->raw_boxes, (size_t)h->cap * NUM_ANCHORS * 16))) break;
+    if ((rc = balloc(h, &h->raw_scores, (size_t)h->cap * NUM_ANCHORS))) break;
+  } while (0);
+  if (rc != FF_OK) {
+    g_blaze_create_error = h->err;
+    ff_blazeface_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return FF_OK;
+}
+
+void ff_blazeface_destroy(ff_blazeface_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+const char* ff_blazeface_last_error(const ff_blazeface_t* h) { return h ? h->err.c_str() : g_blaze_create_error.c_str(); }
+
+int ff_blazeface_load_weight(ff_blazeface_t* h, const char* key, const float* host_fp32, const int64_t* shape, int ndim) {
+  if (!h || !key || !host_fp32 || ndim < 0 || ndim > 8 || (ndim > 0 && !shape)) return bfail(h, FF_ERR_BAD_ARG, "ff_blazeface_load_weight: bad arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->finalized) return bfail(h, FF_ERR_STATE, "weights are already finalized");
+  size_t count = 1;
+  std::vector<int64_t> s(shape, shape + ndim);
+  for (int64_t d : s) {
+    if (d < 0) return bfail(h, FF_ERR_SHAPE, "negative dimension in '%s'", key);
+    count *= (size_t)d;
+  }
+  h->host_w[key].assign(host_fp32, host_fp32 + count);
+  h->host_shape[key] = s;
+  return FF_OK;
+}
+
+int ff_blazeface_finalize(ff_blazeface_t* h) {
+  if (!h) return FF_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->finalized) return FF_OK;
+  BZ_CUDA(h, cudaSetDevice(h->device));
+  return bfinalize(h);
+}
+
+int ff_blazeface_predict(ff_blazeface_t* h, const uint8_t* tiles, int n, float* detections, float* raw_boxes,
+                         float* raw_scores, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!tiles || !detections))) return bfail(h, FF_ERR_BAD_ARG, "ff_blazeface_predict: bad arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->finalized) return bfail(h, FF_ERR_STATE, "ff_blazeface_finalize() has not been called");
+  BZ_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int s0 = 0; s0 < n; s0 += h->cap) {
+    const int ns = std::min(h->cap, n - s0);
+    int rc = bforward(h, tiles + (size_t)s0 * 128 * 128 * 3, ns, detections + (size_t)s0 * NUM_ANCHORS * 17, st);
+    if (rc) return rc;
+    if (raw_boxes) BZ_CUDA(h, cudaMemcpyAsync(raw_boxes + (size_t)s0 * NUM_ANCHORS * 16, h->raw_boxes, (size_t)ns * NUM_ANCHORS * 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (raw_scores) BZ_CUDA(h, cudaMemcpyAsync(raw_scores + (size_t)s0 * NUM_ANCHORS, h->raw_scores, (size_t)ns * NUM_ANCHORS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return FF_OK;
+}
+
+int64_t ff_blazeface_launch_count(const ff_blazeface_t* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -151,6 +151,28 @@ int ff_cvit_get_profile(ff_cvit_t* h, double* ms_by_slot /*[21]*/, int64_t* laun
 /* Tunables (0 keeps the current value): crops per stage-1/2 sub-pass (L2 residency).            */
 int ff_cvit_set_tuning(ff_cvit_t* h, int stage12_sub_batch, int use_cuda_graph);
 
+/* ---- BlazeFace face detector -------------------------------------------------------------
+ * Replaces the `facedet` object the reference builds in cvit_prediction.py:27-33 (`BlazeFace().to(device)`,
+ * `load_weights`, `load_anchors`; helpers/blazeface.py) for its network + box decoding:
+ * `BlazeFace.predict_on_batch(x, apply_nms=False)` (:182-223) = `_preprocess` (:162), `forward` (:109-148),
+ * `_tensors_to_detections` up to the score mask (:236-303).  The data-dependent part — the `>= 0.75` mask and the
+ * blending NMS (:225-234,305-358) — is run by the caller on the dense result, as the reference runs it on the host.
+ *   load_weight   one call per entry of blazeface.pth's state_dict (reference key names, HOST fp32) plus the
+ *                 key "anchors" with the [896,4] array of anchors.npy
+ *   predict       tiles: DEVICE uint8 NHWC [n,128,128,3];  detections: DEVICE fp32 [n,896,17] =
+ *                 (ymin, xmin, ymax, xmax, 6 x (kx, ky), sigmoid(clamp(score, +-100))) for every anchor;
+ *                 raw_boxes [n,896,16] / raw_scores [n,896] (DEVICE, optional, may be NULL) are the network outputs.
+ * fp32 CUDA-core path (the detector is 30 MFLOP per tile and its outputs are thresholded).                    */
+typedef struct ff_blazeface ff_blazeface_t;
+int ff_blazeface_create(ff_blazeface_t** out, int device, int max_tiles);
+void ff_blazeface_destroy(ff_blazeface_t* h);
+const char* ff_blazeface_last_error(const ff_blazeface_t* h); /* h may be NULL: last create() error */
+int ff_blazeface_load_weight(ff_blazeface_t* h, const char* key, const float* host_fp32, const int64_t* shape, int ndim);
+int ff_blazeface_finalize(ff_blazeface_t* h);
+int ff_blazeface_predict(ff_blazeface_t* h, const uint8_t* tiles, int n, float* detections, float* raw_boxes,
+                         float* raw_scores, void* stream);
+int64_t ff_blazeface_launch_count(const ff_blazeface_t* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,3 +79,25 @@ def test_gather_scores_world2_gloo(n_videos):
     want = [v * 0.5 for v in range(n_videos)]
     for _, full in got:
         assert full == want
+
+
+def test_blazeface_host_nms_matches_oracle():
+    """The product's blending NMS (host side of BlazeFaceEngine) against the oracle restatement, random boxes."""
+    from oracle import blazeface_oracle as B
+    from fac_fake_b200.blazeface import BlazeFaceEngine
+    eng = BlazeFaceEngine.__new__(BlazeFaceEngine)           # host logic only: no library / device needed
+    eng.min_suppression_threshold = 0.3
+    g = torch.Generator().manual_seed(0)
+    for trial in range(100):
+        k = int(torch.randint(0, 12, (1,), generator=g))
+        c = torch.rand(k, 2, generator=g) * 0.6
+        s = torch.rand(k, 2, generator=g) * 0.3 + 0.02
+        det = torch.zeros(k, 17)
+        det[:, 0:2], det[:, 2:4] = c, c + s
+        det[:, 4:16] = torch.rand(k, 12, generator=g)
+        det[:, 16] = torch.rand(k, generator=g) * 0.25 + 0.75
+        a, b = B.weighted_nms(det), eng._weighted_non_max_suppression(det)
+        assert len(a) == len(b), trial
+        for x, y in zip(a, b):
+            assert torch.allclose(x, y, atol=1e-6), trial
+    assert eng.nms([torch.zeros((0, 17))])[0].shape == (0, 17)
