@@ -148,8 +148,12 @@ class BlazeFaceEngine:
 
     def predict_on_batch(self, x, apply_nms: bool = True) -> List[torch.Tensor]:
         """blazeface.py:182-223: list of (num_detections, 17) tensors, one per image."""
-        dense = self.predict_dense(x).cpu()
-        detections = [d[d[:, 16] >= self.min_score_thresh] for d in dense]
+        dense = self.predict_dense(x)
+        # score mask on the device (plumbing, like the reference's boolean indexing): only the survivors cross PCIe
+        img, anchor = torch.nonzero(dense[..., 16] >= self.min_score_thresh, as_tuple=True)
+        kept = dense[img, anchor].cpu()
+        counts = torch.bincount(img, minlength=dense.shape[0]).cpu().tolist()
+        detections = list(torch.split(kept, counts))
         return self.nms(detections) if apply_nms else detections
 
     def nms(self, detections: List[torch.Tensor]) -> List[torch.Tensor]:

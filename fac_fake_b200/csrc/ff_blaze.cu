@@ -108,53 +108,69 @@ blaze_stem_kernel(const uint8_t* __restrict__ tiles, const float* __restrict__ w
 // ---- one BlazeBlock (:8-43).  CTA = PIX output pixels of one tile x all channels.
 //   phase 1: depthwise 3x3 (stride 1: pad 1; stride 2: zero pad right/bottom by 2, no other padding) -> smem [PIX][cin]
 //   phase 2: pointwise 1x1 + bias + residual (stride 2: 2x2 max-pool of x; channels >= cin see zeros) -> ReLU
-constexpr int BLAZE_PIX = 32;
+constexpr int BLAZE_PIX = 64, BLAZE_PG = 8;       // pixels per CTA; pixels per thread in the pointwise phase
 __global__ void __launch_bounds__(256)
 blaze_block_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ dw_w,
                    const float* __restrict__ dw_b, const float* __restrict__ pw_w, const float* __restrict__ pw_b,
                    int cin, int cout, int stride, int hw_in) {
-  __shared__ float s_dw[BLAZE_PIX][96 + 1];
+  __shared__ float s_dw[96][BLAZE_PIX + 1];         // [channel][pixel]: the pointwise phase reads 8 consecutive pixels
   const int hw_out = hw_in / stride;
+  const int npix = hw_out * hw_out;
   const int pix0 = blockIdx.x * BLAZE_PIX;
   const size_t img = blockIdx.y;
   const float* xin = x + img * (size_t)hw_in * hw_in * cin;
   for (int i = threadIdx.x; i < BLAZE_PIX * cin; i += blockDim.x) {
-    const int p = i / cin, c = i - p * cin;
+    const int p = i / cin, c = i - p * cin;         // c fastest: coalesced reads of the NHWC input
     const int pix = pix0 + p;
-    if (pix >= hw_out * hw_out) continue;
-    const int oy = pix / hw_out, ox = pix - oy * hw_out;
-    float acc = dw_b[c];
+    float acc = 0.0f;
+    if (pix < npix) {
+      const int oy = pix / hw_out, ox = pix - oy * hw_out;
+      acc = dw_b[c];
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int iy = stride == 2 ? 2 * oy + kh : oy + kh - 1;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int iy = stride == 2 ? 2 * oy + kh : oy + kh - 1;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int ix = stride == 2 ? 2 * ox + kw : ox + kw - 1;
-        if (iy >= 0 && iy < hw_in && ix >= 0 && ix < hw_in)
-          acc = fmaf(xin[((size_t)iy * hw_in + ix) * cin + c], dw_w[(kh * 3 + kw) * cin + c], acc);
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ix = stride == 2 ? 2 * ox + kw : ox + kw - 1;
+          if (iy >= 0 && iy < hw_in && ix >= 0 && ix < hw_in)
+            acc = fmaf(xin[((size_t)iy * hw_in + ix) * cin + c], dw_w[(kh * 3 + kw) * cin + c], acc);
+        }
       }
     }
-    s_dw[p][c] = acc;
+    s_dw[c][p] = acc;
   }
   __syncthreads();
-  float* o = out + img * (size_t)hw_out * hw_out * cout;
-  for (int i = threadIdx.x; i < BLAZE_PIX * cout; i += blockDim.x) {
-    const int p = i / cout, co = i - p * cout;
-    const int pix = pix0 + p;
-    if (pix >= hw_out * hw_out) continue;
-    float acc = pw_b[co];
-    for (int c = 0; c < cin; ++c) acc = fmaf(s_dw[p][c], pw_w[c * cout + co], acc);
-    float res = 0.0f;
-    if (co < cin) {
-      const int oy = pix / hw_out, ox = pix - oy * hw_out;
-      if (stride == 2) {
-        const float* q = xin + ((size_t)(2 * oy) * hw_in + 2 * ox) * cin + co;
-        res = fmaxf(fmaxf(q[0], q[cin]), fmaxf(q[(size_t)hw_in * cin], q[(size_t)hw_in * cin + cin]));
-      } else {
-        res = xin[((size_t)oy * hw_in + ox) * cin + co];
-      }
+  float* o = out + img * (size_t)npix * cout;
+  // item = (pixel group of 8, output channel), channel fastest: the weight load is coalesced and reused for 8 pixels,
+  // the 8 activations of a channel are a shared-memory broadcast
+  for (int i = threadIdx.x; i < (BLAZE_PIX / BLAZE_PG) * cout; i += blockDim.x) {
+    const int pg = i / cout, co = i - pg * cout;
+    float acc[BLAZE_PG];
+    const float bias = pw_b[co];
+#pragma unroll
+    for (int k = 0; k < BLAZE_PG; ++k) acc[k] = bias;
+    for (int c = 0; c < cin; ++c) {
+      const float wv = pw_w[c * cout + co];
+      const float* a = &s_dw[c][pg * BLAZE_PG];
+#pragma unroll
+      for (int k = 0; k < BLAZE_PG; ++k) acc[k] = fmaf(a[k], wv, acc[k]);
     }
-    o[(size_t)pix * cout + co] = fmaxf(acc + res, 0.0f);
+#pragma unroll
+    for (int k = 0; k < BLAZE_PG; ++k) {
+      const int pix = pix0 + pg * BLAZE_PG + k;
+      if (pix >= npix) continue;
+      float res = 0.0f;
+      if (co < cin) {
+        const int oy = pix / hw_out, ox = pix - oy * hw_out;
+        if (stride == 2) {
+          const float* q = xin + ((size_t)(2 * oy) * hw_in + 2 * ox) * cin + co;
+          res = fmaxf(fmaxf(q[0], q[cin]), fmaxf(q[(size_t)hw_in * cin], q[(size_t)hw_in * cin + cin]));
+        } else {
+          res = xin[((size_t)oy * hw_in + ox) * cin + co];
+        }
+      }
+      o[(size_t)pix * cout + co] = fmaxf(acc[k] + res, 0.0f);
+    }
   }
 }
 
