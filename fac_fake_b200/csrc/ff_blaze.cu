@@ -78,42 +78,67 @@ int bfail(ff_blazeface* h, int code, const char* fmt, ...) {
   } while (0)
 
 // ---- stem: x/127.5 - 1, zero pad (1,2,1,2) of the PREPROCESSED image, Conv2d(3,24,5,stride 2) + ReLU (:113-116,162-164)
+// CTA = 16x16 output pixels of one tile: the 35x35x3 input patch is preprocessed once into shared memory (zero =
+// padding), the 75x24 filter sits in shared memory too; one thread = one pixel x all 24 output channels.
 __global__ void __launch_bounds__(256)
 blaze_stem_kernel(const uint8_t* __restrict__ tiles, const float* __restrict__ w, const float* __restrict__ b,
                   float* __restrict__ out, int n) {
-  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;     // (tile, oy, ox, co), co fastest
-  if (idx >= (size_t)n * 64 * 64 * 24) return;
-  const int co = (int)(idx % 24);
-  size_t t = idx / 24;
-  const int ox = (int)(t % 64); t /= 64;
-  const int oy = (int)(t % 64);
-  const size_t img = t / 64;
+  __shared__ float s_in[35 * 35 * 3];
+  __shared__ __align__(16) float s_w[75 * 24];
+  const size_t img = blockIdx.z;
+  const int ty0 = blockIdx.y * 16, tx0 = blockIdx.x * 16;
   const uint8_t* src = tiles + img * 128 * 128 * 3;
-  float acc = b[co];
-  for (int kh = 0; kh < 5; ++kh) {
-    const int iy = 2 * oy + kh - 1;
-    if (iy < 0 || iy >= 128) continue;
-    for (int kw = 0; kw < 5; ++kw) {
-      const int ix = 2 * ox + kw - 1;
-      if (ix < 0 || ix >= 128) continue;
-      const uint8_t* px = src + ((size_t)iy * 128 + ix) * 3;
-      const float* wp = w + ((kh * 5 + kw) * 3) * 24 + co;
+  for (int i = threadIdx.x; i < 75 * 24; i += 256) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < 35 * 35 * 3; i += 256) {
+    const int c = i % 3, px = (i / 3) % 35, py = i / (3 * 35);
+    const int iy = 2 * ty0 + py - 1, ix = 2 * tx0 + px - 1;
+    float v = 0.0f;
+    if (iy >= 0 && iy < 128 && ix >= 0 && ix < 128) v = __fdiv_rn((float)src[((size_t)iy * 128 + ix) * 3 + c], 127.5f) - 1.0f;
+    s_in[i] = v;
+  }
+  __syncthreads();
+  const int ly = threadIdx.x >> 4, lx = threadIdx.x & 15;
+  float acc[24];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) acc = fmaf(__fdiv_rn((float)px[c], 127.5f) - 1.0f, wp[c * 24], acc);
+  for (int co = 0; co < 24; ++co) acc[co] = b[co];
+  for (int kh = 0; kh < 5; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < 5; ++kw) {
+      const float* ip = &s_in[((2 * ly + kh) * 35 + 2 * lx + kw) * 3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = ip[c];
+        const float4* wp = reinterpret_cast<const float4*>(&s_w[((kh * 5 + kw) * 3 + c) * 24]);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const float4 w4 = wp[q];
+          acc[4 * q] = fmaf(v, w4.x, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+        }
+      }
     }
   }
-  out[idx] = fmaxf(acc, 0.0f);
+  float4* o = reinterpret_cast<float4*>(out + ((img * 64 + ty0 + ly) * 64 + tx0 + lx) * 24);
+#pragma unroll
+  for (int q = 0; q < 6; ++q)
+    o[q] = make_float4(fmaxf(acc[4 * q], 0.0f), fmaxf(acc[4 * q + 1], 0.0f), fmaxf(acc[4 * q + 2], 0.0f), fmaxf(acc[4 * q + 3], 0.0f));
 }
 
 // ---- one BlazeBlock (:8-43).  CTA = PIX output pixels of one tile x all channels.
 //   phase 1: depthwise 3x3 (stride 1: pad 1; stride 2: zero pad right/bottom by 2, no other padding) -> smem [PIX][cin]
 //   phase 2: pointwise 1x1 + bias + residual (stride 2: 2x2 max-pool of x; channels >= cin see zeros) -> ReLU
-constexpr int BLAZE_PIX = 64, BLAZE_PG = 8;       // pixels per CTA; pixels per thread in the pointwise phase
+constexpr int BLAZE_PG = 8;                        // pixels per thread in the pointwise phase
+// pixels per CTA: large maps have few channels, so the [cin][PIX+1] staging stays under 32 KB everywhere
+inline int blaze_pix(int hw_out) { return hw_out >= 64 ? 256 : (hw_out >= 32 ? 128 : 64); }
+template <int BLAZE_PIX>
 __global__ void __launch_bounds__(256)
 blaze_block_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ dw_w,
                    const float* __restrict__ dw_b, const float* __restrict__ pw_w, const float* __restrict__ pw_b,
                    int cin, int cout, int stride, int hw_in) {
-  __shared__ float s_dw[96][BLAZE_PIX + 1];         // [channel][pixel]: the pointwise phase reads 8 consecutive pixels
+  extern __shared__ float s_dw_raw[];               // [cin][BLAZE_PIX + 1]: the pointwise phase reads 8 consecutive pixels
+  float (*s_dw)[BLAZE_PIX + 1] = reinterpret_cast<float (*)[BLAZE_PIX + 1]>(s_dw_raw);
   const int hw_out = hw_in / stride;
   const int npix = hw_out * hw_out;
   const int pix0 = blockIdx.x * BLAZE_PIX;
@@ -314,8 +339,7 @@ int bfinalize(ff_blazeface* h) {
 
 int bforward(ff_blazeface* h, const uint8_t* tiles, int n, float* det, cudaStream_t st) {
   {
-    const size_t total = (size_t)n * 64 * 64 * 24;
-    blaze_stem_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tiles, h->stem_w, h->stem_b, h->act_a, n);
+    blaze_stem_kernel<<<dim3(4, 4, n), 256, 0, st>>>(tiles, h->stem_w, h->stem_b, h->act_a, n);
     BZ_CUDA(h, cudaGetLastError());
     ++h->launches;
   }
@@ -325,8 +349,12 @@ int bforward(ff_blazeface* h, const uint8_t* tiles, int n, float* det, cudaStrea
     const BlockPlan& p = kBlocks[i];
     const int hw_out = p.hw_in / p.stride;
     float* dst = (i == 10) ? h->feat8 : nxt;          // backbone1 output (16x16x88) feeds both backbone2 and the heads
-    dim3 grid((hw_out * hw_out + BLAZE_PIX - 1) / BLAZE_PIX, n);
-    blaze_block_kernel<<<grid, 256, 0, st>>>(cur, dst, h->dw_w[i], h->dw_b[i], h->pw_w[i], h->pw_b[i], p.cin, p.cout, p.stride, p.hw_in);
+    const int pix = blaze_pix(hw_out);
+    dim3 grid((hw_out * hw_out + pix - 1) / pix, n);
+    const size_t smem = (size_t)p.cin * (pix + 1) * sizeof(float);
+    if (pix == 256) blaze_block_kernel<256><<<grid, 256, smem, st>>>(cur, dst, h->dw_w[i], h->dw_b[i], h->pw_w[i], h->pw_b[i], p.cin, p.cout, p.stride, p.hw_in);
+    else if (pix == 128) blaze_block_kernel<128><<<grid, 256, smem, st>>>(cur, dst, h->dw_w[i], h->dw_b[i], h->pw_w[i], h->pw_b[i], p.cin, p.cout, p.stride, p.hw_in);
+    else blaze_block_kernel<64><<<grid, 256, smem, st>>>(cur, dst, h->dw_w[i], h->dw_b[i], h->pw_w[i], h->pw_b[i], p.cin, p.cout, p.stride, p.hw_in);
     BZ_CUDA(h, cudaGetLastError());
     ++h->launches;
     if (i == 10) cur = h->feat8;

@@ -79,7 +79,7 @@ def main():
     print(json.dumps({
         "metric": "BlazeFace tiles/sec", "value": args.tiles / ms * 1e3, "unit": "tiles/s", "ms_per_step": ms, "tiles_per_step": args.tiles,
         "gpu_launches_per_step": int(launches), "dtype": "f32", "faces_found": int(sum(len(f) for f in faces)),
-        "e2e": {"value": args.tiles / e2e_s, "unit": "tiles/s", "what": "pinned host uint8 tiles -> H2D -> network+decode -> D2H dense [n,896,17] -> host mask + blending NMS"},
+        "e2e": {"value": args.tiles / e2e_s, "unit": "tiles/s", "what": "pinned host uint8 tiles -> H2D -> network+decode -> score mask on the device -> D2H of the survivors -> host blending NMS"},
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                      "algorithmic_bytes_per_tile": by, "flops_per_tile": fl, "gflops": fl * args.tiles / (ms * 1e-3) / 1e9},
         "cpu_baseline": {"value": len(sample) / cpu_s, "unit": "tiles/s", "cores": os.cpu_count(), "kind": "port",
