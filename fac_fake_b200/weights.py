@@ -255,3 +255,78 @@ def make_ggca_state_dict(seed: int = 0, variant: str = "default") -> "OrderedDic
     _linear(gen, sd, "mlp_head.0", MLP_DIM, DIM)
     _linear(gen, sd, "mlp_head.2", NUM_CLASSES, MLP_DIM)
     return sd
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# S3D (/root/reference/sx_exp_deepfakedetect-master/S3D/model.py)
+S3D_MIXED = {
+    "3b": (192, 64, (96, 128), (16, 32), 32), "3c": (256, 128, (128, 192), (32, 96), 64),
+    "4b": (480, 192, (96, 208), (16, 48), 64), "4c": (512, 160, (112, 224), (24, 64), 64),
+    "4d": (512, 128, (128, 256), (24, 64), 64), "4e": (512, 112, (144, 288), (32, 64), 64),
+    "4f": (528, 256, (160, 320), (32, 128), 128), "5b": (832, 256, (160, 320), (32, 128), 128),
+    "5c": (832, 384, (192, 384), (48, 128), 128),
+}
+S3D_BASE_MIXED = {5: "3b", 6: "3c", 8: "4b", 9: "4c", 10: "4d", 11: "4e", 12: "4f", 14: "5b", 15: "5c"}
+
+
+def _bn3(gen, sd, name, c, variant):
+    if variant == "bn":
+        sd[name + ".weight"] = torch.rand((c,), generator=gen) * 0.5 + 0.75
+        sd[name + ".bias"] = torch.randn((c,), generator=gen) * 0.1
+        sd[name + ".running_mean"] = torch.randn((c,), generator=gen) * 0.1
+        sd[name + ".running_var"] = torch.rand((c,), generator=gen) * 0.5 + 0.75
+    else:
+        sd[name + ".weight"] = torch.ones(c)
+        sd[name + ".bias"] = torch.zeros(c)
+        sd[name + ".running_mean"] = torch.zeros(c)
+        sd[name + ".running_var"] = torch.ones(c)
+    sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+
+def _he3(gen, shape, gain=1.0):
+    fan_in = shape[1] * shape[2] * shape[3] * shape[4]
+    return torch.randn(shape, generator=gen) * gain * math.sqrt(2.0 / fan_in)
+
+
+def _s3d_basic(gen, sd, p, cin, cout, variant, gain=1.0):
+    sd[p + ".conv.weight"] = _he3(gen, (cout, cin, 1, 1, 1), gain)
+    _bn3(gen, sd, p + ".bn", cout, variant)
+
+
+def _s3d_sep(gen, sd, p, cin, cout, k, variant, gain=1.0):
+    sd[p + ".conv_s.weight"] = _he3(gen, (cout, cin, 1, k, k), gain)
+    _bn3(gen, sd, p + ".bn_s", cout, variant)
+    sd[p + ".conv_t.weight"] = _he3(gen, (cout, cout, k, 1, 1))
+    _bn3(gen, sd, p + ".bn_t", cout, variant)
+
+
+def make_s3d_state_dict(seed: int = 0, variant: str = "default", num_class: int = 1) -> "OrderedDict[str, torch.Tensor]":
+    """state_dict of the reference `S3D(num_class, 'no')` (model.py:6-48), key names as in the reference (incl. the
+    always-constructed, unused-without-SRM `SRM.hpf.weight`)."""
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(5000011 * seed + 53)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    sd["SRM.hpf.weight"] = torch.randn((30, 3, 1, 5, 5), generator=gen) * 0.1
+    # the input is raw 0..255 pixels: scale the first kernel so that activations are O(1) after the stem
+    _s3d_sep(gen, sd, "base.0", 3, 64, 7, variant, gain=1.0 / 128.0)
+    _s3d_basic(gen, sd, "base.2", 64, 64, variant)
+    _s3d_sep(gen, sd, "base.3", 64, 192, 3, variant)
+    for idx, name in S3D_BASE_MIXED.items():
+        cin, b0, (m1, o1), (m2, o2), b3 = S3D_MIXED[name]
+        p = f"base.{idx}"
+        _s3d_basic(gen, sd, p + ".branch0.0", cin, b0, variant)
+        _s3d_basic(gen, sd, p + ".branch1.0", cin, m1, variant)
+        _s3d_sep(gen, sd, p + ".branch1.1", m1, o1, 3, variant)
+        _s3d_basic(gen, sd, p + ".branch2.0", cin, m2, variant)
+        _s3d_sep(gen, sd, p + ".branch2.1", m2, o2, 3, variant)
+        _s3d_basic(gen, sd, p + ".branch3.1", cin, b3, variant)
+    sd["fc.0.weight"] = torch.randn((num_class, 1024, 1, 1, 1), generator=gen) * (1.0 / 32.0)
+    sd["fc.0.bias"] = torch.randn((num_class,), generator=gen) * 0.1
+    return sd
+
+
+def synthetic_clips(b: int, t: int, seed: int = 0, hw: int = 224) -> torch.Tensor:
+    """uint8 [b,T,hw,hw,3] uniform clips (BGR, frame-major NHWC: the layout frames come out of the decoder in)."""
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(104729 * seed + 7)
+    return torch.randint(0, 256, (b, t, hw, hw, 3), generator=gen, dtype=torch.uint8)

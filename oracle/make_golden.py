@@ -228,3 +228,43 @@ def main_blazeface():
 
 if __name__ == "__main__" and os.environ.get("FF_GOLDEN_BLAZEFACE", "1") == "1":
     main_blazeface()
+
+
+def load_reference_s3d_class():
+    s3d_dir = os.path.join(os.path.dirname(REF), "sx_exp_deepfakedetect-master", "S3D")
+    if not os.path.isdir(s3d_dir):
+        s3d_dir = "/root/reference/sx_exp_deepfakedetect-master/S3D"
+    sys.path.insert(0, s3d_dir)
+    import importlib
+    return importlib.import_module("model").S3D
+
+
+def clips_to_reference_input(clips_u8):
+    """uint8 [b,T,H,W,3] -> float [b,3,T,H,W] raw 0..255 (S3D-test.py:94-96)."""
+    return clips_u8.permute(0, 4, 1, 2, 3).contiguous().float()
+
+
+def main_s3d():
+    """tests/golden/s3d_{default,bn}.npz from the reference S3D class (S3D/model.py), 2 clips x 16 frames x 224x224."""
+    from oracle import s3d_oracle as S  # noqa: E402
+    S3D = load_reference_s3d_class()
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    for variant in ("default", "bn"):
+        sd = W.make_s3d_state_dict(0, variant)
+        model = S3D(1, "no").eval()
+        model.load_state_dict(sd, strict=True)
+        x = clips_to_reference_input(W.synthetic_clips(2, 16, seed=4))
+        with torch.no_grad():
+            logits = model(x)
+            stats = []
+            h = x
+            for i, m in enumerate(model.base):
+                h = m(h)
+                stats.append([h.double().mean().item(), h.double().abs().mean().item(), h.double().pow(2).mean().sqrt().item()])
+        np.savez_compressed(os.path.join(out_dir, f"s3d_{variant}.npz"), logits=logits.numpy(), layer_stats=np.array(stats),
+                            feat_sample=h[0, :32, 0].numpy().astype(np.float32), seed_weights=0, seed_clips=4, b=2, t=16)
+        print("s3d", variant, "logits", logits.flatten().tolist(), "last stats", stats[-1])
+
+
+if __name__ == "__main__" and os.environ.get("FF_GOLDEN_S3D", "1") == "1":
+    main_s3d()
