@@ -38,7 +38,7 @@ def test_shapes_and_time_reduction():
     taps = {}
     y = S.forward(x, sd, taps)
     assert y.shape == (1, 1)
-    assert taps[0].shape == (1, 64, 16, 32, 32) and taps[7].shape[2] == 8 and taps[13].shape == (1, 832, 4, 1, 1)
+    assert taps[0].shape == (1, 64, 16, 32, 32) and taps[7].shape[2] == 8 and taps[13].shape == (1, 832, 4, 2, 2)
     assert abs(S.video_score(torch.tensor([0.0, 0.0])) - 0.5) < 1e-12
 
 
