@@ -39,6 +39,14 @@ SYMBOLS = [
     ("ff_blazeface_finalize", _i, [_vp]),
     ("ff_blazeface_predict", _i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     ("ff_blazeface_launch_count", _i64, [_vp]),
+    ("ff_s3d_create", _i, [C.POINTER(_vp), _i, _i, _i, _i]),
+    ("ff_s3d_destroy", None, [_vp]),
+    ("ff_s3d_last_error", C.c_char_p, [_vp]),
+    ("ff_s3d_load_weight", _i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i]),
+    ("ff_s3d_finalize", _i, [_vp]),
+    ("ff_s3d_forward", _i, [_vp, _vp, _i, _i, _vp, _vp]),
+    ("ff_s3d_debug_activation", _i64, [_vp, _vp, _i, _i, _i, _vp, _i64, _vp]),
+    ("ff_s3d_launch_count", _i64, [_vp]),
 ]
 
 _lib = None

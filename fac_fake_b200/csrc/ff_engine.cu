@@ -1942,3 +1942,6 @@ int ff_cvit_set_tuning(ff_cvit_t* h, int stage12_sub_batch, int use_cuda_graph) 
 }
 
 }  // extern "C"
+
+// ================================================================================================ S3D
+#include "ff_s3d.cuh"

@@ -173,6 +173,27 @@ int ff_blazeface_predict(ff_blazeface_t* h, const uint8_t* tiles, int n, float* 
                          float* raw_scores, void* stream);
 int64_t ff_blazeface_launch_count(const ff_blazeface_t* h);
 
+/* ---- S3D clip classifier ------------------------------------------------------------------
+ * Replaces `S3D(num_class, 'no')` + `load_state_dict` + `model(video_faces)` of
+ * sx_exp_deepfakedetect-master/S3D/S3D-test.py:210-212,199-205,267-272 (S3D/model.py:6-342).  Weight keys are that
+ * module's state_dict names (`base.N...`, `fc.0.*`; `SRM.hpf.weight` and `num_batches_tracked` are accepted and
+ * ignored: the SRM front-end is not implemented).  Clips are 224x224, `frames_per_clip` in 16..71.
+ *   forward   x: DEVICE, x_layout FF_X_NCHW_F32 = fp32 [n,3,T,224,224] (the module's own input: raw 0..255 BGR,
+ *             S3D-test.py:94-96) or FF_X_NHWC_U8 = uint8 [n,T,224,224,3] (frames as decoded);
+ *             logits: DEVICE fp32 [n,num_class] (temporal mean of the per-window fc outputs, model.py:40-46).
+ *   debug     activation after `base[base_index]` (0..15, model.py:17-34) as fp32 [n,T',H',W',C] on the HOST.
+ * bf16 tensor-core path only.                                                                                   */
+typedef struct ff_s3d ff_s3d_t;
+int ff_s3d_create(ff_s3d_t** out, int device, int max_clips, int frames_per_clip, int num_class);
+void ff_s3d_destroy(ff_s3d_t* h);
+const char* ff_s3d_last_error(const ff_s3d_t* h); /* h may be NULL: last create() error */
+int ff_s3d_load_weight(ff_s3d_t* h, const char* key, const float* host_fp32, const int64_t* shape, int ndim);
+int ff_s3d_finalize(ff_s3d_t* h);
+int ff_s3d_forward(ff_s3d_t* h, const void* x, int x_layout, int n, float* logits, void* stream);
+int64_t ff_s3d_debug_activation(ff_s3d_t* h, const void* x, int x_layout, int n, int base_index, float* out_host,
+                                int64_t out_elems, void* stream);
+int64_t ff_s3d_launch_count(const ff_s3d_t* h);
+
 #ifdef __cplusplus
 }
 #endif
