@@ -173,6 +173,132 @@ def cpu_baseline(sample_crops: int, repeats: int, model: str = "cvit"):
             "seconds_per_run": med}
 
 
+def s3d_flops_per_clip(T: int) -> int:
+    """2*MAC of every convolution of S3D (model.py:17-34) for one [3,T,224,224] clip."""
+    t1 = (T - 1) // 2 + 1
+    t2 = (t1 - 1) // 2 + 1
+    t3 = t2 // 2
+    fl = 2 * T * 112 * 112 * 64 * 3 * 49 + 2 * t1 * 112 * 112 * 64 * 64 * 7                     # base.0 spatial + temporal
+    fl += 2 * t1 * 56 * 56 * 64 * 64                                                            # base.2
+    fl += 2 * t1 * 56 * 56 * 192 * (64 * 9 + 192 * 3)                                           # base.3
+    mixed = [(192, 64, 96, 128, 16, 32, 32), (256, 128, 128, 192, 32, 96, 64), (480, 192, 96, 208, 16, 48, 64),
+             (512, 160, 112, 224, 24, 64, 64), (512, 128, 128, 256, 24, 64, 64), (512, 112, 144, 288, 32, 64, 64),
+             (528, 256, 160, 320, 32, 128, 128), (832, 256, 160, 320, 32, 128, 128), (832, 384, 192, 384, 48, 128, 128)]
+    where = [(t1, 28)] * 2 + [(t2, 14)] * 5 + [(t3, 7)] * 2
+    for (cin, b0, m1, o1, m2, o2, b3), (t, hw) in zip(mixed, where):
+        vox = t * hw * hw
+        fl += 2 * vox * (cin * (b0 + m1 + m2 + b3) + o1 * (m1 * 9 + o1 * 3) + o2 * (m2 * 9 + o2 * 3))
+    return fl + 2 * 1024 * (t3 - 1)
+
+
+def run_s3d(args):
+    """--model s3d: BASELINE configs[4] — 64-frame 224x224 clips, 32 clips per GPU per step."""
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "") and not os.environ.get("FF_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    import torch
+    import torch.distributed as dist
+    from fac_fake_b200 import S3DEngine, weights as W
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T, n = args.frames, args.clips
+    warmup, steps = max(3, args.warmup), max(1, args.steps)
+    peaks = read_peaks()
+    eng = S3DEngine(1, "no", frames_per_clip=T, max_clips=n).to(dev).load_state_dict(W.make_s3d_state_dict(0, "default"))
+    ROT = 2                                           # 2 x 308 MB of uint8 clips > 126 MB L2; > 10 GB of activations per step
+    host = [W.synthetic_clips(n, T, seed=200 + 13 * rank + i).pin_memory() for i in range(ROT)]
+    devb = [b.to(dev) for b in host]
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        lg = eng(devb[i % ROT])
+        if world > 1:                                 # the only exchange: per-clip logits to every rank (n floats)
+            out = [torch.empty_like(lg) for _ in range(world)]
+            dist.all_gather(out, lg)
+            lg = torch.cat(out)
+        return lg
+
+    for i in range(warmup):
+        step(i)
+    sync_all()
+    l0 = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n * steps / (ms_max * 1e-3)
+    e2e_steps = max(1, min(steps, 5))
+    for i in range(2):
+        eng(host[i % ROT]).cpu()
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        eng(host[i % ROT]).cpu()                      # pinned host uint8 clips -> H2D -> forward -> logits D2H
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t.item())
+    if rank == 0:
+        fl = s3d_flops_per_clip(T)
+        tfl = value / world * fl / 1e12
+        out = {
+            "metric": "S3D clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"S3D bf16 inference, synthetic {T}-frame 224x224 uint8 clips, {n} clips per GPU per step "
+                                   f"(BASELINE configs[4]), random-init weights", "clips_per_step_per_gpu": n, "frames_per_clip": T,
+                       "parallelism": f"clip-sharded x{world} (no data-path collective)",
+                       "l2": "inputs rotate over 2 batches (616 MB > 126 MB L2); > 10 GB of activations per step sweep L2",
+                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": n * T * 224 * 224 * 3, "d2h_bytes_per_step": 4 * n,
+                    "steps": e2e_steps, "api": "S3DEngine.forward on pinned host uint8 clips (H2D + ff_s3d_forward + logits D2H)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "ff::rvk_conv2_kernel (all 61 convolutions) + stem; whole pass timed, so this is a lower bound for the kernels",
+                         "achieved": tfl, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": tfl / peaks["bf16_sustained"],
+                         "peak_source": f"bf16_tflops_sustained, {peaks['source']}", "traffic": None,
+                         "algorithmic_flops_per_clip": fl, "frac_of_burst_peak": tfl / peaks["bf16_burst"]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import s3d_oracle as S
+            torch.set_num_threads(os.cpu_count() or 1)
+            sd = W.make_s3d_state_dict(0, "default")
+            x = W.synthetic_clips(1, T, seed=3).permute(0, 4, 1, 2, 3).contiguous().float()
+            S.forward(x, sd)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                S.forward(x, sd)
+            dt = (time.perf_counter() - t0) / 2
+            out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"1 clip of {T} frames x 2 runs; torch {torch.__version__} fp32 CPU oracle", "seconds_per_run": dt}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     """--impl reference: the reference's own (CPU, PyTorch fp32) implementation of the path = the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
@@ -222,13 +348,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--crops", type=int, default=CROPS_PER_STEP)
-    ap.add_argument("--model", default="cvit", choices=sorted(MODELS),
+    ap.add_argument("--clips", type=int, default=32, help="--model s3d: clips per GPU per step")
+    ap.add_argument("--frames", type=int, default=64, help="--model s3d: frames per clip")
+    ap.add_argument("--model", default="cvit", choices=sorted(MODELS) + ["s3d"],
                     help="cvit = the north-star path (default, what the driver runs); resvitkan = SURVEY 8f-1 / BASELINE configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: same as --steps")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.model == "s3d":
+        run_s3d(args)
         return
 
     # keep stdout to the single JSON line: NCCL's version banner goes to stdout when NCCL_DEBUG=VERSION/INFO

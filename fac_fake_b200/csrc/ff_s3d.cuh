@@ -155,8 +155,10 @@ int s3d_add_conv(ff_s3d* h, const std::string& conv_key, const std::string& bn_k
   op.t_in = t_in;
   op.t_out = (mode == ff_s3d::TEMPORAL && stride == 2) ? (t_in - 1) / 2 + 1 : t_in;
   op.taps = mode == ff_s3d::FLAT ? 1 : (mode == ff_s3d::SPATIAL ? 9 : k);
+  // N = 64 MMAs run at half the tensor rate (one M=128,K=16 tcgen05.mma costs ~64 cycles for any N <= 128), so a
+  // 128-wide tile with up to 50 % padded columns is never slower than two 64-wide ones
   const int pad64 = (cout + 63) / 64 * 64, pad128 = (cout + 127) / 128 * 128;
-  op.bn = (pad128 == pad64) ? 128 : 64;
+  op.bn = cout > 64 ? 128 : 64;
   op.cout_pad = op.bn == 128 ? pad128 : pad64;
   const int kb_per_tap = (cin + 63) / 64, kpad = kb_per_tap * 64;
   std::vector<int64_t> wshape;
@@ -219,39 +221,61 @@ void s3d_add_pool(ff_s3d* h, const bf16* in, bf16* out, int c, int hw_in, int t_
   h->ops.push_back(op);
 }
 
-// ---- MaxPool3d on bf16 NDHWC, 8 channels per thread (model.py:19,22,25,31 and branch3 of every Mixed block)
+// ---- MaxPool3d on bf16 NDHWC (model.py:19,22,25,31 and branch3 of every Mixed block).  One thread = 8 channels x 4
+// consecutive output columns: the (time, row) window is reduced once per INPUT column and the 3*SS + KS column maxima
+// are shared by the four outputs (a 3x3x3 stride-1 pool reads 54 vectors per 4 outputs instead of 108).
+template <int KS, int SS>
 __global__ void __launch_bounds__(256)
 s3d_maxpool_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int n, int t_in, int hw_in, int c8, int t_out, int hw_out,
-                   int kt, int ks, int st, int ss, int pt, int ps) {
-  const size_t total = (size_t)n * t_out * hw_out * hw_out * c8;
+                   int kt, int st, int pt, int ps) {
+  constexpr int NC = 3 * SS + KS;
+  const int wg = (hw_out + 3) / 4;
+  const size_t total = (size_t)n * t_out * hw_out * wg * c8;
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int q = (int)(i % c8);
   size_t r = i / c8;
-  const int ow = (int)(r % hw_out); r /= hw_out;
+  const int ow0 = (int)(r % wg) * 4; r /= wg;
   const int oh = (int)(r % hw_out); r /= hw_out;
   const int ot = (int)(r % t_out);
   const size_t b = r / t_out;
-  uint4 m = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // bf16 -inf pairs
   auto mx = [](uint32_t a0, uint32_t b0) {
     __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a0), *reinterpret_cast<__nv_bfloat162*>(&b0));
     return *reinterpret_cast<uint32_t*>(&r2);
   };
+  uint4 col[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) col[j] = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // bf16 -inf pairs
+  const int iw0 = ow0 * SS - ps;
   for (int dt = 0; dt < kt; ++dt) {
     const int it = ot * st - pt + dt;
     if (it < 0 || it >= t_in) continue;
-    for (int dy = 0; dy < ks; ++dy) {
-      const int ih = oh * ss - ps + dy;
+#pragma unroll
+    for (int dy = 0; dy < KS; ++dy) {
+      const int ih = oh * SS - ps + dy;
       if (ih < 0 || ih >= hw_in) continue;
-      for (int dx = 0; dx < ks; ++dx) {
-        const int iw = ow * ss - ps + dx;
+      const bf16* row = in + (((b * t_in + it) * hw_in + ih) * (size_t)hw_in) * c8 * 8 + q * 8;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int iw = iw0 + j;
         if (iw < 0 || iw >= hw_in) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(in + ((((b * t_in + it) * hw_in + ih) * hw_in + iw) * c8 + q) * 8);
-        m.x = mx(m.x, v.x); m.y = mx(m.y, v.y); m.z = mx(m.z, v.z); m.w = mx(m.w, v.w);
+        const uint4 v = *reinterpret_cast<const uint4*>(row + (size_t)iw * c8 * 8);
+        col[j].x = mx(col[j].x, v.x); col[j].y = mx(col[j].y, v.y); col[j].z = mx(col[j].z, v.z); col[j].w = mx(col[j].w, v.w);
       }
     }
   }
-  *reinterpret_cast<uint4*>(out + i * 8) = m;
+  bf16* o = out + ((((b * t_out + ot) * hw_out + oh) * (size_t)hw_out + ow0) * c8 + q) * 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (ow0 + k >= hw_out) break;
+    uint4 m = col[k * SS];
+#pragma unroll
+    for (int j = 1; j < KS; ++j) {
+      const uint4 v = col[k * SS + j];
+      m.x = mx(m.x, v.x); m.y = mx(m.y, v.y); m.z = mx(m.z, v.z); m.w = mx(m.w, v.w);
+    }
+    *reinterpret_cast<uint4*>(o + (size_t)k * c8 * 8) = m;
+  }
 }
 
 // ---- fp32 NCDHW clip [b,3,T,224,224] (the reference module's input) -> bf16 NHWC4 frames
@@ -451,9 +475,16 @@ int s3d_forward(ff_s3d* h, const void* x, int layout, int n, float* logits, cuda
       int rc = s3d_launch_conv(h, op, n, st);
       if (rc) return rc;
     } else {
-      const size_t total = (size_t)n * op.t_out * op.hw * op.hw * (op.c / 8);
-      s3d_maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(op.pin, op.pout, n, op.t_in, op.hw_in, op.c / 8, op.t_out, op.hw,
-                                                                          op.kt, op.ks, op.st, op.ss, op.pt, op.ps);
+      const size_t total = (size_t)n * op.t_out * op.hw * ((op.hw + 3) / 4) * (op.c / 8);
+      const unsigned blocks = (unsigned)((total + 255) / 256);
+      if (op.ks == 3 && op.ss == 1)
+        s3d_maxpool_kernel<3, 1><<<blocks, 256, 0, st>>>(op.pin, op.pout, n, op.t_in, op.hw_in, op.c / 8, op.t_out, op.hw, op.kt, op.st, op.pt, op.ps);
+      else if (op.ks == 3 && op.ss == 2)
+        s3d_maxpool_kernel<3, 2><<<blocks, 256, 0, st>>>(op.pin, op.pout, n, op.t_in, op.hw_in, op.c / 8, op.t_out, op.hw, op.kt, op.st, op.pt, op.ps);
+      else if (op.ks == 2 && op.ss == 2)
+        s3d_maxpool_kernel<2, 2><<<blocks, 256, 0, st>>>(op.pin, op.pout, n, op.t_in, op.hw_in, op.c / 8, op.t_out, op.hw, op.kt, op.st, op.pt, op.ps);
+      else
+        return sfail(h, FF_ERR_STATE, "unsupported pool geometry %d/%d", op.ks, op.ss);
       S3_CUDA(h, cudaGetLastError());
       ++h->launches;
     }
