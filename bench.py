@@ -74,6 +74,30 @@ MODELS = {
 }
 
 
+_JSON_FD = None
+
+
+def keep_stdout_clean():
+    """stdout must carry exactly one JSON line, but NCCL prints its version banner there (NCCL_DEBUG=VERSION and up,
+    not redirected by NCCL_DEBUG_FILE on this build).  Point fd 1 at stderr for the rest of the run and keep the real
+    stdout for emit()."""
+    global _JSON_FD
+    if _JSON_FD is None and not os.environ.get("FF_KEEP_NCCL_DEBUG"):
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = json.dumps(obj) + "\n"
+    if _JSON_FD is None:
+        sys.stdout.write(line)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, line.encode())
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -193,8 +217,7 @@ def s3d_flops_per_clip(T: int) -> int:
 
 def run_s3d(args):
     """--model s3d: BASELINE configs[4] — 64-frame 224x224 clips, 32 clips per GPU per step."""
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "") and not os.environ.get("FF_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    keep_stdout_clean()
     import torch
     import torch.distributed as dist
     from fac_fake_b200 import S3DEngine, weights as W
@@ -293,7 +316,7 @@ def run_s3d(args):
             dt = (time.perf_counter() - t0) / 2
             out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"1 clip of {T} frames x 2 runs; torch {torch.__version__} fp32 CPU oracle", "seconds_per_run": dt}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -338,7 +361,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -362,9 +385,7 @@ def main():
         run_s3d(args)
         return
 
-    # keep stdout to the single JSON line: NCCL's version banner goes to stdout when NCCL_DEBUG=VERSION/INFO
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "") and not os.environ.get("FF_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    keep_stdout_clean()
     import torch
     import torch.distributed as dist
     from fac_fake_b200 import CViTEngine, CViTGGCAEngine, ResVitKanEngine, weights as W
@@ -503,7 +524,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(32, 2, "resvitkan")
-        print(json.dumps(out), flush=True)
+        emit(out)
     elif rank == 0:
         conv_ms, conv_launches = prof["tcgen05_conv"]
         flops_per_crop = model["flops_per_crop"]
@@ -549,7 +570,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(32, 3, args.model)
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
