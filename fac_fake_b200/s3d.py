@@ -103,7 +103,12 @@ class S3DEngine:
         return self.forward(x)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """fp32 [b,3,T,224,224] (raw 0..255 BGR, S3D-test.py:94-96) or uint8 [b,T,224,224,3] -> logits [b, num_class]."""
+        """fp32 [b,3,T,224,224] (raw 0..255 BGR, S3D-test.py:94-96) or uint8 [b,T,224,224,3] -> logits [b, num_class].
+
+        A pinned HOST tensor is streamed: chunk i+1 is copied on a side stream while chunk i is computed (a 64-frame
+        uint8 clip is 9.6 MB, so the copy is as long as the compute and must not be serialised with it)."""
+        if x.device.type == "cpu" and x.is_pinned() and x.shape[0] > 1 and self._h is not None:
+            return self._forward_streamed(x)
         x, layout = self._prep(x)
         b = x.shape[0]
         out = torch.empty((b, self.num_class), dtype=torch.float32, device=self._device)
@@ -111,6 +116,43 @@ class S3DEngine:
             rc = self._lib.ff_s3d_forward(self._h, C.c_void_p(x.data_ptr()), layout, b, C.c_void_p(out.data_ptr()),
                                           C.c_void_p(_stream_ptr(self._device)))
         self._check(rc, "ff_s3d_forward")
+        return out
+
+    def _forward_streamed(self, x: torch.Tensor, chunks: int = 4) -> torch.Tensor:
+        b = x.shape[0]
+        step = max(1, (b + chunks - 1) // chunks)
+        bounds = [(i, min(b, i + step)) for i in range(0, b, step)]
+        if x.dtype != torch.uint8:
+            x = x.to(torch.float32)
+        layout = L.FF_X_NHWC_U8 if x.dtype == torch.uint8 else L.FF_X_NCHW_F32
+        expect = (self.frames_per_clip, 224, 224, 3) if x.dtype == torch.uint8 else (3, self.frames_per_clip, 224, 224)
+        if tuple(x.shape[1:]) != expect:
+            raise ValueError(f"clips must be [b,{','.join(map(str, expect))}], got {tuple(x.shape)}")
+        out = torch.empty((b, self.num_class), dtype=torch.float32, device=self._device)
+        with torch.cuda.device(self._device):
+            main = torch.cuda.current_stream(self._device)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(self._device)
+                self._stage = [None, None]
+            cs = self._copy_stream
+            cs.wait_stream(main)
+            done = [None, None]                       # compute-finished events guarding the two staging buffers
+            for i, (lo, hi) in enumerate(bounds):
+                slot = i & 1
+                if self._stage[slot] is None or self._stage[slot].shape[0] < hi - lo or self._stage[slot].dtype != x.dtype:
+                    self._stage[slot] = torch.empty((step,) + tuple(x.shape[1:]), dtype=x.dtype, device=self._device)
+                with torch.cuda.stream(cs):
+                    if done[slot] is not None:
+                        cs.wait_event(done[slot])
+                    self._stage[slot][: hi - lo].copy_(x[lo:hi], non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(cs)
+                main.wait_event(ready)
+                rc = self._lib.ff_s3d_forward(self._h, C.c_void_p(self._stage[slot].data_ptr()), layout, hi - lo,
+                                              C.c_void_p(out[lo:hi].data_ptr()), C.c_void_p(main.cuda_stream))
+                self._check(rc, "ff_s3d_forward")
+                done[slot] = torch.cuda.Event()
+                done[slot].record(main)
         return out
 
     def video_score(self, clips: torch.Tensor) -> float:

@@ -70,6 +70,15 @@ def test_logits_match_reference_golden(golden_dir, variant, s3d_bn, s3d_default)
     assert np.array_equal(got3[:2], got) and np.array_equal(got3[2], got[0])
 
 
+def test_streamed_host_input_matches_device_input(s3d_bn):
+    """Pinned host clips take the chunked copy/compute-overlap path; results must equal the resident-input path."""
+    eng, sd = s3d_bn
+    clips = W.synthetic_clips(3, T, seed=53)
+    a = eng(clips.cuda()).cpu()
+    b = eng(clips.pin_memory()).cpu()
+    assert torch.equal(a, b)
+
+
 def test_video_score_and_errors(s3d_bn):
     eng, sd = s3d_bn
     clips = W.synthetic_clips(2, T, seed=52)
