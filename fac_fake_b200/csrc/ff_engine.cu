@@ -66,6 +66,9 @@ struct ConvLayerDev {
   bool ws2x = false;        // pixel-pair formulation on a CTA pair (Cin = 64): N = 128, cta_group::2
   bf16* w2x = nullptr;      // pair-expanded filter [128][768]
   CUtensorMap tmA_ws2x, tmW_ws2x;
+  bool ws4 = false;         // pixel-quad formulation (32 -> 32): N = 4*Cout = 128, compact expanded filter
+  bf16* w4 = nullptr;       // [3 kh][64 + 128 + 64 rows][64] (ff_ws.cuh: Ws4Smem)
+  CUtensorMap tmA_ws4, tmW_ws4;
   bool ws2 = false;         // pixel-pair formulation (Cin = 32): N = 2*Cout
   bf16* w2 = nullptr;       // pair-expanded filter [2*Cout][384]
   CUtensorMap tmA_ws2, tmW_ws2;
@@ -96,6 +99,7 @@ struct ff_cvit {
   int use_ws = 1;          // feature layers 2..6 on the weight-stationary halo kernel
   int ws_ctas_per_sm = 2;   // CTAs per SM for the Cin=32 weight-stationary kernels (Cin=64 always 1: smem)
   int use_ptc = 1;         // feature layers 7..17 on the persistent implicit-GEMM kernel
+  int use_ws4 = 0;         // 32 -> 32 layers (2, 3) in the pixel-quad formulation (FF_WS4=1; measured equal to the pair kernel)
   int use_ws2 = 1;         // Cin = 32 layers in the pixel-pair formulation
   int use_ws2x = 1;        // Cin = 64 layers (5, 6) in the pixel-pair formulation on CTA pairs (needs use_ws2)
   int use_c1_tc = 3;       // feature layer 1: 3 = pixel-pair GEMM out of the patch (no im2col), 2 = TMA-fed im2col rows,
@@ -401,6 +405,18 @@ cudaError_t launch_ws2_t(int grid, cudaStream_t st, const CUtensorMap& a, const 
   return launch_k(k, dim3(grid), dim3(192), L::TOTAL, st, true, a, w, args, epi);
 }
 
+template <bool POOL>
+cudaError_t launch_ws4_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args, const WsEpi& epi) {
+  auto k = ws4conv_kernel<POOL>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Ws4Smem::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  return launch_k(k, dim3(grid), dim3(192), Ws4Smem::TOTAL, st, true, a, w, args, epi);
+}
+
 template <int BN, int MSUB, bool POOL, int STAGES>
 cudaError_t launch_ptc_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
   using L = PtcSmem<BN, MSUB, STAGES>;
@@ -527,6 +543,20 @@ int build_conv_maps(ff_cvit* h) {
       rc = tmap_4d(h, &L.tmA_ws2x, conv_input_buffer(h, li, set), 64, p.hw / 2, p.hw, 2 * ncap, 64, 10, 18, 1);
       if (rc) return rc;
       rc = tmap_2d(h, &L.tmW_ws2x, L.w2x, 768, 128, 64, 64);
+      if (rc) return rc;
+    }
+    L.ws4 = h->use_ws && h->use_ws2 && h->use_ws4 && p.cin == 32 && p.cout == 32;
+    if (L.ws4) {
+      // even / odd pair planes: elementStrides = 2 on the pair axis, 18 -> 9 pairs per plane row
+      cuuint64_t dims[4] = {64, (cuuint64_t)(p.hw / 2), (cuuint64_t)p.hw, (cuuint64_t)ncap};
+      cuuint64_t strides[3] = {128, (cuuint64_t)(p.hw / 2) * 128, (cuuint64_t)p.hw * (p.hw / 2) * 128};
+      cuuint32_t box[4] = {64, 18, 18, 1};
+      cuuint32_t estr[4] = {1, 2, 1, 1};
+      CUresult r = g_encode(&L.tmA_ws4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(conv_input_buffer(h, li, set)), dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(quad planes, layer %d) failed: %d", li + 1, (int)r);
+      rc = tmap_2d(h, &L.tmW_ws4, L.w4, 64, 768, 64, 64);
       if (rc) return rc;
     }
     L.ws2 = h->use_ws && h->use_ws2 && p.cin == 32;
@@ -922,6 +952,23 @@ int finalize(ff_cvit* h) {
               }
         if ((rc = dev_upload(h, &L.w2, to_bf16(w2)))) return rc;
       }
+      if (p.cin == 32 && p.cout == 32) {
+        // quad-expanded filter, compact: per kh the 64-element k-blocks b = 0,1,2 (window pixels 2b, 2b+1) keep only the
+        // output pixels p that see them: rows (p,co) for p in {0,1} | {0..3} | {2,3};  B[(p,co)][(wl,ci)] = W[co][kh][2b+wl-p][ci]
+        std::vector<float> w4((size_t)768 * 64, 0.0f);
+        const int p_lo[3] = {0, 0, 2}, p_n[3] = {2, 4, 2}, row_off[3] = {0, 64, 192};
+        for (int kh = 0; kh < 3; ++kh)
+          for (int b = 0; b < 3; ++b)
+            for (int pi = 0; pi < p_n[b]; ++pi)
+              for (int o = 0; o < 32; ++o)
+                for (int wl = 0; wl < 2; ++wl) {
+                  const int kw = 2 * b + wl - (p_lo[b] + pi);
+                  if (kw < 0 || kw > 2) continue;
+                  const size_t row = (size_t)kh * 256 + row_off[b] + pi * 32 + o;
+                  for (int ci = 0; ci < 32; ++ci) w4[row * 64 + wl * 32 + ci] = wr[((size_t)o * 9 + kh * 3 + kw) * 32 + ci];
+                }
+        if ((rc = dev_upload(h, &L.w4, to_bf16(w4)))) return rc;
+      }
       if (p.cin == 64 && p.cout == 64) {
         // CTA-pair variant: B[(pp,co)][(cb,kh,q,ci)] = W[co][kh][q-pp][cb*32+ci]
         std::vector<float> w2((size_t)128 * 768, 0.0f);
@@ -1233,6 +1280,15 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
       cudaError_t e = p.pool ? launch_ws2x_t<true>(g, st, L.tmA_ws2x, L.tmW_ws2x, a, L.epi)
                              : launch_ws2x_t<false>(g, st, L.tmA_ws2x, L.tmW_ws2x, a, L.epi);
       if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of ws2x conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
+      ++h->launches;
+      return FF_OK;
+    }
+    if (L.ws4) {
+      a.tiles_w = p.hw / 32; a.tiles_h = p.hw / 16;
+      const int tiles = a.tiles_w * a.tiles_h * n_img;
+      const int g = std::min(tiles, h->num_sms);
+      cudaError_t e = p.pool ? launch_ws4_t<true>(g, st, L.tmA_ws4, L.tmW_ws4, a, L.epi) : launch_ws4_t<false>(g, st, L.tmA_ws4, L.tmW_ws4, a, L.epi);
+      if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of quad conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
       ++h->launches;
       return FF_OK;
     }
@@ -1607,6 +1663,7 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
   if (const char* v = getenv("FF_GEMM_BN")) h->gemm_bn_wide = atoi(v) == 128 ? 128 : 64;
   if (const char* v = getenv("FF_PTC")) h->use_ptc = atoi(v);
   if (const char* v = getenv("FF_WS2")) h->use_ws2 = atoi(v);
+  if (const char* v = getenv("FF_WS4")) h->use_ws4 = atoi(v);
   if (const char* v = getenv("FF_WS2X")) h->use_ws2x = atoi(v);
   if (const char* v = getenv("FF_C1_TC")) h->use_c1_tc = atoi(v);
   if (const char* v = getenv("FF_C1_CPS")) h->c1_ctas_per_sm = std::max(1, atoi(v));

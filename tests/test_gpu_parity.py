@@ -287,3 +287,20 @@ def test_prediction_api_mirror_end_to_end(tmp_path, eng_bn):
     lg = torch.randn((9, 2), generator=torch.Generator().manual_seed(1))
     got = cp.pre_process_prediction(cp.pred_sig(lg)).item()
     assert abs(got - O.video_score(lg)) <= 1e-5
+
+
+def test_quad_pixel_kernel_option_matches_oracle(monkeypatch):
+    """FF_WS4=1 selects the pixel-quad kernel (N = 128 via even/odd pair planes) for feature layers 2 and 3."""
+    monkeypatch.setenv("FF_WS4", "1")
+    eng, sd = _engine("bn", max_crops=64)
+    monkeypatch.delenv("FF_WS4")
+    crops = W.synthetic_crops(3, seed=27)
+    acts = _oracle_layers(sd, O.normalize_crops(crops), 4)
+    xg = crops.cuda()
+    ref_eng, _ = _engine("bn", max_crops=64)
+    for step in (2, 3, 4):
+        got = eng.debug_activation(xg, step)
+        ref = acts[step]
+        assert (got - ref).abs().max().item() <= ref.abs().max().item() * 0.004 * (step + 1), step
+        # same bf16 inputs, same fp32 accumulation order per output up to the k-block order: equal to one rounding
+        assert (got - ref_eng.debug_activation(xg, step)).abs().max().item() <= ref.abs().max().item() * 0.008, step
