@@ -1,6 +1,6 @@
 """GPU bring-up report: per-step error of the engine against the CPU oracle (no asserts).
 
-    python tools/bringup.py [--n 4] [--variant bn] [--compute bf16]
+    python tests/bringup_report.py [--n 4] [--variant bn] [--compute bf16]
 
 Prints one line per debug tap (conv layers 1..17, tokens, transformer layers, logits) with
 max-abs error, relative error and the oracle's scale, so that a single GPU call localises
@@ -13,7 +13,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tests/)
 sys.path.insert(0, ROOT)
 from fac_fake_b200 import CViTEngine, weights as W  # noqa: E402
 from oracle import cvit_oracle as O  # noqa: E402
