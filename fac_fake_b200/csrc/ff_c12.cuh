@@ -1,0 +1,250 @@
+// ff_c12.cuh — feature layers 1 AND 2 in one kernel (uint8 crops in, conv2 output out).
+// OPTIONAL (FF_C12=1), parity-tested, NOT the default.  Measured on B200: layers 1-6 take 3.42 ms per 512 crops with this
+// kernel against 3.05 ms with the separate conv1 / conv2 kernels, although it removes 3.2 GB of HBM traffic per step:
+// with all five phases on one set of 128 threads and only two CTAs per SM (the 48 KB conv2 filter is per CTA) a tile
+// costs ~4500 cycles per SM, i.e. the phases barely overlap.  The fusion needs the warp-specialised, double-buffered
+// form (producer / two MMA stages / two epilogue groups) to pay off — that is the round-2 item in DESIGN.md §8.
+//
+// Layers 1-3 of the CViT stack are bound by HBM traffic, not by the tensor pipe (profiles/r01_ncu_ws2_kernels.txt,
+// DESIGN.md §8): the 224x224x32 bf16 map between conv1 and conv2 is 3.2 MB per crop, written once and read once.
+// Here it never leaves the SM.  Per 14-row x 16-pixel conv2 output tile:
+//   1. TMA brings the uint8 window (18 rows x 80 B) into shared memory; 128 threads normalise it into the bf16
+//      NHWC4 patch conv1 reads (18 rows x 22 pixels), zero outside the image (= conv1's padding);
+//   2. conv1 as in conv1_pair_kernel (no im2col: non-swizzled K-major descriptors over overlapping 4-pixel windows),
+//      on the 16 x 20-pixel region conv2 needs (its tile + halo): two strips of 8 pixel pairs x 16 rows, 6 MMAs
+//      (M=128, N=64, K=16) into two TMEM accumulators;
+//   3. epilogue 1: BN + ReLU -> bf16 -> written straight into the 128-byte-swizzled halo patch conv2's A descriptors
+//      read ([16 rows][10 pairs][2 px x 32 ch]), with ZEROS where the position lies outside the image (conv2's padding
+//      is of conv1's OUTPUT, so it cannot be produced by running conv1 on padded input);
+//   4. conv2 exactly as ws2conv_kernel<64>: 24 MMAs over the patch with row-shifted SW128 descriptors;
+//   5. epilogue 2: BN + ReLU -> 128 contiguous bytes per pixel pair to global (rows 14, 15 of the M tile are unused).
+// All phases run on the CTA's 128 threads one after the other; two CTAs per SM overlap each other's tensor and
+// CUDA-core phases.  conv1 is recomputed on the halo (16x20 / 14x16 = 1.43x of a cheap layer).
+#pragma once
+#include "ff_ws.cuh"
+
+namespace ff {
+
+struct C12Args {
+  __nv_bfloat16* out;            // conv2 output [n][224][224][32] bf16
+  const __nv_bfloat16* w1;       // conv1 pair-expanded filter [3 kh][64 (p,co)][16 (q,c)] (as conv1_pair_kernel)
+  int n_img;
+  float na[3], nb[3];
+  float scale1[32], shift1[32];
+  float scale2[32], shift2[32];
+};
+
+struct C12Smem {
+  static constexpr int W2_BYTES = 6 * 64 * 128;                       // conv2 pair-expanded filter, 6 k-blocks of [64][64]
+  static constexpr int PATCH_ROWS = 18;                               // 16 produced + 2 only read by the unused M rows
+  static constexpr int PATCH_BYTES = PATCH_ROWS * 10 * 128;
+  static constexpr int W2_OFF = 0;
+  static constexpr int PATCH_OFF = W2_BYTES;                          // 1024-aligned (49152)
+  static constexpr int SIN_PITCH = 192;                               // 22 px x 8 B = 176, padded to a multiple of 16
+  static constexpr int SIN_ROWS = 18;
+  static constexpr int SIN_OFF = PATCH_OFF + ((PATCH_BYTES + 1023) / 1024) * 1024;
+  static constexpr int SIN_BYTES = (SIN_ROWS + 1) * SIN_PITCH;        // +1 row: the last window of the last row reads 16 B past it
+  static constexpr int B1_OFF = SIN_OFF + ((SIN_BYTES + 127) / 128) * 128;
+  static constexpr int B1_BYTES = 3 * 2048;
+  static constexpr int RAW_SLOT = 1536, RING = 3;
+  static constexpr int RAW_OFF = B1_OFF + B1_BYTES;
+  static constexpr int BAR_OFF = RAW_OFF + RING * RAW_SLOT;           // w2, mma1, mma2, raw[RING]
+  static constexpr int SLOT_OFF = BAR_OFF + (3 + RING) * 8;
+  static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(128, 2)
+c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ C12Args a) {
+  using L = C12Smem;
+  constexpr int HW = 224, TW = 16, TH = 14;
+  constexpr int TILES_W = HW / TW, TILES_H = HW / TH, TILES = TILES_W * TILES_H;
+  constexpr int RAW_ROW = 80, RAW_BYTES = 18 * RAW_ROW;
+  constexpr int PW = 22, PH = 18;                                     // conv1 input patch, pixels x rows
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* s_in = base_ptr + L::SIN_OFF;
+  uint8_t* s_b1 = base_ptr + L::B1_OFF;
+  uint8_t* s_rawp = base_ptr + L::RAW_OFF;
+  uint8_t* s_patch = base_ptr + L::PATCH_OFF;
+  const uint32_t bar_w2 = base + L::BAR_OFF;
+  const uint32_t bar_mma1 = bar_w2 + 8;
+  const uint32_t bar_mma2 = bar_w2 + 16;
+  const uint32_t bar_raw = bar_w2 + 24;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // conv1 filter -> core-matrix layout: (n, chunk c) at ((n/8)*2 + c)*128 + (n%8)*16
+  for (int i = tid; i < 3 * 64 * 2; i += 128) {
+    const int kh = i / 128, rem = i % 128, n = rem >> 1, c = rem & 1;
+    *reinterpret_cast<uint4*>(s_b1 + kh * 2048 + ((n >> 3) * 2 + c) * 128 + (n & 7) * 16) = reinterpret_cast<const uint4*>(a.w1)[i];
+  }
+  for (int i = tid; i < L::SIN_BYTES / 16; i += 128) reinterpret_cast<uint4*>(s_in)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < L::PATCH_BYTES / 16; i += 128) reinterpret_cast<uint4*>(s_patch)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW2);
+    mbar_init(bar_w2, 1);
+    mbar_init(bar_mma1, 1);
+    mbar_init(bar_mma2, 1);
+    for (int s = 0; s < L::RING; ++s) mbar_init(bar_raw + 8 * s, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<256>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_c1 = tmem;            // conv1: columns 0..63 = strip 0 (pairs 0..7), 64..127 = strip 1 (pairs 2..9)
+  const uint32_t tm_c2 = tmem + 128;      // conv2: 64 columns
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_w2, L::W2_BYTES);
+    for (int kb = 0; kb < 6; ++kb) tma_load_2d(base + L::W2_OFF + kb * 8192, &tmW2, bar_w2, kb * 64, 0);
+    pdl_trigger();
+  }
+  pdl_wait();
+  const uint32_t sin_addr = base + L::SIN_OFF, b1_addr = base + L::B1_OFF, patch_addr = base + L::PATCH_OFF;
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+  const int num_tiles = TILES * a.n_img;
+  const int hl = tid >> 3, jl = tid & 7;
+
+  auto issue = [&](int t, int slot) {
+    const int n = t / TILES;
+    const int rem = t - n * TILES;
+    const int th = rem / TILES_W, tw = rem - th * TILES_W;
+    mbar_arrive_expect_tx(bar_raw + 8 * slot, RAW_BYTES);
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(s_rawp + slot * L::RAW_SLOT)),
+        "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar_raw + 8 * slot), "r"(48 * tw - 16), "r"(th * TH - 2), "r"(n)
+        : "memory");
+  };
+  if (tid == 0)
+    for (int s = 0; s < L::RING - 1; ++s) {
+      const int t = blockIdx.x + s * gridDim.x;
+      if (t < num_tiles) issue(t, s);
+    }
+  bool w2_ready = false;
+  int it = 0;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    const int n = t / TILES;
+    const int rem = t - n * TILES;
+    const int th = rem / TILES_W, tw = rem - th * TILES_W;
+    const int h0 = th * TH, w0 = tw * TW;
+    const int slot = it % L::RING;
+    // ---- 1. raw uint8 window -> normalised bf16 NHWC4 patch: patch pixel (py, px) = image (h0-2+py, w0-3+px)
+    mbar_wait(bar_raw + 8 * slot, (it / L::RING) & 1);
+    for (int pi = tid; pi < PH * PW; pi += 128) {
+      const int py = pi / PW, px = pi - py * PW;
+      const uint8_t* rp = s_rawp + slot * L::RAW_SLOT + py * RAW_ROW + 7 + 3 * px;     // window starts at byte 48*tw-16 = pixel w0 - 16/3
+      const int gy = h0 - 2 + py, gx = w0 - 3 + px;
+      const bool ok = gy >= 0 && gy < HW && gx >= 0 && gx < HW;
+      const float v0 = ok ? fmaf(static_cast<float>(rp[0]), a.na[0], a.nb[0]) : 0.0f;
+      const float v1 = ok ? fmaf(static_cast<float>(rp[1]), a.na[1], a.nb[1]) : 0.0f;
+      const float v2 = ok ? fmaf(static_cast<float>(rp[2]), a.na[2], a.nb[2]) : 0.0f;
+      *reinterpret_cast<uint2*>(s_in + py * L::SIN_PITCH + px * 8) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, 0.0f));
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      const int tn = t + (L::RING - 1) * gridDim.x;
+      if (tn < num_tiles) issue(tn, (it + L::RING - 1) % L::RING);
+      // ---- 2. conv1 on 16 rows x 10 pairs: strip 0 = pairs 0..7, strip 1 = pairs 2..9 (32 bytes further)
+      tcgen05_fence_after();
+#pragma unroll
+      for (int strip = 0; strip < 2; ++strip)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const uint64_t ad = make_kmajor_desc_noswz(sin_addr + kh * L::SIN_PITCH + strip * 32, 16, L::SIN_PITCH);
+          const uint64_t bd = make_kmajor_desc_noswz(b1_addr + kh * 2048, 128, 256);
+          umma_bf16_ss(tm_c1 + strip * 64, ad, bd, idesc, kh > 0 ? 1u : 0u);
+        }
+      umma_commit(bar_mma1);
+    }
+    mbar_wait(bar_mma1, it & 1);
+    tcgen05_fence_after();
+    // ---- 3. epilogue 1: thread (hl, jl) owns conv1 pair (row hl, pair jl) from strip 0 and (row hl, pair jl+2) from
+    //         strip 1 (kept only for jl >= 6).  Patch row hl = image row h0-1+hl, pair j = image pixels w0-2+2j, +1.
+    {
+      const int gy = h0 - 1 + hl;
+#pragma unroll
+      for (int strip = 0; strip < 2; ++strip) {
+        const bool keep = strip == 0 || jl >= 6;     // tcgen05.ld is warp-collective: every thread loads, few store
+        const int pj = jl + 2 * strip;
+        const int gx = w0 - 2 + 2 * pj;
+        const bool inside = gy >= 0 && gy < HW && gx >= 0 && gx < HW;     // pairs never straddle the image border
+        const int rowidx = hl * 10 + pj;
+        uint8_t* prow = s_patch + rowidx * 128;
+        const int sw = rowidx & 7;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          uint32_t v[32];
+          tmem_ld_32x32(tm_c1 + (static_cast<uint32_t>(warp * 32) << 16) + strip * 64 + p * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const float x0 = fmaf(__uint_as_float(v[c]), a.scale1[c], a.shift1[c]);
+            const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale1[c + 1], a.shift1[c + 1]);
+            pk[c >> 1] = inside ? pack_bf16x2_relu(x0, x1) : 0u;
+          }
+          if (keep) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)    // pixel p of the pair = 16-byte chunks 4p .. 4p+3 of the 128-byte row
+              *reinterpret_cast<uint4*>(prow + (((4 * p + q) ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      // ---- 4. conv2: as ws2conv_kernel<64> over the patch just written
+      if (!w2_ready) { mbar_wait(bar_w2, 0); w2_ready = true; }
+      tcgen05_fence_after();
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint64_t adesc = make_kmajor_desc_sbo<128>(patch_addr + kh * 10 * 128 + 64 + 32 * c, 10 * 128);
+          const uint64_t bdesc = make_kmajor_desc<128>(base + L::W2_OFF + (kh * 2 + (c >> 2)) * 8192) + 2 * (c & 3);
+          umma_bf16_ss(tm_c2, adesc, bdesc, idesc, (kh > 0 || c > 0) ? 1u : 0u);
+        }
+      }
+      umma_commit(bar_mma2);
+    }
+    mbar_wait(bar_mma2, it & 1);
+    tcgen05_fence_after();
+    // ---- 5. epilogue 2: thread = pixel pair (hl, jl) of the 14 x 16 tile: 2 x 32 channels = 128 contiguous bytes
+    {
+      __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * HW + (h0 + hl)) * HW + (w0 + 2 * jl)) * 32;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        uint32_t v[32];
+        tmem_ld_32x32(tm_c2 + (static_cast<uint32_t>(warp * 32) << 16) + p * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float x0 = fmaf(__uint_as_float(v[c]), a.scale2[c], a.shift2[c]);
+          const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale2[c + 1], a.shift2[c + 1]);
+          pk[c >> 1] = pack_bf16x2_relu(x0, x1);
+        }
+        if (hl < TH) {
+          st_global_v8(o + p * 32, pk);
+          st_global_v8(o + p * 32 + 16, pk + 8);
+        }
+      }
+    }
+    tcgen05_fence_before();
+    __syncthreads();          // s_in / the patch / both accumulators are free for the next tile
+  }
+  __syncthreads();
+  if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<256>(tmem); }
+}
+
+}  // namespace ff

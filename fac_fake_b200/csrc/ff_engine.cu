@@ -26,6 +26,7 @@
 #include "ff_ws.cuh"
 #include "ff_c1.cuh"
 #include "ff_rvk.cuh"
+#include "ff_c12.cuh"
 
 namespace {
 
@@ -99,6 +100,7 @@ struct ff_cvit {
   int use_ws = 1;          // feature layers 2..6 on the weight-stationary halo kernel
   int ws_ctas_per_sm = 2;   // CTAs per SM for the Cin=32 weight-stationary kernels (Cin=64 always 1: smem)
   int use_ptc = 1;         // feature layers 7..17 on the persistent implicit-GEMM kernel
+  int use_c12 = 0;         // FF_C12=1: feature layers 1+2 fused in one kernel (ff_c12.cuh); parity-green but slower, see there
   int use_ws4 = 0;         // 32 -> 32 layers (2, 3) in the pixel-quad formulation (FF_WS4=1; measured equal to the pair kernel)
   int use_ws2 = 1;         // Cin = 32 layers in the pixel-pair formulation
   int use_ws2x = 1;        // Cin = 64 layers (5, 6) in the pixel-pair formulation on CTA pairs (needs use_ws2)
@@ -1366,7 +1368,37 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
       FF_CUDA(h, cudaStreamWaitEvent(st, h->h2d_ready[c1], 0));
     }
     dim3 g1(14, 14, ns);
-    {
+    // layers 1 + 2 in one kernel when the uint8 fast path is active and nobody asks for layer 1's output
+    const bool fused12 = h->use_c12 && h->use_c1_tc == 3 && layout == FF_X_NHWC_U8 && h->conv[1].ws2 && !h->conv[1].ws4 && stop != 1;
+    if (fused12) {
+      ProfScope ps(h, st, KC_TC_CONV);
+      CUtensorMap tmX;
+      cuuint64_t dims[3] = {672, 224, (cuuint64_t)ns};
+      cuuint64_t strides[2] = {672, (cuuint64_t)224 * 672};
+      cuuint32_t box[3] = {80, 18, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = g_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(xin), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(uint8 crops) failed: %d (is the input 16-byte aligned?)", (int)r);
+      C12Args ca;
+      ca.out = conv_output_buffer(h, 1, set); ca.w1 = h->c1_wp; ca.n_img = ns;
+      for (int c = 0; c < 3; ++c) { ca.na[c] = h->c1_na[c]; ca.nb[c] = h->c1_nb[c]; }
+      for (int o = 0; o < 32; ++o) {
+        ca.scale1[o] = h->conv1.scale[o]; ca.shift1[o] = h->conv1.shift[o];
+        ca.scale2[o] = h->conv[1].epi.scale[o]; ca.shift2[o] = h->conv[1].epi.shift[o];
+      }
+      static bool c12_attr = false;
+      if (!c12_attr) {
+        FF_CUDA(h, cudaFuncSetAttribute(c12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C12Smem::TOTAL));
+        c12_attr = true;
+      }
+      const ConvLayerDev& L2 = set ? h->conv_alt[1] : h->conv[1];
+      const int grid = std::min(16 * 14 * ns, h->num_sms * 2);
+      cudaError_t e = launch_k(c12_kernel, dim3(grid), dim3(128), C12Smem::TOTAL, st, true, tmX, L2.tmW_ws2, ca);
+      if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of the fused layer-1/2 kernel failed: %s", cudaGetErrorString(e));
+      ++h->launches;
+    } else {
       ProfScope ps(h, st, KC_CONV1);
       if (h->use_c1_tc == 3 && layout == FF_X_NHWC_U8) {
         CUtensorMap tmX;
@@ -1412,10 +1444,12 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
       } else if (layout == FF_X_NHWC_U8) conv1_kernel<2><<<g1, 256, 0, st>>>(xin, bufA, ns, h->conv1);
       else conv1_kernel<0><<<g1, 256, 0, st>>>(xin, bufA, ns, h->conv1);
     }
-    FF_LAUNCH_CHECK(h, "conv1");
-    if (tap_hit(1, bufA, (int64_t)ns * 224 * 224 * 32, true)) return FF_OK;
+    if (!fused12) {
+      FF_LAUNCH_CHECK(h, "conv1");
+      if (tap_hit(1, bufA, (int64_t)ns * 224 * 224 * 32, true)) return FF_OK;
+    }
     for (int li = 1; li <= 5; ++li) {
-      int rc = run_conv(li, ns, li == 5 ? s0 : 0, set, st);
+      int rc = (fused12 && li == 1) ? FF_OK : run_conv(li, ns, li == 5 ? s0 : 0, set, st);
       if (rc) return rc;
       const ConvPlan& p = kConv[li];
       const int ohw = p.pool ? p.hw / 2 : p.hw;
@@ -1664,6 +1698,7 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
   if (const char* v = getenv("FF_PTC")) h->use_ptc = atoi(v);
   if (const char* v = getenv("FF_WS2")) h->use_ws2 = atoi(v);
   if (const char* v = getenv("FF_WS4")) h->use_ws4 = atoi(v);
+  if (const char* v = getenv("FF_C12")) h->use_c12 = atoi(v);
   if (const char* v = getenv("FF_WS2X")) h->use_ws2x = atoi(v);
   if (const char* v = getenv("FF_C1_TC")) h->use_c1_tc = atoi(v);
   if (const char* v = getenv("FF_C1_CPS")) h->c1_ctas_per_sm = std::max(1, atoi(v));

@@ -304,3 +304,22 @@ def test_quad_pixel_kernel_option_matches_oracle(monkeypatch):
         assert (got - ref).abs().max().item() <= ref.abs().max().item() * 0.004 * (step + 1), step
         # same bf16 inputs, same fp32 accumulation order per output up to the k-block order: equal to one rounding
         assert (got - ref_eng.debug_activation(xg, step)).abs().max().item() <= ref.abs().max().item() * 0.008, step
+
+
+def test_fused_layer12_kernel_option_matches_oracle(monkeypatch):
+    """FF_C12=1 runs feature layers 1 and 2 in one kernel (conv1 output never leaves shared memory)."""
+    monkeypatch.setenv("FF_C12", "1")
+    eng, sd = _engine("bn", max_crops=64)
+    monkeypatch.delenv("FF_C12")
+    crops = W.synthetic_crops(3, seed=28)
+    acts = _oracle_layers(sd, O.normalize_crops(crops), 3)
+    xg = crops.cuda()
+    ref_eng, _ = _engine("bn", max_crops=64)
+    for step in (2, 3):
+        got = eng.debug_activation(xg, step)
+        ref = acts[step]
+        assert (got - ref).abs().max().item() <= ref.abs().max().item() * 0.004 * (step + 1), step
+        assert (got - ref_eng.debug_activation(xg, step)).abs().max().item() <= ref.abs().max().item() * 0.008, step
+    # tile grid 14 x 16 with a 14-row tile: the image borders (zero padding of conv1's OUTPUT) are inside `ref`
+    lg = eng.forward_slots(xg, torch.arange(3)).cpu()
+    assert (lg - ref_eng.forward_slots(xg, torch.arange(3)).cpu()).abs().max().item() <= 5e-3
