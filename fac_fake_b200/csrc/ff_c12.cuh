@@ -1,9 +1,13 @@
 // ff_c12.cuh — feature layers 1 AND 2 in one kernel (uint8 crops in, conv2 output out).
-// OPTIONAL (FF_C12=1), parity-tested, NOT the default.  Measured on B200: layers 1-6 take 3.42 ms per 512 crops with this
-// kernel against 3.05 ms with the separate conv1 / conv2 kernels, although it removes 3.2 GB of HBM traffic per step:
-// with all five phases on one set of 128 threads and only two CTAs per SM (the 48 KB conv2 filter is per CTA) a tile
-// costs ~4500 cycles per SM, i.e. the phases barely overlap.  The fusion needs the warp-specialised, double-buffered
-// form (producer / two MMA stages / two epilogue groups) to pay off — that is the round-2 item in DESIGN.md §8.
+// OPTIONAL (FF_C12=1), parity-tested, NOT the default.  Measured on B200: layers 1-6 take 3.37 ms per 512 crops with this
+// kernel against 3.14 ms with the separate conv1 / conv2 kernels, although it removes 3.2 GB of HBM traffic per step.
+// Three versions were timed: 128 threads / phases in sequence (3.42 ms), 256 threads (3.39 ms), and the software pipeline
+// below that runs the conv2 MMAs of tile k under the conversion of tile k+1 and the output epilogue of tile k-1
+// (3.37 ms).  That the pipeline changes nothing, and ncu's 26 % of samples on the conv2-MMA barrier, say the tensor
+// pipe is the limit: a tile costs ~3500 cycles per SM for 30 tcgen05.mma = ~115 cycles per instruction, against 64 for
+// plain operands in tools/umma_rate_test.cu — the row-shifted / overlapping-window descriptors that make the
+// im2col-free formulation possible are slower to fetch.  Same per-pixel cost as the separate kernels (15.6 vs 16.2
+// cycles), so the fusion only pays once the MMA count per pixel drops (e.g. fp8 operands or a wider K window).
 //
 // Layers 1-3 of the CViT stack are bound by HBM traffic, not by the tensor pipe (profiles/r01_ncu_ws2_kernels.txt,
 // DESIGN.md §8): the 224x224x32 bf16 map between conv1 and conv2 is 3.2 MB per crop, written once and read once.
@@ -18,7 +22,7 @@
 //      is of conv1's OUTPUT, so it cannot be produced by running conv1 on padded input);
 //   4. conv2 exactly as ws2conv_kernel<64>: 24 MMAs over the patch with row-shifted SW128 descriptors;
 //   5. epilogue 2: BN + ReLU -> 128 contiguous bytes per pixel pair to global (rows 14, 15 of the M tile are unused).
-// All phases run on the CTA's 128 threads one after the other; two CTAs per SM overlap each other's tensor and
+// All phases run on the CTA's 256 threads one after the other (two threads per accumulator row, one per pixel of the pair); two CTAs per SM overlap each other's tensor and
 // CUDA-core phases.  conv1 is recomputed on the halo (16x20 / 14x16 = 1.43x of a cheap layer).
 #pragma once
 #include "ff_ws.cuh"
@@ -42,18 +46,19 @@ struct C12Smem {
   static constexpr int PATCH_OFF = W2_BYTES;                          // 1024-aligned (49152)
   static constexpr int SIN_PITCH = 192;                               // 22 px x 8 B = 176, padded to a multiple of 16
   static constexpr int SIN_ROWS = 18;
-  static constexpr int SIN_OFF = PATCH_OFF + ((PATCH_BYTES + 1023) / 1024) * 1024;
+  static constexpr int PATCH_STRIDE = ((PATCH_BYTES + 1023) / 1024) * 1024;
+  static constexpr int SIN_OFF = PATCH_OFF + 2 * PATCH_STRIDE;        // two patches: tile k+1 is produced while conv2 reads tile k's
   static constexpr int SIN_BYTES = (SIN_ROWS + 1) * SIN_PITCH;        // +1 row: the last window of the last row reads 16 B past it
   static constexpr int B1_OFF = SIN_OFF + ((SIN_BYTES + 127) / 128) * 128;
   static constexpr int B1_BYTES = 3 * 2048;
   static constexpr int RAW_SLOT = 1536, RING = 3;
   static constexpr int RAW_OFF = B1_OFF + B1_BYTES;
-  static constexpr int BAR_OFF = RAW_OFF + RING * RAW_SLOT;           // w2, mma1, mma2, raw[RING]
-  static constexpr int SLOT_OFF = BAR_OFF + (3 + RING) * 8;
+  static constexpr int BAR_OFF = RAW_OFF + RING * RAW_SLOT;           // w2, mma1, mma2[2], raw[RING]
+  static constexpr int SLOT_OFF = BAR_OFF + (4 + RING) * 8;
   static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
 };
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ C12Args a) {
   using L = C12Smem;
   constexpr int HW = 224, TW = 16, TH = 14;
@@ -70,24 +75,26 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   uint8_t* s_patch = base_ptr + L::PATCH_OFF;
   const uint32_t bar_w2 = base + L::BAR_OFF;
   const uint32_t bar_mma1 = bar_w2 + 8;
-  const uint32_t bar_mma2 = bar_w2 + 16;
-  const uint32_t bar_raw = bar_w2 + 24;
+  const uint32_t bar_mma2 = bar_w2 + 16;      // two: one per conv2 accumulator
+  const uint32_t bar_raw = bar_w2 + 32;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  // 256 threads: thread pair (r, r + 128) shares accumulator row r; `half` picks the pixel of the pair it converts
+  const int tid = threadIdx.x, warp = tid >> 5, half = tid >> 7, lane_grp = warp & 3;
   // conv1 filter -> core-matrix layout: (n, chunk c) at ((n/8)*2 + c)*128 + (n%8)*16
-  for (int i = tid; i < 3 * 64 * 2; i += 128) {
+  for (int i = tid; i < 3 * 64 * 2; i += 256) {
     const int kh = i / 128, rem = i % 128, n = rem >> 1, c = rem & 1;
     *reinterpret_cast<uint4*>(s_b1 + kh * 2048 + ((n >> 3) * 2 + c) * 128 + (n & 7) * 16) = reinterpret_cast<const uint4*>(a.w1)[i];
   }
-  for (int i = tid; i < L::SIN_BYTES / 16; i += 128) reinterpret_cast<uint4*>(s_in)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < L::PATCH_BYTES / 16; i += 128) reinterpret_cast<uint4*>(s_patch)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < L::SIN_BYTES / 16; i += 256) reinterpret_cast<uint4*>(s_in)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 2 * L::PATCH_STRIDE / 16; i += 256) reinterpret_cast<uint4*>(s_patch)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW2);
     mbar_init(bar_w2, 1);
     mbar_init(bar_mma1, 1);
     mbar_init(bar_mma2, 1);
+    mbar_init(bar_mma2 + 8, 1);
     for (int s = 0; s < L::RING; ++s) mbar_init(bar_raw + 8 * s, 1);
     fence_mbar_init();
   }
@@ -98,7 +105,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tm_c1 = tmem;            // conv1: columns 0..63 = strip 0 (pairs 0..7), 64..127 = strip 1 (pairs 2..9)
-  const uint32_t tm_c2 = tmem + 128;      // conv2: 64 columns
+  const uint32_t tm_c2 = tmem + 128;      // conv2: two accumulators of 64 columns
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_w2, L::W2_BYTES);
     for (int kb = 0; kb < 6; ++kb) tma_load_2d(base + L::W2_OFF + kb * 8192, &tmW2, bar_w2, kb * 64, 0);
@@ -108,7 +115,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   const uint32_t sin_addr = base + L::SIN_OFF, b1_addr = base + L::B1_OFF, patch_addr = base + L::PATCH_OFF;
   constexpr uint32_t idesc = make_idesc_bf16(128, 64);
   const int num_tiles = TILES * a.n_img;
-  const int hl = tid >> 3, jl = tid & 7;
+  const int hl = (tid & 127) >> 3, jl = tid & 7;
 
   auto issue = [&](int t, int slot) {
     const int n = t / TILES;
@@ -126,19 +133,26 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       const int t = blockIdx.x + s * gridDim.x;
       if (t < num_tiles) issue(t, s);
     }
-  bool w2_ready = false;
-  int it = 0;
-  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-    const int n = t / TILES;
-    const int rem = t - n * TILES;
-    const int th = rem / TILES_W, tw = rem - th * TILES_W;
-    const int h0 = th * TH, w0 = tw * TW;
+  // Software pipeline over this CTA's tiles k = 0, 1, ...:
+  //   a. wait conv1 MMAs of tile k, epilogue 1 -> patch[k & 1]                     d. (k >= 1) wait conv2 MMAs of tile k-1,
+  //   b. issue conv2 MMAs of tile k  (patch[k & 1] -> accumulator c2[k & 1])          epilogue 2 of tile k-1 -> global
+  //   c. convert tile k+1, issue its conv1 MMAs
+  // so the 24 conv2 MMAs of tile k run under the conversion of tile k+1 and the output epilogue of tile k-1.
+  auto tile_coords = [&](int t, int* n, int* h0, int* w0) {
+    *n = t / TILES;
+    const int rem = t - *n * TILES;
+    const int th = rem / TILES_W;
+    *h0 = th * TH;
+    *w0 = (rem - th * TILES_W) * TW;
+  };
+  auto convert = [&](int t, int it) {          // raw uint8 window -> normalised bf16 NHWC4 patch; pixel (py, px) = image (h0-2+py, w0-3+px)
+    int n, h0, w0;
+    tile_coords(t, &n, &h0, &w0);
     const int slot = it % L::RING;
-    // ---- 1. raw uint8 window -> normalised bf16 NHWC4 patch: patch pixel (py, px) = image (h0-2+py, w0-3+px)
     mbar_wait(bar_raw + 8 * slot, (it / L::RING) & 1);
-    for (int pi = tid; pi < PH * PW; pi += 128) {
+    for (int pi = tid; pi < PH * PW; pi += 256) {
       const int py = pi / PW, px = pi - py * PW;
-      const uint8_t* rp = s_rawp + slot * L::RAW_SLOT + py * RAW_ROW + 7 + 3 * px;     // window starts at byte 48*tw-16 = pixel w0 - 16/3
+      const uint8_t* rp = s_rawp + slot * L::RAW_SLOT + py * RAW_ROW + 7 + 3 * px;     // the window starts 7 bytes before pixel w0-3
       const int gy = h0 - 2 + py, gx = w0 - 3 + px;
       const bool ok = gy >= 0 && gy < HW && gx >= 0 && gx < HW;
       const float v0 = ok ? fmaf(static_cast<float>(rp[0]), a.na[0], a.nb[0]) : 0.0f;
@@ -152,7 +166,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     if (tid == 0) {
       const int tn = t + (L::RING - 1) * gridDim.x;
       if (tn < num_tiles) issue(tn, (it + L::RING - 1) % L::RING);
-      // ---- 2. conv1 on 16 rows x 10 pairs: strip 0 = pairs 0..7, strip 1 = pairs 2..9 (32 bytes further)
+      // conv1 on 16 rows x 10 pairs: strip 0 = pairs 0..7, strip 1 = pairs 2..9 (32 bytes further)
       tcgen05_fence_after();
 #pragma unroll
       for (int strip = 0; strip < 2; ++strip)
@@ -164,10 +178,42 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         }
       umma_commit(bar_mma1);
     }
+  };
+  auto epilogue2 = [&](int t, int it) {        // thread = one pixel of pair (hl, jl) of the 14 x 16 tile: 32 channels = 64 bytes
+    int n, h0, w0;
+    tile_coords(t, &n, &h0, &w0);
+    mbar_wait(bar_mma2 + 8 * (it & 1), (it >> 1) & 1);
+    tcgen05_fence_after();
+    __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * HW + (h0 + hl)) * HW + (w0 + 2 * jl)) * 32 + half * 32;
+    uint32_t v[32];
+    tmem_ld_32x32(tm_c2 + (it & 1) * 64 + (static_cast<uint32_t>(lane_grp * 32) << 16) + half * 32, v);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      const float x0 = fmaf(__uint_as_float(v[c]), a.scale2[c], a.shift2[c]);
+      const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale2[c + 1], a.shift2[c + 1]);
+      pk[c >> 1] = pack_bf16x2_relu(x0, x1);
+    }
+    if (hl < TH) {
+      st_global_v8(o, pk);
+      st_global_v8(o + 16, pk + 8);
+    }
+    tcgen05_fence_before();
+  };
+
+  bool w2_ready = false;
+  if (blockIdx.x < num_tiles) convert(blockIdx.x, 0);
+  int it = 0;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    int n, h0, w0;
+    tile_coords(t, &n, &h0, &w0);
+    uint8_t* patch = s_patch + (it & 1) * L::PATCH_STRIDE;
+    // ---- a. epilogue 1: thread (hl, jl, half) converts pixel `half` of conv1 pair (row hl, pair jl) from strip 0 and of
+    //         (row hl, pair jl+2) from strip 1 (kept only for jl >= 6).  Patch row hl = image row h0-1+hl, pair j = image
+    //         pixels w0-2+2j, +1; positions outside the image are conv2's zero padding.
     mbar_wait(bar_mma1, it & 1);
     tcgen05_fence_after();
-    // ---- 3. epilogue 1: thread (hl, jl) owns conv1 pair (row hl, pair jl) from strip 0 and (row hl, pair jl+2) from
-    //         strip 1 (kept only for jl >= 6).  Patch row hl = image row h0-1+hl, pair j = image pixels w0-2+2j, +1.
     {
       const int gy = h0 - 1 + hl;
 #pragma unroll
@@ -177,72 +223,51 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         const int gx = w0 - 2 + 2 * pj;
         const bool inside = gy >= 0 && gy < HW && gx >= 0 && gx < HW;     // pairs never straddle the image border
         const int rowidx = hl * 10 + pj;
-        uint8_t* prow = s_patch + rowidx * 128;
+        uint8_t* prow = patch + rowidx * 128;
         const int sw = rowidx & 7;
+        uint32_t v[32];
+        tmem_ld_32x32(tm_c1 + (static_cast<uint32_t>(lane_grp * 32) << 16) + strip * 64 + half * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          uint32_t v[32];
-          tmem_ld_32x32(tm_c1 + (static_cast<uint32_t>(warp * 32) << 16) + strip * 64 + p * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
+        for (int c = 0; c < 32; c += 2) {
+          const float x0 = fmaf(__uint_as_float(v[c]), a.scale1[c], a.shift1[c]);
+          const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale1[c + 1], a.shift1[c + 1]);
+          pk[c >> 1] = inside ? pack_bf16x2_relu(x0, x1) : 0u;
+        }
+        if (keep) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const float x0 = fmaf(__uint_as_float(v[c]), a.scale1[c], a.shift1[c]);
-            const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale1[c + 1], a.shift1[c + 1]);
-            pk[c >> 1] = inside ? pack_bf16x2_relu(x0, x1) : 0u;
-          }
-          if (keep) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)    // pixel p of the pair = 16-byte chunks 4p .. 4p+3 of the 128-byte row
-              *reinterpret_cast<uint4*>(prow + (((4 * p + q) ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          }
+          for (int q = 0; q < 4; ++q)      // pixel `half` of the pair = 16-byte chunks 4*half .. 4*half+3 of the 128-byte row
+            *reinterpret_cast<uint4*>(prow + (((4 * half + q) ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
       }
     }
     fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncthreads();
+    // ---- b. conv2 of tile k: as ws2conv_kernel<64> over patch[k & 1] into accumulator c2[k & 1]
     if (tid == 0) {
-      // ---- 4. conv2: as ws2conv_kernel<64> over the patch just written
       if (!w2_ready) { mbar_wait(bar_w2, 0); w2_ready = true; }
       tcgen05_fence_after();
+      const uint32_t pa = patch_addr + (it & 1) * L::PATCH_STRIDE;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const uint64_t adesc = make_kmajor_desc_sbo<128>(patch_addr + kh * 10 * 128 + 64 + 32 * c, 10 * 128);
+          const uint64_t adesc = make_kmajor_desc_sbo<128>(pa + kh * 10 * 128 + 64 + 32 * c, 10 * 128);
           const uint64_t bdesc = make_kmajor_desc<128>(base + L::W2_OFF + (kh * 2 + (c >> 2)) * 8192) + 2 * (c & 3);
-          umma_bf16_ss(tm_c2, adesc, bdesc, idesc, (kh > 0 || c > 0) ? 1u : 0u);
+          umma_bf16_ss(tm_c2 + (it & 1) * 64, adesc, bdesc, idesc, (kh > 0 || c > 0) ? 1u : 0u);
         }
       }
-      umma_commit(bar_mma2);
+      umma_commit(bar_mma2 + 8 * (it & 1));
     }
-    mbar_wait(bar_mma2, it & 1);
-    tcgen05_fence_after();
-    // ---- 5. epilogue 2: thread = pixel pair (hl, jl) of the 14 x 16 tile: 2 x 32 channels = 128 contiguous bytes
-    {
-      __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * HW + (h0 + hl)) * HW + (w0 + 2 * jl)) * 32;
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        uint32_t v[32];
-        tmem_ld_32x32(tm_c2 + (static_cast<uint32_t>(warp * 32) << 16) + p * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          const float x0 = fmaf(__uint_as_float(v[c]), a.scale2[c], a.shift2[c]);
-          const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale2[c + 1], a.shift2[c + 1]);
-          pk[c >> 1] = pack_bf16x2_relu(x0, x1);
-        }
-        if (hl < TH) {
-          st_global_v8(o + p * 32, pk);
-          st_global_v8(o + p * 32 + 16, pk + 8);
-        }
-      }
-    }
-    tcgen05_fence_before();
-    __syncthreads();          // s_in / the patch / both accumulators are free for the next tile
+    // ---- c. next tile: conversion + conv1 MMAs (s_in and the conv1 accumulators were released by step a)
+    const int tn = t + gridDim.x;
+    if (tn < num_tiles) convert(tn, it + 1);
+    // ---- d. previous tile: output epilogue under the conv2 MMAs just issued
+    if (it >= 1) epilogue2(t - gridDim.x, it - 1);
   }
+  if (it >= 1) epilogue2(blockIdx.x + (it - 1) * gridDim.x, it - 1);
   __syncthreads();
   if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<256>(tmem); }
 }

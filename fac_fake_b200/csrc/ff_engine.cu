@@ -1395,7 +1395,7 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
       }
       const ConvLayerDev& L2 = set ? h->conv_alt[1] : h->conv[1];
       const int grid = std::min(16 * 14 * ns, h->num_sms * 2);
-      cudaError_t e = launch_k(c12_kernel, dim3(grid), dim3(128), C12Smem::TOTAL, st, true, tmX, L2.tmW_ws2, ca);
+      cudaError_t e = launch_k(c12_kernel, dim3(grid), dim3(256), C12Smem::TOTAL, st, true, tmX, L2.tmW_ws2, ca);
       if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of the fused layer-1/2 kernel failed: %s", cudaGetErrorString(e));
       ++h->launches;
     } else {
