@@ -3,11 +3,14 @@
 // kernel against 3.14 ms with the separate conv1 / conv2 kernels, although it removes 3.2 GB of HBM traffic per step.
 // Three versions were timed: 128 threads / phases in sequence (3.42 ms), 256 threads (3.39 ms), and the software pipeline
 // below that runs the conv2 MMAs of tile k under the conversion of tile k+1 and the output epilogue of tile k-1
-// (3.37 ms).  That the pipeline changes nothing, and ncu's 26 % of samples on the conv2-MMA barrier, say the tensor
-// pipe is the limit: a tile costs ~3500 cycles per SM for 30 tcgen05.mma = ~115 cycles per instruction, against 64 for
-// plain operands in tools/umma_rate_test.cu — the row-shifted / overlapping-window descriptors that make the
-// im2col-free formulation possible are slower to fetch.  Same per-pixel cost as the separate kernels (15.6 vs 16.2
-// cycles), so the fusion only pays once the MMA count per pixel drops (e.g. fp8 operands or a wider K window).
+// (3.37 ms).  That the pipeline changes nothing, and ncu's 26 % of samples on the conv2-MMA barrier, point at the rate
+// at which ONE thread can issue the 30 tcgen05.mma of a tile: ~3500 cycles per tile per SM = ~115 cycles per MMA.  The
+// operand layouts are not the cause — tools/umma_rate_test.cu measures 53 (N=64) / 64 (N=128) cycles per MMA for the
+// row-shifted SW128 windows and for the overlapping non-swizzled windows alike when the descriptors are ready, and 104
+// cycles when the issuing thread rebuilds them between MMAs; this kernel still has ~14 SASS instructions between
+// consecutive UTCHMMA even with base descriptors + constant offsets.  Same per-pixel cost as the separate kernels
+// (15.6 vs 16.2 cycles), so the fusion pays only with a leaner issue loop (descriptor tables in uniform registers) or
+// fewer MMAs per pixel.
 //
 // Layers 1-3 of the CViT stack are bound by HBM traffic, not by the tensor pipe (profiles/r01_ncu_ws2_kernels.txt,
 // DESIGN.md §8): the 224x224x32 bf16 map between conv1 and conv2 is 3.2 MB per crop, written once and read once.
@@ -114,6 +117,12 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   pdl_wait();
   const uint32_t sin_addr = base + L::SIN_OFF, b1_addr = base + L::B1_OFF, patch_addr = base + L::PATCH_OFF;
   constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+  // base descriptors, built once: the issuing thread only adds compile-time offsets between MMAs (a single thread that
+  // rebuilds descriptors between tcgen05.mma issues at ~104 cycles per MMA instead of 53, tools/umma_rate_test.cu)
+  const uint64_t ad1 = make_kmajor_desc_noswz(sin_addr, 16, L::SIN_PITCH);
+  const uint64_t bd1 = make_kmajor_desc_noswz(b1_addr, 128, 256);
+  const uint64_t ad2 = make_kmajor_desc_sbo<128>(patch_addr + 64, 10 * 128);
+  const uint64_t bd2 = make_kmajor_desc<128>(base + L::W2_OFF);
   const int num_tiles = TILES * a.n_img;
   const int hl = (tid & 127) >> 3, jl = tid & 7;
 
@@ -171,11 +180,9 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
 #pragma unroll
       for (int strip = 0; strip < 2; ++strip)
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const uint64_t ad = make_kmajor_desc_noswz(sin_addr + kh * L::SIN_PITCH + strip * 32, 16, L::SIN_PITCH);
-          const uint64_t bd = make_kmajor_desc_noswz(b1_addr + kh * 2048, 128, 256);
-          umma_bf16_ss(tm_c1 + strip * 64, ad, bd, idesc, kh > 0 ? 1u : 0u);
-        }
+        for (int kh = 0; kh < 3; ++kh)     // descriptors = per-kernel constants + compile-time offsets (16-byte units)
+          umma_bf16_ss(tm_c1 + strip * 64, ad1 + static_cast<uint64_t>((kh * L::SIN_PITCH + strip * 32) >> 4),
+                       bd1 + static_cast<uint64_t>((kh * 2048) >> 4), idesc, kh > 0 ? 1u : 0u);
       umma_commit(bar_mma1);
     }
   };
@@ -249,15 +256,14 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     if (tid == 0) {
       if (!w2_ready) { mbar_wait(bar_w2, 0); w2_ready = true; }
       tcgen05_fence_after();
-      const uint32_t pa = patch_addr + (it & 1) * L::PATCH_STRIDE;
+      const uint64_t adesc0 = ad2 + static_cast<uint64_t>(((it & 1) * L::PATCH_STRIDE) >> 4);
+      const uint32_t d2 = tm_c2 + (it & 1) * 64;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint64_t adesc = make_kmajor_desc_sbo<128>(pa + kh * 10 * 128 + 64 + 32 * c, 10 * 128);
-          const uint64_t bdesc = make_kmajor_desc<128>(base + L::W2_OFF + (kh * 2 + (c >> 2)) * 8192) + 2 * (c & 3);
-          umma_bf16_ss(tm_c2 + (it & 1) * 64, adesc, bdesc, idesc, (kh > 0 || c > 0) ? 1u : 0u);
-        }
+        for (int c = 0; c < 8; ++c)
+          umma_bf16_ss(d2, adesc0 + static_cast<uint64_t>((kh * 10 * 128 + 32 * c) >> 4),
+                       bd2 + static_cast<uint64_t>(((kh * 2 + (c >> 2)) * 8192 + 32 * (c & 3)) >> 4), idesc, (kh > 0 || c > 0) ? 1u : 0u);
       }
       umma_commit(bar_mma2 + 8 * (it & 1));
     }

@@ -364,6 +364,7 @@ ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+      const uint64_t bdesc0 = make_kmajor_desc<128>(base + L::W_OFF);
       mbar_wait(bar_w, 0);
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -374,13 +375,17 @@ ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tcgen05_fence_after();
         const uint32_t patch = base + L::P_OFF + s * L::PATCH_STRIDE;
         const uint32_t d_tmem = tmem_base + acc * BN;
+        // One descriptor per tile, then constant 64-bit offsets (address field is in 16-byte units): the single issuing
+        // thread must not spend more scalar work per MMA than the tensor pipe needs to execute it (tools/umma_rate_test.cu:
+        // 53-64 cycles per MMA with ready descriptors, 104 when they are rebuilt between the MMAs).
+        const uint64_t adesc0 = make_kmajor_desc_sbo<128>(patch + 64, 10 * 128);
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             // A: window starts 64 bytes (one pixel) into pair j of patch row (h_l + kh); 32 bytes per k-step
-            const uint64_t adesc = make_kmajor_desc_sbo<128>(patch + kh * 10 * 128 + 64 + 32 * c, 10 * 128);
-            const uint64_t bdesc = make_kmajor_desc<128>(base + L::W_OFF + (kh * 2 + (c >> 2)) * L::W_TILE) + 2 * (c & 3);
+            const uint64_t adesc = adesc0 + static_cast<uint64_t>((kh * 10 * 128 + 32 * c) >> 4);
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(((kh * 2 + (c >> 2)) * L::W_TILE + 32 * (c & 3)) >> 4);
             umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kh > 0 || c > 0) ? 1u : 0u);
           }
         }
