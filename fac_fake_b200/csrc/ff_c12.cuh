@@ -1,16 +1,20 @@
 // ff_c12.cuh — feature layers 1 AND 2 in one kernel (uint8 crops in, conv2 output out).
-// OPTIONAL (FF_C12=1), parity-tested, NOT the default.  Measured on B200: layers 1-6 take 3.37 ms per 512 crops with this
-// kernel against 3.14 ms with the separate conv1 / conv2 kernels, although it removes 3.2 GB of HBM traffic per step.
-// Three versions were timed: 128 threads / phases in sequence (3.42 ms), 256 threads (3.39 ms), and the software pipeline
-// below that runs the conv2 MMAs of tile k under the conversion of tile k+1 and the output epilogue of tile k-1
-// (3.37 ms).  That the pipeline changes nothing, and ncu's 26 % of samples on the conv2-MMA barrier, point at the rate
-// at which ONE thread can issue the 30 tcgen05.mma of a tile: ~3500 cycles per tile per SM = ~115 cycles per MMA.  The
-// operand layouts are not the cause — tools/umma_rate_test.cu measures 53 (N=64) / 64 (N=128) cycles per MMA for the
-// row-shifted SW128 windows and for the overlapping non-swizzled windows alike when the descriptors are ready, and 104
-// cycles when the issuing thread rebuilds them between MMAs; this kernel still has ~14 SASS instructions between
-// consecutive UTCHMMA even with base descriptors + constant offsets.  Same per-pixel cost as the separate kernels
-// (15.6 vs 16.2 cycles), so the fusion pays only with a leaner issue loop (descriptor tables in uniform registers) or
-// fewer MMAs per pixel.
+// DEFAULT on the uint8 input path (FF_C12=0 selects the separate conv1 / conv2 kernels).  History of this kernel on
+// B200, layers 1-6 per 512 crops (separate kernels: 3.05-3.13 ms):
+//   128 threads, five phases in sequence                      3.42 ms
+//   256 threads (two per accumulator row)                     3.39 ms
+//   + software pipeline over tiles, one role per CTA          3.37 ms   <- unchanged: clock64 instrumentation showed the
+//                                                                          thread issuing the 24 conv2 MMAs BLOCKED for
+//                                                                          ~2200 cycles per tile (busy tensor pipe, two
+//                                                                          CTAs per SM) and with it every thread at the
+//                                                                          next barrier
+//   + dedicated MMA-issuing warp, mbarrier hand-offs          3.11 ms
+//   + 5-deep ring of uint8 windows                            3.01-3.05 ms  (separate kernels in the same run: 3.08-3.09)
+// i.e. the same time as the separate kernels with 3.2 GB less HBM traffic per step and 8 fewer launches; the sustained
+// (power-capped) bench is unchanged at 71.6 k crops/s.  What is left per tile: the conv1 accumulators of strip 1 are
+// converted by all rows although only pairs 8, 9 are kept (tcgen05.ld is warp-collective), and 30 MMAs x 53 cycles.
+// tools/umma_rate_test.cu: the row-shifted SW128 windows and the overlapping non-swizzled windows cost the same as plain
+// operands (53 / 64 cycles per MMA for N = 64 / 128).
 //
 // Layers 1-3 of the CViT stack are bound by HBM traffic, not by the tensor pipe (profiles/r01_ncu_ws2_kernels.txt,
 // DESIGN.md §8): the 224x224x32 bf16 map between conv1 and conv2 is 3.2 MB per crop, written once and read once.
@@ -39,6 +43,7 @@ struct C12Args {
   float na[3], nb[3];
   float scale1[32], shift1[32];
   float scale2[32], shift2[32];
+  long long* dbg;                // optional [8] cycle counters of CTA 0 (FF_C12_DBG=1): phase breakdown of the pipeline
 };
 
 struct C12Smem {
@@ -54,14 +59,15 @@ struct C12Smem {
   static constexpr int SIN_BYTES = (SIN_ROWS + 1) * SIN_PITCH;        // +1 row: the last window of the last row reads 16 B past it
   static constexpr int B1_OFF = SIN_OFF + ((SIN_BYTES + 127) / 128) * 128;
   static constexpr int B1_BYTES = 3 * 2048;
-  static constexpr int RAW_SLOT = 1536, RING = 3;
+  static constexpr int RAW_SLOT = 1536, RING = 5;
   static constexpr int RAW_OFF = B1_OFF + B1_BYTES;
-  static constexpr int BAR_OFF = RAW_OFF + RING * RAW_SLOT;           // w2, mma1, mma2[2], raw[RING]
-  static constexpr int SLOT_OFF = BAR_OFF + (4 + RING) * 8;
+  static constexpr int BAR_OFF = RAW_OFF + RING * RAW_SLOT;           // w2, mma1, mma2[2], raw[RING], sin_ready, patch_ready
+  static constexpr int SLOT_OFF = BAR_OFF + (6 + RING) * 8;
   static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
 };
 
-__global__ void __launch_bounds__(256, 2)
+constexpr int C12_THREADS = 288;      // 8 worker warps + 1 MMA-issuing warp
+__global__ void __launch_bounds__(C12_THREADS, 2)
 c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ C12Args a) {
   using L = C12Smem;
   constexpr int HW = 224, TW = 16, TH = 14;
@@ -80,17 +86,19 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   const uint32_t bar_mma1 = bar_w2 + 8;
   const uint32_t bar_mma2 = bar_w2 + 16;      // two: one per conv2 accumulator
   const uint32_t bar_raw = bar_w2 + 32;
+  const uint32_t bar_sin = bar_raw + 8 * L::RING;       // 256 worker arrivals: conv1's input patch of the next tile is written
+  const uint32_t bar_patch = bar_sin + 8;               // 256 worker arrivals: conv2's patch of this tile is written
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
 
   // 256 threads: thread pair (r, r + 128) shares accumulator row r; `half` picks the pixel of the pair it converts
   const int tid = threadIdx.x, warp = tid >> 5, half = tid >> 7, lane_grp = warp & 3;
   // conv1 filter -> core-matrix layout: (n, chunk c) at ((n/8)*2 + c)*128 + (n%8)*16
-  for (int i = tid; i < 3 * 64 * 2; i += 256) {
+  for (int i = tid; i < 3 * 64 * 2; i += C12_THREADS) {
     const int kh = i / 128, rem = i % 128, n = rem >> 1, c = rem & 1;
     *reinterpret_cast<uint4*>(s_b1 + kh * 2048 + ((n >> 3) * 2 + c) * 128 + (n & 7) * 16) = reinterpret_cast<const uint4*>(a.w1)[i];
   }
-  for (int i = tid; i < L::SIN_BYTES / 16; i += 256) reinterpret_cast<uint4*>(s_in)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 2 * L::PATCH_STRIDE / 16; i += 256) reinterpret_cast<uint4*>(s_patch)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < L::SIN_BYTES / 16; i += C12_THREADS) reinterpret_cast<uint4*>(s_in)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 2 * L::PATCH_STRIDE / 16; i += C12_THREADS) reinterpret_cast<uint4*>(s_patch)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW2);
@@ -99,9 +107,11 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     mbar_init(bar_mma2, 1);
     mbar_init(bar_mma2 + 8, 1);
     for (int s = 0; s < L::RING; ++s) mbar_init(bar_raw + 8 * s, 1);
+    mbar_init(bar_sin, 256);
+    mbar_init(bar_patch, 256);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc<256>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (warp == 8) tmem_alloc<256>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
@@ -109,7 +119,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   const uint32_t tmem = *tmem_slot;
   const uint32_t tm_c1 = tmem;            // conv1: columns 0..63 = strip 0 (pairs 0..7), 64..127 = strip 1 (pairs 2..9)
   const uint32_t tm_c2 = tmem + 128;      // conv2: two accumulators of 64 columns
-  if (tid == 0) {
+  if (tid == 256) {
     mbar_arrive_expect_tx(bar_w2, L::W2_BYTES);
     for (int kb = 0; kb < 6; ++kb) tma_load_2d(base + L::W2_OFF + kb * 8192, &tmW2, bar_w2, kb * 64, 0);
     pdl_trigger();
@@ -124,7 +134,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   const uint64_t ad2 = make_kmajor_desc_sbo<128>(patch_addr + 64, 10 * 128);
   const uint64_t bd2 = make_kmajor_desc<128>(base + L::W2_OFF);
   const int num_tiles = TILES * a.n_img;
-  const int hl = (tid & 127) >> 3, jl = tid & 7;
+  const int hl = (tid & 127) >> 3, jl = tid & 7;          // workers only (tid < 256)
 
   auto issue = [&](int t, int slot) {
     const int n = t / TILES;
@@ -137,16 +147,17 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar_raw + 8 * slot), "r"(48 * tw - 16), "r"(th * TH - 2), "r"(n)
         : "memory");
   };
-  if (tid == 0)
+  if (tid == 256)
     for (int s = 0; s < L::RING - 1; ++s) {
       const int t = blockIdx.x + s * gridDim.x;
       if (t < num_tiles) issue(t, s);
     }
-  // Software pipeline over this CTA's tiles k = 0, 1, ...:
-  //   a. wait conv1 MMAs of tile k, epilogue 1 -> patch[k & 1]                     d. (k >= 1) wait conv2 MMAs of tile k-1,
-  //   b. issue conv2 MMAs of tile k  (patch[k & 1] -> accumulator c2[k & 1])          epilogue 2 of tile k-1 -> global
-  //   c. convert tile k+1, issue its conv1 MMAs
-  // so the 24 conv2 MMAs of tile k run under the conversion of tile k+1 and the output epilogue of tile k-1.
+  // Pipeline over this CTA's tiles k = 0, 1, ...   (a thread blocks while it issues tcgen05.mma into a busy tensor pipe —
+  // ~2200 cycles for the 24 conv2 MMAs when both CTAs of the SM are issuing — so the issuer is a warp of its own):
+  //   issuer (warp 8, one lane):  wait sin_ready(k) -> conv1 MMAs(k);   wait patch_ready(k) -> conv2 MMAs(k)
+  //   workers (warps 0-7):        a. wait conv1(k), epilogue 1 -> patch[k & 1], arrive patch_ready
+  //                               c. convert tile k+1 -> s_in, arrive sin_ready
+  //                               d. wait conv2(k-1), epilogue 2 of tile k-1 -> global
   auto tile_coords = [&](int t, int* n, int* h0, int* w0) {
     *n = t / TILES;
     const int rem = t - *n * TILES;
@@ -154,128 +165,146 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     *h0 = th * TH;
     *w0 = (rem - th * TILES_W) * TW;
   };
-  auto convert = [&](int t, int it) {          // raw uint8 window -> normalised bf16 NHWC4 patch; pixel (py, px) = image (h0-2+py, w0-3+px)
-    int n, h0, w0;
-    tile_coords(t, &n, &h0, &w0);
-    const int slot = it % L::RING;
-    mbar_wait(bar_raw + 8 * slot, (it / L::RING) & 1);
-    for (int pi = tid; pi < PH * PW; pi += 256) {
-      const int py = pi / PW, px = pi - py * PW;
-      const uint8_t* rp = s_rawp + slot * L::RAW_SLOT + py * RAW_ROW + 7 + 3 * px;     // the window starts 7 bytes before pixel w0-3
-      const int gy = h0 - 2 + py, gx = w0 - 3 + px;
-      const bool ok = gy >= 0 && gy < HW && gx >= 0 && gx < HW;
-      const float v0 = ok ? fmaf(static_cast<float>(rp[0]), a.na[0], a.nb[0]) : 0.0f;
-      const float v1 = ok ? fmaf(static_cast<float>(rp[1]), a.na[1], a.nb[1]) : 0.0f;
-      const float v2 = ok ? fmaf(static_cast<float>(rp[2]), a.na[2], a.nb[2]) : 0.0f;
-      *reinterpret_cast<uint2*>(s_in + py * L::SIN_PITCH + px * 8) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, 0.0f));
-    }
-    fence_proxy_async_smem();
-    tcgen05_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      const int tn = t + (L::RING - 1) * gridDim.x;
-      if (tn < num_tiles) issue(tn, (it + L::RING - 1) % L::RING);
-      // conv1 on 16 rows x 10 pairs: strip 0 = pairs 0..7, strip 1 = pairs 2..9 (32 bytes further)
-      tcgen05_fence_after();
-#pragma unroll
-      for (int strip = 0; strip < 2; ++strip)
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh)     // descriptors = per-kernel constants + compile-time offsets (16-byte units)
-          umma_bf16_ss(tm_c1 + strip * 64, ad1 + static_cast<uint64_t>((kh * L::SIN_PITCH + strip * 32) >> 4),
-                       bd1 + static_cast<uint64_t>((kh * 2048) >> 4), idesc, kh > 0 ? 1u : 0u);
-      umma_commit(bar_mma1);
-    }
-  };
-  auto epilogue2 = [&](int t, int it) {        // thread = one pixel of pair (hl, jl) of the 14 x 16 tile: 32 channels = 64 bytes
-    int n, h0, w0;
-    tile_coords(t, &n, &h0, &w0);
-    mbar_wait(bar_mma2 + 8 * (it & 1), (it >> 1) & 1);
-    tcgen05_fence_after();
-    __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * HW + (h0 + hl)) * HW + (w0 + 2 * jl)) * 32 + half * 32;
-    uint32_t v[32];
-    tmem_ld_32x32(tm_c2 + (it & 1) * 64 + (static_cast<uint32_t>(lane_grp * 32) << 16) + half * 32, v);
-    tmem_ld_wait();
-    uint32_t pk[16];
-#pragma unroll
-    for (int c = 0; c < 32; c += 2) {
-      const float x0 = fmaf(__uint_as_float(v[c]), a.scale2[c], a.shift2[c]);
-      const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale2[c + 1], a.shift2[c + 1]);
-      pk[c >> 1] = pack_bf16x2_relu(x0, x1);
-    }
-    if (hl < TH) {
-      st_global_v8(o, pk);
-      st_global_v8(o + 16, pk + 8);
-    }
-    tcgen05_fence_before();
-  };
 
-  bool w2_ready = false;
-  if (blockIdx.x < num_tiles) convert(blockIdx.x, 0);
-  int it = 0;
-  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-    int n, h0, w0;
-    tile_coords(t, &n, &h0, &w0);
-    uint8_t* patch = s_patch + (it & 1) * L::PATCH_STRIDE;
-    // ---- a. epilogue 1: thread (hl, jl, half) converts pixel `half` of conv1 pair (row hl, pair jl) from strip 0 and of
-    //         (row hl, pair jl+2) from strip 1 (kept only for jl >= 6).  Patch row hl = image row h0-1+hl, pair j = image
-    //         pixels w0-2+2j, +1; positions outside the image are conv2's zero padding.
-    mbar_wait(bar_mma1, it & 1);
-    tcgen05_fence_after();
-    {
-      const int gy = h0 - 1 + hl;
+  if (warp == 8) {
+    if (tid == 256) {
+      bool w2_ready = false;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        // conv1 of tile k on 16 rows x 10 pairs: strip 0 = pairs 0..7, strip 1 = pairs 2..9 (32 bytes further)
+        mbar_wait(bar_sin, it & 1);
+        tcgen05_fence_after();
+        const int tn = t + (L::RING - 1) * gridDim.x;      // every worker has consumed the raw window of tile k
+        if (tn < num_tiles) issue(tn, (it + L::RING - 1) % L::RING);
 #pragma unroll
-      for (int strip = 0; strip < 2; ++strip) {
-        const bool keep = strip == 0 || jl >= 6;     // tcgen05.ld is warp-collective: every thread loads, few store
-        const int pj = jl + 2 * strip;
-        const int gx = w0 - 2 + 2 * pj;
-        const bool inside = gy >= 0 && gy < HW && gx >= 0 && gx < HW;     // pairs never straddle the image border
-        const int rowidx = hl * 10 + pj;
-        uint8_t* prow = patch + rowidx * 128;
-        const int sw = rowidx & 7;
-        uint32_t v[32];
-        tmem_ld_32x32(tm_c1 + (static_cast<uint32_t>(lane_grp * 32) << 16) + strip * 64 + half * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+        for (int strip = 0; strip < 2; ++strip)
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          const float x0 = fmaf(__uint_as_float(v[c]), a.scale1[c], a.shift1[c]);
-          const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale1[c + 1], a.shift1[c + 1]);
-          pk[c >> 1] = inside ? pack_bf16x2_relu(x0, x1) : 0u;
+          for (int kh = 0; kh < 3; ++kh)     // descriptors = per-kernel constants + compile-time offsets (16-byte units)
+            umma_bf16_ss(tm_c1 + strip * 64, ad1 + static_cast<uint64_t>((kh * L::SIN_PITCH + strip * 32) >> 4),
+                         bd1 + static_cast<uint64_t>((kh * 2048) >> 4), idesc, kh > 0 ? 1u : 0u);
+        umma_commit(bar_mma1);
+        // conv2 of tile k: as ws2conv_kernel<64> over patch[k & 1] into accumulator c2[k & 1]
+        mbar_wait(bar_patch, it & 1);
+        if (!w2_ready) { mbar_wait(bar_w2, 0); w2_ready = true; }
+        tcgen05_fence_after();
+        const uint64_t adesc0 = ad2 + static_cast<uint64_t>(((it & 1) * L::PATCH_STRIDE) >> 4);
+        const uint32_t d2 = tm_c2 + (it & 1) * 64;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            umma_bf16_ss(d2, adesc0 + static_cast<uint64_t>((kh * 10 * 128 + 32 * c) >> 4),
+                         bd2 + static_cast<uint64_t>(((kh * 2 + (c >> 2)) * 8192 + 32 * (c & 3)) >> 4), idesc, (kh > 0 || c > 0) ? 1u : 0u);
         }
-        if (keep) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)      // pixel `half` of the pair = 16-byte chunks 4*half .. 4*half+3 of the 128-byte row
-            *reinterpret_cast<uint4*>(prow + (((4 * half + q) ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
+        umma_commit(bar_mma2 + 8 * (it & 1));
       }
     }
-    fence_proxy_async_smem();
-    tcgen05_fence_before();
-    __syncthreads();
-    // ---- b. conv2 of tile k: as ws2conv_kernel<64> over patch[k & 1] into accumulator c2[k & 1]
-    if (tid == 0) {
-      if (!w2_ready) { mbar_wait(bar_w2, 0); w2_ready = true; }
+  } else {
+    auto convert = [&](int t, int it) {        // raw uint8 window -> normalised bf16 NHWC4 patch; pixel (py, px) = image (h0-2+py, w0-3+px)
+      int n, h0, w0;
+      tile_coords(t, &n, &h0, &w0);
+      const int slot = it % L::RING;
+      mbar_wait(bar_raw + 8 * slot, (it / L::RING) & 1);
+      for (int pi = tid; pi < PH * PW; pi += 256) {
+        const int py = pi / PW, px = pi - py * PW;
+        const uint8_t* rp = s_rawp + slot * L::RAW_SLOT + py * RAW_ROW + 7 + 3 * px;     // the window starts 7 bytes before pixel w0-3
+        const int gy = h0 - 2 + py, gx = w0 - 3 + px;
+        const bool ok = gy >= 0 && gy < HW && gx >= 0 && gx < HW;
+        const float v0 = ok ? fmaf(static_cast<float>(rp[0]), a.na[0], a.nb[0]) : 0.0f;
+        const float v1 = ok ? fmaf(static_cast<float>(rp[1]), a.na[1], a.nb[1]) : 0.0f;
+        const float v2 = ok ? fmaf(static_cast<float>(rp[2]), a.na[2], a.nb[2]) : 0.0f;
+        *reinterpret_cast<uint2*>(s_in + py * L::SIN_PITCH + px * 8) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, 0.0f));
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(bar_sin);
+    };
+    auto epilogue2 = [&](int t, int it) {      // thread = one pixel of pair (hl, jl) of the 14 x 16 tile: 32 channels = 64 bytes
+      int n, h0, w0;
+      tile_coords(t, &n, &h0, &w0);
+      mbar_wait(bar_mma2 + 8 * (it & 1), (it >> 1) & 1);
       tcgen05_fence_after();
-      const uint64_t adesc0 = ad2 + static_cast<uint64_t>(((it & 1) * L::PATCH_STRIDE) >> 4);
-      const uint32_t d2 = tm_c2 + (it & 1) * 64;
+      __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * HW + (h0 + hl)) * HW + (w0 + 2 * jl)) * 32 + half * 32;
+      uint32_t v[32];
+      tmem_ld_32x32(tm_c2 + (it & 1) * 64 + (static_cast<uint32_t>(lane_grp * 32) << 16) + half * 32, v);
+      tmem_ld_wait();
+      uint32_t pk[16];
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          umma_bf16_ss(d2, adesc0 + static_cast<uint64_t>((kh * 10 * 128 + 32 * c) >> 4),
-                       bd2 + static_cast<uint64_t>(((kh * 2 + (c >> 2)) * 8192 + 32 * (c & 3)) >> 4), idesc, (kh > 0 || c > 0) ? 1u : 0u);
+      for (int c = 0; c < 32; c += 2) {
+        const float x0 = fmaf(__uint_as_float(v[c]), a.scale2[c], a.shift2[c]);
+        const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale2[c + 1], a.shift2[c + 1]);
+        pk[c >> 1] = pack_bf16x2_relu(x0, x1);
       }
-      umma_commit(bar_mma2 + 8 * (it & 1));
+      if (hl < TH) {
+        st_global_v8(o, pk);
+        st_global_v8(o + 16, pk + 8);
+      }
+      tcgen05_fence_before();
+    };
+
+    long long dbg_acc[6] = {0, 0, 0, 0, 0, 0};   // wait conv1 | epilogue 1 | - | convert next | wait conv2 + epilogue 2 | tiles
+    if (blockIdx.x < num_tiles) convert(blockIdx.x, 0);
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      int n, h0, w0;
+      tile_coords(t, &n, &h0, &w0);
+      uint8_t* patch = s_patch + (it & 1) * L::PATCH_STRIDE;
+      // ---- a. epilogue 1: thread (hl, jl, half) converts pixel `half` of conv1 pair (row hl, pair jl) from strip 0 and of
+      //         (row hl, pair jl+2) from strip 1 (kept only for jl >= 6).  Patch row hl = image row h0-1+hl, pair j = image
+      //         pixels w0-2+2j, +1; positions outside the image are conv2's zero padding.
+      const long long c0 = clock64();
+      mbar_wait(bar_mma1, it & 1);
+      tcgen05_fence_after();
+      const long long c1 = clock64();
+      {
+        const int gy = h0 - 1 + hl;
+#pragma unroll
+        for (int strip = 0; strip < 2; ++strip) {
+          const bool keep = strip == 0 || jl >= 6;     // tcgen05.ld is warp-collective: every thread loads, few store
+          const int pj = jl + 2 * strip;
+          const int gx = w0 - 2 + 2 * pj;
+          const bool inside = gy >= 0 && gy < HW && gx >= 0 && gx < HW;     // pairs never straddle the image border
+          const int rowidx = hl * 10 + pj;
+          uint8_t* prow = patch + rowidx * 128;
+          const int sw = rowidx & 7;
+          uint32_t v[32];
+          tmem_ld_32x32(tm_c1 + (static_cast<uint32_t>(lane_grp * 32) << 16) + strip * 64 + half * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const float x0 = fmaf(__uint_as_float(v[c]), a.scale1[c], a.shift1[c]);
+            const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale1[c + 1], a.shift1[c + 1]);
+            pk[c >> 1] = inside ? pack_bf16x2_relu(x0, x1) : 0u;
+          }
+          if (keep) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)      // pixel `half` of the pair = 16-byte chunks 4*half .. 4*half+3 of the 128-byte row
+              *reinterpret_cast<uint4*>(prow + (((4 * half + q) ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(bar_patch);
+      const long long c2 = clock64();
+      // ---- c. next tile: conversion (s_in was released by the conv1 MMAs of tile k, waited for in step a)
+      const int tn = t + gridDim.x;
+      if (tn < num_tiles) convert(tn, it + 1);
+      const long long c4 = clock64();
+      // ---- d. previous tile: output epilogue while the issuer feeds the conv2 MMAs of tile k
+      if (it >= 1) epilogue2(t - gridDim.x, it - 1);
+      const long long c5 = clock64();
+      if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) {
+        dbg_acc[0] += c1 - c0; dbg_acc[1] += c2 - c1; dbg_acc[3] += c4 - c2; dbg_acc[4] += c5 - c4; dbg_acc[5] += 1;
+      }
     }
-    // ---- c. next tile: conversion + conv1 MMAs (s_in and the conv1 accumulators were released by step a)
-    const int tn = t + gridDim.x;
-    if (tn < num_tiles) convert(tn, it + 1);
-    // ---- d. previous tile: output epilogue under the conv2 MMAs just issued
-    if (it >= 1) epilogue2(t - gridDim.x, it - 1);
+    if (it >= 1) epilogue2(blockIdx.x + (it - 1) * gridDim.x, it - 1);
+    if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0)
+      for (int i = 0; i < 6; ++i) a.dbg[i] = dbg_acc[i];
   }
-  if (it >= 1) epilogue2(blockIdx.x + (it - 1) * gridDim.x, it - 1);
   __syncthreads();
-  if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<256>(tmem); }
+  if (warp == 8) { tcgen05_fence_after(); tmem_dealloc<256>(tmem); }
 }
 
 }  // namespace ff

@@ -100,7 +100,7 @@ struct ff_cvit {
   int use_ws = 1;          // feature layers 2..6 on the weight-stationary halo kernel
   int ws_ctas_per_sm = 2;   // CTAs per SM for the Cin=32 weight-stationary kernels (Cin=64 always 1: smem)
   int use_ptc = 1;         // feature layers 7..17 on the persistent implicit-GEMM kernel
-  int use_c12 = 0;         // FF_C12=1: feature layers 1+2 fused in one kernel (ff_c12.cuh); parity-green but slower, see there
+  int use_c12 = 1;         // feature layers 1+2 fused in one kernel (ff_c12.cuh) on the uint8 path; FF_C12=0 -> separate kernels
   int use_ws4 = 0;         // 32 -> 32 layers (2, 3) in the pixel-quad formulation (FF_WS4=1; measured equal to the pair kernel)
   int use_ws2 = 1;         // Cin = 32 layers in the pixel-pair formulation
   int use_ws2x = 1;        // Cin = 64 layers (5, 6) in the pixel-pair formulation on CTA pairs (needs use_ws2)
@@ -1388,6 +1388,13 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
         ca.scale1[o] = h->conv1.scale[o]; ca.shift1[o] = h->conv1.shift[o];
         ca.scale2[o] = h->conv[1].epi.scale[o]; ca.shift2[o] = h->conv[1].epi.shift[o];
       }
+      ca.dbg = nullptr;
+      static long long* c12_dbg = nullptr;
+      static const bool c12_dbg_on = getenv("FF_C12_DBG") != nullptr;
+      if (c12_dbg_on) {
+        if (!c12_dbg) cudaMalloc(&c12_dbg, 8 * sizeof(long long));
+        ca.dbg = c12_dbg;
+      }
       static bool c12_attr = false;
       if (!c12_attr) {
         FF_CUDA(h, cudaFuncSetAttribute(c12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C12Smem::TOTAL));
@@ -1395,9 +1402,17 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
       }
       const ConvLayerDev& L2 = set ? h->conv_alt[1] : h->conv[1];
       const int grid = std::min(16 * 14 * ns, h->num_sms * 2);
-      cudaError_t e = launch_k(c12_kernel, dim3(grid), dim3(256), C12Smem::TOTAL, st, true, tmX, L2.tmW_ws2, ca);
+      cudaError_t e = launch_k(c12_kernel, dim3(grid), dim3(C12_THREADS), C12Smem::TOTAL, st, true, tmX, L2.tmW_ws2, ca);
       if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of the fused layer-1/2 kernel failed: %s", cudaGetErrorString(e));
       ++h->launches;
+      if (c12_dbg_on) {          // developer aid: cycles per pipeline phase of CTA 0 (serialises the stream)
+        long long hd[8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hd, c12_dbg, sizeof(hd), cudaMemcpyDeviceToHost);
+        if (hd[5] > 0)
+          fprintf(stderr, "[c12] tiles %lld | wait conv1 %lld | epi1+sync %lld | issue conv2 %lld | convert+issue conv1 %lld | wait conv2+epi2 %lld cycles/tile\n",
+                  hd[5], hd[0] / hd[5], hd[1] / hd[5], hd[2] / hd[5], hd[3] / hd[5], hd[4] / hd[5]);
+      }
     } else {
       ProfScope ps(h, st, KC_CONV1);
       if (h->use_c1_tc == 3 && layout == FF_X_NHWC_U8) {

@@ -306,15 +306,17 @@ def test_quad_pixel_kernel_option_matches_oracle(monkeypatch):
         assert (got - ref_eng.debug_activation(xg, step)).abs().max().item() <= ref.abs().max().item() * 0.008, step
 
 
-def test_fused_layer12_kernel_option_matches_oracle(monkeypatch):
-    """FF_C12=1 runs feature layers 1 and 2 in one kernel (conv1 output never leaves shared memory)."""
+def test_fused_layer12_kernel_and_separate_kernels_agree(monkeypatch):
+    """Feature layers 1 and 2 run in one kernel by default (conv1 output never leaves shared memory); FF_C12=0 selects
+    the separate conv1 / conv2 kernels.  Both against the oracle, and against each other to one bf16 rounding."""
     monkeypatch.setenv("FF_C12", "1")
     eng, sd = _engine("bn", max_crops=64)
+    monkeypatch.setenv("FF_C12", "0")
+    ref_eng, _ = _engine("bn", max_crops=64)
     monkeypatch.delenv("FF_C12")
     crops = W.synthetic_crops(3, seed=28)
     acts = _oracle_layers(sd, O.normalize_crops(crops), 3)
     xg = crops.cuda()
-    ref_eng, _ = _engine("bn", max_crops=64)
     for step in (2, 3):
         got = eng.debug_activation(xg, step)
         ref = acts[step]
@@ -323,3 +325,8 @@ def test_fused_layer12_kernel_option_matches_oracle(monkeypatch):
     # tile grid 14 x 16 with a 14-row tile: the image borders (zero padding of conv1's OUTPUT) are inside `ref`
     lg = eng.forward_slots(xg, torch.arange(3)).cpu()
     assert (lg - ref_eng.forward_slots(xg, torch.arange(3)).cpu()).abs().max().item() <= 5e-3
+    # 1 crop (fewer tiles than CTAs) and a ragged count
+    for n in (1, 5):
+        c = W.synthetic_crops(n, seed=29).cuda()
+        a, b = eng.debug_activation(c, 2), ref_eng.debug_activation(c, 2)
+        assert (a - b).abs().max().item() <= b.abs().max().item() * 0.008, n
