@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -57,6 +58,7 @@ struct ff_blazeface {
   float *act_a = nullptr, *act_b = nullptr, *feat8 = nullptr;   // ping-pong activations; 16x16x88 map kept for the heads
   float *raw_boxes = nullptr, *raw_scores = nullptr;      // [cap][896][16], [cap][896]
   int64_t launches = 0;
+  int use_chains = 1;                                    // FF_BLAZE_CHAINS=0: one launch per BlazeBlock
 };
 
 namespace {
@@ -126,6 +128,26 @@ blaze_stem_kernel(const uint8_t* __restrict__ tiles, const float* __restrict__ w
     o[q] = make_float4(fmaxf(acc[4 * q], 0.0f), fmaxf(acc[4 * q + 1], 0.0f), fmaxf(acc[4 * q + 2], 0.0f), fmaxf(acc[4 * q + 3], 0.0f));
 }
 
+// Pointwise 1x1 micro-tile: one thread accumulates 8 consecutive pixels x 4 consecutive output channels (32 FMAs per
+// input channel for two 16-byte shared-memory loads and four cached weight loads).  `dw` points at s_dw[0][first pixel],
+// `pitch` is the row pitch of s_dw in floats (a multiple of 4: 16-byte aligned rows).
+__device__ __forceinline__ void blaze_pw_8x4(const float* __restrict__ dw, int pitch, const float* __restrict__ pw_w, int cin, int cout,
+                                             int co, int nco, float (&acc)[8][4]) {
+  for (int c = 0; c < cin; ++c) {
+    const float4 a0 = *reinterpret_cast<const float4*>(dw + c * pitch);
+    const float4 a1 = *reinterpret_cast<const float4*>(dw + c * pitch + 4);
+    const float* wp = pw_w + c * cout + co;
+    float w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = j < nco ? wp[j] : 0.0f;
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[k][j] = fmaf(a[k], w[j], acc[k][j]);
+  }
+}
+
 // ---- one BlazeBlock (:8-43).  CTA = PIX output pixels of one tile x all channels.
 //   phase 1: depthwise 3x3 (stride 1: pad 1; stride 2: zero pad right/bottom by 2, no other padding) -> smem [PIX][cin]
 //   phase 2: pointwise 1x1 + bias + residual (stride 2: 2x2 max-pool of x; channels >= cin see zeros) -> ReLU
@@ -137,66 +159,173 @@ __global__ void __launch_bounds__(256)
 blaze_block_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ dw_w,
                    const float* __restrict__ dw_b, const float* __restrict__ pw_w, const float* __restrict__ pw_b,
                    int cin, int cout, int stride, int hw_in) {
-  extern __shared__ float s_dw_raw[];               // [cin][BLAZE_PIX + 1]: the pointwise phase reads 8 consecutive pixels
-  float (*s_dw)[BLAZE_PIX + 1] = reinterpret_cast<float (*)[BLAZE_PIX + 1]>(s_dw_raw);
+  extern __shared__ __align__(16) float s_dw_raw[];  // [cin][BLAZE_PIX + 4]: the pointwise phase reads 8 consecutive pixels
+  float (*s_dw)[BLAZE_PIX + 4] = reinterpret_cast<float (*)[BLAZE_PIX + 4]>(s_dw_raw);   // rows 16-byte aligned
   const int hw_out = hw_in / stride;
   const int npix = hw_out * hw_out;
   const int pix0 = blockIdx.x * BLAZE_PIX;
   const size_t img = blockIdx.y;
   const float* xin = x + img * (size_t)hw_in * hw_in * cin;
-  for (int i = threadIdx.x; i < BLAZE_PIX * cin; i += blockDim.x) {
-    const int p = i / cin, c = i - p * cin;         // c fastest: coalesced reads of the NHWC input
-    const int pix = pix0 + p;
-    float acc = 0.0f;
+  // depthwise: item = (4 consecutive output pixels of a row, channel), channel fastest (coalesced NHWC reads); the three
+  // input rows x (6 | 9) columns and the 9 taps are loaded once for the 4 outputs
+  for (int i = threadIdx.x; i < (BLAZE_PIX / 4) * cin; i += blockDim.x) {
+    const int q = i / cin, c = i - q * cin;
+    const int pix = pix0 + q * 4;                    // hw_out is a multiple of 4: the quad never wraps
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (pix < npix) {
       const int oy = pix / hw_out, ox = pix - oy * hw_out;
-      acc = dw_b[c];
+      float w[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) w[t] = dw_w[t * cin + c];
+      const float bias = dw_b[c];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = bias;
+      const int nc = stride == 2 ? 9 : 6;            // input columns touched by the quad
+      const int ix0 = stride == 2 ? 2 * ox : ox - 1, iy0 = stride == 2 ? 2 * oy : oy - 1;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
-        const int iy = stride == 2 ? 2 * oy + kh : oy + kh - 1;
+        const int iy = iy0 + kh;
+        if (iy < 0 || iy >= hw_in) continue;
+        float v[9];
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int ix = stride == 2 ? 2 * ox + kw : ox + kw - 1;
-          if (iy >= 0 && iy < hw_in && ix >= 0 && ix < hw_in)
-            acc = fmaf(xin[((size_t)iy * hw_in + ix) * cin + c], dw_w[(kh * 3 + kw) * cin + c], acc);
+        for (int j = 0; j < 9; ++j) {
+          const int ix = ix0 + j;
+          v[j] = (j < nc && ix >= 0 && ix < hw_in) ? xin[((size_t)iy * hw_in + ix) * cin + c] : 0.0f;
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            // stride 1: column k + kw; stride 2: column 2k + kw  (selected without dynamic indexing)
+            const float xv = stride == 2 ? v[2 * k + kw] : v[k + kw];
+            acc[k] = fmaf(xv, w[kh * 3 + kw], acc[k]);
+          }
       }
     }
-    s_dw[c][p] = acc;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_dw[c][q * 4 + k] = acc[k];
   }
   __syncthreads();
   float* o = out + img * (size_t)npix * cout;
-  // item = (pixel group of 8, output channel), channel fastest: the weight load is coalesced and reused for 8 pixels,
-  // the 8 activations of a channel are a shared-memory broadcast
-  for (int i = threadIdx.x; i < (BLAZE_PIX / BLAZE_PG) * cout; i += blockDim.x) {
-    const int pg = i / cout, co = i - pg * cout;
-    float acc[BLAZE_PG];
-    const float bias = pw_b[co];
+  // item = (pixel group of 8, group of 4 output channels), channel group fastest
+  const int cog = (cout + 3) / 4;
+  for (int i = threadIdx.x; i < (BLAZE_PIX / BLAZE_PG) * cog; i += blockDim.x) {
+    const int pg = i / cog, co = (i - pg * cog) * 4;
+    const int nco = min(4, cout - co);
+    float acc[8][4];
 #pragma unroll
-    for (int k = 0; k < BLAZE_PG; ++k) acc[k] = bias;
-    for (int c = 0; c < cin; ++c) {
-      const float wv = pw_w[c * cout + co];
-      const float* a = &s_dw[c][pg * BLAZE_PG];
+    for (int k = 0; k < 8; ++k)
 #pragma unroll
-      for (int k = 0; k < BLAZE_PG; ++k) acc[k] = fmaf(a[k], wv, acc[k]);
-    }
+      for (int j = 0; j < 4; ++j) acc[k][j] = j < nco ? pw_b[co + j] : 0.0f;
+    blaze_pw_8x4(&s_dw[0][pg * BLAZE_PG], BLAZE_PIX + 4, pw_w, cin, cout, co, nco, acc);
 #pragma unroll
     for (int k = 0; k < BLAZE_PG; ++k) {
       const int pix = pix0 + pg * BLAZE_PG + k;
       if (pix >= npix) continue;
-      float res = 0.0f;
-      if (co < cin) {
-        const int oy = pix / hw_out, ox = pix - oy * hw_out;
-        if (stride == 2) {
-          const float* q = xin + ((size_t)(2 * oy) * hw_in + 2 * ox) * cin + co;
-          res = fmaxf(fmaxf(q[0], q[cin]), fmaxf(q[(size_t)hw_in * cin], q[(size_t)hw_in * cin + cin]));
-        } else {
-          res = xin[((size_t)oy * hw_in + ox) * cin + co];
+      const int oy = pix / hw_out, ox = pix - oy * hw_out;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= nco) break;
+        float res = 0.0f;
+        if (co + j < cin) {
+          if (stride == 2) {
+            const float* q = xin + ((size_t)(2 * oy) * hw_in + 2 * ox) * cin + co + j;
+            res = fmaxf(fmaxf(q[0], q[cin]), fmaxf(q[(size_t)hw_in * cin], q[(size_t)hw_in * cin + cin]));
+          } else {
+            res = xin[((size_t)oy * hw_in + ox) * cin + co + j];
+          }
         }
+        o[(size_t)pix * cout + co + j] = fmaxf(acc[k][j] + res, 0.0f);
       }
-      o[(size_t)pix * cout + co] = fmaxf(acc[k] + res, 0.0f);
     }
   }
+}
+
+// ---- a CHAIN of stride-1 BlazeBlocks at one resolution in a single launch: the 16x16 (blocks 6..10, 48 -> 88 channels)
+// and 8x8 (blocks 12..15, 96 channels) maps of one tile fit in shared memory, so the activation makes one round trip to
+// global memory per chain instead of one per block (the ncu launch list had 1.45 of 4.0 ms in these nine launches).
+// One CTA = one tile.  Per block: depthwise 3x3 from the resident map into s_dw[c][p]; pointwise 1x1 + residual + ReLU
+// written back IN PLACE (element (p, co) is read and written by the one thread that owns it; the channel count only
+// grows, the row pitch CP is that of the widest block).
+struct BlazeChain {
+  int nblk;
+  int cin[5], cout[5];
+  const float *dw_w[5], *dw_b[5], *pw_w[5], *pw_b[5];
+};
+template <int HW, int CP, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+blaze_chain_kernel(const float* __restrict__ x, float* __restrict__ out, const BlazeChain ch) {
+  constexpr int P = HW * HW;
+  extern __shared__ float s_chain[];
+  float (*s_act)[CP + 1] = reinterpret_cast<float (*)[CP + 1]>(s_chain);                    // [P][CP + 1]
+  float (*s_dw)[P + 4] = reinterpret_cast<float (*)[P + 4]>(s_chain + ((P * (CP + 1) + 3) & ~3));   // [<= CP][P + 4], rows 16-byte aligned
+  const size_t img = blockIdx.x;
+  const int c0 = ch.cin[0];
+  const float* xin = x + img * (size_t)P * c0;
+  for (int i = threadIdx.x; i < P * c0; i += THREADS) s_act[i / c0][i % c0] = xin[i];
+  __syncthreads();
+  for (int b = 0; b < ch.nblk; ++b) {
+    const int cin = ch.cin[b], cout = ch.cout[b];
+    const float* dw_w = ch.dw_w[b];
+    const float* dw_b = ch.dw_b[b];
+    const float* pw_w = ch.pw_w[b];
+    const float* pw_b = ch.pw_b[b];
+    for (int i = threadIdx.x; i < (P / 4) * cin; i += THREADS) {      // item = (4 consecutive pixels of a row, channel)
+      const int q = i / cin, c = i - q * cin;
+      const int p = q * 4;
+      const int oy = p / HW, ox = p - oy * HW;
+      float w[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) w[t] = dw_w[t * cin + c];
+      float acc[4];
+      const float bias = dw_b[c];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = bias;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int iy = oy + kh - 1;
+        if (iy < 0 || iy >= HW) continue;
+        float v[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int ix = ox - 1 + j;
+          v[j] = (ix >= 0 && ix < HW) ? s_act[iy * HW + ix][c] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) acc[k] = fmaf(v[k + kw], w[kh * 3 + kw], acc[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s_dw[c][p + k] = acc[k];
+    }
+    __syncthreads();
+    const int cog = (cout + 3) / 4;
+    for (int i = threadIdx.x; i < (P / BLAZE_PG) * cog; i += THREADS) {
+      const int pg = i / cog, co = (i - pg * cog) * 4;
+      const int nco = min(4, cout - co);
+      float acc[8][4];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[k][j] = j < nco ? pw_b[co + j] : 0.0f;
+      blaze_pw_8x4(&s_dw[0][pg * BLAZE_PG], P + 4, pw_w, cin, cout, co, nco, acc);
+#pragma unroll
+      for (int k = 0; k < BLAZE_PG; ++k) {
+        const int p = pg * BLAZE_PG + k;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j >= nco) break;
+          const float res = co + j < cin ? s_act[p][co + j] : 0.0f;
+          s_act[p][co + j] = fmaxf(acc[k][j] + res, 0.0f);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int cl = ch.cout[ch.nblk - 1];
+  float* o = out + img * (size_t)P * cl;
+  for (int i = threadIdx.x; i < P * cl; i += THREADS) o[i] = s_act[i / cl][i % cl];
 }
 
 // ---- heads (:118-148): classifier_8 / regressor_8 on the 16x16x88 map, classifier_16 / regressor_16 on 8x8x96,
@@ -345,13 +474,45 @@ int bforward(ff_blazeface* h, const uint8_t* tiles, int n, float* det, cudaStrea
   }
   float* cur = h->act_a;
   float* nxt = h->act_b;
+  auto make_chain = [&](int first, int count) {
+    BlazeChain ch;
+    ch.nblk = count;
+    for (int j = 0; j < count; ++j) {
+      ch.cin[j] = kBlocks[first + j].cin; ch.cout[j] = kBlocks[first + j].cout;
+      ch.dw_w[j] = h->dw_w[first + j]; ch.dw_b[j] = h->dw_b[first + j];
+      ch.pw_w[j] = h->pw_w[first + j]; ch.pw_b[j] = h->pw_b[first + j];
+    }
+    return ch;
+  };
   for (int i = 0; i < 16; ++i) {
+    if (h->use_chains && i == 6) {             // blocks 6..10: the whole 16x16 stage -> feat8
+      constexpr int SM = (256 * 89 + 88 * 260 + 4) * 4;
+      static bool attr = false;
+      if (!attr) { BZ_CUDA(h, cudaFuncSetAttribute(blaze_chain_kernel<16, 88, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); attr = true; }
+      blaze_chain_kernel<16, 88, 512><<<n, 512, SM, st>>>(cur, h->feat8, make_chain(6, 5));
+      BZ_CUDA(h, cudaGetLastError());
+      ++h->launches;
+      cur = h->feat8;
+      i = 10;
+      continue;
+    }
+    if (h->use_chains && i == 12) {            // blocks 12..15: the 8x8 stage after the stride-2 block 11
+      constexpr int SM = (64 * 97 + 96 * 68 + 4) * 4;
+      static bool attr = false;
+      if (!attr) { BZ_CUDA(h, cudaFuncSetAttribute(blaze_chain_kernel<8, 96, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); attr = true; }
+      blaze_chain_kernel<8, 96, 256><<<n, 256, SM, st>>>(cur, nxt, make_chain(12, 4));
+      BZ_CUDA(h, cudaGetLastError());
+      ++h->launches;
+      cur = nxt;
+      i = 15;
+      continue;
+    }
     const BlockPlan& p = kBlocks[i];
     const int hw_out = p.hw_in / p.stride;
     float* dst = (i == 10) ? h->feat8 : nxt;          // backbone1 output (16x16x88) feeds both backbone2 and the heads
     const int pix = blaze_pix(hw_out);
     dim3 grid((hw_out * hw_out + pix - 1) / pix, n);
-    const size_t smem = (size_t)p.cin * (pix + 1) * sizeof(float);
+    const size_t smem = (size_t)p.cin * (pix + 4) * sizeof(float);
     if (pix == 256) blaze_block_kernel<256><<<grid, 256, smem, st>>>(cur, dst, h->dw_w[i], h->dw_b[i], h->pw_w[i], h->pw_b[i], p.cin, p.cout, p.stride, p.hw_in);
     else if (pix == 128) blaze_block_kernel<128><<<grid, 256, smem, st>>>(cur, dst, h->dw_w[i], h->dw_b[i], h->pw_w[i], h->pw_b[i], p.cin, p.cout, p.stride, p.hw_in);
     else blaze_block_kernel<64><<<grid, 256, smem, st>>>(cur, dst, h->dw_w[i], h->dw_b[i], h->pw_w[i], h->pw_b[i], p.cin, p.cout, p.stride, p.hw_in);
@@ -388,6 +549,7 @@ int ff_blazeface_create(ff_blazeface_t** out, int device, int max_tiles) {
   ff_blazeface* h = new ff_blazeface();
   h->device = device;
   h->cap = max_tiles;
+  if (const char* v = getenv("FF_BLAZE_CHAINS")) h->use_chains = atoi(v);
   int rc = FF_OK;
   do {
     if ((rc = balloc(h, &h->act_a, (size_t)h->cap * ACT_ELEMS))) break;
