@@ -1279,10 +1279,24 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
       a.out_blocked = (li == 4) ? 1 : 0;          // layer 5 feeds layer 6 (also a pair kernel); layer 6 writes plain NHWC
       const int tiles = a.tiles_w * a.tiles_h * n_img;
       const int g = std::min(2 * ((tiles + 1) / 2), h->num_sms & ~1);
+      static long long* ws2x_dbg = nullptr;
+      static const bool ws2x_dbg_on = getenv("FF_WS2X_DBG") != nullptr;
+      if (ws2x_dbg_on) {
+        if (!ws2x_dbg) cudaMalloc(&ws2x_dbg, 4 * sizeof(long long));
+        a.resid = ws2x_dbg;
+      }
       cudaError_t e = p.pool ? launch_ws2x_t<true>(g, st, L.tmA_ws2x, L.tmW_ws2x, a, L.epi)
                              : launch_ws2x_t<false>(g, st, L.tmA_ws2x, L.tmW_ws2x, a, L.epi);
       if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of ws2x conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
       ++h->launches;
+      if (ws2x_dbg_on) {          // developer aid: cycles of the leader's MMA thread per tile pair (serialises the stream)
+        long long hd[4];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hd, ws2x_dbg, sizeof(hd), cudaMemcpyDeviceToHost);
+        if (hd[3] > 0)
+          fprintf(stderr, "[ws2x layer %d] tile pairs %lld | wait TMEM drained %lld | wait patch %lld | issue 48 MMAs %lld cycles/pair\n", li + 1,
+                  hd[3], hd[0] / hd[3], hd[1] / hd[3], hd[2] / hd[3]);
+      }
       return FF_OK;
     }
     if (L.ws4) {

@@ -751,12 +751,17 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      long long* dbg = (a.resid != nullptr && blockIdx.x == 0) ? reinterpret_cast<long long*>(const_cast<void*>(a.resid)) : nullptr;
+      long long d_tempty = 0, d_full = 0, d_issue = 0;   // developer aid (FF_WS2X_DBG): where the MMA thread spends its cycles
       int it = 0;
       for (int pi = cluster_id; pi < num_pairs; pi += num_clusters, ++it) {
         const int s = it & 1;
         const int acc = it & 1;
+        const long long c0 = clock64();
         if (it >= 2) mbar_wait(bar_tempty + 8 * acc, ((it >> 1) - 1) & 1);
+        const long long c1 = clock64();
         mbar_wait(bar_full + 8 * s, (it >> 1) & 1);
+        const long long c2 = clock64();
         tcgen05_fence_after();
         const uint32_t patch = base + L::P_OFF + s * L::PATCH_STRIDE;
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -774,7 +779,9 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         umma_commit_2cta(bar_empty + 8 * s, 0x3);
         umma_commit_2cta(bar_tfull + 8 * acc, 0x3);
+        d_tempty += c1 - c0; d_full += c2 - c1; d_issue += clock64() - c2;
       }
+      if (dbg != nullptr) { dbg[0] = d_tempty; dbg[1] = d_full; dbg[2] = d_issue; dbg[3] = it; }
     }
   } else {
     const int g = warp & 3;
