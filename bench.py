@@ -386,7 +386,7 @@ def run_blazeface(args):
     emit({
         "metric": "BlazeFace tiles/sec", "value": args.tiles / ms * 1e3, "unit": "tiles/s", "ms_per_step": ms, "tiles_per_step": args.tiles,
         "gpu_launches_per_step": int(launches), "dtype": "f32", "faces_found": int(sum(len(f) for f in faces)),
-        "e2e": {"value": args.tiles / e2e_s, "unit": "tiles/s", "what": "pinned host uint8 tiles -> H2D -> network+decode -> score mask on the device -> D2H of the survivors -> host blending NMS"},
+        "e2e": {"value": args.tiles / e2e_s, "unit": "tiles/s", "what": "pinned host uint8 tiles -> H2D -> network + decode -> mask + blending NMS on the device (ff_blazeface_nms) -> D2H of [n,16,17] faces + counts"},
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                      "algorithmic_bytes_per_tile": by, "flops_per_tile": fl, "gflops": fl * args.tiles / (ms * 1e-3) / 1e9},
         "cpu_baseline": {"value": len(sample) / cpu_s, "unit": "tiles/s", "cores": os.cpu_count(), "kind": "port",

@@ -149,12 +149,37 @@ class BlazeFaceEngine:
     def predict_on_batch(self, x, apply_nms: bool = True) -> List[torch.Tensor]:
         """blazeface.py:182-223: list of (num_detections, 17) tensors, one per image."""
         dense = self.predict_dense(x)
+        if apply_nms:
+            return self._nms_on_device(dense)
         # score mask on the device (plumbing, like the reference's boolean indexing): only the survivors cross PCIe
         img, anchor = torch.nonzero(dense[..., 16] >= self.min_score_thresh, as_tuple=True)
         kept = dense[img, anchor].cpu()
         counts = torch.bincount(img, minlength=dense.shape[0]).cpu().tolist()
         detections = list(torch.split(kept, counts))
         return self.nms(detections) if apply_nms else detections
+
+    def _nms_on_device(self, dense: torch.Tensor) -> List[torch.Tensor]:
+        """Mask + blending NMS of every tile in one kernel (``ff_blazeface_nms``); tiles it cannot hold (> 64
+        candidates or > 16 faces) fall back to the host loop."""
+        b = dense.shape[0]
+        faces = torch.empty((b, 16, 17), dtype=torch.float32, device=self._device)
+        counts = torch.empty((b,), dtype=torch.int32, device=self._device)
+        with torch.cuda.device(self._device):
+            rc = self._lib.ff_blazeface_nms(self._h, C.c_void_p(dense.data_ptr()), b, C.c_float(self.min_score_thresh),
+                                            C.c_float(self.min_suppression_threshold), C.c_void_p(faces.data_ptr()),
+                                            C.c_void_p(counts.data_ptr()), C.c_void_p(_stream_ptr(self._device)))
+        self._check(rc, "ff_blazeface_nms")
+        counts_h = counts.cpu().tolist()
+        faces_h = faces.cpu()
+        out = []
+        for i, k in enumerate(counts_h):
+            if k >= 0:
+                out.append(faces_h[i, :k].clone())
+            else:
+                d = dense[i].cpu()
+                f = self._weighted_non_max_suppression(d[d[:, 16] >= self.min_score_thresh])
+                out.append(torch.stack(f) if f else torch.zeros((0, 17)))
+        return out
 
     def nms(self, detections: List[torch.Tensor]) -> List[torch.Tensor]:
         """blazeface.py:225-234."""

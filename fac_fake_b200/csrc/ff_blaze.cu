@@ -381,6 +381,110 @@ blaze_decode_kernel(const float* __restrict__ raw_boxes, const float* __restrict
   d[16] = 1.0f / (1.0f + expf(-s));
 }
 
+// ---- blending NMS on the device (blazeface.py:305-358) for predict_on_batch(apply_nms=True): one warp per tile.
+// Candidates = anchors with score >= min_score (the mask of :262); they are ranked by score (ties: lower anchor index
+// first), then greedily: the best remaining detection absorbs every remaining one with IoU > thr (itself included) into
+// their score-weighted mean, the merged score being the mean score — exactly the reference's loop.  Up to 64
+// candidates and 16 faces per tile are handled here; a tile with more sets its count to -1 and the mirror falls back to
+// the host loop for that tile.
+constexpr int NMS_MAX_CAND = 64, NMS_MAX_FACES = 16;
+__global__ void __launch_bounds__(128)
+blaze_nms_kernel(const float* __restrict__ det, int n, float min_score, float iou_thr, float* __restrict__ faces, int* __restrict__ counts) {
+  __shared__ int s_idx[4][NMS_MAX_CAND];
+  __shared__ float s_score[4][NMS_MAX_CAND];
+  __shared__ float s_box[4][NMS_MAX_CAND][4];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * 4 + w;
+  if (tile >= n) return;
+  const float* d = det + (size_t)tile * NUM_ANCHORS * 17;
+  // 1. candidates in anchor order
+  int ncand = 0;
+  bool overflow = false;
+  for (int a0 = 0; a0 < NUM_ANCHORS; a0 += 32) {
+    const int a = a0 + lane;
+    const float sc = d[a * 17 + 16];
+    const bool keep = sc >= min_score;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    const int pos = ncand + __popc(m & ((1u << lane) - 1u));
+    if (keep && pos < NMS_MAX_CAND) { s_idx[w][pos] = a; s_score[w][pos] = sc; }
+    ncand += __popc(m);
+  }
+  if (ncand > NMS_MAX_CAND) overflow = true;
+  __syncwarp();
+  if (overflow) { if (lane == 0) counts[tile] = -1; return; }
+  // 2. rank by score, descending (stable in the anchor index): rank[i] = #{j: s_j > s_i or (s_j == s_i and j < i)}
+  int my_rank[2] = {-1, -1};
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h;
+    if (i < ncand) {
+      const float si = s_score[w][i];
+      int r = 0;
+      for (int j = 0; j < ncand; ++j) { const float sj = s_score[w][j]; r += (sj > si || (sj == si && j < i)) ? 1 : 0; }
+      my_rank[h] = r;
+    }
+  }
+  int my_anchor[2]; float my_sc[2];
+  for (int h = 0; h < 2; ++h) { const int i = lane + 32 * h; my_anchor[h] = i < ncand ? s_idx[w][i] : 0; my_sc[h] = i < ncand ? s_score[w][i] : 0.f; }
+  __syncwarp();
+  for (int h = 0; h < 2; ++h)
+    if (my_rank[h] >= 0) { s_idx[w][my_rank[h]] = my_anchor[h]; s_score[w][my_rank[h]] = my_sc[h]; }
+  __syncwarp();
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h;
+    if (i < ncand) {
+      const float* b = d + s_idx[w][i] * 17;
+      s_box[w][i][0] = b[0]; s_box[w][i][1] = b[1]; s_box[w][i][2] = b[2]; s_box[w][i][3] = b[3];
+    }
+  }
+  __syncwarp();
+  // 3. greedy blending; alive flags live in two 32-bit masks
+  unsigned alive[2] = {ncand >= 32 ? 0xffffffffu : ((1u << ncand) - 1u), ncand > 32 ? ((ncand >= 64) ? 0xffffffffu : ((1u << (ncand - 32)) - 1u)) : 0u};
+  int nfaces = 0;
+  float* out = faces + (size_t)tile * NMS_MAX_FACES * 17;
+  while ((alive[0] | alive[1]) != 0u) {
+    const int first = alive[0] ? __ffs(alive[0]) - 1 : 32 + __ffs(alive[1]) - 1;     // sorted: lowest index = best score
+    const float fy0 = s_box[w][first][0], fx0 = s_box[w][first][1], fy1 = s_box[w][first][2], fx1 = s_box[w][first][3];
+    const float farea = (fy1 - fy0) * (fx1 - fx0);
+    unsigned ov[2];
+    for (int h = 0; h < 2; ++h) {
+      const int i = lane + 32 * h;
+      bool o = false;
+      if (i < ncand && ((alive[h] >> lane) & 1u)) {
+        const float ih = fmaxf(fminf(fy1, s_box[w][i][2]) - fmaxf(fy0, s_box[w][i][0]), 0.f);
+        const float iw = fmaxf(fminf(fx1, s_box[w][i][3]) - fmaxf(fx0, s_box[w][i][1]), 0.f);
+        const float inter = ih * iw;
+        const float area = (s_box[w][i][2] - s_box[w][i][0]) * (s_box[w][i][3] - s_box[w][i][1]);
+        o = inter / (farea + area - inter) > iou_thr;
+      }
+      ov[h] = __ballot_sync(0xffffffffu, o);
+    }
+    ov[first >> 5] |= 1u << (first & 31);            // a degenerate (zero-area) best box must still be consumed
+    const int cnt = __popc(ov[0]) + __popc(ov[1]);
+    if (nfaces < NMS_MAX_FACES) {
+      if (cnt > 1) {
+        // lane k < 17 accumulates coordinate k (k = 16: the score sum) over the overlapping set in rank order
+        if (lane < 17) {
+          float num = 0.f, tot = 0.f;
+          for (int h = 0; h < 2; ++h)
+            for (unsigned m = ov[h]; m; m &= m - 1) {
+              const int i = 32 * h + __ffs(m) - 1;
+              const float sc = s_score[w][i];
+              tot += sc;
+              if (lane < 16) num += d[s_idx[w][i] * 17 + lane] * sc;
+            }
+          out[nfaces * 17 + lane] = lane < 16 ? num / tot : tot / (float)cnt;
+        }
+      } else if (lane < 17) {
+        out[nfaces * 17 + lane] = d[s_idx[w][first] * 17 + lane];
+      }
+    }
+    ++nfaces;
+    alive[0] &= ~ov[0];
+    alive[1] &= ~ov[1];
+  }
+  if (lane == 0) counts[tile] = nfaces <= NMS_MAX_FACES ? nfaces : -1;
+}
+
 template <typename T>
 int balloc(ff_blazeface* h, T** p, size_t count) {
   void* q = nullptr;
@@ -614,6 +718,18 @@ int ff_blazeface_predict(ff_blazeface_t* h, const uint8_t* tiles, int n, float* 
     if (raw_boxes) BZ_CUDA(h, cudaMemcpyAsync(raw_boxes + (size_t)s0 * NUM_ANCHORS * 16, h->raw_boxes, (size_t)ns * NUM_ANCHORS * 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (raw_scores) BZ_CUDA(h, cudaMemcpyAsync(raw_scores + (size_t)s0 * NUM_ANCHORS, h->raw_scores, (size_t)ns * NUM_ANCHORS * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
+  return FF_OK;
+}
+
+int ff_blazeface_nms(ff_blazeface_t* h, const float* detections, int n, float min_score, float iou_threshold, float* faces,
+                     int32_t* counts, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!detections || !faces || !counts))) return bfail(h, FF_ERR_BAD_ARG, "ff_blazeface_nms: bad arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  BZ_CUDA(h, cudaSetDevice(h->device));
+  if (n == 0) return FF_OK;
+  blaze_nms_kernel<<<(n + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(detections, n, min_score, iou_threshold, faces, counts);
+  BZ_CUDA(h, cudaGetLastError());
+  ++h->launches;
   return FF_OK;
 }
 

@@ -171,6 +171,13 @@ int ff_blazeface_load_weight(ff_blazeface_t* h, const char* key, const float* ho
 int ff_blazeface_finalize(ff_blazeface_t* h);
 int ff_blazeface_predict(ff_blazeface_t* h, const uint8_t* tiles, int n, float* detections, float* raw_boxes,
                          float* raw_scores, void* stream);
+/* Blending NMS of blazeface.py:305-358 on the device for `predict_on_batch(apply_nms=True)` (:223): per tile, the
+ * detections with score >= min_score are merged greedily (IoU > iou_threshold, score-weighted mean, mean score).
+ * detections: DEVICE [n,896,17] from ff_blazeface_predict;  faces: DEVICE [n,16,17];  counts: DEVICE int32 [n] —
+ * number of faces of the tile, or -1 when a tile has more than 64 candidates / 16 faces (the caller then runs the
+ * reference's host loop on that tile).                                                                      */
+int ff_blazeface_nms(ff_blazeface_t* h, const float* detections, int n, float min_score, float iou_threshold, float* faces,
+                     int32_t* counts, void* stream);
 int64_t ff_blazeface_launch_count(const ff_blazeface_t* h);
 
 /* ---- S3D clip classifier ------------------------------------------------------------------

@@ -54,11 +54,38 @@ def test_detections_and_faces_match_reference(blaze):
     faces = eng.nms(det)
     assert [len(f) for f in faces] == g["face_counts"].tolist()
     np.testing.assert_allclose(torch.cat(faces).numpy(), g["faces"], rtol=0, atol=2e-4)
-    faces2 = eng.predict_on_batch(g["tiles"])                          # apply_nms=True path
-    assert all(torch.equal(a, b) for a, b in zip(faces, faces2))
+    faces2 = eng.predict_on_batch(g["tiles"])                          # apply_nms=True path: mask + NMS on the device
+    assert [len(f) for f in faces2] == g["face_counts"].tolist()
+    assert all(torch.allclose(a, b, atol=1e-6) for a, b in zip(faces, faces2))
     one = eng.predict_on_image(g["tiles"][0])
     assert torch.allclose(one, faces[0], atol=1e-6)
     assert eng.predict_on_batch(np.zeros((1, 128, 128, 3), np.uint8))[0].shape[1] == 17
+
+
+def test_device_nms_matches_oracle_on_crowded_tiles(blaze):
+    """ff_blazeface_nms on fabricated dense detections: 0 / few / many overlapping candidates, chains of merges, and a
+    tile with more than 64 candidates (host fallback)."""
+    eng, sd, anchors, g = blaze
+    eng.predict_dense(g["tiles"][:1])                                  # make sure the handle exists
+    gen = torch.Generator().manual_seed(3)
+    n = 9
+    dense = torch.zeros((n, 896, 17))
+    dense[..., 16] = torch.rand((n, 896), generator=gen) * 0.7         # below the 0.75 threshold
+    for t, k in enumerate((0, 1, 2, 5, 12, 30, 50, 64, 90)):
+        idx = torch.randperm(896, generator=gen)[:k]
+        c = torch.rand((k, 2), generator=gen) * 0.5 + 0.1
+        sz = torch.rand((k, 2), generator=gen) * 0.25 + 0.05
+        dense[t, idx, 0:2] = c
+        dense[t, idx, 2:4] = c + sz
+        dense[t, idx, 4:16] = torch.rand((k, 12), generator=gen)
+        dense[t, idx, 16] = torch.rand((k,), generator=gen) * 0.24 + 0.755
+    got = eng._nms_on_device(dense.cuda())
+    for t in range(n):
+        d = dense[t]
+        ref = B.weighted_nms(d[d[:, 16] >= B.MIN_SCORE])
+        assert len(got[t]) == len(ref), t
+        if ref:
+            assert torch.allclose(got[t], torch.stack(ref), atol=2e-6), t
 
 
 def test_errors_are_loud(blaze):
