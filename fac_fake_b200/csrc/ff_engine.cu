@@ -1202,7 +1202,7 @@ int rvk_features(ff_cvit* h, const void* x, int layout, int slot_base, int n, cu
     if (layout == FF_X_NHWC_U8) {
       // (u/255 - mean)/std as one fp32 FMA per channel (cvit_prediction.py:41-45 convention)
       const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
-      rvk_convert_kernel<2><<<blocks, 256, 0, st>>>(x, h->rvk_x4, n, 1.0f / (255.0f * sd[0]), -mean[0] / sd[0],
+      rvk_convert_kernel<2><<<(blocks + 3) / 4, 256, 0, st>>>(x, h->rvk_x4, n, 1.0f / (255.0f * sd[0]), -mean[0] / sd[0],
                                                     1.0f / (255.0f * sd[1]), -mean[1] / sd[1], 1.0f / (255.0f * sd[2]), -mean[2] / sd[2]);
     } else {
       rvk_convert_kernel<0><<<blocks, 256, 0, st>>>(x, h->rvk_x4, n, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f);

@@ -456,7 +456,7 @@ int s3d_forward(ff_s3d* h, const void* x, int layout, int n, float* logits, cuda
                 int64_t* tap_elems) {
   const int T = h->frames, frames = n * T;
   const unsigned blocks = (unsigned)(((size_t)frames * 224 * 224 + 255) / 256);
-  if (layout == FF_X_NHWC_U8) rvk_convert_kernel<2><<<blocks, 256, 0, st>>>(x, h->x4, frames, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f);
+  if (layout == FF_X_NHWC_U8) rvk_convert_kernel<2><<<(blocks + 3) / 4, 256, 0, st>>>(x, h->x4, frames, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f);
   else s3d_convert_ncdhw_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), h->x4, n, T);
   S3_CUDA(h, cudaGetLastError());
   static bool stem_attr = false;
