@@ -27,6 +27,7 @@
 #include "ff_c1.cuh"
 #include "ff_rvk.cuh"
 #include "ff_c12.cuh"
+#include "ff_xf.cuh"
 
 namespace {
 
@@ -178,6 +179,12 @@ struct ff_cvit {
   bf16* clsb = nullptr;                    // [cap128][1024]
   float* hid = nullptr;                    // [cap128][2048]
   CUtensorMap tm_feat, tm_xn, tm_att, tm_ffh, tm_cls;
+  // whole-encoder cluster kernel (ff_xf.cuh): device copy of the tensor maps it indexes, readiness, opt-out (FF_XF=0)
+  CUtensorMap* xf_maps = nullptr;
+  unsigned int* xf_sync = nullptr;   // group-barrier counters
+  int xf_groups = 0;                 // co-resident groups of 16 CTAs
+  int use_xf = 1;
+  bool xf_ready = false;
   // fp32-path workspace
   float *fA = nullptr, *fB = nullptr;
   // grow-only scratch for predict()
@@ -464,6 +471,8 @@ const std::vector<float>* get_w(ff_cvit* h, const std::string& key, std::initial
   }
   return &it->second;
 }
+
+int xf_setup(ff_cvit* h);   // encoder cluster kernel (defined next to its launch)
 
 int upload_linear(ff_cvit* h, LinearDev* L, const std::string& name, int out_f, int in_f, bool bias, int bn) {
   const auto* w = get_w(h, name + ".weight", {out_f, in_f});
@@ -1029,10 +1038,88 @@ int finalize(ff_cvit* h) {
     if ((rc = tmap_2d(h, &h->tm_att, h->att, DIM, h->rows_cap, 64, 128))) return rc;
     if ((rc = tmap_2d(h, &h->tm_ffh, h->ffh, MLP, h->rows_cap, 64, 128))) return rc;
     if ((rc = tmap_2d(h, &h->tm_cls, h->clsb, DIM, cap128, 64, 128))) return rc;
+    if ((rc = xf_setup(h))) return rc;
   }
   h->host_w.clear();
   h->host_shape.clear();
   h->finalized = true;
+  return FF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ encoder kernel
+// One cooperative launch for the 6 transformer layers (ff_xf.cuh): groups of 16 CTAs, one group per 128-row token tile
+// (groups loop over tiles when there are more tiles than co-resident groups).
+int xf_setup(ff_cvit* h) {
+  h->xf_ready = false;
+  if (!h->use_xf || h->gemm_bn_wide != 64) return FF_OK;   // the kernel loads weights as 64-row boxes
+  int coop = 0;
+  FF_CUDA(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+  if (!coop) return FF_OK;
+  std::vector<CUtensorMap> maps(3 + 4 * DEPTH);
+  maps[0] = h->tm_xn;
+  maps[1] = h->tm_att;
+  maps[2] = h->tm_ffh;
+  for (int l = 0; l < DEPTH; ++l) {
+    maps[3 + 4 * l + 0] = h->xf[l].qkv.tmB;
+    maps[3 + 4 * l + 1] = h->xf[l].out.tmB;
+    maps[3 + 4 * l + 2] = h->xf[l].ff1.tmB;
+    maps[3 + 4 * l + 3] = h->xf[l].ff2.tmB;
+  }
+  int rc = dev_alloc(h, &h->xf_maps, maps.size());
+  if (rc) return rc;
+  FF_CUDA(h, cudaMemcpy(h->xf_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  if ((rc = dev_alloc(h, &h->xf_sync, (size_t)XF_MAX_GROUPS))) return rc;
+  FF_CUDA(h, cudaFuncSetAttribute(xf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XF_SMEM_TOTAL));
+  int per_sm = 0;
+  FF_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xf_kernel, XF_THREADS, XF_SMEM_TOTAL));
+  h->xf_groups = std::min(per_sm * h->num_sms / XF_CS, (int)XF_MAX_GROUPS);
+  if (getenv("FF_VERBOSE")) fprintf(stderr, "ff: encoder kernel: %d co-resident groups of %d CTAs\n", h->xf_groups, XF_CS);
+  h->xf_ready = h->xf_groups >= 1;
+  return FF_OK;
+}
+
+int launch_xf(ff_cvit* h, cudaStream_t st, int n, int depth) {
+  XfArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = h->x; a.xn = h->xn; a.qkv = h->qkvb; a.att = h->att; a.ffh = h->ffh;
+  a.maps = h->xf_maps;
+  a.sync = h->xf_sync;
+  a.rows = 2 * n; a.n_crops = n; a.depth = depth;
+  a.eps1 = 1e-5f; a.eps2 = h->ln2_eps;
+  for (int l = 0; l < DEPTH; ++l) {
+    const XfLayerDev& X = h->xf[l];
+    a.L[l] = XfLayerP{X.ln1_g, X.ln1_b, X.ln2_g, X.ln2_b, X.out.b, X.ff1.b, X.ff2.b};
+  }
+  const int tiles = (a.rows + 127) / 128;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(XF_CS * std::min(tiles, h->xf_groups));
+  cfg.blockDim = dim3(XF_THREADS);
+  cfg.dynamicSmemBytes = XF_SMEM_TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;    // all CTAs co-resident: the group barriers spin on global counters
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static long long* trace_buf = nullptr;
+  static const bool trace_on = getenv("FF_XF_TRACE") != nullptr;
+  if (trace_on && !trace_buf) cudaMalloc(&trace_buf, 64 * sizeof(long long));
+  a.trace = trace_on ? trace_buf : nullptr;
+  ProfScope ps(h, st, KC_GEMM_XF);
+  FF_CUDA(h, cudaMemsetAsync(h->xf_sync, 0, XF_MAX_GROUPS * sizeof(unsigned int), st));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, xf_kernel, a);
+  if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of the encoder kernel failed: %s", cudaGetErrorString(e));
+  ++h->launches;
+  if (trace_on) {   // developer aid: phase-boundary stamps (cycles between stamps) of CTA 0
+    long long t[64];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(t, trace_buf, sizeof(t), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "ff: xf trace (%d rows):", a.rows);
+    for (int i = 1; i < (int)t[63] && i < 56; ++i) fprintf(stderr, " %lld", t[i] - t[i - 1]);
+    fprintf(stderr, "\nff: xf trace producer: empty-wait %lld cycles over %lld k-blocks | mma thread: full-wait %lld, issue %lld, first-full..last-commit %lld\n",
+            t[56], t[57], t[58], t[59], t[60]);
+  }
   return FF_OK;
 }
 
@@ -1522,7 +1609,13 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   FF_LAUNCH_CHECK(h, "tokens");
   const int rows = 2 * n;
   if (tap_hit(18, h->x, (int64_t)rows * DIM, false)) return FF_OK;
-  // ---- transformer
+  // ---- transformer: one cluster-kernel launch for all layers (a debug tap inside the encoder shortens the depth)
+  if (h->xf_ready) {
+    const int depth = (stop >= 19 && stop < 19 + DEPTH) ? stop - 18 : DEPTH;
+    if ((rc = launch_xf(h, st, n, depth))) return rc;
+    if (getenv("FF_XF_TWICE") && (rc = launch_xf(h, st, n, depth))) return rc;   // developer aid: second run sees L2-hot weights
+    if (tap_hit(18 + depth, h->x, (int64_t)rows * DIM, false)) return FF_OK;
+  } else
   for (int l = 0; l < DEPTH; ++l) {
     const XfLayerDev& X = h->xf[l];
     { ProfScope ps(h, st, KC_SMALL); launch_k(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, true, (const float*)h->x, (const float*)X.ln1_g, (const float*)X.ln1_b, h->xn, rows, 1e-5f); }
@@ -1724,6 +1817,7 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
   if (const char* v = getenv("FF_PDL")) g_use_pdl = atoi(v) != 0;
   if (const char* v = getenv("FF_DUAL")) h->use_dual = atoi(v);
   if (const char* v = getenv("FF_GEMM_BN")) h->gemm_bn_wide = atoi(v) == 128 ? 128 : 64;
+  if (const char* v = getenv("FF_XF")) h->use_xf = atoi(v);
   if (const char* v = getenv("FF_PTC")) h->use_ptc = atoi(v);
   if (const char* v = getenv("FF_WS2")) h->use_ws2 = atoi(v);
   if (const char* v = getenv("FF_WS4")) h->use_ws4 = atoi(v);

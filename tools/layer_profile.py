@@ -65,7 +65,7 @@ def main():
         if i < 17:
             cin, cout, hw = PLAN[i]
             fl = 2 * 9 * cin * cout * hw * hw * n
-            print(f"  {name:>16s} {cin:3d}->{cout:3d} @{hw:3d}: {ms:8.3f} ms  {cnt/args.steps:5.0f} launches  {fl/ms/1e9:8.1f} TFLOP/s")
+            print(f"  {name:>16s} {cin:3d}->{cout:3d} @{hw:3d}: {ms:8.3f} ms  {cnt/args.steps:5.0f} launches  {fl/max(ms, 1e-9)/1e9:8.1f} TFLOP/s")
         else:
             print(f"  {name:>16s}              : {ms:8.3f} ms  {cnt/args.steps:5.0f} launches")
     print(f"  sum of kernels {tot:.3f} ms")
