@@ -1068,7 +1068,8 @@ int xf_setup(ff_cvit* h) {
   int rc = dev_alloc(h, &h->xf_maps, maps.size());
   if (rc) return rc;
   FF_CUDA(h, cudaMemcpy(h->xf_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-  if ((rc = dev_alloc(h, &h->xf_sync, (size_t)XF_MAX_GROUPS))) return rc;
+  if ((rc = dev_alloc(h, &h->xf_sync, (size_t)2 * XF_MAX_GROUPS))) return rc;
+  FF_CUDA(h, cudaMemset(h->xf_sync, 0, 2 * XF_MAX_GROUPS * sizeof(unsigned int)));   // the kernel re-arms them itself
   FF_CUDA(h, cudaFuncSetAttribute(xf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XF_SMEM_TOTAL));
   int per_sm = 0;
   FF_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xf_kernel, XF_THREADS, XF_SMEM_TOTAL));
@@ -1107,7 +1108,6 @@ int launch_xf(ff_cvit* h, cudaStream_t st, int n, int depth) {
   if (trace_on && !trace_buf) cudaMalloc(&trace_buf, 64 * sizeof(long long));
   a.trace = trace_on ? trace_buf : nullptr;
   ProfScope ps(h, st, KC_GEMM_XF);
-  FF_CUDA(h, cudaMemsetAsync(h->xf_sync, 0, XF_MAX_GROUPS * sizeof(unsigned int), st));
   cudaError_t e = cudaLaunchKernelEx(&cfg, xf_kernel, a);
   if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of the encoder kernel failed: %s", cudaGetErrorString(e));
   ++h->launches;

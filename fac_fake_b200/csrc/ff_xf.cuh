@@ -54,7 +54,7 @@ struct XfArgs {
   // device array of tensor maps: [0] xn, [1] att, [2] ffh (box {64, 128});
   // [3 + 4*l + {0,1,2,3}] = to_qkv, to_out, net.0, net.2 weights of layer l (box {64, 64})
   const CUtensorMap* maps;
-  unsigned int* sync;        // [groups] arrival counters of the group barrier, zeroed before the launch
+  unsigned int* sync;        // [2][XF_MAX_GROUPS] group-barrier arrival counters + exit counters; zero at rest
   int rows, n_crops, depth;
   float eps1, eps2;
   long long* trace;          // developer aid (FF_XF_TRACE=1): clock64 stamps of CTA 0's first epilogue thread, else nullptr
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
   unsigned int sync_target = 0;
 
   if (threadIdx.x == 0) {
+    pdl_trigger();     // the next kernel in the stream (launched with PDL) may be scheduled as SMs free up
     for (int s = 0; s < XF_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -435,6 +436,16 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
     }
   }
   if (tracer) a.trace[63] = tp;
+  // Every CTA of the group has left the last barrier once it arrives here; the 16th arrival re-arms both counters for
+  // the next launch (nobody reads them any more), so no memset is needed between launches.
+  if (threadIdx.x == 0) {
+    unsigned int* done = a.sync + XF_MAX_GROUPS + group;
+    if (atomicAdd(done, 1u) == XF_CS - 1) {
+      *sync_ctr = 0u;
+      *done = 0u;
+      __threadfence();
+    }
+  }
   if (tr_on && is_producer) { a.trace[56] = tr_empty; a.trace[57] = tr_nb; }
   if (tr_on && is_mma) { a.trace[58] = tr_full; a.trace[59] = tr_issue; a.trace[60] = tr_gemm; }
 

@@ -330,3 +330,28 @@ def test_fused_layer12_kernel_and_separate_kernels_agree(monkeypatch):
         c = W.synthetic_crops(n, seed=29).cuda()
         a, b = eng.debug_activation(c, 2), ref_eng.debug_activation(c, 2)
         assert (a - b).abs().max().item() <= b.abs().max().item() * 0.008, n
+
+
+def test_encoder_kernel_matches_per_op_launches(monkeypatch):
+    """The six transformer layers run as ONE cooperative kernel by default (ff_xf.cuh: 16-CTA groups per 128-row token
+    tile); FF_XF=0 selects the per-op launches (LayerNorm / GEMM / attention kernels).  Same bf16 operands, same fp32
+    accumulation: the residual stream after every layer and the logits must agree to rounding — including a partial
+    last tile, a single crop, and more tiles than co-resident groups (640 crops = 10 tiles on 9 groups)."""
+    eng, sd = _engine("bn", max_crops=640)
+    monkeypatch.setenv("FF_XF", "0")
+    ref_eng, _ = _engine("bn", max_crops=640)
+    monkeypatch.delenv("FF_XF")
+    crops = W.synthetic_crops(5, seed=31).cuda()
+    for step in range(19, 25):          # residual stream after transformer layer step-18
+        a, b = eng.debug_activation(crops, step), ref_eng.debug_activation(crops, step)
+        assert a.numel() == b.numel() == 2 * 5 * 1024
+        assert torch.isfinite(a).all()
+        assert (a - b).abs().max().item() <= 2e-3 * max(1.0, b.abs().max().item()), step
+    for n in (1, 31, 64, 65, 200, 640):
+        c = W.synthetic_crops(n, seed=32 + n).cuda()
+        before = eng.launch_count(), ref_eng.launch_count()
+        lg, lr = eng.forward_slots(c).cpu(), ref_eng.forward_slots(c).cpu()
+        assert torch.isfinite(lg).all()
+        assert (lg - lr).abs().max().item() <= 5e-3, n
+        # one encoder launch instead of 42 (7 per layer)
+        assert (ref_eng.launch_count() - before[1]) - (eng.launch_count() - before[0]) == 41, n
