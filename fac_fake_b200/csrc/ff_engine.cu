@@ -1613,7 +1613,6 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   if (h->xf_ready) {
     const int depth = (stop >= 19 && stop < 19 + DEPTH) ? stop - 18 : DEPTH;
     if ((rc = launch_xf(h, st, n, depth))) return rc;
-    if (getenv("FF_XF_TWICE") && (rc = launch_xf(h, st, n, depth))) return rc;   // developer aid: second run sees L2-hot weights
     if (tap_hit(18 + depth, h->x, (int64_t)rows * DIM, false)) return FF_OK;
   } else
   for (int l = 0; l < DEPTH; ++l) {
