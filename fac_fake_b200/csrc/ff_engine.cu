@@ -1109,6 +1109,12 @@ int launch_xf(ff_cvit* h, cudaStream_t st, int n, int depth) {
   a.trace = trace_on ? trace_buf : nullptr;
   ProfScope ps(h, st, KC_GEMM_XF);
   cudaError_t e = cudaLaunchKernelEx(&cfg, xf_kernel, a);
+  if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+    // the device cannot hold the groups any more (e.g. SMs reserved by another client): the per-op GPU launches take over
+    cudaGetLastError();
+    h->xf_ready = false;
+    return 1;
+  }
   if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of the encoder kernel failed: %s", cudaGetErrorString(e));
   ++h->launches;
   if (trace_on) {   // developer aid: phase-boundary stamps (cycles between stamps) of CTA 0
@@ -1610,12 +1616,17 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   const int rows = 2 * n;
   if (tap_hit(18, h->x, (int64_t)rows * DIM, false)) return FF_OK;
   // ---- transformer: one cluster-kernel launch for all layers (a debug tap inside the encoder shortens the depth)
+  bool encoder_done = false;
   if (h->xf_ready) {
     const int depth = (stop >= 19 && stop < 19 + DEPTH) ? stop - 18 : DEPTH;
-    if ((rc = launch_xf(h, st, n, depth))) return rc;
-    if (tap_hit(18 + depth, h->x, (int64_t)rows * DIM, false)) return FF_OK;
-  } else
-  for (int l = 0; l < DEPTH; ++l) {
+    rc = launch_xf(h, st, n, depth);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      if (tap_hit(18 + depth, h->x, (int64_t)rows * DIM, false)) return FF_OK;
+      encoder_done = true;
+    }
+  }
+  for (int l = 0; l < DEPTH && !encoder_done; ++l) {
     const XfLayerDev& X = h->xf[l];
     { ProfScope ps(h, st, KC_SMALL); launch_k(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, true, (const float*)h->x, (const float*)X.ln1_g, (const float*)X.ln1_b, h->xn, rows, 1e-5f); }
     FF_LAUNCH_CHECK(h, "layernorm1");
