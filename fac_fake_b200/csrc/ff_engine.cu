@@ -179,7 +179,7 @@ struct ff_cvit {
   bf16* clsb = nullptr;                    // [cap128][1024]
   float* hid = nullptr;                    // [cap128][2048]
   CUtensorMap tm_feat, tm_xn, tm_att, tm_ffh, tm_cls;
-  // whole-encoder cluster kernel (ff_xf.cuh): device copy of the tensor maps it indexes, readiness, opt-out (FF_XF=0)
+  // whole-encoder cooperative kernel (ff_xf.cuh): device copy of the tensor maps it indexes, readiness, opt-out (FF_XF=0)
   CUtensorMap* xf_maps = nullptr;
   unsigned int* xf_sync = nullptr;   // group-barrier counters
   int xf_groups = 0;                 // co-resident groups of 16 CTAs
@@ -472,7 +472,7 @@ const std::vector<float>* get_w(ff_cvit* h, const std::string& key, std::initial
   return &it->second;
 }
 
-int xf_setup(ff_cvit* h);   // encoder cluster kernel (defined next to its launch)
+int xf_setup(ff_cvit* h);   // encoder cooperative kernel (defined next to its launch)
 
 int upload_linear(ff_cvit* h, LinearDev* L, const std::string& name, int out_f, int in_f, bool bias, int bn) {
   const auto* w = get_w(h, name + ".weight", {out_f, in_f});
@@ -1615,7 +1615,7 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   FF_LAUNCH_CHECK(h, "tokens");
   const int rows = 2 * n;
   if (tap_hit(18, h->x, (int64_t)rows * DIM, false)) return FF_OK;
-  // ---- transformer: one cluster-kernel launch for all layers (a debug tap inside the encoder shortens the depth)
+  // ---- transformer: one cooperative launch for all layers (a debug tap inside the encoder shortens the depth)
   bool encoder_done = false;
   if (h->xf_ready) {
     const int depth = (stop >= 19 && stop < 19 + DEPTH) ? stop - 18 : DEPTH;
