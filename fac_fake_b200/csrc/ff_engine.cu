@@ -28,6 +28,7 @@
 #include "ff_rvk.cuh"
 #include "ff_c12.cuh"
 #include "ff_xf.cuh"
+#include "ff_ptc2.cuh"
 
 namespace {
 
@@ -62,6 +63,8 @@ struct ConvLayerDev {
   CUtensorMap tmA, tmB;
   int rowb = 128, bn = 128;
   int bw = 16, bh = 8, bi = 1;
+  bool ptc2 = false;        // CTA-pair kernel (ff_ptc2.cuh): half filter tile per CTA
+  CUtensorMap tmB_half;     // box {64, 128}
   bool ws = false;          // persistent weight-stationary halo kernel (ff_ws.cuh)
   CUtensorMap tmA_ws, tmW_ws;
   WsEpi epi;                // host copy of (scale, shift) passed by value to the ws kernel
@@ -101,6 +104,7 @@ struct ff_cvit {
   int use_ws = 1;          // feature layers 2..6 on the weight-stationary halo kernel
   int ws_ctas_per_sm = 2;   // CTAs per SM for the Cin=32 weight-stationary kernels (Cin=64 always 1: smem)
   int use_ptc = 1;         // feature layers 7..17 on the persistent implicit-GEMM kernel
+  int use_ptc2 = 1;        // layers 10..17 on the CTA-pair kernel (ff_ptc2.cuh); FF_PTC2=0: single-CTA persistent kernel
   int use_c12 = 1;         // feature layers 1+2 fused in one kernel (ff_c12.cuh) on the uint8 path; FF_C12=0 -> separate kernels
   int use_ws4 = 0;         // 32 -> 32 layers (2, 3) in the pixel-quad formulation (FF_WS4=1; measured equal to the pair kernel)
   int use_ws2 = 1;         // Cin = 32 layers in the pixel-pair formulation
@@ -440,6 +444,18 @@ cudaError_t launch_ptc_t(int grid, cudaStream_t st, const CUtensorMap& a, const 
 }
 
 template <bool POOL>
+cudaError_t launch_ptc2_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
+  auto k = ptc2_conv_kernel<POOL>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Ptc2Smem::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  return launch_k(k, dim3(grid), dim3(192), Ptc2Smem::TOTAL, st, true, a, b, args);
+}
+
+template <bool POOL>
 cudaError_t launch_ws2x_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args,
                           const WsEpi& epi) {
   auto k = ws2x_conv_kernel<POOL>;
@@ -549,6 +565,8 @@ int build_conv_maps(ff_cvit* h) {
     if (rc) return rc;
     rc = tmap_2d(h, &L.tmB, L.w, (uint64_t)9 * p.cin, p.cout, L.rowb / 2, L.bn);
     if (rc) return rc;
+    L.ptc2 = h->use_ptc2 && L.bn == 256 && L.rowb == 128;
+    if (L.ptc2 && (rc = tmap_2d(h, &L.tmB_half, L.w, (uint64_t)9 * p.cin, p.cout, 64, 128))) return rc;
     L.ws2x = h->use_ws && h->use_ws2 && h->use_ws2x && p.cin == 64 && p.cout == 64 && li <= 5;
     if (L.ws2x) {
       rc = tmap_4d(h, &L.tmA_ws2x, conv_input_buffer(h, li, set), 64, p.hw / 2, p.hw, 2 * ncap, 64, 10, 18, 1);
@@ -1433,6 +1451,11 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
       const int tiles = ((m_tiles + msub - 1) / msub) * (p.cout / L.bn);
       const int g = std::min(tiles, h->num_sms);
       cudaError_t e;
+      if (L.ptc2) {          // one item = two pixel tiles x one 256-channel tile on a CTA pair
+        const int items = ((m_tiles + 1) / 2) * (p.cout / 256);
+        const int g2 = std::min(2 * items, h->num_sms & ~1);
+        e = p.pool ? launch_ptc2_t<true>(g2, st, L.tmA, L.tmB_half, a) : launch_ptc2_t<false>(g2, st, L.tmA, L.tmB_half, a);
+      } else
       if (L.bn == 128) e = p.pool ? launch_ptc_t<128, 2, true, 4>(g, st, L.tmA, L.tmB, a) : launch_ptc_t<128, 2, false, 4>(g, st, L.tmA, L.tmB, a);
       else e = p.pool ? launch_ptc_t<256, 1, true, 4>(g, st, L.tmA, L.tmB, a) : launch_ptc_t<256, 1, false, 4>(g, st, L.tmA, L.tmB, a);
       if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of persistent conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
@@ -1828,6 +1851,7 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
   if (const char* v = getenv("FF_DUAL")) h->use_dual = atoi(v);
   if (const char* v = getenv("FF_GEMM_BN")) h->gemm_bn_wide = atoi(v) == 128 ? 128 : 64;
   if (const char* v = getenv("FF_XF")) h->use_xf = atoi(v);
+  if (const char* v = getenv("FF_PTC2")) h->use_ptc2 = atoi(v);
   if (const char* v = getenv("FF_PTC")) h->use_ptc = atoi(v);
   if (const char* v = getenv("FF_WS2")) h->use_ws2 = atoi(v);
   if (const char* v = getenv("FF_WS4")) h->use_ws4 = atoi(v);

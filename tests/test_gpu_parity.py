@@ -355,3 +355,29 @@ def test_encoder_kernel_matches_per_op_launches(monkeypatch):
         assert (lg - lr).abs().max().item() <= 5e-3, n
         # one encoder launch instead of 42 (7 per layer)
         assert (ref_eng.launch_count() - before[1]) - (eng.launch_count() - before[0]) == 41, n
+
+
+def test_cta_pair_conv_kernel_matches_single_cta_kernel(monkeypatch):
+    """Feature layers 10..17 run on ptc2_conv_kernel by default (cta_group::2, 256 pixels x 256 channels per CTA pair,
+    ff_ptc2.cuh); FF_PTC2=0 selects the single-CTA persistent kernel.  Same operands and the same k order: activations
+    must match to one bf16 rounding, and the oracle."""
+    eng, sd = _engine("bn", max_crops=64)
+    monkeypatch.setenv("FF_PTC2", "0")
+    ref_eng, _ = _engine("bn", max_crops=64)
+    monkeypatch.delenv("FF_PTC2")
+    for n in (3, 33):                     # 33 crops: odd tile counts (the pair's second tile falls off the end)
+        crops = W.synthetic_crops(n, seed=41 + n)
+        xg = crops.cuda()
+        acts = _oracle_layers(sd, O.normalize_crops(crops), 17) if n == 3 else None
+        for step in range(10, 18):
+            got, ref = eng.debug_activation(xg, step), ref_eng.debug_activation(xg, step)
+            assert torch.isfinite(got).all(), step
+            assert (got - ref).abs().max().item() <= ref.abs().max().item() * 0.008, (n, step)
+            if acts is not None:
+                assert (got - acts[step]).abs().max().item() <= acts[step].abs().max().item() * min(0.03, 0.004 * (step + 1)), step
+    # launch count is unchanged: the pair kernel replaces the single-CTA launch one for one
+    c = W.synthetic_crops(8, seed=77).cuda()
+    b0, b1 = eng.launch_count(), ref_eng.launch_count()
+    lg, lr = eng.forward_slots(c).cpu(), ref_eng.forward_slots(c).cpu()
+    assert (lg - lr).abs().max().item() <= 5e-3
+    assert eng.launch_count() - b0 == ref_eng.launch_count() - b1
