@@ -64,6 +64,7 @@ struct ConvLayerDev {
   int rowb = 128, bn = 128;
   int bw = 16, bh = 8, bi = 1;
   bool ptc2 = false;        // CTA-pair kernel (ff_ptc2.cuh): half filter tile per CTA
+  bool ptc2m = false;       // unvalidated Cout = 128 pair kernel (tmB_half then has 64-row boxes)
   CUtensorMap tmB_half;     // box {64, 128}
   bool ws = false;          // persistent weight-stationary halo kernel (ff_ws.cuh)
   CUtensorMap tmA_ws, tmW_ws;
@@ -105,6 +106,7 @@ struct ff_cvit {
   int ws_ctas_per_sm = 2;   // CTAs per SM for the Cin=32 weight-stationary kernels (Cin=64 always 1: smem)
   int use_ptc = 1;         // feature layers 7..17 on the persistent implicit-GEMM kernel
   int use_ptc2 = 1;        // layers 10..17 on the CTA-pair kernel (ff_ptc2.cuh); FF_PTC2=0: single-CTA persistent kernel
+  int use_ptc2m = 0;       // NOT VALIDATED ON HARDWARE (FF_PTC2_128=1): layers 7..9 on the Cout = 128 pair kernel
   int use_c12 = 1;         // feature layers 1+2 fused in one kernel (ff_c12.cuh) on the uint8 path; FF_C12=0 -> separate kernels
   int use_ws4 = 0;         // 32 -> 32 layers (2, 3) in the pixel-quad formulation (FF_WS4=1; measured equal to the pair kernel)
   int use_ws2 = 1;         // Cin = 32 layers in the pixel-pair formulation
@@ -456,6 +458,18 @@ cudaError_t launch_ptc2_t(int grid, cudaStream_t st, const CUtensorMap& a, const
 }
 
 template <bool POOL>
+cudaError_t launch_ptc2m_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
+  auto k = ptc2m_conv_kernel<POOL>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Ptc2mSmem::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  return launch_k(k, dim3(grid), dim3(192), Ptc2mSmem::TOTAL, st, true, a, b, args);
+}
+
+template <bool POOL>
 cudaError_t launch_ws2x_t(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args,
                           const WsEpi& epi) {
   auto k = ws2x_conv_kernel<POOL>;
@@ -567,6 +581,8 @@ int build_conv_maps(ff_cvit* h) {
     if (rc) return rc;
     L.ptc2 = h->use_ptc2 && L.bn == 256 && L.rowb == 128;
     if (L.ptc2 && (rc = tmap_2d(h, &L.tmB_half, L.w, (uint64_t)9 * p.cin, p.cout, 64, 128))) return rc;
+    L.ptc2m = h->use_ptc2m && L.bn == 128 && L.rowb == 128 && p.cout == 128 && li >= 6;
+    if (L.ptc2m && (rc = tmap_2d(h, &L.tmB_half, L.w, (uint64_t)9 * p.cin, p.cout, 64, 64))) return rc;
     L.ws2x = h->use_ws && h->use_ws2 && h->use_ws2x && p.cin == 64 && p.cout == 64 && li <= 5;
     if (L.ws2x) {
       rc = tmap_4d(h, &L.tmA_ws2x, conv_input_buffer(h, li, set), 64, p.hw / 2, p.hw, 2 * ncap, 64, 10, 18, 1);
@@ -1455,6 +1471,10 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
         const int items = ((m_tiles + 1) / 2) * (p.cout / 256);
         const int g2 = std::min(2 * items, h->num_sms & ~1);
         e = p.pool ? launch_ptc2_t<true>(g2, st, L.tmA, L.tmB_half, a) : launch_ptc2_t<false>(g2, st, L.tmA, L.tmB_half, a);
+      } else if (L.ptc2m) {   // unvalidated opt-in: one item = four pixel tiles x the 128-channel tile on a CTA pair
+        const int items = ((m_tiles + 3) / 4) * (p.cout / 128);
+        const int g2 = std::min(2 * items, h->num_sms & ~1);
+        e = p.pool ? launch_ptc2m_t<true>(g2, st, L.tmA, L.tmB_half, a) : launch_ptc2m_t<false>(g2, st, L.tmA, L.tmB_half, a);
       } else
       if (L.bn == 128) e = p.pool ? launch_ptc_t<128, 2, true, 4>(g, st, L.tmA, L.tmB, a) : launch_ptc_t<128, 2, false, 4>(g, st, L.tmA, L.tmB, a);
       else e = p.pool ? launch_ptc_t<256, 1, true, 4>(g, st, L.tmA, L.tmB, a) : launch_ptc_t<256, 1, false, 4>(g, st, L.tmA, L.tmB, a);
@@ -1852,6 +1872,7 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
   if (const char* v = getenv("FF_GEMM_BN")) h->gemm_bn_wide = atoi(v) == 128 ? 128 : 64;
   if (const char* v = getenv("FF_XF")) h->use_xf = atoi(v);
   if (const char* v = getenv("FF_PTC2")) h->use_ptc2 = atoi(v);
+  if (const char* v = getenv("FF_PTC2_128")) h->use_ptc2m = atoi(v);
   if (const char* v = getenv("FF_PTC")) h->use_ptc = atoi(v);
   if (const char* v = getenv("FF_WS2")) h->use_ws2 = atoi(v);
   if (const char* v = getenv("FF_WS4")) h->use_ws4 = atoi(v);
