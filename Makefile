@@ -1,16 +1,27 @@
-# Builds the C-ABI library in-tree (the .so travels to the GPU box with the snapshot).
+# Builds the C-ABI library in-tree (the .so travels to the GPU box with the snapshot).  One object per engine
+# translation unit, so `make -j` compiles them in parallel.
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
-SRC := fac_fake_b200/csrc/ff_engine.cu fac_fake_b200/csrc/ff_blaze.cu
-HDR := $(wildcard fac_fake_b200/csrc/*.cuh) include/facfake.h
+CSRC := fac_fake_b200/csrc
+UNITS := ff_host ff_cvit ff_resvitkan ff_ggca ff_s3d ff_blaze
+OBJ := $(patsubst %,build/%.o,$(UNITS))
+HDR := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/facfake.h
 LIB := fac_fake_b200/libfacfake.so
 
 all: $(LIB)
 
-$(LIB): $(SRC) $(HDR)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC) 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
+build/%.o: $(CSRC)/%.cu $(HDR)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)
+	@cat $(patsubst %,build/%.ptxas.log,$(UNITS)) > build_ptxas.log
+
+oracle:
+	$(MAKE) -C oracle
 
 clean:
-	rm -f $(LIB) build_ptxas.log
-.PHONY: all clean
+	rm -rf build $(LIB) build_ptxas.log
+.PHONY: all clean oracle

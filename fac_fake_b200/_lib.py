@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libfacfake.so")
 FF_OK, FF_ERR_BAD_ARG, FF_ERR_SHAPE, FF_ERR_CUDA, FF_ERR_STATE = 0, -1, -2, -3, -4
 FF_X_NCHW_F32, FF_X_NHWC_U8 = 0, 2
 FF_COMPUTE_BF16, FF_COMPUTE_FP32 = 0, 1
-FF_REDUCE_REFERENCE, FF_REDUCE_SOFTMAX_MEAN = 0, 1
+FF_REDUCE_REFERENCE, FF_REDUCE_SOFTMAX_MEAN, FF_REDUCE_REFERENCE_PROBS = 0, 1, 2
 
 # every symbol include/facfake.h declares: (name, restype, argtypes)
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
@@ -22,6 +22,7 @@ SYMBOLS = [
     ("ff_last_error", C.c_char_p, [_vp]),
     ("ff_cvit_load_weight", _i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i]),
     ("ff_cvit_finalize_weights", _i, [_vp]),
+    ("ff_cvit_unused_keys", C.c_char_p, [_vp]),
     ("ff_preprocess_crops", _i, [_vp, C.POINTER(_vp), C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i, _i, _vp, _vp, _vp]),
     ("ff_cvit_forward", _i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     ("ff_video_scores", _i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
@@ -29,7 +30,7 @@ SYMBOLS = [
     ("ff_cvit_predict_host", _i, [_vp, _vp, C.POINTER(C.c_int32), _i, _i, _vp, _vp]),
     ("ff_cvit_launch_count", _i64, [_vp]),
     ("ff_cvit_debug_activation", _i64, [_vp, _vp, _i, _vp, _i, _i, _vp, _i64, _vp]),
-    ("ff_cvit_set_tuning", _i, [_vp, _i, _i]),
+    ("ff_cvit_set_tuning", _i, [_vp, _i]),
     ("ff_cvit_set_profiling", _i, [_vp, _i]),
     ("ff_cvit_get_profile", _i, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
     ("ff_blazeface_create", _i, [C.POINTER(_vp), _i, _i]),

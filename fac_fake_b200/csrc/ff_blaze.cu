@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "../../include/facfake.h"
+#include "ff_host.h"
 
 namespace {
 
@@ -591,8 +592,7 @@ int bforward(ff_blazeface* h, const uint8_t* tiles, int n, float* det, cudaStrea
   for (int i = 0; i < 16; ++i) {
     if (h->use_chains && i == 6) {             // blocks 6..10: the whole 16x16 stage -> feat8
       constexpr int SM = (256 * 89 + 88 * 260 + 4) * 4;
-      static bool attr = false;
-      if (!attr) { BZ_CUDA(h, cudaFuncSetAttribute(blaze_chain_kernel<16, 88, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); attr = true; }
+      BZ_CUDA(h, ffh::ensure_dyn_smem(reinterpret_cast<const void*>(blaze_chain_kernel<16, 88, 512>), SM));
       blaze_chain_kernel<16, 88, 512><<<n, 512, SM, st>>>(cur, h->feat8, make_chain(6, 5));
       BZ_CUDA(h, cudaGetLastError());
       ++h->launches;
@@ -602,8 +602,7 @@ int bforward(ff_blazeface* h, const uint8_t* tiles, int n, float* det, cudaStrea
     }
     if (h->use_chains && i == 12) {            // blocks 12..15: the 8x8 stage after the stride-2 block 11
       constexpr int SM = (64 * 97 + 96 * 68 + 4) * 4;
-      static bool attr = false;
-      if (!attr) { BZ_CUDA(h, cudaFuncSetAttribute(blaze_chain_kernel<8, 96, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); attr = true; }
+      BZ_CUDA(h, ffh::ensure_dyn_smem(reinterpret_cast<const void*>(blaze_chain_kernel<8, 96, 256>), SM));
       blaze_chain_kernel<8, 96, 256><<<n, 256, SM, st>>>(cur, nxt, make_chain(12, 4));
       BZ_CUDA(h, cudaGetLastError());
       ++h->launches;
@@ -649,7 +648,8 @@ int ff_blazeface_create(ff_blazeface_t** out, int device, int max_tiles) {
   if (e != cudaSuccess || ndev <= 0)
     return bfail(nullptr, FF_ERR_CUDA, "no CUDA device (%s): libfacfake has no CPU fallback", cudaGetErrorString(e));
   if (device < 0 || device >= ndev) return bfail(nullptr, FF_ERR_BAD_ARG, "device %d out of range (%d devices)", device, ndev);
-  if ((e = cudaSetDevice(device)) != cudaSuccess) return bfail(nullptr, FF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  ffh::DeviceGuard guard(device);
+  if (guard.status != cudaSuccess) return bfail(nullptr, FF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.status));
   ff_blazeface* h = new ff_blazeface();
   h->device = device;
   h->cap = max_tiles;
@@ -673,9 +673,11 @@ int ff_blazeface_create(ff_blazeface_t** out, int device, int max_tiles) {
 
 void ff_blazeface_destroy(ff_blazeface_t* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
-  cudaDeviceSynchronize();
-  for (void* p : h->allocs) cudaFree(p);
+  {
+    ffh::DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+  }
   delete h;
 }
 
@@ -700,7 +702,7 @@ int ff_blazeface_finalize(ff_blazeface_t* h) {
   if (!h) return FF_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   if (h->finalized) return FF_OK;
-  BZ_CUDA(h, cudaSetDevice(h->device));
+  ffh::DeviceGuard guard(h->device);
   return bfinalize(h);
 }
 
@@ -709,7 +711,7 @@ int ff_blazeface_predict(ff_blazeface_t* h, const uint8_t* tiles, int n, float* 
   if (!h || n < 0 || (n > 0 && (!tiles || !detections))) return bfail(h, FF_ERR_BAD_ARG, "ff_blazeface_predict: bad arguments");
   std::lock_guard<std::mutex> lk(h->mu);
   if (!h->finalized) return bfail(h, FF_ERR_STATE, "ff_blazeface_finalize() has not been called");
-  BZ_CUDA(h, cudaSetDevice(h->device));
+  ffh::DeviceGuard guard(h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   for (int s0 = 0; s0 < n; s0 += h->cap) {
     const int ns = std::min(h->cap, n - s0);
@@ -725,7 +727,7 @@ int ff_blazeface_nms(ff_blazeface_t* h, const float* detections, int n, float mi
                      int32_t* counts, void* stream) {
   if (!h || n < 0 || (n > 0 && (!detections || !faces || !counts))) return bfail(h, FF_ERR_BAD_ARG, "ff_blazeface_nms: bad arguments");
   std::lock_guard<std::mutex> lk(h->mu);
-  BZ_CUDA(h, cudaSetDevice(h->device));
+  ffh::DeviceGuard guard(h->device);
   if (n == 0) return FF_OK;
   blaze_nms_kernel<<<(n + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(detections, n, min_score, iou_threshold, faces, counts);
   BZ_CUDA(h, cudaGetLastError());

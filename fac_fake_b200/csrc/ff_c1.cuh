@@ -1,43 +1,34 @@
-// ff_c1.cuh — feature layer 1 on the tensor cores: Conv2d(3,32,3,p=1)+BN+ReLU (cvit.py:88-90) with the crop
-// normalisation (cvit_prediction.py:41-45,214-215) fused into the operand build.
-//
-// K = 27 is too small for TMA-fed implicit GEMM, so the A operand is built by the CTA itself:
-//   * the (16+2) x (8+2) input patch of an 8x16-pixel tile is staged in shared memory ALREADY normalised and
-//     rounded to bf16, 4 channels per pixel (c = 3 is zero): uint8 codes go through a per-channel table
-//     lut[c][u] = bf16((u/255 - mean_c)/std_c); out-of-image pixels are stored as 0 (= padding after normalise);
-//   * each of the 128 threads owns one output pixel and copies, per filter row kh, the 3 neighbouring pixels
-//     (24 contiguous bytes) into its 128-byte K-major row in the SWIZZLE_128B pattern; K index = kh*16 + kw*4 + c
-//     (48 used columns, the rest multiply zero weights), fence.proxy.async publishes the rows to the tensor core;
-//   * three tcgen05.mma (M=128, N=32, K=16) produce the tile; the epilogue goes registers -> global with one
-//     32-byte store per L2 sector.
-// CTAs are small (128 threads, ~24 KB smem, 32 TMEM columns) and persistent; several per SM overlap their
-// build / MMA / store phases, and the next tile's patch is prefetched into registers.
-// HBM-bound by construction: 150 KB read + 3.2 MB written per crop.
+// ff_c1.cuh — feature layer 1 as a stand-alone launch: Conv2d(3,32,3,p=1)+BN+ReLU (cvit.py:88-90).
+// The default uint8 path fuses this layer into c12_kernel (ff_c12.cuh); the two kernels here serve
+//   * conv1_f32_kernel: `model(x)` compatibility — fp32 NCHW input that the caller already normalised
+//     (cvit_prediction.py:209-229).  K = 27 is too small for a TMA-fed implicit GEMM, so the CTA builds the A operand:
+//     the (16+2) x (8+2) patch of an 8x16-pixel tile is staged in shared memory as bf16 with 4 channels per pixel
+//     (c = 3 is zero, 0 outside the image = the padding), each thread copies per filter row the 3 neighbouring pixels
+//     (24 contiguous bytes) into its 128-byte K-major row in the SWIZZLE_128B pattern (K index = kh*16 + kw*4 + c),
+//     three tcgen05.mma (M=128, N=32, K=16) produce the tile, registers -> global epilogue;
+//   * conv1_pair_kernel: uint8 crops, no im2col at all (debug tap 1 and the reference point of c12_kernel's first half).
+// HBM-bound by construction: 150 KB (uint8) or 602 KB (fp32) read + 3.2 MB written per crop.
 #pragma once
-#include <type_traits>
 #include "ff_tc.cuh"
 
 namespace ff {
 
 struct C1Args {
-  const void* x;                 // IN_KIND 2: uint8 NHWC [n,224,224,3];  IN_KIND 0: fp32 NCHW [n,3,224,224]
+  const float* x;                // fp32 NCHW [n,3,224,224], already normalised (what `model(x)` receives)
   __nv_bfloat16* out;            // bf16 NHWC [n,224,224,32]
   const __nv_bfloat16* w;        // [32][64] bf16: [cout][k], k = kh*16 + kw*4 + cin (other columns zero)
-  const __nv_bfloat16* lut;      // [3][256] bf16 normalisation table (IN_KIND 2)
   int n_img;
   float scale[32];               // folded BN scale / shift, read as constant-bank operands by the epilogue FMAs
   float shift[32];
 };
 
-template <int IN_KIND>
-__global__ void __launch_bounds__(128, 6)
-conv1_tc_kernel(const __grid_constant__ C1Args a) {
+static __global__ void __launch_bounds__(128, 6)
+conv1_f32_kernel(const __grid_constant__ C1Args a) {
   constexpr int HW = 224, TW = 8, TH = 16, PW = TW + 2, PH = TH + 2;
   constexpr int TILES_W = HW / TW, TILES_H = HW / TH, TILES = TILES_W * TILES_H;
   constexpr int NELEM = PH * PW * 3;
   __shared__ __align__(1024) uint8_t sA[128 * 128];
   __shared__ __align__(1024) uint8_t sB[32 * 128];
-  __shared__ __align__(16) __nv_bfloat16 s_lut[3 * 256];
   __shared__ __align__(16) __nv_bfloat16 s_in[PH * PW * 4];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
@@ -49,8 +40,6 @@ conv1_tc_kernel(const __grid_constant__ C1Args a) {
     const int row = i >> 3, ch = i & 7;
     *reinterpret_cast<uint4*>(sB + row * 128 + ((ch ^ (row & 7)) << 4)) = reinterpret_cast<const uint4*>(a.w)[i];
   }
-  if (IN_KIND == 2)
-    for (int i = tid; i < 3 * 256 / 8; i += 128) reinterpret_cast<uint4*>(s_lut)[i] = reinterpret_cast<const uint4*>(a.lut)[i];
   for (int i = tid; i < PH * PW * 4 / 8; i += 128) reinterpret_cast<uint4*>(s_in)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 128 * 8; i += 128) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -69,12 +58,10 @@ conv1_tc_kernel(const __grid_constant__ C1Args a) {
   const int hl = tid >> 3, wl = tid & 7;
   // Software pipeline: the patch of the NEXT tile is fetched into registers while the current tile is processed.
   constexpr int NPF = (NELEM + 127) / 128;
-  typedef typename std::conditional<IN_KIND == 2, uint8_t, float>::type in_t;
-  in_t pf[NPF];
-  // element i of the patch -> (py, px, c); uint8 input is walked in memory order (HWC), fp32 input plane by plane
+  float pf[NPF];
+  // element i of the patch -> (py, px, c), walked plane by plane (NCHW input)
   auto decode = [&](int i, int* py, int* px, int* c) {
-    if (IN_KIND == 2) { *py = i / (PW * 3); const int r = i - *py * (PW * 3); *px = r / 3; *c = r - *px * 3; }
-    else { *c = i / (PH * PW); const int r = i - *c * (PH * PW); *py = r / PW; *px = r - *py * PW; }
+    *c = i / (PH * PW); const int r = i - *c * (PH * PW); *py = r / PW; *px = r - *py * PW;
   };
   auto prefetch = [&](int t) {
     const int n = t / TILES;
@@ -83,14 +70,13 @@ conv1_tc_kernel(const __grid_constant__ C1Args a) {
 #pragma unroll
     for (int j = 0; j < NPF; ++j) {
       const int i = tid + j * 128;
-      in_t v = 0;
+      float v = 0.0f;
       if (i < NELEM) {
         int py, px, c;
         decode(i, &py, &px, &c);
         const int gy = th * TH - 1 + py, gx = tw * TW - 1 + px;
         if (gy >= 0 && gy < HW && gx >= 0 && gx < HW) {
-          if (IN_KIND == 2) v = reinterpret_cast<const uint8_t*>(a.x)[((static_cast<size_t>(n) * HW + gy) * HW + gx) * 3 + c];
-          else v = reinterpret_cast<const float*>(a.x)[((static_cast<size_t>(n) * 3 + c) * HW + gy) * HW + gx];
+          v = a.x[((static_cast<size_t>(n) * 3 + c) * HW + gy) * HW + gx];
         }
       }
       pf[j] = v;
@@ -112,10 +98,7 @@ conv1_tc_kernel(const __grid_constant__ C1Args a) {
         decode(i, &py, &px, &c);
         const int gy = h0 - 1 + py, gx = w0 - 1 + px;
         const bool ok = gy >= 0 && gy < HW && gx >= 0 && gx < HW;
-        __nv_bfloat16 b;
-        if (IN_KIND == 2) b = s_lut[c * 256 + static_cast<int>(pf[j])];
-        else b = __float2bfloat16_rn(static_cast<float>(pf[j]));
-        s_in[(py * PW + px) * 4 + c] = ok ? b : __float2bfloat16_rn(0.0f);
+        s_in[(py * PW + px) * 4 + c] = __float2bfloat16_rn(ok ? pf[j] : 0.0f);
       }
     }
     __syncthreads();
@@ -166,166 +149,6 @@ conv1_tc_kernel(const __grid_constant__ C1Args a) {
 }
 
 }  // namespace ff
-
-namespace ff {
-
-// -----------------------------------------------------------------------------------------------------------------
-// uint8 fast path of feature layer 1: same math as conv1_tc_kernel<2>, but the raw patch arrives by TMA
-// (3-D map over the uint8 [n][224][672] view) through a 3-deep ring.  TMA needs a 16-byte aligned inner
-// coordinate (measured: tools/tma_u8_test.cu), and the 30-byte row segment of an 8-pixel-wide tile starts at byte
-// 24*tw-3, so the box is 48 bytes wide starting at 24*tw-16 (tw even) / 24*tw-8 (tw odd); out-of-image bytes are
-// zero-filled by TMA and masked to 0 AFTER normalisation by the conversion step.
-struct C1TmaArgs {
-  __nv_bfloat16* out;
-  const __nv_bfloat16* w;        // [32][64] bf16, k = kh*16 + kw*4 + cin
-  int n_img;
-  float na[3], nb[3];            // normalisation as one FMA: bf16(u*na[c] + nb[c]) == bf16((u/255 - mean_c)/std_c)
-                                 // for all 256 codes (checked on the host at finalize)
-  float scale[32];
-  float shift[32];
-};
-
-__global__ void __launch_bounds__(128, 8)
-conv1_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C1TmaArgs a) {
-  constexpr int HW = 224, TW = 8, TH = 16, PW = TW + 2, PH = TH + 2;
-  constexpr int TILES_W = HW / TW, TILES_H = HW / TH, TILES = TILES_W * TILES_H;
-  constexpr int RING = 3, ROW_WORDS = 12, RAW_BYTES = PH * ROW_WORDS * 4;
-  __shared__ __align__(1024) uint8_t sA[128 * 128];
-  __shared__ __align__(1024) uint8_t sB[32 * 128];
-  __shared__ __align__(128) uint8_t s_raw[RING][896];   // 864 B used per slot; TMA destinations must be 128-B aligned
-  // patch rows are padded to 192 bytes (= 64 mod 128) so that the 16 lanes of a half-warp, which read two
-  // consecutive patch rows of 8 pixels x 8 bytes, fall into disjoint bank halves
-  constexpr int SPITCH = 96;   // bf16 elements per patch row
-  __shared__ __align__(16) __nv_bfloat16 s_in[PH * SPITCH];
-  __shared__ __align__(8) uint64_t s_bar[1 + RING];
-  __shared__ uint32_t s_tmem;
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t bar_mma = smem_u32(&s_bar[0]);
-  const uint32_t bar_raw = smem_u32(&s_bar[1]);
-  for (int i = tid; i < 32 * 8; i += 128) {
-    const int row = i >> 3, ch = i & 7;
-    *reinterpret_cast<uint4*>(sB + row * 128 + ((ch ^ (row & 7)) << 4)) = reinterpret_cast<const uint4*>(a.w)[i];
-  }
-  for (int i = tid; i < PH * SPITCH / 8; i += 128) reinterpret_cast<uint4*>(s_in)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 128 * 8; i += 128) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
-  if (tid == 0) {
-    tma_prefetch_desc(&tmX);
-    mbar_init(bar_mma, 1);
-    for (int s = 0; s < RING; ++s) mbar_init(bar_raw + 8 * s, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc<32>(smem_u32(&s_tmem));
-  fence_proxy_async_smem();
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = s_tmem;
-  if (tid == 0) pdl_trigger();
-  pdl_wait();
-  const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-  constexpr uint32_t idesc = make_idesc_bf16(128, 32);
-  const int num_tiles = TILES * a.n_img;
-  const int hl = tid >> 3, wl = tid & 7;
-
-  // conversion job of this thread: patch pixels tid and tid + 128 (180 pixels, 3 raw bytes -> 4 bf16 each)
-  int job_py[2], job_px[2];
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int pi = tid + j * 128;
-    job_py[j] = pi / PW;
-    job_px[j] = pi - job_py[j] * PW;
-  }
-  auto issue = [&](int t, int slot) {
-    const int n = t / TILES;
-    const int rem = t - n * TILES;
-    const int th = rem / TILES_W, tw = rem - th * TILES_W;
-    mbar_arrive_expect_tx(bar_raw + 8 * slot, RAW_BYTES);
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-            smem_u32(&s_raw[slot][0])),
-        "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar_raw + 8 * slot), "r"(24 * tw - ((tw & 1) ? 8 : 16)), "r"(th * TH - 1), "r"(n)
-        : "memory");
-  };
-  if (tid == 0) {
-    for (int s = 0; s < RING - 1; ++s) {
-      const int t = blockIdx.x + s * gridDim.x;
-      if (t < num_tiles) issue(t, s);
-    }
-  }
-  int it = 0;
-  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-    const int n = t / TILES;
-    const int rem = t - n * TILES;
-    const int th = rem / TILES_W, tw = rem - th * TILES_W;
-    const int h0 = th * TH, w0 = tw * TW;
-    const int slot = it % RING;
-    // ---- 1. raw uint8 window -> normalised bf16 patch (0 outside the image)
-    mbar_wait(bar_raw + 8 * slot, (it / RING) & 1);
-    const int off = (tw & 1) ? 5 : 13;            // first segment byte inside the 48-byte window
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int pi = tid + j * 128;
-      if (pi < PH * PW) {
-        const uint8_t* rp = &s_raw[slot][job_py[j] * (ROW_WORDS * 4) + off + 3 * job_px[j]];
-        const int gy = h0 - 1 + job_py[j], gx = w0 - 1 + job_px[j];
-        const bool ok = gy >= 0 && gy < HW && gx >= 0 && gx < HW;
-        const float v0 = ok ? fmaf(static_cast<float>(rp[0]), a.na[0], a.nb[0]) : 0.0f;
-        const float v1 = ok ? fmaf(static_cast<float>(rp[1]), a.na[1], a.nb[1]) : 0.0f;
-        const float v2 = ok ? fmaf(static_cast<float>(rp[2]), a.na[2], a.nb[2]) : 0.0f;
-        *reinterpret_cast<uint2*>(s_in + job_py[j] * SPITCH + job_px[j] * 4) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, 0.0f));
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {                       // the slot two tiles ahead is free: its consumer (tile it-1) has passed the barrier
-      const int tn = t + (RING - 1) * gridDim.x;
-      if (tn < num_tiles) issue(tn, (it + RING - 1) % RING);
-    }
-    // ---- 2. this thread's K-major row
-    {
-      const int sw = tid & 7;
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const uint2* src = reinterpret_cast<const uint2*>(s_in + (hl + kh) * SPITCH + wl * 4);
-        const uint2 p0 = src[0], p1 = src[1], p2 = src[2];
-        *reinterpret_cast<uint4*>(sA + tid * 128 + (((2 * kh) ^ sw) << 4)) = make_uint4(p0.x, p0.y, p1.x, p1.y);
-        *reinterpret_cast<uint4*>(sA + tid * 128 + (((2 * kh + 1) ^ sw) << 4)) = make_uint4(p2.x, p2.y, 0u, 0u);
-      }
-    }
-    fence_proxy_async_smem();
-    tcgen05_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tcgen05_fence_after();
-      const uint64_t ad = make_kmajor_desc<128>(sA_addr), bd = make_kmajor_desc<128>(sB_addr);
-      umma_bf16_ss(tmem, ad, bd, idesc, 0u);
-      umma_bf16_ss(tmem, ad + 2, bd + 2, idesc, 1u);
-      umma_bf16_ss(tmem, ad + 4, bd + 4, idesc, 1u);
-      umma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, it & 1);
-    tcgen05_fence_after();
-    uint32_t v[32];
-    tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16), v);
-    tmem_ld_wait();
-    uint32_t p[16];
-#pragma unroll
-    for (int c = 0; c < 32; c += 2) {
-      const float x0 = fmaf(__uint_as_float(v[c]), a.scale[c], a.shift[c]);
-      const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale[c + 1], a.shift[c + 1]);
-      p[c >> 1] = pack_bf16x2_relu(x0, x1);
-    }
-    __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * HW + (h0 + hl)) * HW + (w0 + wl)) * 32;
-    st_global_v8(o, p);
-    st_global_v8(o + 16, p + 8);
-    tcgen05_fence_before();
-  }
-  __syncthreads();
-  if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<32>(tmem); }
-}
-
-}  // namespace ff
-
 namespace ff {
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -356,7 +179,7 @@ __device__ __forceinline__ uint64_t make_kmajor_desc_noswz(uint32_t smem_addr, u
   return d;
 }
 
-__global__ void __launch_bounds__(128, 8)
+static __global__ void __launch_bounds__(128, 8)
 conv1_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C1PairArgs a) {
   constexpr int HW = 224, TW = 16, TH = 16, PW = TW + 2, PH = TH + 2;
   constexpr int TILES_W = HW / TW, TILES_H = HW / TH, TILES = TILES_W * TILES_H;

@@ -43,7 +43,6 @@ struct C12Args {
   float na[3], nb[3];
   float scale1[32], shift1[32];
   float scale2[32], shift2[32];
-  long long* dbg;                // optional [8] cycle counters of CTA 0 (FF_C12_DBG=1): phase breakdown of the pipeline
 };
 
 struct C12Smem {
@@ -67,7 +66,7 @@ struct C12Smem {
 };
 
 constexpr int C12_THREADS = 288;      // 8 worker warps + 1 MMA-issuing warp
-__global__ void __launch_bounds__(C12_THREADS, 2)
+static __global__ void __launch_bounds__(C12_THREADS, 2)
 c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ C12Args a) {
   using L = C12Smem;
   constexpr int HW = 224, TW = 16, TH = 14;
@@ -242,7 +241,6 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       tcgen05_fence_before();
     };
 
-    long long dbg_acc[6] = {0, 0, 0, 0, 0, 0};   // wait conv1 | epilogue 1 | - | convert next | wait conv2 + epilogue 2 | tiles
     if (blockIdx.x < num_tiles) convert(blockIdx.x, 0);
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -252,10 +250,8 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       // ---- a. epilogue 1: thread (hl, jl, half) converts pixel `half` of conv1 pair (row hl, pair jl) from strip 0 and of
       //         (row hl, pair jl+2) from strip 1 (kept only for jl >= 6).  Patch row hl = image row h0-1+hl, pair j = image
       //         pixels w0-2+2j, +1; positions outside the image are conv2's zero padding.
-      const long long c0 = clock64();
       mbar_wait(bar_mma1, it & 1);
       tcgen05_fence_after();
-      const long long c1 = clock64();
       {
         const int gy = h0 - 1 + hl;
 #pragma unroll
@@ -287,24 +283,20 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       fence_proxy_async_smem();
       tcgen05_fence_before();
       mbar_arrive(bar_patch);
-      const long long c2 = clock64();
       // ---- c. next tile: conversion (s_in was released by the conv1 MMAs of tile k, waited for in step a)
       const int tn = t + gridDim.x;
       if (tn < num_tiles) convert(tn, it + 1);
-      const long long c4 = clock64();
       // ---- d. previous tile: output epilogue while the issuer feeds the conv2 MMAs of tile k
       if (it >= 1) epilogue2(t - gridDim.x, it - 1);
-      const long long c5 = clock64();
-      if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) {
-        dbg_acc[0] += c1 - c0; dbg_acc[1] += c2 - c1; dbg_acc[3] += c4 - c2; dbg_acc[4] += c5 - c4; dbg_acc[5] += 1;
-      }
     }
     if (it >= 1) epilogue2(blockIdx.x + (it - 1) * gridDim.x, it - 1);
-    if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0)
-      for (int i = 0; i < 6; ++i) a.dbg[i] = dbg_acc[i];
   }
   __syncthreads();
   if (warp == 8) { tcgen05_fence_after(); tmem_dealloc<256>(tmem); }
+}
+
+inline cudaError_t launch_c12(int grid, cudaStream_t st, const CUtensorMap& x, const CUtensorMap& w2, const C12Args& args) {
+  return ffh::launch_smem(c12_kernel, dim3(grid), dim3(C12_THREADS), C12Smem::TOTAL, st, true, x, w2, args);
 }
 
 }  // namespace ff

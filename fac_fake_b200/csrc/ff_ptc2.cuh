@@ -215,207 +215,9 @@ ptc2_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-
-// =================================================================================================================
-// NOT VALIDATED ON HARDWARE YET (written after the GPU budget of round 1 was spent; opt-in FF_PTC2_128=1, off by
-// default; tests/test_gpu_parity.py::test_unvalidated_cta_pair_kernel_cout128 is skipped unless FF_TEST_PTC2_128=1).
-// The same CTA-pair scheme for feature layers 7..9 (Cout = 128): every CTA owns TWO 128-pixel sub-tiles and half
-// (64 rows) of the 128-channel filter tile: 40 KB instead of 48 KB of shared-memory fill per k-block per SM, and the
-// pair issues 8 MMAs of M = 256 per k-block where two independent CTAs issue 16 of M = 128.
-struct Ptc2mSmem {
-  static constexpr int STAGES = 5;
-  static constexpr int A_BYTES = 2 * 128 * 128;  // this CTA's two 128-pixel sub-tiles x 64 channels
-  static constexpr int B_BYTES = 64 * 128;       // this CTA's half of the 128-channel filter tile
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SS_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = SS_OFF + 2 * 512 * 4;
-  static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
-  static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
-};
-
 template <bool POOL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
-ptc2m_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-  using L = Ptc2mSmem;
-  constexpr int BN = 128, MSUB = 2, BKE = 64, STAGES = L::STAGES;
-  constexpr int TMEM_COLS = 2 * MSUB * BN;       // 512: two accumulator sets of two sub-tiles
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  float* ss = reinterpret_cast<float*>(base_ptr + L::SS_OFF);
-  const uint32_t bar_full = base + L::BAR_OFF;
-  const uint32_t bar_empty = bar_full + STAGES * 8;
-  const uint32_t bar_tfull = bar_empty + STAGES * 8;
-  const uint32_t bar_tempty = bar_tfull + 16;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const int n_tiles = a.cout / BN;
-  const int lg_bi = 7 - a.lg_bw - a.lg_bh;
-  const int m_tiles = a.tiles_w * a.tiles_h * ((a.n_img + (1 << lg_bi) - 1) >> lg_bi);
-  const int num_items = ((m_tiles + 2 * MSUB - 1) / (2 * MSUB)) * n_tiles;   // item = (four pixel tiles, channel tile)
-  const int kb_total = a.kb_total;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    mbar_init(bar_tfull, 1);
-    mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, 256);
-    mbar_init(bar_tempty + 8, 256);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  if (warp >= 2)
-    for (int i = threadIdx.x - 64; i < a.cout; i += 128) {
-      ss[i] = a.scale[i];
-      ss[512 + i] = a.shift[i];
-    }
-  tcgen05_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // item, sub-tile j -> channel tile and THIS CTA's j-th pixel tile
-  auto item_coords = [&](int item, int j, int* w0, int* h0, int* n0, int* col0) {
-    const int nt = item % n_tiles, mt = (item / n_tiles) * 2 * MSUB + static_cast<int>(rank) * MSUB + j;
-    const int tw = mt % a.tiles_w;
-    const int th = (mt / a.tiles_w) % a.tiles_h;
-    const int nb = mt / (a.tiles_w * a.tiles_h);
-    *w0 = tw << a.lg_bw;
-    *h0 = th << a.lg_bh;
-    *n0 = nb << lg_bi;
-    *col0 = nt * BN;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      pdl_trigger();
-      pdl_wait();
-      int s = 0, ph = 0;
-      for (int item = cluster_id; item < num_items; item += num_clusters) {
-        int w0[MSUB], h0[MSUB], n0[MSUB], col0;
-#pragma unroll
-        for (int j = 0; j < MSUB; ++j) item_coords(item, j, &w0[j], &h0[j], &n0[j], &col0);
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          const uint32_t sa = base + s * L::STAGE_BYTES;
-          const uint32_t bar = bar_full + 8 * s;
-          if (leader) mbar_arrive_expect_tx(bar, 2 * L::STAGE_BYTES);
-          const int tap = kb / a.kb_per_tap;
-          const int cc = kb - tap * a.kb_per_tap;
-          const int kh = tap / 3, kw = tap - kh * 3;
-#pragma unroll
-          for (int j = 0; j < MSUB; ++j)
-            tma_load_4d_2cta(sa + j * 128 * 128, &tmA, bar, cc * BKE, w0[j] + kw - 1, h0[j] + kh - 1, n0[j]);
-          tma_load_2d_2cta(sa + L::A_BYTES, &tmB, bar, kb * BKE, col0 + 64 * static_cast<int>(rank));
-          if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
-      int s = 0, ph = 0, it = 0;
-      for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
-        const int acc = it & 1;
-        if (it >= 2) mbar_wait(bar_tempty + 8 * acc, ((it >> 1) - 1) & 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * MSUB * BN;
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(bar_full + 8 * s, ph);
-          tcgen05_fence_after();
-          const uint32_t sa = base + s * L::STAGE_BYTES;
-          const uint64_t bdesc = make_kmajor_desc<128>(sa + L::A_BYTES);
-#pragma unroll
-          for (int j = 0; j < MSUB; ++j) {
-            const uint64_t adesc = make_kmajor_desc<128>(sa + j * 128 * 128);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss_2cta(d_tmem + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit_2cta(bar_empty + 8 * s, 0x3);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
-        umma_commit_2cta(bar_tfull + 8 * acc, 0x3);
-      }
-    }
-  } else {
-    const int g = warp & 3;
-    const int r = g * 32 + lane;
-    const int BW = 1 << a.lg_bw, BH = 1 << a.lg_bh;
-    const int wl = r & (BW - 1);
-    const int hl = (r >> a.lg_bw) & (BH - 1);
-    const int nl = r >> (a.lg_bw + a.lg_bh);
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
-    int it = 0;
-    for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
-      const int acc = it & 1;
-      mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
-      tcgen05_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < MSUB; ++j) {
-        int w0, h0, n0, col0;
-        item_coords(item, j, &w0, &h0, &n0, &col0);
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + (acc * MSUB + j) * BN;
-        const int n = n0 + nl;
-        const bool img_ok = n < a.n_img;
-        __nv_bfloat16* orow;
-        if (!POOL) orow = out + ((static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * a.W + (w0 + wl)) * a.cout + col0;
-        else orow = out + ((static_cast<size_t>(a.img_off_out + n) * (a.H >> 1) + ((h0 + hl) >> 1)) * (a.W >> 1) + ((w0 + wl) >> 1)) * a.cout + col0;
-        const bool writer = img_ok && (!POOL || (((wl | hl) & 1) == 0));
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c0, v);
-          tmem_ld_wait();
-          if (j == MSUB - 1 && c0 + 32 == BN) {
-            tcgen05_fence_before();
-            mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
-          }
-          uint32_t p[16];
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const float x0 = fmaf(__uint_as_float(v[c]), ss[col0 + c0 + c], ss[512 + col0 + c0 + c]);
-            const float x1 = fmaf(__uint_as_float(v[c + 1]), ss[col0 + c0 + c + 1], ss[512 + col0 + c0 + c + 1]);
-            p[c >> 1] = pack_bf16x2_relu(x0, x1);
-          }
-          if (POOL) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              uint32_t o1 = __shfl_xor_sync(0xffffffffu, p[i], 1);
-              __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&p[i]), *reinterpret_cast<__nv_bfloat162*>(&o1));
-              uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
-              uint32_t o2 = __shfl_xor_sync(0xffffffffu, mu, BW);
-              m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o2));
-              p[i] = *reinterpret_cast<uint32_t*>(&m);
-            }
-          }
-          if (writer) {
-            st_global_v8(orow + c0, p);
-            st_global_v8(orow + c0 + 16, p + 8);
-          }
-        }
-      }
-    }
-  }
-
-  tcgen05_fence_before();
-  cluster_sync_all();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
-  }
+inline cudaError_t launch_ptc2(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
+  return ffh::launch_smem(ptc2_conv_kernel<POOL>, dim3(grid), dim3(192), Ptc2Smem::TOTAL, st, true, a, b, args);
 }
 
 }  // namespace ff

@@ -1,10 +1,10 @@
-// ff_rvk.cuh — kernels specific to ResVitKan inference (SURVEY.md §8f-1;
-// /root/reference/CViT-main/ResVitKan/ResVitKan.py:185-240,284-329 and kan.py:90-206).
-// The bottleneck convolutions reuse ff_tc.cuh (1x1 convs = GEMM over pixels with a folded-BN / residual epilogue,
-// 3x3 and strided convs = the implicit-GEMM kernel with elementStrides in the TMA descriptor); this file adds the
-// stem (7x7 stride 2), the 3x3 stride-2 max-pool, the input conversion and the KAN head.
+// ff_rvk.cuh — kernels of ResVitKan inference (SURVEY.md §8f-1;
+// /root/reference/CViT-main/ResVitKan/ResVitKan.py:185-240,284-329 and kan.py:90-206): input conversion, the stem
+// (7x7 stride 2, no im2col), the 3x3 stride-2 max-pool, rvk_conv2_kernel (every bottleneck convolution; also used by
+// the S3D and GGCA engines), the KAN head and the GGCA gate.
 #pragma once
 #include "ff_c1.cuh"
+#include "ff_small.cuh"
 
 namespace ff {
 
@@ -59,7 +59,7 @@ struct RvkStemArgs {
 
 constexpr int RVK_STEM_RING = 3, RVK_STEM_PSLOT = 7168;
 constexpr int RVK_STEM_SMEM = RVK_STEM_RING * RVK_STEM_PSLOT + 7 * 4096 + 128;
-__global__ void __launch_bounds__(128, 4)
+static __global__ void __launch_bounds__(128, 4)
 rvk_stem_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ RvkStemArgs a) {
   constexpr int OW = 112, TW = 8, TH = 16, TILES_W = OW / TW, TILES_H = OW / TH, TILES = TILES_W * TILES_H;
   constexpr int RING = RVK_STEM_RING, PROW = 192, PROWS = 37, PBYTES = PROWS * PROW, PSLOT = RVK_STEM_PSLOT;
@@ -162,228 +162,15 @@ rvk_stem_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 }
 
 
-// ---- persistent implicit-GEMM convolution for the ResNet bottlenecks (1x1 / 3x3, stride 1 / 2) ----------------------
-// Same skeleton as ptc_conv_kernel (ff_tc.cuh): one CTA per SM walks (MSUB pixel tiles x BN channels) work items,
-// warp 0 = TMA producer, warp 1 = tcgen05 issuer, double-buffered TMEM accumulators; differences:
+// ---- persistent implicit-GEMM convolution for the ResNet bottlenecks (1x1 / 3x3, stride 1 / 2), the S3D convolutions
+// and the GGCA variant's BN-less conv.  Same skeleton as ptc_conv_kernel (ff_tc.cuh): one CTA per SM walks (2 pixel
+// tiles x BN channels) work items, warp 0 = TMA producer, warp 1 = tcgen05 issuer, double-buffered TMEM accumulators;
 //   * the tap loop and the TMA coordinates follow a.taps / a.stride (the strided maps carry elementStrides);
 //   * a stride-1 1x1 convolution is run "flat": W = all pixels of the batch, H = N = 1, boxes of 128 pixels;
 //   * 8 epilogue warps (two per TMEM lane group, each owning half of the BN columns): the bottleneck outputs are
-//     HBM-bound (K is as small as 64), so the epilogue needs the loads/stores of 256 threads in flight;
-//   * epilogue = folded BN, optional ReLU, optional bf16 residual add + ReLU (ResVitKan.py:169-176), with the
-//     residual of the next sub-tile prefetched into registers while the current one is converted and stored.
-template <int BN, int MSUB, int STAGES>
-struct RvkSmem {
-  static constexpr int A_BYTES = MSUB * 128 * 128;
-  static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SS_OFF = STAGES * STAGE_BYTES;                 // scale/shift floats [2][2048]
-  static constexpr int BAR_OFF = SS_OFF + 2 * 2048 * 4;               // full[S], empty[S], tfull[2], tempty[2]
-  static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
-  static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
-};
-
-template <int BN, int MSUB, int STAGES>
-__global__ void __launch_bounds__(320, 1)
-rvk_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-  using L = RvkSmem<BN, MSUB, STAGES>;
-  constexpr int BKE = 64;
-  constexpr int TMEM_COLS = 2 * MSUB * BN;
-  constexpr int HALF = BN / 2, NCH = HALF / 32;        // columns / 32-column chunks per epilogue thread
-  static_assert(MSUB == 2, "the residual prefetch ping-pong assumes two sub-tiles");
-  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  float* ss = reinterpret_cast<float*>(base_ptr + L::SS_OFF);
-  const uint32_t bar_full = base + L::BAR_OFF;
-  const uint32_t bar_empty = bar_full + STAGES * 8;
-  const uint32_t bar_tfull = bar_empty + STAGES * 8;
-  const uint32_t bar_tempty = bar_tfull + 16;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int n_tiles = a.cout / BN;
-  const int lg_bi = 7 - a.lg_bw - a.lg_bh;
-  const int m_tiles = a.tiles_w * a.tiles_h * ((a.n_img + (1 << lg_bi) - 1) >> lg_bi);
-  const int num_tiles = ((m_tiles + MSUB - 1) / MSUB) * n_tiles;
-  const int kb_total = a.kb_total;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    mbar_init(bar_tfull, 1);
-    mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, 256);
-    mbar_init(bar_tempty + 8, 256);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  if (warp >= 2)
-    for (int i = threadIdx.x - 64; i < a.cout; i += 256) {      // weights: not produced by the previous kernel
-      ss[i] = a.scale[i];
-      ss[2048 + i] = a.shift[i];
-    }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) pdl_trigger();
-  pdl_wait();                    // every thread: the epilogue reads the residual written by earlier kernels
-
-  // consecutive work items share the pixel tiles and walk the channel tiles (A stays hot in L2)
-  auto tile_coords = [&](int t, int j, int* w0, int* h0, int* n0, int* col0) {
-    const int nt = t % n_tiles, mt = (t / n_tiles) * MSUB + j;
-    const int tw = mt % a.tiles_w;
-    const int th = (mt / a.tiles_w) % a.tiles_h;
-    const int nb = mt / (a.tiles_w * a.tiles_h);
-    *w0 = tw << a.lg_bw;
-    *h0 = th << a.lg_bh;
-    *n0 = nb << lg_bi;
-    *col0 = nt * BN;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const int sd = a.stride == 2 ? 2 : 1;
-      int s = 0, ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int w0[MSUB], h0[MSUB], n0[MSUB], col0;
-#pragma unroll
-        for (int j = 0; j < MSUB; ++j) tile_coords(t, j, &w0[j], &h0[j], &n0[j], &col0);
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          const uint32_t sa = base + s * L::STAGE_BYTES;
-          const uint32_t bar = bar_full + 8 * s;
-          mbar_arrive_expect_tx(bar, L::STAGE_BYTES);
-          const int tap = kb / a.kb_per_tap;
-          const int cc = kb - tap * a.kb_per_tap;
-          int dx = 0, dy = 0;
-          if (a.taps == 9) { const int kh = tap / 3; dy = kh - 1; dx = tap - kh * 3 - 1; }
-#pragma unroll
-          for (int j = 0; j < MSUB; ++j) tma_load_4d(sa + j * 128 * 128, &tmA, bar, cc * BKE, sd * w0[j] + dx, sd * h0[j] + dy, n0[j]);
-          tma_load_2d(sa + L::A_BYTES, &tmB, bar, kb * BKE, col0);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
-      int s = 0, ph = 0, it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        if (it >= 2) mbar_wait(bar_tempty + 8 * acc, ((it >> 1) - 1) & 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * MSUB * BN;
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(bar_full + 8 * s, ph);
-          tcgen05_fence_after();
-          const uint32_t sa = base + s * L::STAGE_BYTES;
-          const uint64_t bdesc = make_kmajor_desc<128>(sa + L::A_BYTES);
-#pragma unroll
-          for (int j = 0; j < MSUB; ++j) {
-            const uint64_t adesc = make_kmajor_desc<128>(sa + j * 128 * 128);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(d_tmem + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(bar_empty + 8 * s);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
-        umma_commit(bar_tfull + 8 * acc);
-      }
-    }
-  } else {
-    const int g = warp & 3;                      // TMEM lane group of this warp
-    const int cb = ((warp - 2) >> 2) * HALF;     // first of this thread's columns inside the BN tile
-    const int r = g * 32 + lane;
-    const int BW = 1 << a.lg_bw, BH = 1 << a.lg_bh;
-    const int wl = r & (BW - 1);
-    const int hl = (r >> a.lg_bw) & (BH - 1);
-    const int nl = r >> (a.lg_bw + a.lg_bh);
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
-    const __nv_bfloat16* resid = reinterpret_cast<const __nv_bfloat16*>(a.resid);
-    const bool relu1 = a.conv_act == 0;
-    // element offset of this thread's output run for sub-tile j of work item t (or -1: masked)
-    auto row_off = [&](int t, int j) -> long long {
-      if (t >= num_tiles) return -1;
-      int w0, h0, n0, col0;
-      tile_coords(t, j, &w0, &h0, &n0, &col0);
-      const int n = n0 + nl, w = w0 + wl, hh = h0 + hl;
-      if (n >= a.n_img || w >= a.W || hh >= a.H) return -1;
-      return ((static_cast<long long>(n) * a.H + hh) * a.W + w) * a.cout + col0 + cb;
-    };
-    uint32_t rr[MSUB][NCH * 16];
-    auto prefetch = [&](long long off, uint32_t* dst) {
-      if (resid != nullptr && off >= 0) {
-#pragma unroll
-        for (int i = 0; i < NCH * 2; ++i) ld_global_v8(resid + off + 16 * i, dst + 8 * i);
-      }
-    };
-    long long off_cur = row_off(blockIdx.x, 0);
-    prefetch(off_cur, rr[0]);
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int acc = it & 1;
-      int col0;
-      { int w0, h0, n0; tile_coords(t, 0, &w0, &h0, &n0, &col0); }
-      mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
-      tcgen05_fence_after();
-#pragma unroll
-      for (int j = 0; j < MSUB; ++j) {
-        const long long off_next = (j + 1 < MSUB) ? row_off(t, j + 1) : row_off(t + gridDim.x, 0);
-        prefetch(off_next, rr[(j + 1) % MSUB]);
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + (acc * MSUB + j) * BN + cb;
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + ch * 32, v);
-          tmem_ld_wait();
-          if (j == MSUB - 1 && ch == NCH - 1) {   // accumulators fully read: hand the TMEM buffer back to the MMA warp
-            tcgen05_fence_before();
-            mbar_arrive(bar_tempty + 8 * acc);
-          }
-          const float* sc = ss + col0 + cb + ch * 32;
-          uint32_t p[16];
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float x0 = fmaf(__uint_as_float(v[c]), sc[c], sc[2048 + c]);
-            float x1 = fmaf(__uint_as_float(v[c + 1]), sc[c + 1], sc[2048 + c + 1]);
-            if (relu1) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
-            if (resid != nullptr) {
-              const float2 rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[j][ch * 16 + (c >> 1)]));
-              x0 = fmaxf(x0 + rf.x, 0.0f);
-              x1 = fmaxf(x1 + rf.y, 0.0f);
-            }
-            p[c >> 1] = pack_bf16x2(x0, x1);
-          }
-          if (off_cur >= 0) {
-            st_global_v8(out + off_cur + ch * 32, p);
-            st_global_v8(out + off_cur + ch * 32 + 16, p + 8);
-          }
-        }
-        off_cur = off_next;
-      }
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
-  }
-}
-
-// ---- the same persistent kernel with ALL global traffic on TMA ------------------------------------------------------
-// ncu on rvk_conv_kernel (profiles/r01_ncu_rvk_conv.txt): the per-thread 32-byte residual loads / output stores run
-// at 32 sectors per request and hold the LSU at 71 % while DRAM sits at 50 %.  Here the epilogue converts a sub-tile
+//     HBM-bound (K is as small as 64), so ALL global traffic is on TMA.  ncu on the register-direct predecessor
+//     (profiles/r01_ncu_rvk_conv.txt): per-thread 32-byte residual loads / output stores ran at 32 sectors per
+//     request and held the LSU at 71 % while DRAM sat at 50 %.  Here the epilogue converts a sub-tile
 // in a swizzled shared-memory panel ([128 pixels][64 channels] bf16, the TMA SW128 layout) and one elected thread
 // stores it with cp.async.bulk.tensor; the residual arrives in the same panel by TMA (LA sub-tiles ahead) and is
 // overwritten in place.  NSTG panels-sets rotate; set b is owned by elected thread E_b, which is the only one that
@@ -624,8 +411,22 @@ rvk_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// pixel-tile box (bw x bh pixels x bi images = 128 rows) of rvk_conv2_kernel per output size
+inline void rvk_tile_geometry(int out_hw, int* bw, int* bh, int* bi) {
+  if (out_hw == 56) { *bw = 8; *bh = 8; *bi = 2; }
+  else if (out_hw == 28) { *bw = 4; *bh = 4; *bi = 8; }
+  else if (out_hw == 14) { *bw = 2; *bh = 2; *bi = 32; }
+  else { *bw = 8; *bh = 8; *bi = 2; }                         // 7x7: one masked 8x8 box per image
+}
+
+template <int BN, int STAGES, bool RESID>
+inline cudaError_t launch_rvk_conv2(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o,
+                                    const CUtensorMap& r, const TcArgs& args) {
+  return ffh::launch_smem(rvk_conv2_kernel<BN, STAGES, RESID>, dim3(grid), dim3(320), Rvk2Smem<BN, STAGES, RESID>::TOTAL, st, true, a, b, o, r, args);
+}
+
 // ---- MaxPool2d(kernel 3, stride 2, pad 1) on NHWC bf16 with C = 64 (ResVitKan.py:194,232): [n,112,112,64] -> [n,56,56,64]
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 rvk_maxpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n_img) {
   constexpr int IW = 112, OW = 56, C8 = 8;     // 8 chunks of 8 channels
   const size_t total = static_cast<size_t>(n_img) * OW * OW * C8;
@@ -681,7 +482,7 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x));
 // the fly in shared memory) with w0: block = 64 inputs x 32 samples, so w0 is streamed once per 32 samples instead
 // of once per sample; the 32 K-chunks write private slabs part[chunk][n_cap][64] that layer 1 sums in a fixed order.
 constexpr int KAN_KC = 64, KAN_SUB = 16, KAN_SG = 32, KAN_CHUNKS = 2048 / KAN_KC;
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 kan_l0_kernel(const float* __restrict__ hid, const float* __restrict__ w0, const float* __restrict__ g0,
               float* __restrict__ part, int n, int n_cap) {
   __shared__ float s_feat[KAN_SG][KAN_SUB * 9 + 1];
@@ -724,7 +525,7 @@ kan_l0_kernel(const float* __restrict__ hid, const float* __restrict__ w0, const
 
 // Layer 1 (64 -> 2): one warp per sample; sums the K-chunk slabs of layer 0, then silu / B-spline features of the 64
 // hidden values against w1.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 kan_l1_kernel(const float* __restrict__ part, const float* __restrict__ w1, const float* __restrict__ g1,
               float* __restrict__ logits, int n, int n_cap) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -760,7 +561,7 @@ kan_l1_kernel(const float* __restrict__ part, const float* __restrict__ w1, cons
 //   128 channels: 128 -> 8 (+BN, folded on the host) -> ReLU -> 128;  out = x * (x * att_h * att_w).
 // One block per crop, one thread per channel; the 7x7 map of the thread's channel lives in registers, the pooled
 // vectors and the hidden units go through shared memory.  In place on the bf16 NHWC feature map [n][7][7][512].
-__global__ void __launch_bounds__(512)
+static __global__ void __launch_bounds__(512)
 ggca_gate_kernel(__nv_bfloat16* __restrict__ feat, const float* __restrict__ w1, const float* __restrict__ b1,
                  const float* __restrict__ w2, const float* __restrict__ b2, int n) {
   __shared__ float s_pool[7][512];             // pooled vectors of one type: [pos][channel]

@@ -1,5 +1,5 @@
 // ff_s3d.cuh — S3D clip classifier on the GPU (SURVEY.md §8f-2;
-// /root/reference/sx_exp_deepfakedetect-master/S3D/model.py:6-342, SRM_net == 'no').  Included by ff_engine.cu.
+// /root/reference/sx_exp_deepfakedetect-master/S3D/model.py:6-342, SRM_net == 'no').
 //
 // Activations are bf16 [clip][frame][h][w][channel] (NDHWC) with the TRUE channel count of each tensor.  Every
 // convolution is one launch of rvk_conv2_kernel (ff_rvk.cuh: persistent tcgen05 implicit GEMM, TMA-store epilogue):
@@ -14,7 +14,26 @@
 // conv stores through a tensor-map VIEW of its slice of the Inception concat, so the hardware clips the padded
 // columns and the four branches write the concat in place.  Eval-mode BatchNorm3d (eps 1e-3) + ReLU are folded into
 // the producing launch.  Max-pools and the head (avg-pool (2,7,7), 1x1x1 fc, temporal mean) are small CUDA-core kernels.
-#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/facfake.h"
+#include "ff_host.h"
+#include "ff_rvk.cuh"
+#include "ff_small.cuh"
+
+using namespace ff;
+using ffh::bf16;
+using ffh::ilog2;
+using ffh::launch_k;
+using ffh::to_bf16;
 
 namespace {
 
@@ -121,7 +140,7 @@ int s3d_tmap(ff_s3d* h, CUtensorMap* m, const void* base, int c, int pitch_c, lo
   cuuint64_t strides[3] = {(cuuint64_t)pitch_c * 2, (cuuint64_t)w * pitch_c * 2, (cuuint64_t)hh * w * pitch_c * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)(bw * es_w), (cuuint32_t)(bh * es_h), (cuuint32_t)bi};
   cuuint32_t estr[4] = {1, (cuuint32_t)es_w, (cuuint32_t)es_h, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = ffh::encode_tiled()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return sfail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(C%d/%d W%lld H%d N%d box %dx%dx%d) failed: %d", c, pitch_c, w, hh, n, bw, bh, bi, (int)r);
@@ -183,7 +202,7 @@ int s3d_add_conv(ff_s3d* h, const std::string& conv_key, const std::string& bn_k
     cuuint64_t strides[1] = {(cuuint64_t)op.taps * kpad * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)op.bn};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(&op.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, op.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = ffh::encode_tiled()(&op.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, op.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sfail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(filter %s) failed: %d", conv_key.c_str(), (int)r);
   }
@@ -349,7 +368,7 @@ int s3d_finalize(ff_s3d* h) {
     cuuint64_t strides[2] = {896 * 2, (cuuint64_t)224 * 896 * 2};
     cuuint32_t box[3] = {96, 37, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(&h->tm_x4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, h->x4, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = ffh::encode_tiled()(&h->tm_x4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, h->x4, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sfail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(stem input) failed: %d", (int)r);
   }
@@ -444,8 +463,8 @@ int s3d_launch_conv(ff_s3d* h, const ff_s3d::Op& op, int n, cudaStream_t st) {
   const int m_tiles = a.tiles_w * a.tiles_h * ((a.n_img + bi - 1) / bi);
   const int tiles = ((m_tiles + 1) / 2) * (op.cout_pad / op.bn);
   const int grid = std::min(tiles, h->num_sms);
-  cudaError_t e = op.bn == 128 ? launch_rvk_conv2_t<128, 3, false>(grid, st, op.tmA, op.tmB, op.tmO, op.tmO, a)
-                               : launch_rvk_conv2_t<64, 4, false>(grid, st, op.tmA, op.tmB, op.tmO, op.tmO, a);
+  cudaError_t e = op.bn == 128 ? launch_rvk_conv2<128, 3, false>(grid, st, op.tmA, op.tmB, op.tmO, op.tmO, a)
+                               : launch_rvk_conv2<64, 4, false>(grid, st, op.tmA, op.tmB, op.tmO, op.tmO, a);
   if (e != cudaSuccess) return sfail(h, FF_ERR_CUDA, "launch of %s failed: %s", op.name.c_str(), cudaGetErrorString(e));
   ++h->launches;
   return FF_OK;
@@ -459,11 +478,7 @@ int s3d_forward(ff_s3d* h, const void* x, int layout, int n, float* logits, cuda
   if (layout == FF_X_NHWC_U8) rvk_convert_kernel<2><<<(blocks + 3) / 4, 256, 0, st>>>(x, h->x4, frames, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f);
   else s3d_convert_ncdhw_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), h->x4, n, T);
   S3_CUDA(h, cudaGetLastError());
-  static bool stem_attr = false;
-  if (!stem_attr) {
-    S3_CUDA(h, cudaFuncSetAttribute(rvk_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RVK_STEM_SMEM));
-    stem_attr = true;
-  }
+  S3_CUDA(h, ffh::ensure_dyn_smem(reinterpret_cast<const void*>(rvk_stem_kernel), RVK_STEM_SMEM));
   RvkStemArgs sa;
   sa.out = h->buf[0]; sa.w = h->stem_w; sa.n_img = frames;
   for (int o = 0; o < 64; ++o) { sa.scale[o] = h->stem_scale[o]; sa.shift[o] = h->stem_shift[o]; }
@@ -515,14 +530,9 @@ int ff_s3d_create(ff_s3d_t** out, int device, int max_clips, int frames_per_clip
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return sfail(nullptr, FF_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
   if (prop.major != 10) return sfail(nullptr, FF_ERR_CUDA, "device %d is sm_%d%d; libfacfake is built for sm_100a (B200) only", device, prop.major, prop.minor);
-  if ((e = cudaSetDevice(device)) != cudaSuccess) return sfail(nullptr, FF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
-  if (!g_encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || !fn) return sfail(nullptr, FF_ERR_CUDA, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
-    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  }
+  ffh::DeviceGuard guard(device);
+  if (guard.status != cudaSuccess) return sfail(nullptr, FF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.status));
+  if (!ffh::encode_tiled()) return sfail(nullptr, FF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   ff_s3d* h = new ff_s3d();
   h->device = device;
   h->cap = max_clips;
@@ -548,9 +558,11 @@ int ff_s3d_create(ff_s3d_t** out, int device, int max_clips, int frames_per_clip
 
 void ff_s3d_destroy(ff_s3d_t* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
-  cudaDeviceSynchronize();
-  for (void* p : h->allocs) cudaFree(p);
+  {
+    ffh::DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+  }
   delete h;
 }
 
@@ -575,7 +587,7 @@ int ff_s3d_finalize(ff_s3d_t* h) {
   if (!h) return FF_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   if (h->finalized) return FF_OK;
-  S3_CUDA(h, cudaSetDevice(h->device));
+  ffh::DeviceGuard guard(h->device);
   return s3d_finalize(h);
 }
 
@@ -584,7 +596,7 @@ int ff_s3d_forward(ff_s3d_t* h, const void* x, int x_layout, int n, float* logit
   if (x_layout != FF_X_NCHW_F32 && x_layout != FF_X_NHWC_U8) return sfail(h, FF_ERR_BAD_ARG, "ff_s3d_forward: unknown layout %d", x_layout);
   std::lock_guard<std::mutex> lk(h->mu);
   if (!h->finalized) return sfail(h, FF_ERR_STATE, "ff_s3d_finalize() has not been called");
-  S3_CUDA(h, cudaSetDevice(h->device));
+  ffh::DeviceGuard guard(h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t clip_bytes = (size_t)h->frames * 224 * 224 * 3 * (x_layout == FF_X_NHWC_U8 ? 1 : 4);
   for (int s0 = 0; s0 < n; s0 += h->cap) {
@@ -599,7 +611,7 @@ int64_t ff_s3d_debug_activation(ff_s3d_t* h, const void* x, int x_layout, int n,
   if (!h || !x || !out_host || n <= 0 || n > h->cap || base_index < 0 || base_index > 15) return sfail(h, FF_ERR_BAD_ARG, "ff_s3d_debug_activation: bad arguments");
   std::lock_guard<std::mutex> lk(h->mu);
   if (!h->finalized) return sfail(h, FF_ERR_STATE, "ff_s3d_finalize() has not been called");
-  cudaSetDevice(h->device);
+  ffh::DeviceGuard guard(h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bf16* ptr = nullptr;
   int64_t elems = 0;
@@ -614,7 +626,7 @@ int64_t ff_s3d_debug_activation(ff_s3d_t* h, const void* x, int x_layout, int n,
       float* tmp = nullptr;
       cudaError_t e = cudaMalloc(&tmp, (size_t)elems * sizeof(float));
       if (e == cudaSuccess) {
-        bf16_to_f32_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(ptr, tmp, (size_t)elems);
+        act16_to_f32_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(reinterpret_cast<const unsigned short*>(ptr), tmp, (size_t)elems, 0);
         e = cudaMemcpyAsync(out_host, tmp, (size_t)elems * sizeof(float), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         cudaFree(tmp);

@@ -1,77 +1,12 @@
 // ff_small.cuh — the non-tensor-core kernels of the CViT path (HBM- or latency-bound):
-//   conv1 (3->32, K=27) with the crop normalisation fused, LayerNorm, 2-token attention, token assembly,
-//   cls gather, the 2048->2 head GEMV and the per-video score reduction.
+//   LayerNorm, 2-token attention, token assembly, cls gather, the 2048->2 head GEMV, the per-video score reduction
+//   and the debug-tap conversions.
 // Reference lines are /root/reference/CViT-main/{model/cvit.py, cvit_prediction.py}.
 #pragma once
+#include <cuda_fp16.h>
 #include "ff_ptx.cuh"
 
 namespace ff {
-
-// ------------------------------------------------------------------------------------------------
-// conv1: Conv2d(3,32,3,p=1)+BN+ReLU (cvit.py:88-90) on CUDA cores, fp32 FMA with the 864 weights in the
-// kernel-parameter constant bank (every thread of a warp uses the same weight at the same time).
-// IN_KIND 0: fp32 NCHW normalised input (what model(x) receives, cvit_prediction.py:229)
-// IN_KIND 2: uint8 NHWC crops; (x/255 - mean)/std of cvit_prediction.py:41-45,214-215 fused into the load.
-// Output: bf16 NHWC [n,224,224,32].
-struct Conv1Params {
-  float w[32][27];   // [cout][(kh*3+kw)*3 + cin]
-  float scale[32];
-  float shift[32];
-};
-
-template <int IN_KIND>
-__global__ void __launch_bounds__(256)
-conv1_kernel(const void* __restrict__ xin, __nv_bfloat16* __restrict__ out, int n_img,
-             const __grid_constant__ Conv1Params p) {
-  constexpr int HW = 224, T = 16, P = T + 2;
-  __shared__ float patch[P * P * 3];
-  const int n = blockIdx.z;
-  const int h0 = blockIdx.y * T, w0 = blockIdx.x * T;
-  for (int idx = threadIdx.x; idx < P * P * 3; idx += 256) {
-    int py, px, c;
-    if (IN_KIND == 2) { c = idx % 3; const int pi = idx / 3; px = pi % P; py = pi / P; }
-    else              { px = idx % P; const int t = idx / P; py = t % P; c = t / P; }
-    const int gy = h0 - 1 + py, gx = w0 - 1 + px;
-    float v = 0.0f;                                   // zero padding applies AFTER normalisation
-    if (gy >= 0 && gy < HW && gx >= 0 && gx < HW) {
-      if (IN_KIND == 2) {
-        const uint8_t* x = reinterpret_cast<const uint8_t*>(xin);
-        const float u = static_cast<float>(x[((static_cast<size_t>(n) * HW + gy) * HW + gx) * 3 + c]);
-        const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
-        const float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
-        v = __fdiv_rn(__fdiv_rn(u, 255.0f) - mean, sd);
-      } else {
-        const float* x = reinterpret_cast<const float*>(xin);
-        v = x[((static_cast<size_t>(n) * 3 + c) * HW + gy) * HW + gx];
-      }
-    }
-    patch[(py * P + px) * 3 + c] = v;
-  }
-  __syncthreads();
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  float in[27];
-#pragma unroll
-  for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) in[(kh * 3 + kw) * 3 + c] = patch[((ty + kh) * P + (tx + kw)) * 3 + c];
-  float acc[32];
-#pragma unroll
-  for (int co = 0; co < 32; ++co) {
-    float s = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 27; ++k) s = fmaf(in[k], p.w[co][k], s);
-    acc[co] = fmaxf(fmaf(s, p.scale[co], p.shift[co]), 0.0f);
-  }
-  if (n < n_img) {
-    uint4* o = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * HW + (h0 + ty)) * HW + (w0 + tx)) * 32);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      o[i] = make_uint4(pack_bf16x2(acc[8 * i], acc[8 * i + 1]), pack_bf16x2(acc[8 * i + 2], acc[8 * i + 3]),
-                        pack_bf16x2(acc[8 * i + 4], acc[8 * i + 5]), pack_bf16x2(acc[8 * i + 6], acc[8 * i + 7]));
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -82,7 +17,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // LayerNorm(1024), affine (cvit.py:16,20: eps 1e-5; the LinearNorm of the GGCA variant uses 1e-6).  One warp per row;
 // fp32 in, bf16 out (next GEMM's A operand).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ y, int rows, float eps) {
   pdl_trigger();
@@ -122,7 +57,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 
 // 2-token attention (cvit.py:43-60): one warp per (crop, head).  qkv fp32 [2n][3072] with feature index
 // which*1024 + head*128 + d (cvit.py:46); scale = dim**-0.5 = 1/32 (cvit.py:38); out bf16 [2n][1024] '(h d)'.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 attention2_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_crops) {
   pdl_trigger();
   pdl_wait();
@@ -158,7 +93,7 @@ attention2_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restri
 
 // Token assembly (cvit.py:171-175): tok0 = cls + pos[slot], tok1 = (patch embedding + bias) + pos[slot].
 // The patch embedding arrives as n_splits split-K partial slabs that are summed here in a fixed order.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 tokens_kernel(const float* __restrict__ emb, int n_splits, long long split_stride, const float* __restrict__ bias,
               const float* __restrict__ cls, const float* __restrict__ pos, const int* __restrict__ slot, int slot_base,
               float* __restrict__ x, int n) {
@@ -182,7 +117,7 @@ tokens_kernel(const float* __restrict__ emb, int n_splits, long long split_strid
 }
 
 // cls select (cvit.py:177): bf16 copy of token 0 of every crop -> A operand of mlp_head.0.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 cls_gather_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int n) {
   pdl_trigger();
   pdl_wait();
@@ -194,7 +129,7 @@ cls_gather_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, 
 }
 
 // mlp_head.2: Linear(2048 -> 2) (cvit.py:164) — one warp per crop, fp32.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 head2_kernel(const float* __restrict__ hid, const float* __restrict__ w, const float* __restrict__ bias,
              float* __restrict__ logits, int n) {
   pdl_trigger();
@@ -221,17 +156,19 @@ head2_kernel(const float* __restrict__ hid, const float* __restrict__ w, const f
 }
 
 // Per-video reduction (cvit_prediction.py:258-281): sigmoid per logit, mean over the video's frames,
-// f if f > r else |1 - r|; <= 2 frames (or none) -> 0.5.  One warp per video.
-// mode 1: mean of softmax(logits)[0] (extra).
-__global__ void __launch_bounds__(256)
-video_reduce_kernel(const float* __restrict__ logits, const int* __restrict__ off, int n_videos, int mode,
+// f if f > r else |1 - r|; <= 2 frames (or none) -> 0.5.  One warp per video.  Only the first `max_frames` frames of a
+// video count: the reference evaluates the chunks [0:32],[32:64],[64:90] and drops the rest (cvit_prediction.py:224-238).
+// mode 1: mean of softmax(logits)[0] (extra).  mode 2: the rows already are pred_sig outputs (probabilities).
+static __global__ void __launch_bounds__(256)
+video_reduce_kernel(const float* __restrict__ logits, const int* __restrict__ off, int n_videos, int mode, int max_frames,
                     float* __restrict__ scores) {
   pdl_trigger();
   pdl_wait();
   const int v = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (v >= n_videos) return;
-  const int a = off[v], e = off[v + 1];
+  const int a = off[v];
+  const int e = min(off[v + 1], a + max_frames);
   const int cnt = e - a;
   float f = 0.0f, r = 0.0f;
   for (int i = a + lane; i < e; i += 32) {
@@ -239,6 +176,9 @@ video_reduce_kernel(const float* __restrict__ logits, const int* __restrict__ of
     if (mode == 0) {
       f += 1.0f / (1.0f + expf(-z.x));
       r += 1.0f / (1.0f + expf(-z.y));
+    } else if (mode == 2) {
+      f += z.x;
+      r += z.y;
     } else {
       f += 1.0f / (1.0f + expf(z.y - z.x));
     }
@@ -247,7 +187,7 @@ video_reduce_kernel(const float* __restrict__ logits, const int* __restrict__ of
   r = warp_sum(r);
   if (lane == 0) {
     float s = 0.5f;
-    if (mode == 0) {
+    if (mode == 0 || mode == 2) {
       if (cnt > 2) {
         const float fc = f / static_cast<float>(cnt), rc = r / static_cast<float>(cnt);
         s = (fc > rc) ? fc : fabsf(1.0f - rc);
@@ -257,6 +197,34 @@ video_reduce_kernel(const float* __restrict__ logits, const int* __restrict__ of
     }
     scores[v] = s;
   }
+}
+
+// ---- debug-tap conversions: 16-bit activations (bf16, or fp16 when f16 != 0) -> fp32
+__device__ __forceinline__ float act16_to_f32(unsigned short bits, int f16) {
+  if (f16) { __half hv; memcpy(&hv, &bits, 2); return __half2float(hv); }
+  __nv_bfloat16 bv; memcpy(&bv, &bits, 2); return __bfloat162float(bv);
+}
+static __global__ void act16_to_f32_kernel(const unsigned short* __restrict__ in, float* __restrict__ out, size_t n, int f16) {
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = act16_to_f32(in[i], f16);
+}
+// channel-blocked [n][2][hw][hw][32] -> NHWC fp32 [n][hw][hw][64] (debug tap of feature layers 4, 5)
+static __global__ void unblock_act16_to_f32_kernel(const unsigned short* __restrict__ in, float* __restrict__ out, int n, int hw, int f16) {
+  const size_t total = static_cast<size_t>(n) * hw * hw * 64;
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % 64);
+  const size_t pix = i / 64;
+  const size_t per = static_cast<size_t>(hw) * hw;
+  const size_t img = pix / per, rem = pix % per;
+  out[i] = act16_to_f32(in[((img * 2 + c / 32) * per + rem) * 32 + (c % 32)], f16);
+}
+// slot = (frame index within the video) % 32: the reference's [0:32],[32:64],[64:90] chunking (cvit_prediction.py:226-238)
+static __global__ void slots_from_offsets_kernel(const int* __restrict__ off, int n_videos, int* __restrict__ slot) {
+  const int v = blockIdx.x;
+  if (v >= n_videos) return;
+  const int a = off[v], e = off[v + 1];
+  for (int i = a + threadIdx.x; i < e; i += blockDim.x) slot[i] = (i - a) & 31;
 }
 
 }  // namespace ff

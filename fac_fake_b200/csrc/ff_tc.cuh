@@ -1,27 +1,20 @@
-// ff_tc.cuh — the tensor-core kernel of the engine: one warp-specialised tcgen05 mainloop used as
-//   * MODE_CONV: implicit-GEMM 3x3 / pad 1 / stride 1 convolution over NHWC bf16 activations
-//                (reference op: nn.Conv2d + BatchNorm2d(eval) + ReLU [+ MaxPool2d(2)],
-//                 /root/reference/CViT-main/model/cvit.py:88-147), and
-//   * MODE_GEMM: y = x W^T (+bias, activation, residual) for the patch embedding, the ViT
-//                encoder linears and the MLP head (cvit.py:26-28,40-41,155,161-165).
-//
-// Tile: 128 (M: output pixels / token rows) x BN (output channels) per CTA, fp32 accumulator in TMEM.
-// K loop: one k-block = 64 (SW128) or 32 (SW64) bf16 input channels of one filter tap.
-//
-//   warp 0   TMA producer   A tile: 4-D box {chan, BW, BH, BI} of the NHWC input at (c0, w0+kw-1, h0+kh-1, n0)
-//                           — out-of-bounds coordinates are zero-filled by TMA, which IS the conv padding;
-//                           B tile: 2-D box {chan, BN} of the [Cout][tap][Cin] weights.
-//   warp 1   TMEM alloc + single-thread tcgen05.mma issue (cta_group::1, kind::f16, M=128, N=BN, K=16),
-//            tcgen05.commit releases smem stages / signals the epilogue.
-//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns, fp32 scale/shift (+ReLU), bf16 pack, XOR-swizzled smem
-//            staging, optional 2x2 max-pool, coalesced 16-byte global stores.
+// ff_tc.cuh — the two generic tensor-core kernels of the engine:
+//   * tc_gemm_kernel: y = x W^T (+bias, activation, residual) for the patch embedding, the per-op encoder linears
+//     (fallback when the one-launch encoder cannot be co-resident) and the MLP head (cvit.py:26-28,40-41,155,161-165):
+//     one 128 x BN tile per CTA, fp32 accumulator in TMEM, 64-element (SW128) k-blocks.
+//       warp 0   TMA producer (A: 2-D box of the activation rows, B: 2-D box {64, BN} of the [out][in] weights)
+//       warp 1   TMEM alloc + single-thread tcgen05.mma issue (cta_group::1, kind::f16, M=128, N=BN, K=16),
+//                tcgen05.commit releases smem stages / signals the epilogue
+//       warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns, bias / activation / residual, 32-byte global stores
+//   * ptc_conv_kernel: persistent implicit-GEMM 3x3 / pad 1 convolution over NHWC bf16 activations (reference op:
+//     nn.Conv2d + BatchNorm2d(eval) + ReLU [+ MaxPool2d(2)], /root/reference/CViT-main/model/cvit.py:110-119).
 #pragma once
+#include "ff_host.h"
 #include "ff_ptx.cuh"
 
 namespace ff {
 
-enum { MODE_CONV = 0, MODE_GEMM = 1 };
-enum { EPI_STORE_F32 = 0, EPI_STORE_BF16 = 1, EPI_RESID_F32 = 2, EPI_ATOMIC_F32 = 3, EPI_BN_BF16 = 4 };
+enum { EPI_STORE_F32 = 0, EPI_STORE_BF16 = 1, EPI_RESID_F32 = 2 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
 struct TcArgs {
@@ -36,8 +29,7 @@ struct TcArgs {
   int taps;               // conv: 0/9 = 3x3 (pad 1), 1 = 1x1 (pad 0)
   int stride;             // conv: 0/1 = stride 1, 2 = stride 2 (the tensor map carries elementStrides = 2)
   int conv_act;           // conv epilogue: 0 = ReLU (CViT layers), 1 = none (ResNet downsample / channel conv)
-  const void* resid;      // gemm EPI_BN_BF16: optional bf16 residual [M][ldo] added after the first activation
-  int act2;               // gemm EPI_BN_BF16: activation after the residual add (ACT_*)
+  const void* resid;      // rvk_conv2_kernel: bf16 residual tensor (non-null selects the residual epilogue)
   int kb_per_tap;         // Cin / (channels per k-block)
   int cin;                // input channels
   // ---- gemm geometry
@@ -63,7 +55,7 @@ struct TcSmem {
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STAGING_BYTES = 128 * BN * 2;
   static constexpr int MAIN_BYTES = PIPE_BYTES > STAGING_BYTES ? PIPE_BYTES : STAGING_BYTES;
-  static constexpr int SS_OFF = MAIN_BYTES;                 // scale/shift floats [2*BN]
+  static constexpr int SS_OFF = MAIN_BYTES;                 // bias floats [BN]
   static constexpr int BAR_OFF = SS_OFF + 2 * BN * 4;       // full[S], empty[S], tmem_full
   static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 1) * 8;
   static constexpr int TOTAL = SLOT_OFF + 16 + 1024;        // + manual 1024-B alignment slack
@@ -71,101 +63,15 @@ struct TcSmem {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// ---- conv epilogue, phase 1: TMEM accumulator row r (one per thread) -> scale/shift/ReLU -> bf16 -> staging smem.
-// Staging is [128 rows][BN] bf16 with the 16-byte chunk index XOR-swizzled by the row (bank-conflict-free).
-template <int BN>
-__device__ __forceinline__ void conv_epilogue_to_staging(uint32_t taddr, const float* ss, uint8_t* stg, int r, bool relu = true) {
-  constexpr int CPR = BN / 8;
-  const int swz = (CPR >= 8) ? (r & 7) : ((r >> 1) & (CPR - 1));
-#pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld_32x32(taddr + c0, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t p[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = c0 + j * 8 + e * 2;
-        float x0 = fmaf(__uint_as_float(v[j * 8 + e * 2]), ss[c], ss[BN + c]);
-        float x1 = fmaf(__uint_as_float(v[j * 8 + e * 2 + 1]), ss[c + 1], ss[BN + c + 1]);
-        if (relu) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
-        p[e] = pack_bf16x2(x0, x1);
-      }
-      const int q = (c0 >> 3) + j;
-      *reinterpret_cast<uint4*>(stg + r * (BN * 2) + ((q ^ swz) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
-    }
-  }
-}
-
-// ---- conv epilogue, phase 2: staging -> global NHWC bf16 with coalesced 16-byte stores (optional 2x2 max-pool).
-template <int BN, bool POOL>
-__device__ __forceinline__ void conv_staging_to_global(const uint8_t* stg, const TcArgs& a, int w0, int h0, int n0,
-                                                       int col0, int te) {
-  constexpr int CPR = BN / 8;
-  const int BW = 1 << a.lg_bw, BH = 1 << a.lg_bh;
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
-  if (!POOL) {
-    for (int idx = te; idx < 128 * CPR; idx += 128) {
-      const int row = idx / CPR, q = idx % CPR;
-      const int rs = (CPR >= 8) ? (row & 7) : ((row >> 1) & (CPR - 1));
-      const uint4 val = *reinterpret_cast<const uint4*>(stg + row * (BN * 2) + ((q ^ rs) << 4));
-      const int wl = row & (BW - 1);
-      const int hl = (row >> a.lg_bw) & (BH - 1);
-      const int nl = row >> (a.lg_bw + a.lg_bh);
-      const int n = n0 + nl;
-      if (n < a.n_img && (w0 + wl) < a.W && (h0 + hl) < a.H) {   // W/H bounds matter for 7x7 maps tiled by 8x8 boxes
-        const size_t pix = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * a.W + (w0 + wl);
-        *reinterpret_cast<uint4*>(out + pix * a.cout + col0 + q * 8) = val;
-      }
-    }
-  } else {
-    const int PW = BW >> 1, PH = BH >> 1;
-    const int Ho = a.H >> 1, Wo = a.W >> 1;
-    for (int idx = te; idx < 32 * CPR; idx += 128) {
-      const int p = idx / CPR, q = idx % CPR;
-      const int pw = p % PW;
-      const int ph = (p / PW) % PH;
-      const int pn = p / (PW * PH);
-      const int r00 = ((pn << a.lg_bh) + 2 * ph) * BW + 2 * pw;
-      uint4 m;
-      {
-        const int rows[4] = {r00, r00 + 1, r00 + BW, r00 + BW + 1};
-        uint4 x[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = rows[i];
-          const int rs = (CPR >= 8) ? (row & 7) : ((row >> 1) & (CPR - 1));
-          x[i] = *reinterpret_cast<const uint4*>(stg + row * (BN * 2) + ((q ^ rs) << 4));
-        }
-        auto mx = [](uint32_t a0, uint32_t b0) {
-          __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a0), *reinterpret_cast<__nv_bfloat162*>(&b0));
-          return *reinterpret_cast<uint32_t*>(&r2);
-        };
-        m.x = mx(mx(x[0].x, x[1].x), mx(x[2].x, x[3].x));
-        m.y = mx(mx(x[0].y, x[1].y), mx(x[2].y, x[3].y));
-        m.z = mx(mx(x[0].z, x[1].z), mx(x[2].z, x[3].z));
-        m.w = mx(mx(x[0].w, x[1].w), mx(x[2].w, x[3].w));
-      }
-      const int n = n0 + pn;
-      if (n < a.n_img) {
-        const size_t pix = (static_cast<size_t>(a.img_off_out + n) * Ho + ((h0 >> 1) + ph)) * Wo + ((w0 >> 1) + pw);
-        *reinterpret_cast<uint4*>(out + pix * a.cout + col0 + q * 8) = m;
-      }
-    }
-  }
-}
-
-template <int MODE, int ROWB, int BN, bool POOL, int STAGES>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
-tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  constexpr int ROWB = 128;
   using L = TcSmem<ROWB, BN, STAGES>;
   constexpr int BKE = ROWB / 2;        // bf16 elements per k-block row
   constexpr int KSTEPS = ROWB / 32;    // UMMA K=16 steps per k-block
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
-  static_assert(ROWB == 64 || ROWB == 128, "ROWB");
+  constexpr int TMEM_COLS = BN;
+  static_assert(BN == 64 || BN == 128, "BN");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -179,26 +85,14 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- tile coordinates
-  int w0 = 0, h0 = 0, n0 = 0, m0 = 0;
-  if (MODE == MODE_CONV) {
-    const int t = blockIdx.x;
-    const int tw = t % a.tiles_w;
-    const int th = (t / a.tiles_w) % a.tiles_h;
-    const int nb = t / (a.tiles_w * a.tiles_h);
-    w0 = tw << a.lg_bw;
-    h0 = th << a.lg_bh;
-    n0 = nb << (7 - a.lg_bw - a.lg_bh);
-  } else {
-    m0 = blockIdx.x * 128;
-  }
+  const int m0 = blockIdx.x * 128;
   const int col0 = blockIdx.y * BN;   // first output channel / column of this CTA
   const int kb_begin = blockIdx.z * a.kb_per_split;
   const int kb_end = min(a.kb_total, kb_begin + a.kb_per_split);
 
   // ---- one-time setup
   if (warp == 0 && lane == 0) {
-    if (MODE == MODE_GEMM) pdl_trigger();   // <= 2 waves of CTAs: let the next (small) kernel pre-stage
+    pdl_trigger();   // <= 2 waves of CTAs: let the next (small) kernel pre-stage
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
@@ -215,13 +109,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int t = threadIdx.x - 64;
     for (int i = t; i < BN; i += 128) {
       const int c = col0 + i;
-      if (MODE == MODE_CONV) {
-        ss[i] = a.scale[c];
-        ss[BN + i] = a.shift[c];
-      } else {
-        ss[i] = (a.epi == EPI_BN_BF16 && c < a.N) ? a.scale[c] : 1.0f;
-        ss[BN + i] = (a.shift != nullptr && c < a.N) ? a.shift[c] : 0.0f;
-      }
+      ss[i] = (a.shift != nullptr && c < a.N) ? a.shift[c] : 0.0f;
     }
   }
   tcgen05_fence_before();
@@ -240,19 +128,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t sb = sa + L::A_BYTES;
         const uint32_t bar = bar_full + 8 * s;
         mbar_arrive_expect_tx(bar, L::STAGE_BYTES);
-        if (MODE == MODE_CONV) {
-          const int tap = kb / a.kb_per_tap;
-          const int cc = kb - tap * a.kb_per_tap;
-          const int sd = a.stride == 2 ? 2 : 1;
-          if (a.taps == 1) {          // 1x1 (possibly strided) conv: one tap, no padding
-            tma_load_4d(sa, &tmA, bar, cc * BKE, sd * w0, sd * h0, n0);
-          } else {
-            const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d(sa, &tmA, bar, cc * BKE, sd * w0 + kw - 1, sd * h0 + kh - 1, n0);
-          }
-        } else {
-          tma_load_2d(sa, &tmA, bar, kb * BKE, m0);
-        }
+        tma_load_2d(sa, &tmA, bar, kb * BKE, m0);
         tma_load_2d(sb, &tmB, bar, kb * BKE, col0);
         if (++s == STAGES) { s = 0; ++it; }
       }
@@ -282,17 +158,11 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // =========================== epilogue (warps 2..5) ===========================
     const int g = warp & 3;               // TMEM lane group this warp may access
     const int r = g * 32 + lane;          // accumulator row == TMEM lane
-    const int te = threadIdx.x - 64;      // 0..127
     mbar_wait(bar_tmem, 0);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16);
 
-    if (MODE == MODE_CONV) {
-      uint8_t* stg = base_ptr;            // pipeline stages are idle now: reuse as staging [128][BN] bf16
-      conv_epilogue_to_staging<BN>(taddr, ss, stg, r, a.conv_act == 0);
-      named_bar_sync(1, 128);
-      conv_staging_to_global<BN, POOL>(stg, a, w0, h0, n0, col0, te);
-    } else {
+    {
       // ---- GEMM epilogue: direct stores, one accumulator row per thread
       const int m = m0 + r;
       const bool row_ok = m < a.M;
@@ -306,41 +176,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float x = fmaf(__uint_as_float(v[i]), ss[c0 + i], ss[BN + c0 + i]);    // scale is 1 except for EPI_BN_BF16
+            float x = __uint_as_float(v[i]) + ss[c0 + i];
             if (a.act == ACT_RELU) x = fmaxf(x, 0.0f);
             else if (a.act == ACT_GELU) x = gelu_erf(x);
             f[i] = x;
           }
           const size_t off = static_cast<size_t>(blockIdx.z) * a.split_stride + static_cast<size_t>(m) * a.ldo + nb;
-          if (a.epi == EPI_BN_BF16) {
-            // 1x1 conv + folded BN (+ReLU) [+ bf16 residual, + ReLU]  (ResNet bottleneck, ResVitKan.py:150-177)
-            if (a.resid != nullptr) {
-              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.resid) + off;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                uint32_t rr[8];
-                ld_global_v8(rp + 16 * i, rr);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float2 rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[e]));
-                  f[16 * i + 2 * e] += rf.x;
-                  f[16 * i + 2 * e + 1] += rf.y;
-                }
-              }
-            }
-            if (a.act2 == ACT_RELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-            }
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + off;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(f[16 * i + 2 * e], f[16 * i + 2 * e + 1]);
-              st_global_v8(o + 16 * i, pk);
-            }
-          } else
           if (a.epi == EPI_STORE_F32) {
             float* o = reinterpret_cast<float*>(a.out) + off;
 #pragma unroll
@@ -364,10 +205,6 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               for (int e = 0; e < 8; ++e) t[e] = __float_as_uint(__uint_as_float(t[e]) + f[8 * i + e]);
               st_global_v8(o + 8 * i, t);
             }
-          } else {
-            float* o = reinterpret_cast<float*>(a.out) + off;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(o + i, f[i]);
           }
         }
       }
@@ -587,6 +424,18 @@ ptc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tcgen05_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
+}
+
+
+// ---- host launchers (opt the kernel in to its dynamic shared memory on the current device, PDL attribute set)
+template <int BN>
+inline cudaError_t launch_tc_gemm(dim3 grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
+  // (a deeper TMA ring - 8 stages - was measured slower: 192 KB of smem leaves one CTA per SM instead of two)
+  return ffh::launch_smem(tc_gemm_kernel<BN, 4>, grid, dim3(192), TcSmem<128, BN, 4>::TOTAL, st, true, a, b, args);
+}
+template <int BN, int MSUB, bool POOL, int STAGES>
+inline cudaError_t launch_ptc(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
+  return ffh::launch_smem(ptc_conv_kernel<BN, MSUB, POOL, STAGES>, dim3(grid), dim3(192), PtcSmem<BN, MSUB, STAGES>::TOTAL, st, true, a, b, args);
 }
 
 }  // namespace ff

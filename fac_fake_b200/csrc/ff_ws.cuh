@@ -19,20 +19,6 @@
 
 namespace ff {
 
-template <int ROWB, int BN, int STAGES>
-struct WsSmem {
-  static constexpr int W_BYTES = 9 * BN * ROWB;                       // all filter taps
-  static constexpr int PATCH_ROWS = 180;                              // 18 x 10 pixels
-  static constexpr int PATCH_BYTES = PATCH_ROWS * ROWB;
-  static constexpr int PATCH_STRIDE = (PATCH_BYTES + 1023) / 1024 * 1024;
-  static constexpr int W_OFF = 0;
-  static constexpr int P_OFF = (W_BYTES + 1023) / 1024 * 1024;
-  static constexpr int SS_OFF = P_OFF + STAGES * PATCH_STRIDE;
-  static constexpr int BAR_OFF = SS_OFF + 2 * BN * 4;                 // w, full[S], empty[S], tfull[2], tempty[2]
-  static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 5) * 8;
-  static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
-};
-
 // K-major descriptor with an explicit stride-byte-offset (bytes between consecutive 8-row groups).
 template <int ROWB>
 __device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
@@ -52,163 +38,6 @@ struct WsEpi {
   float scale[64];
   float shift[64];
 };
-
-// Epilogue of one 8x16 tile for the thread owning accumulator row r = h_l*8 + w_l (TMEM lane r).
-// `arrive_bar`: mbarrier to arrive on as soon as the accumulator has been read out of TMEM.
-template <int BN, bool POOL>
-__device__ __forceinline__ void ws_epilogue_direct(uint32_t taddr, const WsEpi& ss, const TcArgs& a, int w0, int h0, int n,
-                                                   int r, int lane, uint32_t arrive_bar) {
-  uint32_t v[BN];
-#pragma unroll
-  for (int c0 = 0; c0 < BN; c0 += 32) tmem_ld_32x32(taddr + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[c0]));
-  tmem_ld_wait();
-  tcgen05_fence_before();
-  mbar_arrive(arrive_bar);
-  uint32_t p[BN / 2];
-#pragma unroll
-  for (int c = 0; c < BN; c += 2) {
-    const float x0 = fmaf(__uint_as_float(v[c]), ss.scale[c], ss.shift[c]);
-    const float x1 = fmaf(__uint_as_float(v[c + 1]), ss.scale[c + 1], ss.shift[c + 1]);
-    p[c >> 1] = pack_bf16x2_relu(x0, x1);
-  }
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
-  const int hl = r >> 3, wl = r & 7;
-  if (!POOL) {
-    const size_t pix = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * a.W + (w0 + wl);
-#pragma unroll
-    for (int i = 0; i < BN / 16; ++i) st_global_v8(out + pix * BN + i * 16, p + 8 * i);
-  } else {
-#pragma unroll
-    for (int i = 0; i < BN / 2; ++i) {
-      uint32_t o1 = __shfl_xor_sync(0xffffffffu, p[i], 1);
-      __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&p[i]), *reinterpret_cast<__nv_bfloat162*>(&o1));
-      uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
-      uint32_t o2 = __shfl_xor_sync(0xffffffffu, mu, 8);
-      m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o2));
-      p[i] = *reinterpret_cast<uint32_t*>(&m);
-    }
-    if ((lane & 9) == 0) {
-      const size_t pix = (static_cast<size_t>(a.img_off_out + n) * (a.H >> 1) + ((h0 + hl) >> 1)) * (a.W >> 1) + ((w0 + wl) >> 1);
-#pragma unroll
-      for (int i = 0; i < BN / 16; ++i) st_global_v8(out + pix * BN + i * 16, p + 8 * i);
-    }
-  }
-}
-
-// args reuse TcArgs: H, W, tiles_w (= W/8), tiles_h (= H/16), n_img, img_off_out, cout, scale, shift, out.
-template <int ROWB, int BN, bool POOL, int STAGES>
-__global__ void __launch_bounds__(192, 1)
-wsconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs a,
-              const __grid_constant__ WsEpi epi) {
-  using L = WsSmem<ROWB, BN, STAGES>;
-  constexpr int KSTEPS = ROWB / 32;
-  constexpr int CIN = ROWB / 2;
-  constexpr int TMEM_COLS = 2 * BN;       // double-buffered accumulator (64 or 128 columns)
-  static_assert(BN == 32 || BN == 64, "BN");
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar_w = base + L::BAR_OFF;
-  const uint32_t bar_full = bar_w + 8;
-  const uint32_t bar_empty = bar_full + STAGES * 8;
-  const uint32_t bar_tfull = bar_empty + STAGES * 8;
-  const uint32_t bar_tempty = bar_tfull + 16;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int tiles_per_img = a.tiles_w * a.tiles_h;
-  const int num_tiles = tiles_per_img * a.n_img;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmW);
-    mbar_init(bar_w, 1);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    mbar_init(bar_tfull, 1);
-    mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, 128);
-    mbar_init(bar_tempty + 8, 128);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ---- filters: resident for the whole kernel
-      mbar_arrive_expect_tx(bar_w, L::W_BYTES);
-      for (int tap = 0; tap < 9; ++tap) tma_load_2d(base + L::W_OFF + tap * BN * ROWB, &tmW, bar_w, tap * CIN, 0);
-      pdl_trigger();
-      pdl_wait();                  // activations are produced by the previous kernel (filters are static)
-      // ---- halo patches
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int s = it % STAGES;
-        if (it >= STAGES) mbar_wait(bar_empty + 8 * s, ((it / STAGES) - 1) & 1);
-        const int n = t / tiles_per_img;
-        const int rem = t - n * tiles_per_img;
-        const int th = rem / a.tiles_w, tw = rem - th * a.tiles_w;
-        mbar_arrive_expect_tx(bar_full + 8 * s, L::PATCH_BYTES);
-        tma_load_4d(base + L::P_OFF + s * L::PATCH_STRIDE, &tmA, bar_full + 8 * s, 0, tw * 8 - 1, th * 16 - 1, n);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
-      mbar_wait(bar_w, 0);
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int s = it % STAGES;
-        const int acc = it & 1;
-        if (it >= 2) mbar_wait(bar_tempty + 8 * acc, ((it >> 1) - 1) & 1);
-        mbar_wait(bar_full + 8 * s, (it / STAGES) & 1);
-        tcgen05_fence_after();
-        const uint32_t patch = base + L::P_OFF + s * L::PATCH_STRIDE;
-        const uint32_t d_tmem = tmem_base + acc * BN;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int kh = tap / 3, kw = tap % 3;
-          const uint64_t adesc = make_kmajor_desc_sbo<ROWB>(patch + (kh * 10 + kw) * ROWB, 10 * ROWB);
-          const uint64_t bdesc = make_kmajor_desc<ROWB>(base + L::W_OFF + tap * BN * ROWB);
-#pragma unroll
-          for (int k = 0; k < KSTEPS; ++k)
-            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (tap > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(bar_empty + 8 * s);
-        umma_commit(bar_tfull + 8 * acc);
-      }
-    }
-  } else {
-    const int g = warp & 3;
-    const int r = g * 32 + lane;
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const int n = t / tiles_per_img;
-      const int rem = t - n * tiles_per_img;
-      const int th = rem / a.tiles_w, tw = rem - th * a.tiles_w;
-      mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
-      tcgen05_fence_after();
-      ws_epilogue_direct<BN, POOL>(tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN, epi, a, tw * 8, th * 16, n, r,
-                                   lane, bar_tempty + 8 * acc);
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
-  }
-}
 
 // =================================================================================================================
 // Pixel-pair formulation for the Cin = 32 layers (feature layers 2, 3, 4).
@@ -419,232 +248,6 @@ ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 
 // =================================================================================================================
-// Pixel-QUAD formulation for the 32 -> 32 layers (feature layers 2, 3): N = 4 pixels x 32 cout = 128.
-// OPTIONAL (FF_WS4=1), parity-tested, NOT the default: it removes 25 % of the tensor cycles but measures the same as
-// the pair kernel (conv2 0.776 vs 0.781 ms, conv3 0.747 vs 0.780 ms per 512 crops) — at 64-crop sub-passes these
-// layers move 3.2 / 2.0 GB at 4.1 / 2.7 TB/s and are bound by memory latency/bandwidth, not by MMA issue.
-//
-// ncu on ws2conv_kernel<64,*,2> (profiles/r01_ncu_ws2_kernels.txt): SM throughput 78 %, DRAM 55 % — with N = 64 the
-// pair kernel is bound by tcgen05.mma issue (>= 64 cycles per M=128,K=16 instruction whatever N <= 128 is): 24 MMAs per
-// 256 pixels = 6 cycles / pixel.  Four adjacent pixels give N = 128 at the same cost per instruction:
-//     rows    = pixel QUADS (4j .. 4j+3)                     M = 128 quads = a 32 x 16 pixel tile
-//     columns = (pixel-in-quad p, cout)                      N = 128
-//     K       = (kh, window pixel w in 0..5, cin)            window = pixels 4j-1 .. 4j+4
-// 36 MMAs per 512 pixels = 4.5 cycles / pixel.  Two obstacles and their answers:
-//   * a quad is 256 bytes but a SW128 K-major operand has its rows 128 bytes apart -> the halo patch is loaded as TWO
-//     planes with TMA elementStrides = 2 on the pair axis: E = even pairs (pair 2j = first half of quad j), O = odd
-//     pairs starting one pair earlier (O column j = pair 2j-1).  The six window pixels of quad j are then
-//       w = 0       O column j   bytes 64..127      w = 1,2   E column j     (whole row)
-//       w = 3,4     O column j+1 (whole row)        w = 5     E column j+1   bytes 0..63
-//     i.e. four row-shifted descriptors (the hardware swizzle is a function of the absolute smem address, so a
-//     descriptor may start at any row / 32-byte offset) — still one patch, no im2col.
-//   * the quad-expanded filter B[(p,co)][(kh,w,ci)] = W[co][kh][w-p][ci] is half zeros (147 KB dense).  Per 64-element
-//     k-block b (window pixels 2b, 2b+1) only p in {0,1} / {0..3} / {2,3} is non-zero, so the blocks are stored and
-//     multiplied with N = 64 / 128 / 64 into the matching TMEM column range: 96 KB, same MMA count.  The N = 128
-//     block is issued first for each tile so that one instruction initialises all 128 accumulator columns.
-struct Ws4Smem {
-  static constexpr int W_KH = 32768;                                  // per kh: blocks of 64 + 128 + 64 rows x 128 B
-  static constexpr int W_BYTES = 3 * W_KH;
-  static constexpr int PLANE_BYTES = 18 * 9 * 128;                    // 18 rows x 9 pairs x 128 B
-  static constexpr int PLANE_STRIDE = (PLANE_BYTES + 1023) / 1024 * 1024;
-  static constexpr int PATCH_STRIDE = 2 * PLANE_STRIDE;
-  static constexpr int STAGES = 3;
-  static constexpr int W_OFF = 0;
-  static constexpr int P_OFF = W_BYTES;
-  static constexpr int BAR_OFF = P_OFF + STAGES * PATCH_STRIDE;       // w, full[S], empty[S], tfull[2], tempty[2]
-  static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 5) * 8;
-  static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
-  static_assert(TOTAL <= 232448, "shared memory budget");
-};
-
-// Epilogue for one accumulator row = one pixel quad (COUT = 32).  POOL: horizontal max inside the quad (pixels 0|1 and
-// 2|3), vertical max with lane ^ 8 (rows h_l and h_l + 1).
-template <bool POOL>
-__device__ __forceinline__ void ws4_epilogue(uint32_t taddr, const WsEpi& ss, const TcArgs& a, int q0, int h0, int n, int r,
-                                             int lane, uint32_t arrive_bar) {
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
-  const int hl = r >> 3, jl = r & 7;
-  uint32_t pk[4][16];
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    uint32_t v[32];
-    tmem_ld_32x32(taddr + p * 32, v);
-    tmem_ld_wait();
-    if (p == 3) {
-      tcgen05_fence_before();
-      mbar_arrive(arrive_bar);
-    }
-#pragma unroll
-    for (int c = 0; c < 32; c += 2) {
-      const float x0 = fmaf(__uint_as_float(v[c]), ss.scale[c], ss.shift[c]);
-      const float x1 = fmaf(__uint_as_float(v[c + 1]), ss.scale[c + 1], ss.shift[c + 1]);
-      pk[p][c >> 1] = pack_bf16x2_relu(x0, x1);
-    }
-    if (!POOL && n < a.n_img) {
-      const size_t pix = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * a.W + (4 * (q0 + jl) + p);
-      __nv_bfloat16* o = out + pix * 32;
-      st_global_v8(o, &pk[p][0]);
-      st_global_v8(o + 16, &pk[p][8]);
-    }
-  }
-  if (POOL) {
-#pragma unroll
-    for (int pp = 0; pp < 2; ++pp) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[2 * pp][i]), *reinterpret_cast<__nv_bfloat162*>(&pk[2 * pp + 1][i]));
-        uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
-        uint32_t o2 = __shfl_xor_sync(0xffffffffu, mu, 8);
-        m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o2));
-        pk[2 * pp][i] = *reinterpret_cast<uint32_t*>(&m);
-      }
-    }
-    if ((lane & 8) == 0 && n < a.n_img) {
-#pragma unroll
-      for (int pp = 0; pp < 2; ++pp) {
-        const size_t pix = (static_cast<size_t>(a.img_off_out + n) * (a.H >> 1) + ((h0 + hl) >> 1)) * (a.W >> 1) + (2 * (q0 + jl) + pp);
-        __nv_bfloat16* o = out + pix * 32;
-        st_global_v8(o, &pk[2 * pp][0]);
-        st_global_v8(o + 16, &pk[2 * pp][8]);
-      }
-    }
-  }
-}
-
-// TcArgs: H, W, tiles_w (= W/32), tiles_h (= H/16), n_img, img_off_out, out.  tmA: (64, W/2 pairs, H, n) with
-// elementStrides {1,2,1,1} and box {64, 18 -> 9 pairs, 18, 1};  tmW: (64, 768 rows) box {64, 64}.
-template <bool POOL>
-__global__ void __launch_bounds__(192, 1)
-ws4conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs a,
-               const __grid_constant__ WsEpi epi) {
-  using L = Ws4Smem;
-  constexpr int STAGES = L::STAGES;
-  constexpr int TMEM_COLS = 256;          // double-buffered 128-column accumulator
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar_w = base + L::BAR_OFF;
-  const uint32_t bar_full = bar_w + 8;
-  const uint32_t bar_empty = bar_full + STAGES * 8;
-  const uint32_t bar_tfull = bar_empty + STAGES * 8;
-  const uint32_t bar_tempty = bar_tfull + 16;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int tiles_per_img = a.tiles_w * a.tiles_h;
-  const int num_tiles = tiles_per_img * a.n_img;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmW);
-    mbar_init(bar_w, 1);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    mbar_init(bar_tfull, 1);
-    mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, 128);
-    mbar_init(bar_tempty + 8, 128);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bar_w, L::W_BYTES);
-      for (int kb = 0; kb < 12; ++kb) tma_load_2d(base + L::W_OFF + kb * 8192, &tmW, bar_w, 0, kb * 64);
-      pdl_trigger();
-      pdl_wait();                  // activations are produced by the previous kernel (filters are static)
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int s = it % STAGES;
-        if (it >= STAGES) mbar_wait(bar_empty + 8 * s, ((it / STAGES) - 1) & 1);
-        const int n = t / tiles_per_img;
-        const int rem = t - n * tiles_per_img;
-        const int th = rem / a.tiles_w, tw = rem - th * a.tiles_w;
-        const uint32_t dst = base + L::P_OFF + s * L::PATCH_STRIDE;
-        mbar_arrive_expect_tx(bar_full + 8 * s, 2 * L::PLANE_BYTES);
-        tma_load_4d(dst, &tmA, bar_full + 8 * s, 0, tw * 16, th * 16 - 1, n);                          // E: pairs 16tw, 16tw+2, ...
-        tma_load_4d(dst + L::PLANE_STRIDE, &tmA, bar_full + 8 * s, 0, tw * 16 - 1, th * 16 - 1, n);    // O: pairs 16tw-1, 16tw+1, ...
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc128 = make_idesc_bf16(128, 128);
-      constexpr uint32_t idesc64 = make_idesc_bf16(128, 64);
-      constexpr uint32_t SBO = 9 * 128;
-      mbar_wait(bar_w, 0);
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int s = it % STAGES;
-        const int acc = it & 1;
-        if (it >= 2) mbar_wait(bar_tempty + 8 * acc, ((it >> 1) - 1) & 1);
-        mbar_wait(bar_full + 8 * s, (it / STAGES) & 1);
-        tcgen05_fence_after();
-        const uint32_t pe = base + L::P_OFF + s * L::PATCH_STRIDE;      // E plane
-        const uint32_t po = pe + L::PLANE_STRIDE;                        // O plane
-        const uint32_t d_tmem = tmem_base + acc * 128;
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const uint32_t row = kh * 9 * 128;
-          const uint32_t wb = base + L::W_OFF + kh * L::W_KH;
-          // block 1 first (window pixels 2,3 = the second pixel of pair 2j and the first of pair 2j+1; N = 128)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t a_addr = k < 2 ? pe + row + 64 + 32 * k : po + row + 128 + 32 * (k - 2);
-            umma_bf16_ss(d_tmem, make_kmajor_desc_sbo<128>(a_addr, SBO), make_kmajor_desc<128>(wb + 8192) + 2 * k, idesc128,
-                         (kh > 0 || k > 0) ? 1u : 0u);
-          }
-          // block 0 (window pixels 0,1 = second pixel of pair 2j-1, first pixel of pair 2j; p in {0,1}: columns 0..63)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t a_addr = k < 2 ? po + row + 64 + 32 * k : pe + row + 32 * (k - 2);
-            umma_bf16_ss(d_tmem, make_kmajor_desc_sbo<128>(a_addr, SBO), make_kmajor_desc<128>(wb) + 2 * k, idesc64, 1u);
-          }
-          // block 2 (window pixels 4,5 = second pixel of pair 2j+1, first pixel of pair 2j+2; p in {2,3}: columns 64..127)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t a_addr = k < 2 ? po + row + 128 + 64 + 32 * k : pe + row + 128 + 32 * (k - 2);
-            umma_bf16_ss(d_tmem + 64, make_kmajor_desc_sbo<128>(a_addr, SBO), make_kmajor_desc<128>(wb + 24576) + 2 * k, idesc64, 1u);
-          }
-        }
-        umma_commit(bar_empty + 8 * s);
-        umma_commit(bar_tfull + 8 * acc);
-      }
-    }
-  } else {
-    const int g = warp & 3;
-    const int r = g * 32 + lane;
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const int n = t / tiles_per_img;
-      const int rem = t - n * tiles_per_img;
-      const int th = rem / a.tiles_w, tw = rem - th * a.tiles_w;
-      mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
-      tcgen05_fence_after();
-      ws4_epilogue<POOL>(tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * 128, epi, a, tw * 8, th * 16, n, r, lane,
-                         bar_tempty + 8 * acc);
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
-  }
-}
-
-
-// =================================================================================================================
 // Pixel-pair formulation for Cin = 64 (feature layers 5, 6) on a CTA PAIR (cta_group::2).
 //
 // With 64 input channels the pair-expanded filter is [N = 2*64 = 128][K = 2 blocks * 3 * 4 * 32 = 768] = 196 KB and
@@ -751,17 +354,12 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN);
-      long long* dbg = (a.resid != nullptr && blockIdx.x == 0) ? reinterpret_cast<long long*>(const_cast<void*>(a.resid)) : nullptr;
-      long long d_tempty = 0, d_full = 0, d_issue = 0;   // developer aid (FF_WS2X_DBG): where the MMA thread spends its cycles
       int it = 0;
       for (int pi = cluster_id; pi < num_pairs; pi += num_clusters, ++it) {
         const int s = it & 1;
         const int acc = it & 1;
-        const long long c0 = clock64();
         if (it >= 2) mbar_wait(bar_tempty + 8 * acc, ((it >> 1) - 1) & 1);
-        const long long c1 = clock64();
         mbar_wait(bar_full + 8 * s, (it >> 1) & 1);
-        const long long c2 = clock64();
         tcgen05_fence_after();
         const uint32_t patch = base + L::P_OFF + s * L::PATCH_STRIDE;
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -779,9 +377,7 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         umma_commit_2cta(bar_empty + 8 * s, 0x3);
         umma_commit_2cta(bar_tfull + 8 * acc, 0x3);
-        d_tempty += c1 - c0; d_full += c2 - c1; d_issue += clock64() - c2;
       }
-      if (dbg != nullptr) { dbg[0] = d_tempty; dbg[1] = d_full; dbg[2] = d_issue; dbg[3] = it; }
     }
   } else {
     const int g = warp & 3;
@@ -804,6 +400,16 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tcgen05_fence_after();
     tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
   }
+}
+
+
+template <int BN, bool POOL, int STAGES>
+inline cudaError_t launch_ws2(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args, const WsEpi& epi) {
+  return ffh::launch_smem(ws2conv_kernel<BN, POOL, STAGES>, dim3(grid), dim3(192), Ws2Smem<BN, STAGES>::TOTAL, st, true, a, w, args, epi);
+}
+template <bool POOL>
+inline cudaError_t launch_ws2x(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args, const WsEpi& epi) {
+  return ffh::launch_smem(ws2x_conv_kernel<POOL>, dim3(grid), dim3(192), Ws2xSmem::TOTAL, st, true, a, w, args, epi);
 }
 
 }  // namespace ff

@@ -57,7 +57,6 @@ struct XfArgs {
   unsigned int* sync;        // [2][XF_MAX_GROUPS] group-barrier arrival counters + exit counters; zero at rest
   int rows, n_crops, depth;
   float eps1, eps2;
-  long long* trace;          // developer aid (FF_XF_TRACE=1): clock64 stamps of CTA 0's first epilogue thread, else nullptr
   XfLayerP L[XF_MAX_DEPTH];
 };
 
@@ -65,22 +64,25 @@ struct XfArgs {
 __device__ __forceinline__ void xf_cta_sync() { asm volatile("barrier.sync 0;" ::: "memory"); }
 
 // Barrier of the 16 CTAs of a group.  Writers have executed fence.proxy.async; the CTA barrier orders their stores
-// before thread 0's gpu-scope release; thread 0's acquire + the second CTA barrier order them before every reader.
+// before thread 0's gpu-scope fence (release side: fence + relaxed arrival); the spin is a RELAXED load — an acquire
+// load costs a MEMBAR.ALL.GPU per iteration — followed by one fence (acquire side), and the second CTA barrier orders
+// the other CTAs' stores before every reader of this CTA.  Two gpu-scope fences per barrier, none inside the spin.
 __device__ __forceinline__ void xf_group_sync(unsigned int* counter, unsigned int target) {
   xf_cta_sync();
   if (threadIdx.x == 0) {
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     unsigned int v;
     const long long t0 = clock64();
     while (true) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
       if (static_cast<int>(v - target) >= 0) break;
       if (clock64() - t0 > 4000000000LL) {   // a protocol bug becomes a launch error instead of a hung GPU
         printf("ff: encoder group barrier timeout block %d target %u seen %u\n", blockIdx.x, target, v);
         __trap();
       }
     }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   xf_cta_sync();
 }
@@ -223,14 +225,10 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
   const int r = g4 * 32 + lane;            // accumulator row of an epilogue thread
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g4 * 32) << 16);
 
-  const bool tr_on = a.trace != nullptr && blockIdx.x == 0;
-  long long tr_empty = 0, tr_full = 0, tr_issue = 0, tr_nb = 0, tr_gemm = 0;
   // ---- producer state: B pointer runs ahead (acquires stages), A pointer follows
   int sB = 0, phB = 0, sA = 0, npre = 0;
   auto issue_b = [&](int layer, int g, int kb) {     // acquire the next stage and load the weight boxes of k-block kb
-    const long long c0 = tr_on ? clock64() : 0;
     mbar_wait(bar_empty + 8 * sB, phB ^ 1);
-    if (tr_on) { tr_empty += clock64() - c0; ++tr_nb; }
     const int nb = gemm_nb(g);
     const uint32_t bar = bar_full + 8 * sB;
     mbar_arrive_expect_tx(bar, XF_A_BYTES + nb * XF_BBOX_BYTES);
@@ -272,9 +270,7 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
     const uint32_t idesc = g == XF_G_QKV ? make_idesc_bf16(128, 192) : (g == XF_G_FF1 ? make_idesc_bf16(128, 128) : make_idesc_bf16(128, 64));
     tcgen05_fence_after();
     for (int kb = 0; kb < kbt; ++kb) {
-      const long long c0 = tr_on ? clock64() : 0;
       mbar_wait(bar_full + 8 * sM, phM);
-      const long long c1 = tr_on ? clock64() : 0;
       tcgen05_fence_after();
       const uint32_t sa = base + sM * XF_STAGE_BYTES;
       const uint64_t adesc = make_kmajor_desc<128>(sa);
@@ -282,23 +278,16 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
       umma_commit(bar_empty + 8 * sM);
-      if (tr_on) { tr_full += c1 - c0; tr_issue += clock64() - c1; if (kb == 0) tr_gemm -= c1; if (kb == kbt - 1) tr_gemm += clock64(); }
       if (++sM == XF_STAGES) { sM = 0; phM ^= 1; }
     }
     umma_commit(bar_acc);
   };
-
-  int tp = 0;
-  const bool tracer = a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
-  auto stamp = [&]() { if (tracer && tp < 56) a.trace[tp++] = clock64(); };
-  stamp();
 
   int acc_phase = 0;
   auto acc_wait = [&]() {
     mbar_wait(bar_acc, acc_phase);
     acc_phase ^= 1;
     tcgen05_fence_after();
-    stamp();
   };
   // every global store of a phase is followed by this before the group barrier
   auto publish = [&]() {
@@ -308,7 +297,6 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
   auto group_sync = [&]() {
     sync_target += XF_CS;
     xf_group_sync(sync_ctr, sync_target);
-    stamp();
   };
 
   if (is_producer && group < ntiles) preissue(0, XF_G_QKV);
@@ -435,7 +423,6 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
       }
     }
   }
-  if (tracer) a.trace[63] = tp;
   // Every CTA of the group has left the last barrier once it arrives here; the 16th arrival re-arms both counters for
   // the next launch (nobody reads them any more), so no memset is needed between launches.
   if (threadIdx.x == 0) {
@@ -446,8 +433,6 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
       __threadfence();
     }
   }
-  if (tr_on && is_producer) { a.trace[56] = tr_empty; a.trace[57] = tr_nb; }
-  if (tr_on && is_mma) { a.trace[58] = tr_full; a.trace[59] = tr_issue; a.trace[60] = tr_gemm; }
 
   tcgen05_fence_before();
   __syncthreads();

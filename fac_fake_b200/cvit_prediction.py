@@ -32,6 +32,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+from ._lib import FF_REDUCE_REFERENCE_PROBS
 from .engine import CViTEngine
 
 mean = [0.485, 0.456, 0.406]      # cvit_prediction.py:41
@@ -145,10 +146,10 @@ def predict_crops(store_rec: np.ndarray, filename: str = "") -> float:
     if len(store_rec) == 0:                                   # :218-219
         return torch.tensor(0.5).item()
     dfdc_tensor = torch.from_numpy(np.ascontiguousarray(store_rec)).to(model._device)
-    dfdc_tensor = dfdc_tensor[:90]                            # frames >= 90 are dropped (:235-238)
     n = dfdc_tensor.shape[0]
-    # slot = index inside the <=32 chunk, chunks [0:32],[32:64],[64:90]  (:226-238)
-    scores, logits = model.predict_videos(dfdc_tensor, [0, n], return_logits=True)
+    # slot = index inside the <=32 chunk, chunks [0:32],[32:64],[64:90]; frames >= 90 do not enter the score
+    # (:226-238) — both rules are applied by ff_cvit_predict itself
+    scores = model.predict_videos(dfdc_tensor, [0, n])
     decCViT = scores[0]
     if verbose:
         print('CViT', filename, "Prediction:", decCViT.item())
@@ -183,11 +184,9 @@ def pre_process_prediction(y_pred: torch.Tensor) -> torch.Tensor:
         raise RuntimeError("configure(model_=...) first")
     if y_pred.dim() != 2 or len(y_pred) <= 2:
         return torch.tensor(0.5)
-    # y_pred already holds sigmoid outputs; the kernel applies sigmoid itself, so feed logits = logit(p)
-    p = y_pred.to(torch.float32).clamp(1e-7, 1 - 1e-7)
-    logits = torch.log(p) - torch.log1p(-p)
+    # y_pred already holds pred_sig outputs: the kernel averages the probabilities it is handed
     off = torch.tensor([0, len(y_pred)], dtype=torch.int32)
-    return model.video_scores(logits, off)[0].cpu()
+    return model.video_scores(y_pred, off, mode=FF_REDUCE_REFERENCE_PROBS)[0].cpu()
 
 
 def real_or_fake(predictions_or_score):

@@ -14,6 +14,7 @@ PyTorch tensors appear only at this boundary (device memory + streams); every ke
 from __future__ import annotations
 
 import ctypes as C
+import fnmatch
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -34,6 +35,10 @@ def _stream_ptr(device: torch.device) -> int:
 
 class CViTEngine:
     """Drop-in for ``cvit.CViT`` at inference time (model/cvit.py:80-179)."""
+
+    # state_dict keys that exist in the reference module but are not on its inference path (glob patterns);
+    # everything else that finalize did not consume is an "unexpected key" under strict loading
+    _IGNORED_KEYS: tuple = ()
 
     def __init__(self, image_size=224, patch_size=7, num_classes=2, channels=512, dim=1024, depth=6, heads=8,
                  mlp_dim=2048, *, max_crops: int = 512, compute_dtype: str = "bf16"):
@@ -103,7 +108,11 @@ class CViTEngine:
         return self._lib.ff_cvit_create(C.byref(h), self._device.index, self._max_crops, self._compute)
 
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
-        """Accepts a bare CViT state_dict or ``{'state_dict': ...}`` (cvit_prediction.py:66-69)."""
+        """Accepts a bare CViT state_dict or ``{'state_dict': ...}`` (cvit_prediction.py:66-69).
+
+        Missing keys always fail (``EngineError``), wrong shapes raise ``ValueError``.  With ``strict`` (the
+        ``nn.Module.load_state_dict`` default) keys the model does not have raise too; ``strict=False`` ignores them
+        like the reference's training script does (cvit_train.py:70-71)."""
         if "state_dict" in state_dict and isinstance(state_dict["state_dict"], dict):
             state_dict = state_dict["state_dict"]
         if self._h is not None:
@@ -118,6 +127,15 @@ class CViTEngine:
             rc = self._lib.ff_cvit_load_weight(self._h, key.encode(), C.c_void_p(t.data_ptr()), shape, t.dim())
             self._check(rc, f"load_weight({key})")
         self._check(self._lib.ff_cvit_finalize_weights(self._h), "finalize_weights")
+        if strict:
+            raw = self._lib.ff_cvit_unused_keys(self._h)
+            unused = [k for k in (raw.decode() if raw else "").split(",") if k]
+            unexpected = [k for k in unused if not any(fnmatch.fnmatchcase(k, pat) for pat in self._IGNORED_KEYS)]
+            if unexpected:
+                self._lib.ff_cvit_destroy(self._h)
+                self._h = None
+                raise EngineError("Unexpected key(s) in state_dict: " + ", ".join(sorted(unexpected)[:8])
+                                  + (" ..." if len(unexpected) > 8 else ""))
         return self
 
     def __del__(self):
@@ -152,10 +170,11 @@ class CViTEngine:
                 "dimension 0 (CViT.forward: batch > 32, model/cvit.py:175)")
         return self.forward_slots(x, None)
 
-    def forward_slots(self, x: torch.Tensor, slots: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Any batch size.  x: fp32 NCHW normalised, or uint8 NHWC [n,224,224,3] raw crops.
-        slots: int32 [n] in [0,32) (default i % 32)."""
-        self._require_ready()
+    def _checked_input(self, x: torch.Tensor):
+        """(contiguous tensor, layout code) for a crop batch on the engine's device: uint8 NHWC [n,224,224,3] raw crops
+        or fp32 NCHW [n,3,224,224] normalised — anything else raises instead of handing a wild pointer to the library."""
+        if not isinstance(x, torch.Tensor):
+            raise ValueError("input must be a torch.Tensor")
         if x.device != self._device:
             raise EngineError(f"input is on {x.device}, engine on {self._device}")
         if x.dtype == torch.uint8:
@@ -168,7 +187,13 @@ class CViTEngine:
             layout = L.FF_X_NCHW_F32
         else:
             raise ValueError(f"unsupported input dtype {x.dtype}")
-        x = x.contiguous()
+        return x.contiguous(), layout
+
+    def forward_slots(self, x: torch.Tensor, slots: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Any batch size.  x: fp32 NCHW normalised, or uint8 NHWC [n,224,224,3] raw crops.
+        slots: int32 [n] in [0,32) (default i % 32)."""
+        self._require_ready()
+        x, layout = self._checked_input(x)
         n = x.shape[0]
         logits = torch.empty((n, 2), dtype=torch.float32, device=self._device)
         sp = None
@@ -209,10 +234,9 @@ class CViTEngine:
         nv = off_host.numel() - 1
         if nv < 0:
             raise ValueError("offsets needs at least one entry")
-        layout = L.FF_X_NHWC_U8 if crops.dtype == torch.uint8 else L.FF_X_NCHW_F32
-        crops = crops.contiguous()
-        if crops.device != self._device:
-            raise EngineError(f"crops are on {crops.device}, engine on {self._device}")
+        crops, layout = self._checked_input(crops)
+        if off_host.numel() and (int(off_host[0]) != 0 or bool((off_host[1:] < off_host[:-1]).any())):
+            raise ValueError("offsets must start at 0 and be non-decreasing")
         n = int(off_host[-1]) if nv >= 0 and off_host.numel() else 0
         if n > crops.shape[0]:
             raise ValueError("offsets exceed the number of crops")
@@ -232,7 +256,8 @@ class CViTEngine:
         """End-to-end call with HOST buffers (pinned preferred): H2D of the uint8 crops, forward, reduction, D2H of
         the scores, stream-synchronised on return."""
         self._require_ready()
-        if crops_host.device.type != "cpu" or crops_host.dtype != torch.uint8:
+        if (crops_host.device.type != "cpu" or crops_host.dtype != torch.uint8 or crops_host.dim() != 4
+                or tuple(crops_host.shape[1:]) != (224, 224, 3)):
             raise ValueError("crops_host must be a CPU uint8 tensor [n,224,224,3]")
         crops_host = crops_host.contiguous()
         off = list(offsets)
@@ -240,6 +265,8 @@ class CViTEngine:
         scores = torch.empty((max(nv, 0),), dtype=torch.float32)
         if nv <= 0:
             return scores
+        if off[0] != 0 or any(b < a for a, b in zip(off, off[1:])):
+            raise ValueError("offsets must start at 0 and be non-decreasing")
         if off[-1] > crops_host.shape[0]:
             raise ValueError("offsets exceed the number of crops")
         off_c = (C.c_int32 * (nv + 1))(*off)
@@ -283,9 +310,9 @@ class CViTEngine:
     def launch_count(self) -> int:
         return int(self._lib.ff_cvit_launch_count(self._h)) if self._h is not None else 0
 
-    def set_tuning(self, stage12_sub_batch: int = 0, use_cuda_graph: int = 0):
+    def set_tuning(self, stage12_sub_batch: int = 0):
         self._require_ready()
-        self._check(self._lib.ff_cvit_set_tuning(self._h, stage12_sub_batch, use_cuda_graph), "ff_cvit_set_tuning")
+        self._check(self._lib.ff_cvit_set_tuning(self._h, stage12_sub_batch), "ff_cvit_set_tuning")
 
     KERNEL_CLASSES = ("conv1", "tcgen05_conv", "tcgen05_gemm", "small_kernels")
 
@@ -313,14 +340,15 @@ class CViTEngine:
     def debug_activation(self, x: torch.Tensor, stop_after: int, slots: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Activation after step `stop_after` (see include/facfake.h) as a flat fp32 CPU tensor."""
         self._require_ready()
-        layout = L.FF_X_NHWC_U8 if x.dtype == torch.uint8 else L.FF_X_NCHW_F32
-        x = x.contiguous()
+        x, layout = self._checked_input(x)
         n = x.shape[0]
         cap = n * 224 * 224 * 32
         out = torch.empty((cap,), dtype=torch.float32)
         sp = None
         if slots is not None:
             slots = slots.to(self._device, torch.int32).contiguous()
+            if slots.numel() != n:
+                raise ValueError("slots must have one entry per crop")
             sp = C.c_void_p(slots.data_ptr())
         cnt = self._lib.ff_cvit_debug_activation(self._h, C.c_void_p(x.data_ptr()), layout, sp, n, stop_after,
                                                  C.c_void_p(out.data_ptr()), cap, C.c_void_p(_stream_ptr(self._device)))
@@ -338,6 +366,8 @@ class ResVitKanEngine(CViTEngine):
     Only the bf16 tensor-core path exists for this variant.
     """
 
+    _IGNORED_KEYS = ("mlp_head.*",)      # defined by the module, not on its forward path (ResVitKan.py:296-300)
+
     def __init__(self, image_size=224, patch_size=7, num_classes=2, channels=512, dim=1024, depth=6, heads=8,
                  mlp_dim=2048, *, max_crops: int = 256):
         super().__init__(image_size, patch_size, num_classes, channels, dim, depth, heads, mlp_dim,
@@ -353,6 +383,11 @@ class CViTGGCAEngine(CViTEngine):
     (folded to plain 3x3 kernels at load), one BN-less conv pair, the GGCA gate on the 7x7x512 map and
     LinearNorm (= LayerNorm eps 1e-6 in eval) in the MLP branches.  Same surface as ``CViTEngine``; bf16 path only.
     """
+
+    # RepBN / LinearNorm training-schedule state and the unused Deconv block (cvit_GGCA_ADD_DEConv_RepBn8.py:22-60,425)
+    _IGNORED_KEYS = ("Deconv.*", "transformer.layers.*.1.fn.norm.norm2.*", "transformer.layers.*.1.fn.norm.warm",
+                     "transformer.layers.*.1.fn.norm.iter", "transformer.layers.*.1.fn.norm.total_step",
+                     "transformer.layers.*.1.fn.norm.r0", "*.num_batches_tracked")
 
     def __init__(self, image_size=224, patch_size=7, num_classes=2, channels=512, dim=1024, depth=6, heads=8,
                  mlp_dim=2048, *, max_crops: int = 512):

@@ -46,8 +46,10 @@ enum {
 
 /* per-video reduction modes for ff_video_scores / ff_cvit_predict */
 enum {
-  FF_REDUCE_REFERENCE = 0,   /* sigmoid per logit, mean, decision rule: cvit_prediction.py:258-281 */
-  FF_REDUCE_SOFTMAX_MEAN = 1 /* mean over frames of softmax(logits)[fake] (extra, not the oracle)  */
+  FF_REDUCE_REFERENCE = 0,    /* sigmoid per logit, mean, decision rule: cvit_prediction.py:258-281     */
+  FF_REDUCE_SOFTMAX_MEAN = 1, /* mean over frames of softmax(logits)[fake] (extra, not the oracle)      */
+  FF_REDUCE_REFERENCE_PROBS = 2 /* ff_video_scores only: the rows already went through pred_sig
+                                   (cvit_prediction.py:258-259) — pre_process_prediction (:266-281) alone */
 };
 
 /* ---- lifetime ----------------------------------------------------------------------------
@@ -83,10 +85,14 @@ const char* ff_last_error(const ff_cvit_t* h); /* h may be NULL: last create() e
  * data, C-contiguous.  `num_batches_tracked` entries are accepted and ignored.
  * `ff_cvit_finalize_weights` folds conv bias + eval BatchNorm (eps 1e-5) into per-channel
  * (scale, shift), converts to the kernels' layouts ([Cout][kh][kw][Cin] bf16, linears as
- * stored) and builds the TMA descriptors.                                                   */
+ * stored) and builds the TMA descriptors.  A missing key fails with FF_ERR_STATE, a key of the
+ * wrong shape with FF_ERR_SHAPE.  `ff_cvit_unused_keys` returns, after finalize, the comma-
+ * separated keys that were loaded but are not part of the model (what `load_state_dict(strict=
+ * True)` reports as "unexpected keys"); the string lives as long as the handle.              */
 int ff_cvit_load_weight(ff_cvit_t* h, const char* state_dict_key, const float* host_fp32,
                         const int64_t* shape, int ndim);
 int ff_cvit_finalize_weights(ff_cvit_t* h);
+const char* ff_cvit_unused_keys(const ff_cvit_t* h);
 
 /* ---- crop preprocessing (K0) ----------------------------------------------------------------
  * Replaces `cv2.resize(face, (224,224), interpolation=cv2.INTER_AREA)` + `cv2.cvtColor(RGB2BGR)`
@@ -110,6 +116,8 @@ int ff_cvit_forward(ff_cvit_t* h, const void* x, int x_layout, const int32_t* sl
 /* ---- per-video reduction (K8) -----------------------------------------------------------------
  * Replaces `pre_process_prediction(pred_sig(y))` (cvit_prediction.py:240,258-281) for many videos:
  * video v owns logits rows [video_offsets[v], video_offsets[v+1]).  <= 2 frames -> 0.5.
+ * Only the first 90 frames of a video count: the reference evaluates the chunks [0:32], [32:64],
+ * [64:90] and drops the rest (cvit_prediction.py:224-238, `upper_bound=90`).
  * video_offsets is a DEVICE int32 [n_videos+1]; scores a DEVICE fp32 [n_videos].               */
 int ff_video_scores(ff_cvit_t* h, const float* logits, const int32_t* video_offsets, int n_videos,
                     int mode, float* scores, void* stream);
@@ -117,8 +125,12 @@ int ff_video_scores(ff_cvit_t* h, const float* logits, const int32_t* video_offs
 /* ---- fused predict: forward + reduction --------------------------------------------------------
  * The model half of `predict()` (cvit_prediction.py:209-242) for n_videos at once.  Crops of
  * video v are rows [off[v], off[v+1]) of x; slot = (frame index within the video) % 32, i.e.
- * the reference's [0:32],[32:64],[64:90] chunking.  HOST copy of the offsets is required to
- * size the pass; `video_offsets_host` and `video_offsets_dev` hold the same n_videos+1 values. */
+ * the reference's [0:32],[32:64],[64:90] chunking; frames >= 90 of a video do not enter its score
+ * (cvit_prediction.py:235-238) — their rows of `logits_out` are still written.  HOST copy of the
+ * offsets is required to size the pass; `video_offsets_host` and `video_offsets_dev` hold the same
+ * n_videos+1 values.  Calls on one handle are serialised by a mutex (the reference drives
+ * predict() from a ThreadPoolExecutor, cvit_prediction.py:73-83); every entry point runs on the
+ * handle's device and restores the caller's current device before returning.                   */
 int ff_cvit_predict(ff_cvit_t* h, const void* x, int x_layout, const int32_t* video_offsets_host,
                     const int32_t* video_offsets_dev, int n_videos, int mode, float* logits_out,
                     float* scores, void* stream);
@@ -148,8 +160,9 @@ int64_t ff_cvit_debug_activation(ff_cvit_t* h, const void* x, int x_layout, cons
  * ff_cvit_set_profiling resets the accumulators.                                                            */
 int ff_cvit_set_profiling(ff_cvit_t* h, int enable);
 int ff_cvit_get_profile(ff_cvit_t* h, double* ms_by_slot /*[21]*/, int64_t* launches_by_slot /*[21]*/);
-/* Tunables (0 keeps the current value): crops per stage-1/2 sub-pass (L2 residency).            */
-int ff_cvit_set_tuning(ff_cvit_t* h, int stage12_sub_batch, int use_cuda_graph);
+/* Tunable (0 keeps the current value): crops per stage-1/2 sub-pass, 1..256.  There are no environment switches:
+ * each layer has exactly one kernel.                                                           */
+int ff_cvit_set_tuning(ff_cvit_t* h, int stage12_sub_batch);
 
 /* ---- BlazeFace face detector -------------------------------------------------------------
  * Replaces the `facedet` object the reference builds in cvit_prediction.py:27-33 (`BlazeFace().to(device)`,

@@ -155,10 +155,12 @@ def test_full_size_properties(eng_default):
     perm = torch.randperm(512, generator=torch.Generator().manual_seed(0))
     permd = eng.forward_slots(crops[perm.cuda()], slots[perm])
     assert (permd - full[perm.cuda()]).abs().max().item() <= 1e-5
-    # (c) oracle spot-check on one reference-sized chunk of the same batch
-    x = O.normalize_crops(crops[64:96].cpu())
-    ref = O.forward(x, sd)
-    assert (full[64:96].cpu() - ref).abs().max().item() <= BF16_TOL
+    # (c) ALL 512 logits against the oracle, evaluated the only way the reference can: 16 chunks of 32 (model/cvit.py:175)
+    torch.set_num_threads(os.cpu_count() or 4)
+    x = O.normalize_crops(crops.cpu())
+    with torch.no_grad():
+        ref = torch.cat([O.forward(x[c:c + 32], sd) for c in range(0, 512, 32)])
+    assert (full.cpu() - ref).abs().max().item() <= BF16_TOL
     # (d) host-buffer entry point gives the same scores as the device one
     offs = list(range(0, 513, 32))
     s_dev = eng.predict_videos(crops, offs).cpu()
@@ -171,16 +173,17 @@ def test_preprocess_matches_oracle(eng_bn):
     from oracle import resize_oracle as R
     eng, _ = eng_bn
     rng = np.random.default_rng(5)
-    sizes = [(448, 448), (672, 448), (300, 300), (500, 333), (905, 640), (159, 159), (100, 180), (300, 180), (225, 225), (224, 224)]
+    # integer ratios (incl. 2x2 and non-square), fractional down-scaling, up-scaling in one or both axes, identity,
+    # the sample clips' extreme crop sizes (159 / 905 px) and degenerate 1-pixel / 2-row sources
+    sizes = [(448, 448), (672, 448), (896, 224), (300, 300), (500, 333), (905, 640), (640, 905), (159, 159), (100, 180),
+             (300, 180), (180, 300), (225, 225), (223, 223), (230, 225), (449, 449), (224, 224), (333, 777), (2, 500), (1, 1)]
     srcs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
     out, norm = eng.preprocess_crops([torch.from_numpy(s).cuda() for s in srcs], swap_rb=True, normalized=True)
     out = out.cpu().numpy()
     for i, s in enumerate(srcs):
         ref = cv2.cvtColor(cv2.resize(s, (224, 224), interpolation=cv2.INTER_AREA), cv2.COLOR_RGB2BGR)
-        d = np.abs(out[i].astype(int) - ref.astype(int))
-        assert d.max() <= 1, sizes[i]
-        assert (d > 0).mean() < 1e-3, sizes[i]
-        np.testing.assert_array_equal(R.crop_to_model_input(s), ref)
+        np.testing.assert_array_equal(out[i], ref, err_msg=str(sizes[i]))           # byte work: bit-exact
+        np.testing.assert_array_equal(R.crop_to_model_input(s), ref, err_msg=str(sizes[i]))
     want = O.normalize_crops(torch.from_numpy(out))
     assert (norm.cpu() - want).abs().max().item() <= 1e-6
 
@@ -289,117 +292,163 @@ def test_prediction_api_mirror_end_to_end(tmp_path, eng_bn):
     assert abs(got - O.video_score(lg)) <= 1e-5
 
 
-def test_quad_pixel_kernel_option_matches_oracle(monkeypatch):
-    """FF_WS4=1 selects the pixel-quad kernel (N = 128 via even/odd pair planes) for feature layers 2 and 3."""
-    monkeypatch.setenv("FF_WS4", "1")
+def test_fused_layer12_kernel_and_separate_conv1_agree():
+    """Feature layers 1 and 2 run in ONE kernel on the uint8 path (conv1's output never leaves shared memory).  Its
+    conv2 output against the oracle, incl. the image borders (zero padding of conv1's OUTPUT), a single crop (fewer
+    tiles than CTAs) and a ragged count; debug tap 1 runs the stand-alone conv1 kernel, which must match the oracle
+    too; and the fp32-NCHW entry (conv1_f32_kernel + the stand-alone conv2) must agree with the fused uint8 entry."""
     eng, sd = _engine("bn", max_crops=64)
-    monkeypatch.delenv("FF_WS4")
-    crops = W.synthetic_crops(3, seed=27)
-    acts = _oracle_layers(sd, O.normalize_crops(crops), 4)
-    xg = crops.cuda()
-    ref_eng, _ = _engine("bn", max_crops=64)
-    for step in (2, 3, 4):
-        got = eng.debug_activation(xg, step)
-        ref = acts[step]
-        assert (got - ref).abs().max().item() <= ref.abs().max().item() * 0.004 * (step + 1), step
-        # same bf16 inputs, same fp32 accumulation order per output up to the k-block order: equal to one rounding
-        assert (got - ref_eng.debug_activation(xg, step)).abs().max().item() <= ref.abs().max().item() * 0.008, step
+    for n, seed in ((3, 28), (1, 29), (5, 30)):
+        crops = W.synthetic_crops(n, seed=seed)
+        x = O.normalize_crops(crops)
+        acts = _oracle_layers(sd, x, 3)
+        xg = crops.cuda()
+        for step in (1, 2, 3):
+            got, ref = eng.debug_activation(xg, step), acts[step]
+            assert (got - ref).abs().max().item() <= ref.abs().max().item() * 0.004 * (step + 1), (n, step)
+        got_f = eng.debug_activation(x.cuda(), 2)
+        assert (got_f - eng.debug_activation(xg, 2)).abs().max().item() <= acts[2].abs().max().item() * 0.008, n
 
 
-def test_fused_layer12_kernel_and_separate_kernels_agree(monkeypatch):
-    """Feature layers 1 and 2 run in one kernel by default (conv1 output never leaves shared memory); FF_C12=0 selects
-    the separate conv1 / conv2 kernels.  Both against the oracle, and against each other to one bf16 rounding."""
-    monkeypatch.setenv("FF_C12", "1")
-    eng, sd = _engine("bn", max_crops=64)
-    monkeypatch.setenv("FF_C12", "0")
-    ref_eng, _ = _engine("bn", max_crops=64)
-    monkeypatch.delenv("FF_C12")
-    crops = W.synthetic_crops(3, seed=28)
-    acts = _oracle_layers(sd, O.normalize_crops(crops), 3)
-    xg = crops.cuda()
-    for step in (2, 3):
-        got = eng.debug_activation(xg, step)
-        ref = acts[step]
-        assert (got - ref).abs().max().item() <= ref.abs().max().item() * 0.004 * (step + 1), step
-        assert (got - ref_eng.debug_activation(xg, step)).abs().max().item() <= ref.abs().max().item() * 0.008, step
-    # tile grid 14 x 16 with a 14-row tile: the image borders (zero padding of conv1's OUTPUT) are inside `ref`
-    lg = eng.forward_slots(xg, torch.arange(3)).cpu()
-    assert (lg - ref_eng.forward_slots(xg, torch.arange(3)).cpu()).abs().max().item() <= 5e-3
-    # 1 crop (fewer tiles than CTAs) and a ragged count
-    for n in (1, 5):
-        c = W.synthetic_crops(n, seed=29).cuda()
-        a, b = eng.debug_activation(c, 2), ref_eng.debug_activation(c, 2)
-        assert (a - b).abs().max().item() <= b.abs().max().item() * 0.008, n
-
-
-def test_encoder_kernel_matches_per_op_launches(monkeypatch):
-    """The six transformer layers run as ONE cooperative kernel by default (ff_xf.cuh: 16-CTA groups per 128-row token
-    tile); FF_XF=0 selects the per-op launches (LayerNorm / GEMM / attention kernels).  Same bf16 operands, same fp32
-    accumulation: the residual stream after every layer and the logits must agree to rounding — including a partial
-    last tile, a single crop, and more tiles than co-resident groups (640 crops = 10 tiles on 9 groups)."""
+def test_encoder_kernel_tiles_and_launch_count():
+    """The six transformer layers run as ONE cooperative kernel (ff_xf.cuh: 16-CTA groups per 128-row token tile).
+    Against the fp32 oracle after every layer, and for batch shapes that exercise a partial last tile, a single crop
+    and more tiles than co-resident groups (640 crops = 10 tiles on 9 groups) through batch-composition invariance."""
     eng, sd = _engine("bn", max_crops=640)
-    monkeypatch.setenv("FF_XF", "0")
-    ref_eng, _ = _engine("bn", max_crops=640)
-    monkeypatch.delenv("FF_XF")
-    crops = W.synthetic_crops(5, seed=31).cuda()
-    for step in range(19, 25):          # residual stream after transformer layer step-18
-        a, b = eng.debug_activation(crops, step), ref_eng.debug_activation(crops, step)
-        assert a.numel() == b.numel() == 2 * 5 * 1024
-        assert torch.isfinite(a).all()
-        assert (a - b).abs().max().item() <= 2e-3 * max(1.0, b.abs().max().item()), step
-    for n in (1, 31, 64, 65, 200, 640):
-        c = W.synthetic_crops(n, seed=32 + n).cuda()
-        before = eng.launch_count(), ref_eng.launch_count()
-        lg, lr = eng.forward_slots(c).cpu(), ref_eng.forward_slots(c).cpu()
-        assert torch.isfinite(lg).all()
-        assert (lg - lr).abs().max().item() <= 5e-3, n
-        # one encoder launch instead of 42 (7 per layer)
-        assert (ref_eng.launch_count() - before[1]) - (eng.launch_count() - before[0]) == 41, n
+    crops = W.synthetic_crops(5, seed=31)
+    slots = torch.tensor([3, 0, 31, 7, 7])
+    with torch.no_grad():
+        t = O.embed_tokens(O.features(O.normalize_crops(crops), sd), sd, slots)
+        for depth in range(1, 7):          # residual stream after transformer layer `depth`
+            ref = O.transformer(t, sd, depth=depth)
+            got = eng.debug_activation(crops.cuda(), 18 + depth, slots).view(5, 2, 1024)
+            assert torch.isfinite(got).all()
+            assert (got - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item()), depth
+    big = W.synthetic_crops(640, seed=33).cuda()
+    before = eng.launch_count()
+    full = eng.forward_slots(big).cpu()
+    per_call = eng.launch_count() - before
+    assert torch.isfinite(full).all()
+    for n in (1, 31, 64, 65, 200):
+        part = eng.forward_slots(big[:n]).cpu()
+        assert (part - full[:n]).abs().max().item() <= 1e-5, n
+    # 640 crops = 10 sub-passes x (fused layer-1/2 + 4) + 11 + embed, tokens, ONE encoder launch, cls, head1, head2
+    assert per_call == 10 * 5 + 11 + 6, per_call
 
 
-def test_cta_pair_conv_kernel_matches_single_cta_kernel(monkeypatch):
-    """Feature layers 10..17 run on ptc2_conv_kernel by default (cta_group::2, 256 pixels x 256 channels per CTA pair,
-    ff_ptc2.cuh); FF_PTC2=0 selects the single-CTA persistent kernel.  Same operands and the same k order: activations
-    must match to one bf16 rounding, and the oracle."""
+def test_cta_pair_conv_kernel_odd_tile_counts():
+    """Feature layers 10..17 run on ptc2_conv_kernel (cta_group::2, 256 pixels x 256 channels per CTA pair).  33 crops
+    give odd pixel-tile counts (the pair's second tile falls off the end): activations against the oracle."""
     eng, sd = _engine("bn", max_crops=64)
-    monkeypatch.setenv("FF_PTC2", "0")
-    ref_eng, _ = _engine("bn", max_crops=64)
-    monkeypatch.delenv("FF_PTC2")
-    for n in (3, 33):                     # 33 crops: odd tile counts (the pair's second tile falls off the end)
-        crops = W.synthetic_crops(n, seed=41 + n)
-        xg = crops.cuda()
-        acts = _oracle_layers(sd, O.normalize_crops(crops), 17) if n == 3 else None
-        for step in range(10, 18):
-            got, ref = eng.debug_activation(xg, step), ref_eng.debug_activation(xg, step)
-            assert torch.isfinite(got).all(), step
-            assert (got - ref).abs().max().item() <= ref.abs().max().item() * 0.008, (n, step)
-            if acts is not None:
-                assert (got - acts[step]).abs().max().item() <= acts[step].abs().max().item() * min(0.03, 0.004 * (step + 1)), step
-    # launch count is unchanged: the pair kernel replaces the single-CTA launch one for one
-    c = W.synthetic_crops(8, seed=77).cuda()
-    b0, b1 = eng.launch_count(), ref_eng.launch_count()
-    lg, lr = eng.forward_slots(c).cpu(), ref_eng.forward_slots(c).cpu()
-    assert (lg - lr).abs().max().item() <= 5e-3
-    assert eng.launch_count() - b0 == ref_eng.launch_count() - b1
+    crops = W.synthetic_crops(33, seed=74)
+    acts = _oracle_layers(sd, O.normalize_crops(crops), 17)
+    xg = crops.cuda()
+    for step in range(7, 18):
+        got = eng.debug_activation(xg, step)
+        assert torch.isfinite(got).all(), step
+        assert (got - acts[step]).abs().max().item() <= acts[step].abs().max().item() * min(0.03, 0.004 * (step + 1)), step
 
 
-@pytest.mark.skipif(os.environ.get("FF_TEST_PTC2_128") != "1",
-                    reason="ptc2m_conv_kernel (FF_PTC2_128=1) was written after round 1's GPU budget was spent and has not "
-                           "run on hardware yet: opt-in, run with FF_TEST_PTC2_128=1")
-def test_unvalidated_cta_pair_kernel_cout128(monkeypatch):
-    """FF_PTC2_128=1 routes feature layers 7..9 (Cout = 128) through ptc2m_conv_kernel (cta_group::2, two pixel sub-tiles
-    per CTA).  Gate for turning it on: activations equal to the default kernel's to one bf16 rounding, and the oracle."""
-    monkeypatch.setenv("FF_PTC2_128", "1")
+def test_long_videos_follow_the_reference_chunking():
+    """cvit_prediction.py:224-238: chunks [0:32], [32:64], [64:90]; frames >= 90 never reach the model.  65-, 90- and
+    95-frame videos through the C-ABI predict against the oracle's restatement of those lines."""
+    eng, sd = _engine("bn", max_crops=128)
+    torch.set_num_threads(os.cpu_count() or 4)
+    lens = [65, 90, 95, 3]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).tolist()
+    crops = W.synthetic_crops(offsets[-1], seed=61)
+    scores, logits = eng.predict_videos(crops.cuda(), offsets, return_logits=True)
+    scores, logits = scores.cpu(), logits.cpu()
+    for v, ln in enumerate(lens):
+        ref_score, ref_logits = O.predict_from_crops(crops[offsets[v]:offsets[v + 1]], sd)
+        kept = min(ln, 90)
+        assert ref_logits.shape[0] == kept
+        assert (logits[offsets[v]:offsets[v] + kept] - ref_logits).abs().max().item() <= BF16_TOL, v
+        assert abs(scores[v].item() - ref_score) <= 1e-2, v
+        # the kernel's own logits through the oracle's reduction: the score must ignore frames >= 90 exactly
+        assert abs(scores[v].item() - O.video_score(logits[offsets[v]:offsets[v] + kept])) <= 2e-6, v
+    # the mirror module takes the same path (predict_crops -> ff_cvit_predict)
+    from fac_fake_b200 import cvit_prediction as cp
+    cp.configure(model_=eng)
+    got = cp.predict_crops(crops[offsets[2]:offsets[3]].numpy())
+    assert abs(got - scores[2].item()) <= 1e-6
+
+
+def test_config2_video_decisions_at_scale():
+    """BASELINE configs[2] shape on one GPU: 64 videos x 30 frames, video_offsets = 30 * arange(65), slot = frame index,
+    passes cut at 512 crops (17 videos + 2 frames: videos straddle pass boundaries).  Scores and REAL/FAKE decisions
+    against the oracle for every video."""
+    from fac_fake_b200 import CViTEngine
+    sd = W.make_state_dict(0, "bn")
+    eng = CViTEngine(max_crops=512).to("cuda:0").load_state_dict(sd)
+    torch.set_num_threads(os.cpu_count() or 4)
+    nv, fr = 64, 30
+    crops = torch.cat([W.synthetic_crops(fr, seed=1000 + v) for v in range(nv)])      # per-video seed = video id
+    offsets = list(range(0, nv * fr + 1, fr))
+    scores, logits = eng.predict_videos(crops.cuda(), offsets, return_logits=True)
+    host_scores = eng.predict_videos_host(crops.pin_memory(), offsets)
+    assert torch.equal(scores.cpu(), host_scores)
+    x = O.normalize_crops(crops)
+    with torch.no_grad():
+        ref = torch.cat([O.forward(x[o:o + fr], sd) for o in offsets[:-1]])
+    assert (logits.cpu() - ref).abs().max().item() <= BF16_TOL
+    ref_scores = O.video_scores(ref, offsets)
+    undecided = 0
+    for v in range(nv):
+        assert abs(scores[v].item() - ref_scores[v]) <= 1e-2, v
+        if abs(ref_scores[v] - 0.5) > 1e-2:
+            assert O.real_or_fake(scores[v].item()) == O.real_or_fake(ref_scores[v]), v
+        else:
+            undecided += 1
+    assert undecided < nv // 2
+
+
+def test_strict_state_dict_and_shape_errors():
+    """load_state_dict(strict=True) reports keys the model does not have; shape errors are ValueError, missing keys
+    EngineError — like nn.Module.load_state_dict tells the two apart."""
+    from fac_fake_b200 import CViTEngine, EngineError
+    sd = W.make_state_dict(0, "default")
+    extra = dict(sd)
+    extra["mlp_head.3.weight"] = torch.zeros((2, 2))
+    with pytest.raises(EngineError, match="Unexpected key"):
+        CViTEngine(max_crops=32).to("cuda:0").load_state_dict(extra)
+    CViTEngine(max_crops=32).to("cuda:0").load_state_dict(extra, strict=False)
+    bad = dict(sd)
+    bad["transformer.layers.0.0.fn.fn.to_out.bias"] = torch.zeros((7,))
+    with pytest.raises(ValueError):
+        CViTEngine(max_crops=32).to("cuda:0").load_state_dict(bad)
+    eng = CViTEngine(max_crops=32).to("cuda:0").load_state_dict(sd)
+    for wrong in (torch.zeros((2, 224, 224, 3), dtype=torch.float16, device="cuda"),
+                  torch.zeros((2, 224, 224, 3), dtype=torch.float64, device="cuda"),
+                  torch.zeros((2, 3, 224, 224), dtype=torch.uint8, device="cuda")):
+        with pytest.raises(ValueError):
+            eng.predict_videos(wrong, [0, 2])
+        with pytest.raises(ValueError):
+            eng.debug_activation(wrong, 2)
+    with pytest.raises(ValueError):
+        eng.predict_videos(torch.zeros((4, 224, 224, 3), dtype=torch.uint8, device="cuda"), [0, 3, 2])
+
+
+def test_calls_leave_the_current_device_alone_and_threads_are_serialised():
+    """Every C-ABI entry point restores the caller's device; concurrent predict_host calls on ONE handle (the
+    reference drives predict() from a ThreadPoolExecutor, cvit_prediction.py:73-83) give each caller its own scores."""
+    from concurrent.futures import ThreadPoolExecutor
     eng, sd = _engine("bn", max_crops=64)
-    monkeypatch.delenv("FF_PTC2_128")
-    ref_eng, _ = _engine("bn", max_crops=64)
-    for n in (3, 33):
-        crops = W.synthetic_crops(n, seed=51 + n)
-        xg = crops.cuda()
-        acts = _oracle_layers(sd, O.normalize_crops(crops), 9) if n == 3 else None
-        for step in (7, 8, 9):
-            got, ref = eng.debug_activation(xg, step), ref_eng.debug_activation(xg, step)
-            assert torch.isfinite(got).all(), step
-            assert (got - ref).abs().max().item() <= ref.abs().max().item() * 0.008, (n, step)
-            if acts is not None:
-                assert (got - acts[step]).abs().max().item() <= acts[step].abs().max().item() * min(0.03, 0.004 * (step + 1)), step
+    dev0 = torch.cuda.current_device()
+    batches = [W.synthetic_crops(9 + i, seed=90 + i).pin_memory() for i in range(6)]
+    want = [eng.predict_videos(b.cuda(), [0, b.shape[0]]).cpu() for b in batches]
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        got = list(ex.map(lambda b: eng.predict_videos_host(b, [0, b.shape[0]]), batches * 3))
+    for i, g in enumerate(got):
+        assert torch.equal(g, want[i % len(batches)]), i
+    assert torch.cuda.current_device() == dev0
+    if torch.cuda.device_count() > 1:       # a second engine on another GPU of the same process
+        from fac_fake_b200 import CViTEngine
+        e1 = CViTEngine(max_crops=32).to("cuda:1").load_state_dict(sd)
+        c = W.synthetic_crops(4, seed=5)
+        a = eng.forward_slots(c.cuda()).cpu()
+        b = e1.forward_slots(c.to("cuda:1")).cpu()
+        assert torch.equal(a, b)
+        assert torch.cuda.current_device() == dev0
+        del e1
+        assert torch.cuda.current_device() == dev0

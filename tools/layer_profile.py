@@ -56,7 +56,7 @@ def main():
     torch.cuda.synchronize()
     prof_ms = e0.elapsed_time(e1) / args.steps
     prof = eng.get_profile(per_layer=True)
-    print(f"variant={os.environ.get('FF_TC_VARIANT','0')} s12={args.s12 or 'default'} crops={n}: step {plain_ms:.3f} ms "
+    print(f"s12={args.s12 or 'default'} crops={n}: step {plain_ms:.3f} ms "
           f"({n/plain_ms*1e3:.0f} crops/s), with per-launch events {prof_ms:.3f} ms")
     tot = 0.0
     for i, (name, (ms, cnt)) in enumerate(prof.items()):

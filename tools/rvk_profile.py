@@ -36,10 +36,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--crops", type=int, default=256)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--ops", type=int, default=0, help="per-op times of ResNet layer L (1..4) instead of the per-layer table")
     args = ap.parse_args()
-    if args.ops:
-        os.environ["FF_RVK_PROF_LAYER"] = str(args.ops)
     n = args.crops
     eng = ResVitKanEngine(max_crops=n).to("cuda:0").load_state_dict(W.make_resvitkan_state_dict(0, "default"))
     crops = [W.synthetic_crops(n, seed=i).cuda() for i in range(2)]
@@ -62,24 +59,6 @@ def main():
     fl = resnet_flops_per_crop()
     print(f"ResVitKan crops={n}: pass {plain_ms:.3f} ms ({n / plain_ms * 1e3:.0f} crops/s), "
           f"{sum(fl.values()) / 1e9:.2f} GFLOP/crop in the ResNet trunk")
-    if args.ops:
-        planes, blocks, stride = ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2))[args.ops - 1]
-        hw_in = (56, 56, 28, 14)[args.ops - 1]
-        inpl = (64, 256, 512, 1024)[args.ops - 1]
-        ops = []
-        for b in range(blocks):
-            s = stride if b == 0 else 1
-            oh = hw_in // s
-            ops.append((f"b{b}.conv1 1x1 {inpl}->{planes} @{hw_in}", 2 * hw_in * hw_in * inpl * planes))
-            ops.append((f"b{b}.conv2 3x3/s{s} {planes}->{planes} @{oh}", 2 * oh * oh * planes * planes * 9))
-            if b == 0:
-                ops.append((f"b{b}.down 1x1/s{s} {inpl}->{planes * 4} @{oh}", 2 * oh * oh * inpl * planes * 4))
-            ops.append((f"b{b}.conv3 1x1 {planes}->{planes * 4} @{oh} +res", 2 * oh * oh * planes * planes * 4))
-            inpl, hw_in = planes * 4, oh
-        for i, (name, f) in enumerate(ops[:16]):
-            ms = prof[1 + i][0] / args.steps
-            print(f"  {name:>40s}: {ms * 1e3:8.1f} us  {f * n / ms / 1e9:8.1f} TFLOP/s")
-        return
     names = ["stem", "layer1", "layer2", "layer3", "layer4", "channel"]
     for i, name in enumerate(names):
         ms, cnt = prof[i]
