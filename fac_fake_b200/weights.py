@@ -50,7 +50,20 @@ def state_dict_keys():
 
 
 def make_state_dict(seed: int = 0, variant: str = "default") -> "OrderedDict[str, torch.Tensor]":
-    """Return a CViT state_dict. variant: "default" | "bn" | "shape_only"."""
+    """Return a CViT state_dict. variant: "default" | "bn" | "decisive" | "shape_only".
+
+    "decisive" = "bn" re-balanced so that REAL/FAKE decisions mean something on synthetic inputs.  With random weights
+    the logits are dominated by pos_embedding[slot] (sigma = 1) while the conv features barely move them, so every
+    30-frame video scores 0.498 +- 0.002 and its decision is a coin flip of rounding noise.  Here pos_embedding is
+    scaled by 0.02 (content decides), the last head layer by 60 and its bias re-centred on the mean logit of
+    `synthetic_video_crops` inputs: per-video scores then spread over 0.15 .. 0.75 on both sides of the threshold."""
+    if variant == "decisive":
+        sd = make_state_dict(seed, "bn")
+        sd["pos_embedding"] = sd["pos_embedding"] * 0.02
+        centre = torch.tensor([-0.2253, 0.0540])          # mean logit of the bn variant with the scaled pos_embedding
+        sd["mlp_head.2.weight"] = sd["mlp_head.2.weight"] * 60.0
+        sd["mlp_head.2.bias"] = (sd["mlp_head.2.bias"] - centre) * 60.0
+        return sd
     gen = torch.Generator(device="cpu")
     gen.manual_seed(1000003 * seed + 17)
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
@@ -101,6 +114,17 @@ def synthetic_crops(n: int, seed: int = 0) -> torch.Tensor:
     gen = torch.Generator(device="cpu")
     gen.manual_seed(7919 * seed + 3)
     return torch.randint(0, 256, (n, 224, 224, 3), generator=gen, dtype=torch.uint8)
+
+
+def synthetic_video_crops(video_id: int, frames: int = 30) -> torch.Tensor:
+    """uint8 [frames,224,224,3]: uniform noise (per-video seed = video id) with a per-video
+    contrast and brightness, so that different videos have different content statistics (and different scores)."""
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(5000 + video_id)
+    a = float(torch.rand((), generator=gen)) * 0.9 + 0.1
+    b = float(torch.rand((), generator=gen)) * (255.0 * (1.0 - a))
+    c = synthetic_crops(frames, seed=1000 + video_id).float() * a + b
+    return c.round().clamp(0, 255).to(torch.uint8)
 
 
 # ----------------------------------------------------------------------------------------------------------------
