@@ -129,13 +129,74 @@ __device__ __forceinline__ void ws2_epilogue(uint32_t taddr, const WsEpi& ss, co
   }
 }
 
+// Cout = 64 variant for EIGHT epilogue warps (two per TMEM lane group): this thread owns channels [32*HALF, 32*HALF+32)
+// of BOTH pixels of its pair, so the 2x2 max-pool stays inside the thread (+ one shuffle for the row neighbour) and every
+// store is one 64-byte run.  ncu on the 4-warp epilogue (profiles/r02_ncu_stage12_before.txt): with 128 columns per
+// thread the N = 128 kernels kept the tensor pipe's shared-memory port only 48-50 % busy — the MMA thread waited for
+// TMEM to drain.  HALF is a template parameter so that the folded BN constants stay immediate constant-bank operands.
+template <int HALF, bool POOL, bool ARRIVE_ON_LEADER>
+__device__ __forceinline__ void ws2_epilogue_c64_half(uint32_t taddr, const WsEpi& ss, const TcArgs& a, int pw0, int h0, int n, int r,
+                                                      int lane, uint32_t arrive_bar) {
+  constexpr int COUT = 64, C0 = 32 * HALF;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
+  const int hl = r >> 3, jl = r & 7;
+  const int Wp = a.W >> 1;
+  uint32_t pk[2][16];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + p * COUT + C0, v);
+    tmem_ld_wait();
+    if (p == 1) {
+      tcgen05_fence_before();
+      if (ARRIVE_ON_LEADER) mbar_arrive_cluster(arrive_bar, 0);
+      else mbar_arrive(arrive_bar);
+    }
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      const float x0 = fmaf(__uint_as_float(v[c]), ss.scale[C0 + c], ss.shift[C0 + c]);
+      const float x1 = fmaf(__uint_as_float(v[c + 1]), ss.scale[C0 + c + 1], ss.shift[C0 + c + 1]);
+      pk[p][c >> 1] = pack_bf16x2_relu(x0, x1);
+    }
+    if (!POOL && n < a.n_img) {
+      __nv_bfloat16* o;
+      if (a.out_blocked) {   // channel-blocked [n][2][H][W][32]: block HALF, pixel 2j+p
+        const size_t pix = (static_cast<size_t>((a.img_off_out + n) * 2 + HALF) * a.H + (h0 + hl)) * a.W + (2 * (pw0 + jl) + p);
+        o = out + pix * 32;
+      } else {
+        const size_t pair = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * Wp + (pw0 + jl);
+        o = out + pair * (2 * COUT) + p * COUT + C0;
+      }
+      st_global_v8(o, &pk[p][0]);
+      st_global_v8(o + 16, &pk[p][8]);
+    }
+  }
+  if (POOL) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[0][i]), *reinterpret_cast<__nv_bfloat162*>(&pk[1][i]));
+      uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
+      uint32_t o2 = __shfl_xor_sync(0xffffffffu, mu, 8);
+      m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o2));
+      pk[0][i] = *reinterpret_cast<uint32_t*>(&m);
+    }
+    if ((lane & 8) == 0 && n < a.n_img) {
+      const size_t pix = (static_cast<size_t>(a.img_off_out + n) * (a.H >> 1) + ((h0 + hl) >> 1)) * Wp + (pw0 + jl);
+      __nv_bfloat16* o = out + pix * COUT + C0;
+      st_global_v8(o, &pk[0][0]);
+      st_global_v8(o + 16, &pk[0][8]);
+    }
+  }
+}
+
 // TcArgs: H, W, tiles_w (= W/16), tiles_h (= H/16), n_img, img_off_out, out.  epi.scale/shift indexed by cout.
 template <int BN, bool POOL, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(BN == 128 ? 320 : 192, 1)
 ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs a,
                const __grid_constant__ WsEpi epi) {
   using L = Ws2Smem<BN, STAGES>;
   constexpr int TMEM_COLS = 2 * BN;       // double-buffered accumulator (128 or 256 columns)
+  constexpr int EPI_THREADS = BN == 128 ? 256 : 128;   // N = 128: two epilogue warps per TMEM lane group
   static_assert(BN == 64 || BN == 128, "BN");
 
   extern __shared__ uint8_t smem_raw[];
@@ -163,8 +224,8 @@ ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_init(bar_tfull, 1);
     mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, 128);
-    mbar_init(bar_tempty + 8, 128);
+    mbar_init(bar_tempty, EPI_THREADS);
+    mbar_init(bar_tempty + 8, EPI_THREADS);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
@@ -233,8 +294,13 @@ ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int th = rem / a.tiles_w, tw = rem - th * a.tiles_w;
       mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
       tcgen05_fence_after();
-      ws2_epilogue<BN, POOL>(tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN, epi, a, tw * 8, th * 16, n, r, lane,
-                             bar_tempty + 8 * acc);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN;
+      if (BN == 128) {
+        if (warp < 6) ws2_epilogue_c64_half<0, POOL, false>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
+        else ws2_epilogue_c64_half<1, POOL, false>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
+      } else {
+        ws2_epilogue<BN, POOL>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
+      }
     }
   }
 
@@ -274,7 +340,7 @@ struct Ws2xSmem {
 };
 
 template <bool POOL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs a,
                  const __grid_constant__ WsEpi epi) {
   using L = Ws2xSmem;
@@ -310,8 +376,8 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     mbar_init(bar_tfull, 1);
     mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, 256);        // both CTAs' epilogue threads (only the leader's copy is used)
-    mbar_init(bar_tempty + 8, 256);
+    mbar_init(bar_tempty, 512);        // both CTAs' 256 epilogue threads (only the leader's copy is used)
+    mbar_init(bar_tempty + 8, 512);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
@@ -389,8 +455,9 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tile_of(pi, &n, &th, &tw);
       mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
       tcgen05_fence_after();
-      ws2_epilogue<BN, POOL, true>(tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN, epi, a, tw * 8, th * 16, n, r, lane,
-                                   bar_tempty + 8 * acc);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN;
+      if (warp < 6) ws2_epilogue_c64_half<0, POOL, true>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
+      else ws2_epilogue_c64_half<1, POOL, true>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
     }
   }
 
@@ -405,11 +472,11 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BN, bool POOL, int STAGES>
 inline cudaError_t launch_ws2(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args, const WsEpi& epi) {
-  return ffh::launch_smem(ws2conv_kernel<BN, POOL, STAGES>, dim3(grid), dim3(192), Ws2Smem<BN, STAGES>::TOTAL, st, true, a, w, args, epi);
+  return ffh::launch_smem(ws2conv_kernel<BN, POOL, STAGES>, dim3(grid), dim3(BN == 128 ? 320 : 192), Ws2Smem<BN, STAGES>::TOTAL, st, true, a, w, args, epi);
 }
 template <bool POOL>
 inline cudaError_t launch_ws2x(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args, const WsEpi& epi) {
-  return ffh::launch_smem(ws2x_conv_kernel<POOL>, dim3(grid), dim3(192), Ws2xSmem::TOTAL, st, true, a, w, args, epi);
+  return ffh::launch_smem(ws2x_conv_kernel<POOL>, dim3(grid), dim3(320), Ws2xSmem::TOTAL, st, true, a, w, args, epi);
 }
 
 }  // namespace ff
