@@ -141,7 +141,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, capped = [], [], set(), 0
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
@@ -153,17 +153,20 @@ class ClockSampler:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
+                    capped += name == "sw_power_cap"
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_power_capped": capped}
 
 
 def cpu_baseline(sample_crops: int, repeats: int, model: str = "cvit"):
-    """The CPU oracle port (torch fp32, all host threads) on `sample_crops` crops of the same workload."""
+    """The reference's CPU path (torch fp32, all host threads) on `sample_crops` crops of the same workload: the
+    unmodified reference class when it was vendored (kind "reference"), else the oracle port (kind "port")."""
     import torch
     from fac_fake_b200 import weights as W
     from oracle import cvit_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    kind, where = "port", "oracle port"
     if model == "resvitkan":
         from oracle import resvitkan_oracle as R
         sd = W.make_resvitkan_state_dict(0, "default")
@@ -173,17 +176,17 @@ def cpu_baseline(sample_crops: int, repeats: int, model: str = "cvit"):
         sd = W.make_ggca_state_dict(0, "default")
         fwd = lambda x: torch.cat([G.forward(x[i:i + 32], sd) for i in range(0, x.shape[0], 32)])   # noqa: E731
     else:
-        sd = W.make_state_dict(0, "default")
-        fwd = lambda x: O.forward_chunked(x, sd, chunk=32)                                          # noqa: E731
+        f32, kind, where = reference_forward_fn()
+        fwd = lambda x: torch.cat([f32(x[i:i + 32]) for i in range(0, x.shape[0], 32)])             # noqa: E731
     crops = W.synthetic_crops(sample_crops, seed=11)
     offs = list(range(0, sample_crops + 1, CROPS_PER_VIDEO))
     if offs[-1] != sample_crops:
         offs.append(sample_crops)
 
-    def one():
-        x = O.normalize_crops(crops)
+    def one(c=crops, o=offs):
+        x = O.normalize_crops(c)
         lg = fwd(x)
-        return O.video_scores(lg, offs)
+        return O.video_scores(lg, o)
 
     one()                                         # warm-up
     times = []
@@ -192,9 +195,25 @@ def cpu_baseline(sample_crops: int, repeats: int, model: str = "cvit"):
         one()
         times.append(time.perf_counter() - t0)
     med = statistics.median(times)
-    return {"value": sample_crops / med, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{sample_crops} crops (chunks of 32) x {repeats} runs, median; torch {torch.__version__} fp32 CPU oracle",
-            "seconds_per_run": med}
+    out = {"value": sample_crops / med, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"{sample_crops} crops (chunks of 32) x {repeats} runs, median; torch {torch.__version__} fp32, {where}",
+           "seconds_per_run": med}
+    # BASELINE configs[0]: batch 15 = the 15 face crops of one sample clip (tests/golden/sample_clip_crops.npz)
+    fx = os.path.join(ROOT, "tests", "golden", "sample_clip_crops.npz")
+    if model == "cvit" and os.path.exists(fx):
+        import numpy as np
+        g = np.load(fx)
+        real = torch.from_numpy(g["crops"][:15])
+        one(real, [0, 15])
+        ts = []
+        for _ in range(max(2, repeats)):
+            t0 = time.perf_counter()
+            one(real, [0, 15])
+            ts.append(time.perf_counter() - t0)
+        m15 = statistics.median(ts)
+        out["configs0_batch15"] = {"value": 15 / m15, "unit": UNIT, "videos_per_s": 1.0 / m15, "seconds_per_video": m15,
+                                   "sample": "15 real face crops of one clip of sample__prediction_data (BASELINE configs[0]), one chunk"}
+    return out
 
 
 def s3d_flops_per_clip(T: int) -> int:
@@ -396,8 +415,45 @@ def run_blazeface(args):
 
 
 
+def load_reference_class():
+    """The UNMODIFIED reference module model/cvit.py, vendored by __graft_entry__.build() into baseline/_ref/ (git-ignored,
+    travels to the GPU box with the snapshot).  Returns (CViT class, where) or (None, why)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "cvit.py")):
+        return None, "baseline/_ref/cvit.py not present (build() vendors it when /root/reference is mounted)"
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ff_reference_cvit", os.path.join(ref_dir, "cvit.py"))
+    mod = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(mod)
+    except Exception as e:  # einops missing etc.
+        return None, f"import of baseline/_ref/cvit.py failed: {e!r}"
+    return mod.CViT, "baseline/_ref/cvit.py (unmodified /root/reference/CViT-main/model/cvit.py)"
+
+
+def reference_forward_fn():
+    """(callable x[n<=32,3,224,224] fp32 -> logits, kind, description): the reference's own class when vendored, else the port."""
+    import torch
+    from fac_fake_b200 import weights as W
+    from oracle import cvit_oracle as O
+    sd = W.make_state_dict(0, "default")
+    cls, where = load_reference_class()
+    if cls is None:
+        return (lambda x: O.forward(x, sd)), "port", f"oracle/cvit_oracle.py ({where})"
+    model = cls(image_size=224, patch_size=7, num_classes=2, channels=512, dim=1024, depth=6, heads=8, mlp_dim=2048)
+    model.load_state_dict(sd)
+    model.eval()
+
+    def fwd(x):
+        with torch.no_grad():
+            return model(x)
+    return fwd, "reference", where
+
+
 def run_reference(args):
-    """--impl reference: the reference's own (CPU, PyTorch fp32) implementation of the path = the oracle port."""
+    """--impl reference: the reference's own CPU implementation of the path — the unmodified `cvit.CViT` class under
+    torch.no_grad() on all host cores, fed exactly like cvit_prediction.py:209-242 feeds it (normalised fp32 NCHW chunks
+    of <= 32 crops, pred_sig + pre_process_prediction per video).  Each step is a bounded sample of configs[1]."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -407,13 +463,13 @@ def run_reference(args):
     from oracle import cvit_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = W.make_state_dict(0, "default")
+    fwd, kind, where = reference_forward_fn()
     crops = W.synthetic_crops(sample, seed=11)
     offs = [0, sample]
 
     def one():
         x = O.normalize_crops(crops)
-        lg = O.forward_chunked(x, sd, chunk=32)
+        lg = torch.cat([fwd(x[i:i + 32]) for i in range(0, sample, 32)])
         return O.video_scores(lg, offs)
 
     for _ in range(max(1, min(args.warmup, 2))):
@@ -429,8 +485,8 @@ def run_reference(args):
         "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "CViT inference, synthetic 224x224 uint8 face crops, bounded CPU sample of BASELINE configs[1]",
-                   "crops_per_step": sample, "videos_per_s_30f": val / 30.0},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                   "crops_per_step": sample, "videos_per_s_30f": val / 30.0, "reference_code": where},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{sample} crops per step (one reference-sized chunk), {steps} steps; torch fp32 on host cores"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -451,6 +507,8 @@ def main():
     ap.add_argument("--model", default="cvit", choices=sorted(MODELS) + ["s3d", "blazeface"],
                     help="cvit = the north-star path (default, what the driver runs); resvitkan = SURVEY 8f-1 / BASELINE configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config2", action="store_true", help="skip the configs[2] strong-scaling block (8192 videos x 30 frames)")
+    ap.add_argument("--config2-videos", type=int, default=8192)
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: same as --steps")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -467,7 +525,7 @@ def main():
     import torch
     import torch.distributed as dist
     from fac_fake_b200 import CViTEngine, CViTGGCAEngine, ResVitKanEngine, weights as W
-    from fac_fake_b200.sharding import gather_scores
+    from fac_fake_b200.sharding import gather_scores, shard_range
     model = MODELS[args.model]
     rvk = args.model == "resvitkan"
 
@@ -502,11 +560,15 @@ def main():
     dev_batches = [b.to(dev) for b in host_batches]
     torch.cuda.synchronize()
 
+    # per-rank score store: every step's scores stay on the device; ONE gather after the last step
+    score_store = torch.empty((max(warmup, steps), n_videos), dtype=torch.float32, device=dev)
+
     def step(i):
-        scores = eng.predict_videos(dev_batches[i % ROT], offsets)
-        if world > 1:
-            scores = gather_scores(scores, n_videos * world, rank, world)
-        return scores
+        score_store[i] = eng.predict_videos(dev_batches[i % ROT], offsets)
+
+    def gather_all(k):
+        flat = score_store[:k].reshape(-1)
+        return gather_scores(flat, flat.numel() * world, rank, world) if world > 1 else flat
 
     def sync_all():
         if world > 1:
@@ -515,23 +577,26 @@ def main():
 
     for i in range(warmup):
         step(i)
+    gather_all(warmup)
     sync_all()
     l0 = eng.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # ---- timed region A: K steps, no instrumentation -> `value`
+    # ---- timed region A: K steps + the one score gather, no instrumentation -> `value`
     sync_all()
     e0.record()
     for i in range(steps):
         step(i)
+    all_scores = gather_all(steps)
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
+    assert bool(torch.isfinite(all_scores).all())
     # ---- timed region B: the same K steps with a CUDA-event pair around every kernel launch (on the launching
-    #      stream) -> per-kernel-class device time for the roofline.  The event records serialise the launches
+    #      stream) -> per-layer device time for the rooflines.  The event records serialise the launches
     #      (no programmatic-dependent-launch overlap), so this pass is slower than A and is NOT the reported value.
     eng.set_profiling(True)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -543,6 +608,7 @@ def main():
     ms_instr = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
     prof = eng.get_profile()
+    prof_layers = eng.get_profile(per_layer=True)
     eng.set_profiling(False)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -567,6 +633,47 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / (float(t.item()) * 1e-3)
+
+    # ---- BASELINE configs[2] as written: 8192 videos x 30 uint8 frames, per-video seed = video id,
+    #      video_offsets = 30 * arange, slot = frame index, rank r owns videos [r*V/W, (r+1)*V/W); STRONG scaling: the
+    #      total is fixed, one gather of the V scores at the end.  Inputs are generated on the device before the timed
+    #      region (37 GB of uint8 over all ranks), frames of a video are contiguous.
+    config2 = None
+    if args.model == "cvit" and not args.no_config2:
+        V, FR = args.config2_videos, 30
+        lo, hi = shard_range(V, rank, world)
+        nv_local = hi - lo
+        store = torch.empty((nv_local * FR, 224, 224, 3), dtype=torch.uint8, device=dev)
+        gen = torch.Generator(device=dev)
+        for v in range(lo, hi):
+            gen.manual_seed(v)
+            torch.randint(0, 256, (FR, 224, 224, 3), dtype=torch.uint8, device=dev, generator=gen, out=store[(v - lo) * FR:(v - lo + 1) * FR])
+        CH = 256                                   # videos per call = 7680 crops = 15 full passes of 512
+        local_scores = torch.empty((nv_local,), dtype=torch.float32, device=dev)
+
+        def run_config2():
+            for c0 in range(0, nv_local, CH):
+                c1 = min(nv_local, c0 + CH)
+                local_scores[c0:c1] = eng.predict_videos(store[c0 * FR:c1 * FR], [FR * k for k in range(c1 - c0 + 1)])
+            return gather_scores(local_scores, V, rank, world)
+
+        eng.predict_videos(store[:FR * min(nv_local, 34)], [FR * k for k in range(min(nv_local, 34) + 1)])     # warm-up
+        sync_all()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        sc = run_config2()
+        g1.record()
+        sync_all()
+        t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = float(t.item())
+        config2 = {"what": f"BASELINE configs[2]: {V} synthetic videos x {FR} uint8 frames (per-video seed), sharded by whole videos over {world} GPU(s), "
+                           "slot = frame index, one gather of the scores at the end",
+                   "scaling": "strong", "videos": V, "frames_per_video": FR, "videos_per_s": V / (ms2 * 1e-3),
+                   "crops_per_s": V * FR / (ms2 * 1e-3), "seconds": ms2 * 1e-3, "n_gpus": world,
+                   "scores_finite": bool(torch.isfinite(sc).all()), "scores_gathered": int(sc.numel())}
+        del store
 
     if rank == 0 and rvk:
         fl, by = resvitkan_trunk_work()
@@ -606,34 +713,65 @@ def main():
     elif rank == 0:
         conv_ms, conv_launches = prof["tcgen05_conv"]
         flops_per_crop = model["flops_per_crop"]
-        # default build: feature layers 1+2 are ONE kernel (ff::c12_kernel) timed in this class, so the class covers the
-        # whole conv stack (conv1's HBM-bound time included); FF_C12=0: conv1 is a class of its own and excluded
-        fused12 = prof["conv1"][0] == 0.0
-        class_flops = CONV_FLOPS if fused12 else TC_CONV_FLOPS
-        tc_tflops = (class_flops * n * steps) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        peak = peaks["bf16_sustained"]
+        # Which peak: the burst figure for a short timed region at full clocks, the sustained one only when the clock
+        # record of THIS run shows the power cap on every sample (B200_PROFILING.md).
+        capped = bool(clocks and clocks.get("samples") and clocks.get("samples_power_capped", 0) >= clocks["samples"])
+        peak = peaks["bf16_sustained"] if capped else peaks["bf16_burst"]
+        peak_name = "bf16_tflops_sustained" if capped else "bf16_tflops (burst)"
+        # per-layer event times -> one roofline per kernel family.  Profile slot k (k >= 1) = feature layer k+1; slot 1 also
+        # carries layer 1 (layers 1+2 are one kernel, ff::c12_kernel).
+        plan = [(3, 32, 224), (32, 32, 224), (32, 32, 224), (32, 64, 112), (64, 64, 112), (64, 64, 112), (64, 128, 56), (128, 128, 56),
+                (128, 128, 56), (128, 256, 28), (256, 256, 28), (256, 256, 28), (256, 256, 28), (256, 512, 14), (512, 512, 14),
+                (512, 512, 14), (512, 512, 14)]
+        lf = [2 * 9 * ci * co * hw * hw for ci, co, hw in plan]
+        lt = list(prof_layers.values())
+        fams = {"ff::c12_kernel (layers 1+2 fused)": ([1], lf[0] + lf[1]), "ff::ws2conv_kernel (layers 3, 4)": ([2, 3], lf[2] + lf[3]),
+                "ff::ws2x_conv_kernel (layers 5, 6)": ([4, 5], lf[4] + lf[5]), "ff::ptc_conv_kernel (layers 7-9)": ([6, 7, 8], sum(lf[6:9])),
+                "ff::ptc2_conv_kernel (layers 10-17)": (list(range(9, 17)), sum(lf[9:17]))}
+        by_kernel = {}
+        for name, (slots, fl) in fams.items():
+            kms = sum(lt[k][0] for k in slots)
+            kl = sum(lt[k][1] for k in slots)
+            tf = fl * n * steps / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+            by_kernel[name] = {"ms_per_step": kms / steps, "launches_per_step": kl / steps, "tflops": tf, "frac": tf / peak,
+                               "flops_per_crop": fl}
+        gemm_ms = prof["tcgen05_gemm"][0]
+        by_kernel["ff::xf_kernel + ff::tc_gemm_kernel (embed, encoder, head)"] = {
+            "ms_per_step": gemm_ms / steps, "launches_per_step": prof["tcgen05_gemm"][1] / steps,
+            "tflops": (flops_per_crop - CONV_FLOPS) * n * steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0,
+            "flops_per_crop": flops_per_crop - CONV_FLOPS}
+        by_kernel[list(by_kernel)[-1]]["frac"] = by_kernel[list(by_kernel)[-1]]["tflops"] / peak
+        dom_name = max(fams, key=lambda k: by_kernel[k]["ms_per_step"])
+        dom = by_kernel[dom_name]
+        # traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu
+        # --set full capture of THIS kernel (profiles/r02_roofline_traffic.json, written by tools/ncu_summary.py)
+        traffic, traffic_src = None, "no committed ncu capture for this kernel"
+        tf_path = os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")
+        if os.path.exists(tf_path):
+            tj = json.load(open(tf_path))
+            for key, ent in tj.items():
+                if key in dom_name:
+                    traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
+        class_tflops = (CONV_FLOPS * n * steps) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         roofline = {
-            "bound": "tensor", "kernel": ("tcgen05 conv kernels of feature layers 1..17 (ff::c12_kernel = layers 1+2 fused, ff::ws2conv_kernel, ff::ws2x_conv_kernel, ff::ptc_conv_kernel, ff::ptc2_conv_kernel)"
-                                          if fused12 else "tcgen05 conv kernels of feature layers 2..17 (ff::ws2conv_kernel, ff::ws2x_conv_kernel, ff::ptc_conv_kernel, ff::ptc2_conv_kernel)"),
-            "achieved": tc_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tc_tflops / peak,
-            "peak_source": f"bf16_tflops_sustained, {peaks['source']} (kernel timed inside a long step)",
-            "frac_of_burst_peak": tc_tflops / peaks["bf16_burst"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel
-            # ff::ptc_conv_kernel<256,1,false,4> (feature layer 11/12: 256->256 @28x28, 512 crops) from the
-            # `ncu --set full` capture in profiles/r01_ncu_ptc_conv_raw.csv: 107.5 MB read + 68.1 MB written,
-            # below the layer's algorithmic 411 MB (205 MB in + 205 MB out + 1.2 MB weights) because the previous
-            # layer's output is still L2-resident.
-            "traffic": 175.6e6,
-            "traffic_unit": ("bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum), kernel ff::ptc_conv_kernel<256,1,0,4> "
-                             "(feature layer 11/12; the CTA-pair kernel ff::ptc2_conv_kernel that runs this layer by default reads and writes "
-                             "the same tensors and has not been captured under ncu yet)"),
-            "algorithmic_flops_per_crop": class_flops,
-            "kernel_ms_per_step": conv_ms / steps, "kernel_launches_per_step": conv_launches / steps,
-            "step_share": conv_ms / ms_instr if ms_instr > 0 else None,
+            "bound": "tensor", "kernel": dom_name,
+            "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": dom["tflops"] / peak,
+            "peak_source": f"{peak_name}, {peaks['source']}; power cap on {clocks.get('samples_power_capped') if clocks else None} of "
+                           f"{clocks.get('samples') if clocks else None} clock samples",
+            "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_flops_per_launch": dom["flops_per_crop"] * n / max(dom["launches_per_step"], 1.0),
+            "avg_launch_ms": dom["ms_per_step"] / max(dom["launches_per_step"], 1.0),
+            "kernel_ms_per_step": dom["ms_per_step"], "kernel_launches_per_step": dom["launches_per_step"],
+            "step_share": dom["ms_per_step"] * steps / ms_instr if ms_instr > 0 else None,
+            "how": "second pass of the same K steps with a CUDA-event pair around every launch on the launching stream; "
+                   "value/ms_per_step come from the uninstrumented pass",
+            "by_kernel": by_kernel,
+            "conv_stack": {"tflops": class_tflops, "frac": class_tflops / peak, "frac_of_burst_peak": class_tflops / peaks["bf16_burst"],
+                           "frac_of_sustained_peak": class_tflops / peaks["bf16_sustained"], "ms_per_step": conv_ms / steps,
+                           "launches_per_step": conv_launches / steps, "algorithmic_flops_per_crop": CONV_FLOPS},
+            "whole_step": {"tflops": value / world * flops_per_crop / 1e12, "frac_of_burst_peak": value / world * flops_per_crop / 1e12 / peaks["bf16_burst"],
+                           "frac_of_sustained_peak": value / world * flops_per_crop / 1e12 / peaks["bf16_sustained"]},
             "instrumented_ms_per_step": ms_instr / steps,
-            "how": "second pass of the same K steps with a CUDA-event pair around every launch; value/ms_per_step come from the uninstrumented pass",
-            "whole_step_tflops": value / world * flops_per_crop / 1e12,
-            "whole_step_frac_of_burst": value / world * flops_per_crop / 1e12 / peaks["bf16_burst"],
             "by_class_ms_per_step": {k: v[0] / steps for k, v in prof.items()},
         }
         out = {
@@ -641,9 +779,10 @@ def main():
             "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{model['name']} bf16 inference, synthetic batch of {n} uint8 face crops 224x224 per GPU "
-                                   f"({n_videos} videos x {CROPS_PER_VIDEO} crops, slot = i % 32), random-init weights",
+                                   f"({n_videos} videos x {CROPS_PER_VIDEO} crops, slot = i % 32; BASELINE {model['baseline_config']}), random-init weights",
                        "crops_per_step_per_gpu": n, "videos_per_step_per_gpu": n_videos,
-                       "videos_per_s_30f": value / 30.0, "parallelism": f"video-sharded x{world} (no data-path collective)",
+                       "videos_per_s_30f": value / 30.0,
+                       "parallelism": f"video-sharded x{world} (no data-path collective; one gather of the per-video scores after the last step, inside the timed region)",
                        "l2": "inputs rotate over 4 distinct batches (308 MB > 126 MB L2); >1.6 GB of activations per step sweep L2",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "clocks": clocks,
@@ -653,6 +792,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
+        if config2 is not None:
+            out["config2"] = config2
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(32, 3, args.model)
         emit(out)

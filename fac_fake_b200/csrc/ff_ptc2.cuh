@@ -75,8 +75,8 @@ ptc2_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     mbar_init(bar_tfull, 1);
     mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, 256);        // both CTAs' epilogue threads (only the leader's copy is used)
-    mbar_init(bar_tempty + 8, 256);
+    mbar_init(bar_tempty, 8);          // one arrival per epilogue warp of both CTAs (only the leader's copy is used)
+    mbar_init(bar_tempty + 8, 8);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
@@ -179,7 +179,8 @@ ptc2_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_wait();
         if (c0 + 32 == BN) {             // accumulator fully read: hand the TMEM buffer back to the leader's MMA thread
           tcgen05_fence_before();
-          mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+          __syncwarp();                  // one cluster-scope release per warp (a MEMBAR each), not one per thread
+          if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
         }
         uint32_t p[16];
 #pragma unroll

@@ -84,7 +84,7 @@ __device__ __forceinline__ void ws2_epilogue(uint32_t taddr, const WsEpi& ss, co
     tmem_ld_wait();
     if (p == 1) {
       tcgen05_fence_before();
-      if (ARRIVE_ON_LEADER) mbar_arrive_cluster(arrive_bar, 0);   // CTA pair: the leader (rank 0) issues the MMAs
+      if (ARRIVE_ON_LEADER) { __syncwarp(); if (lane == 0) mbar_arrive_cluster(arrive_bar, 0); }   // CTA pair: one cluster-scope release per WARP
       else mbar_arrive(arrive_bar);
     }
 #pragma unroll
@@ -149,7 +149,9 @@ __device__ __forceinline__ void ws2_epilogue_c64_half(uint32_t taddr, const WsEp
     tmem_ld_wait();
     if (p == 1) {
       tcgen05_fence_before();
-      if (ARRIVE_ON_LEADER) mbar_arrive_cluster(arrive_bar, 0);
+      // one remote arrival per warp: a cluster-scope release costs a MEMBAR, and 512 of them per tile pair showed up as
+      // the top stall of this kernel (ncu: stall_membar 2.0 per issued instruction)
+      if (ARRIVE_ON_LEADER) { __syncwarp(); if (lane == 0) mbar_arrive_cluster(arrive_bar, 0); }
       else mbar_arrive(arrive_bar);
     }
 #pragma unroll
@@ -376,8 +378,8 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     mbar_init(bar_tfull, 1);
     mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, 512);        // both CTAs' 256 epilogue threads (only the leader's copy is used)
-    mbar_init(bar_tempty + 8, 512);
+    mbar_init(bar_tempty, 16);         // one arrival per epilogue warp of both CTAs (only the leader's copy is used)
+    mbar_init(bar_tempty + 8, 16);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
