@@ -85,8 +85,8 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   const uint32_t bar_mma1 = bar_w2 + 8;
   const uint32_t bar_mma2 = bar_w2 + 16;      // two: one per conv2 accumulator
   const uint32_t bar_raw = bar_w2 + 32;
-  const uint32_t bar_sin = bar_raw + 8 * L::RING;       // 256 worker arrivals: conv1's input patch of the next tile is written
-  const uint32_t bar_patch = bar_sin + 8;               // 256 worker arrivals: conv2's patch of this tile is written
+  const uint32_t bar_sin = bar_raw + 8 * L::RING;       // 8 worker-warp arrivals: conv1's input patch of the next tile is written
+  const uint32_t bar_patch = bar_sin + 8;               // 8 worker-warp arrivals: conv2's patch of this tile is written
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
 
   // 256 threads: thread pair (r, r + 128) shares accumulator row r; `half` picks the pixel of the pair it converts
@@ -106,8 +106,8 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     mbar_init(bar_mma2, 1);
     mbar_init(bar_mma2 + 8, 1);
     for (int s = 0; s < L::RING; ++s) mbar_init(bar_raw + 8 * s, 1);
-    mbar_init(bar_sin, 256);
-    mbar_init(bar_patch, 256);
+    mbar_init(bar_sin, 8);            // one arrival per worker warp
+    mbar_init(bar_patch, 8);
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc<256>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
@@ -225,7 +225,8 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
-      mbar_arrive(bar_sin);
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(bar_sin);
     };
     auto epilogue2 = [&](int t, int it) {      // thread = one pixel of pair (hl, jl) of the 14 x 16 tile: 32 channels = 64 bytes
       int n, h0, w0;
@@ -291,7 +292,8 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
-      mbar_arrive(bar_patch);
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(bar_patch);
       // ---- c. next tile: conversion (s_in was released by the conv1 MMAs of tile k, waited for in step a)
       const int tn = t + gridDim.x;
       if (tn < num_tiles) convert(tn, it + 1);

@@ -84,8 +84,8 @@ __device__ __forceinline__ void ws2_epilogue(uint32_t taddr, const WsEpi& ss, co
     tmem_ld_wait();
     if (p == 1) {
       tcgen05_fence_before();
-      if (ARRIVE_ON_LEADER) { __syncwarp(); if (lane == 0) mbar_arrive_cluster(arrive_bar, 0); }   // CTA pair: one cluster-scope release per WARP
-      else mbar_arrive(arrive_bar);
+      __syncwarp();                                    // one arrival per warp (leader CTA of a pair, else this CTA)
+      if (lane == 0) { if (ARRIVE_ON_LEADER) mbar_arrive_cluster(arrive_bar, 0); else mbar_arrive(arrive_bar); }
     }
 #pragma unroll
     for (int c = 0; c < COUT; c += 2) {
@@ -151,8 +151,8 @@ __device__ __forceinline__ void ws2_epilogue_c64_half(uint32_t taddr, const WsEp
       tcgen05_fence_before();
       // one remote arrival per warp: a cluster-scope release costs a MEMBAR, and 512 of them per tile pair showed up as
       // the top stall of this kernel (ncu: stall_membar 2.0 per issued instruction)
-      if (ARRIVE_ON_LEADER) { __syncwarp(); if (lane == 0) mbar_arrive_cluster(arrive_bar, 0); }
-      else mbar_arrive(arrive_bar);
+      __syncwarp();
+      if (lane == 0) { if (ARRIVE_ON_LEADER) mbar_arrive_cluster(arrive_bar, 0); else mbar_arrive(arrive_bar); }
     }
 #pragma unroll
     for (int c = 0; c < 32; c += 2) {
@@ -198,7 +198,7 @@ ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ WsEpi epi) {
   using L = Ws2Smem<BN, STAGES>;
   constexpr int TMEM_COLS = 2 * BN;       // double-buffered accumulator (128 or 256 columns)
-  constexpr int EPI_THREADS = BN == 128 ? 256 : 128;   // N = 128: two epilogue warps per TMEM lane group
+  constexpr int EPI_WARPS = BN == 128 ? 8 : 4;         // N = 128: two epilogue warps per TMEM lane group
   static_assert(BN == 64 || BN == 128, "BN");
 
   extern __shared__ uint8_t smem_raw[];
@@ -226,8 +226,8 @@ ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_init(bar_tfull, 1);
     mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, EPI_THREADS);
-    mbar_init(bar_tempty + 8, EPI_THREADS);
+    mbar_init(bar_tempty, EPI_WARPS);           // one arrival per epilogue warp
+    mbar_init(bar_tempty + 8, EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
