@@ -19,9 +19,6 @@ $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)
 	@cat $(patsubst %,build/%.ptxas.log,$(UNITS)) > build_ptxas.log
 
-oracle:
-	$(MAKE) -C oracle
-
 clean:
 	rm -rf build $(LIB) build_ptxas.log
-.PHONY: all clean oracle
+.PHONY: all clean

@@ -268,3 +268,74 @@ def main_s3d():
 
 if __name__ == "__main__" and os.environ.get("FF_GOLDEN_S3D", "1") == "1":
     main_s3d()
+
+
+def main_sample_clips():
+    """tests/golden/sample_clip_crops.npz — BASELINE configs[0]: the reference's own front-end on its own sample clips.
+
+    For every clip of sample__prediction_data: 15 frames by ``VideoReader.read_random_frames(path, 15, seed=0)``
+    (helpers_read_video_1.py:50-69), ``FaceExtractor.process_video`` with the reference BlazeFace and its shipped weights
+    (helpers_face_extract_1.py:120-317, blazeface.py), first 15 face crops, ``cv2.resize(INTER_AREA, 224)`` +
+    ``cvtColor(RGB2BGR)`` exactly as ``face_blaze`` does (cvit_prediction.py:124-149).  Stored: the uint8 crops, per-clip
+    offsets, one clip's RAW variable-size crops (for the resize kernel), and the reference CViT class's logits / scores for
+    the "bn" and "decisive" synthetic state_dicts (chunks of <= 32 crops per clip, cvit_prediction.py:224-242)."""
+    import cv2
+    helpers = os.path.join(REF, "helpers")
+    sys.path.insert(0, helpers)
+    from blazeface import BlazeFace  # noqa: E402
+    from helpers_face_extract_1 import FaceExtractor  # noqa: E402
+    from helpers_read_video_1 import VideoReader  # noqa: E402
+    net = BlazeFace()
+    net.load_weights(os.path.join(helpers, "blazeface.pth"))
+    net.load_anchors(os.path.join(helpers, "anchors.npy"))
+    net.train(False)
+    reader = VideoReader(verbose=False)
+    extractor = FaceExtractor(lambda p: reader.read_random_frames(p, num_frames=15, seed=0), net)
+    clip_dir = os.path.join(REF, "sample__prediction_data")
+    names = sorted(f for f in os.listdir(clip_dir) if f.endswith(".mp4"))
+    crops, offsets, raw, raw_name = [], [0], [], None
+    for name in names:
+        frames = extractor.process_video(os.path.join(clip_dir, name))
+        got = []
+        for fd in frames:
+            for face in fd["faces"]:
+                if len(got) < 15 and face.size > 0:
+                    if raw_name in (None, name) and len(raw) < 15:
+                        raw_name = name
+                        raw.append(np.ascontiguousarray(face))
+                    f224 = cv2.resize(face, (224, 224), interpolation=cv2.INTER_AREA)
+                    got.append(cv2.cvtColor(f224, cv2.COLOR_RGB2BGR))
+        crops += got
+        offsets.append(offsets[-1] + len(got))
+        print("sample clip", name, "frames", len(frames), "crops kept", len(got),
+              "raw sizes", sorted({f.shape[:2] for fd in frames for f in fd["faces"]})[:4])
+    crops = np.stack(crops)
+    pred_sig, pre_process_prediction = reference_reduction_functions()
+    out = {"crops": crops, "offsets": np.array(offsets, np.int32), "clip_names": np.array(names),
+           "raw_clip": np.array(raw_name), "raw_hw": np.array([r.shape[:2] for r in raw], np.int32),
+           "raw_bytes": np.concatenate([r.reshape(-1) for r in raw])}
+    x = O.normalize_crops(torch.from_numpy(crops))
+    for variant in ("bn", "decisive"):
+        sd = W.make_state_dict(0, variant)
+        model = CViT(image_size=224, patch_size=7, num_classes=2, channels=512, dim=1024, depth=6, heads=8, mlp_dim=2048).eval()
+        model.load_state_dict(sd, strict=True)
+        logits, scores = [], []
+        with torch.no_grad():
+            for v in range(len(names)):
+                a, b = offsets[v], offsets[v + 1]
+                if b == a:
+                    scores.append(0.5)
+                    continue
+                lg = torch.cat([model(x[c:min(b, c + 32)]) for c in range(a, b, 32)])
+                logits.append(lg)
+                scores.append(float(pre_process_prediction(pred_sig(lg))))
+        out[f"logits_{variant}"] = torch.cat(logits).numpy()
+        out[f"scores_{variant}"] = np.array(scores, np.float32)
+        print("sample clips", variant, "scores", [round(s, 4) for s in scores])
+    path = os.path.join(ROOT, "tests", "golden", "sample_clip_crops.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) / 1e6, "MB")
+
+
+if __name__ == "__main__" and os.environ.get("FF_GOLDEN_SAMPLE_CLIPS", "1") == "1":
+    main_sample_clips()

@@ -1,0 +1,74 @@
+"""BASELINE configs[0]: the reference's own front-end on its own sample clips (tests/golden/sample_clip_crops.npz, made by
+oracle/make_golden.py::main_sample_clips with the reference VideoReader + FaceExtractor + BlazeFace + CViT classes)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fac_fake_b200 import weights as W
+from oracle import cvit_oracle as O
+from oracle import resize_oracle as R
+
+
+@pytest.fixture(scope="module")
+def clips(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sample_clip_crops.npz"))
+    raw, p = [], 0
+    for h, w in g["raw_hw"]:
+        raw.append(g["raw_bytes"][p:p + h * w * 3].reshape(h, w, 3))
+        p += h * w * 3
+    return g, raw
+
+
+def test_fixture_is_the_reference_workload(clips):
+    g, raw = clips
+    off = g["offsets"]
+    assert len(g["clip_names"]) == 8 and off[0] == 0 and off[-1] == g["crops"].shape[0]
+    assert all(0 < b - a <= 15 for a, b in zip(off[:-1], off[1:]))
+    assert g["crops"].dtype == np.uint8 and g["crops"].shape[1:] == (224, 224, 3)
+    # the stored crops of the first clip ARE cv2.resize(INTER_AREA) + RGB2BGR of the raw detections: the resize oracle
+    # reproduces them bit for bit from the raw crops
+    for i, r in enumerate(raw):
+        np.testing.assert_array_equal(R.crop_to_model_input(r), g["crops"][i])
+
+
+def test_oracle_matches_reference_class_on_real_crops(clips):
+    g, _ = clips
+    off = g["offsets"]
+    sd = W.make_state_dict(0, "bn")
+    torch.set_num_threads(os.cpu_count() or 4)
+    for v in (0, 5):                                     # two short clips keep the CPU suite quick
+        a, b = int(off[v]), int(off[v + 1])
+        score, lg = O.predict_from_crops(torch.from_numpy(g["crops"][a:b]), sd)
+        assert np.abs(lg.numpy() - g["logits_bn"][a:b]).max() <= 1e-4
+        assert abs(score - float(g["scores_bn"][v])) <= 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,scale", [("bn", 1.0), ("decisive", 60.0)])
+def test_engine_on_real_crops(clips, variant, scale):
+    """15 face crops per clip through ff_cvit_predict: logits within 2e-2 of the REFERENCE CLASS's own outputs (the
+    "decisive" weights scale the last layer, and the gate, by 60), per-clip scores within 1e-2 and identical decisions."""
+    from fac_fake_b200 import CViTEngine
+    g, raw = clips
+    sd = W.make_state_dict(0, variant)
+    eng = CViTEngine(max_crops=128).to("cuda:0").load_state_dict(sd)
+    crops = torch.from_numpy(g["crops"]).cuda()
+    off = g["offsets"].tolist()
+    scores, logits = eng.predict_videos(crops, off, return_logits=True)
+    assert np.abs(logits.cpu().numpy() - g[f"logits_{variant}"]).max() <= 2e-2 * scale
+    ref = g[f"scores_{variant}"]
+    got = scores.cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-2
+    compared = 0
+    for v in range(len(ref)):
+        if abs(float(ref[v]) - 0.5) > 5e-3:
+            assert O.real_or_fake(float(got[v])) == O.real_or_fake(float(ref[v])), (variant, v)
+            compared += 1
+    assert compared >= (8 if variant == "decisive" else 2)
+    # the whole device chain on the first clip: raw detections -> K0 (resize + swap) -> forward gives the same bits
+    dev_crops = eng.preprocess_crops([torch.from_numpy(np.ascontiguousarray(r)).cuda() for r in raw], swap_rb=True)
+    np.testing.assert_array_equal(dev_crops.cpu().numpy(), g["crops"][:len(raw)])
+    s2 = eng.predict_videos(dev_crops, [0, len(raw)])
+    assert float(s2[0]) == float(scores[0])
