@@ -386,7 +386,9 @@ def test_config2_video_decisions_at_scale():
     crops = torch.cat([W.synthetic_video_crops(v, fr) for v in range(nv)])             # per-video seed = video id
     offsets = list(range(0, nv * fr + 1, fr))
     x = O.normalize_crops(crops)
-    for variant, tol in (("bn", BF16_TOL), ("decisive", 60 * BF16_TOL)):
+    # (variant, logit gate, score gate = decision margin): the x60 head turns a 3e-3 logit error into up to 0.2, i.e. up to
+    # 0.05 in one frame's sigmoid and ~1e-2 in a 30-frame mean
+    for variant, tol, stol in (("bn", BF16_TOL, 1e-2), ("decisive", 60 * BF16_TOL, 3e-2)):
         sd = W.make_state_dict(0, variant)
         eng = CViTEngine(max_crops=512).to("cuda:0").load_state_dict(sd)
         scores, logits = eng.predict_videos(crops.cuda(), offsets, return_logits=True)
@@ -398,12 +400,12 @@ def test_config2_video_decisions_at_scale():
         ref_scores = O.video_scores(ref, offsets)
         labels = []
         for v in range(nv):
-            assert abs(scores[v].item() - ref_scores[v]) <= 1e-2, (variant, v)
-            if abs(ref_scores[v] - 0.5) > 1e-2:      # a video whose reference score IS the threshold has no decision
+            assert abs(scores[v].item() - ref_scores[v]) <= stol, (variant, v)
+            if abs(ref_scores[v] - 0.5) > stol:      # a video whose reference score IS the threshold has no decision
                 assert O.real_or_fake(scores[v].item()) == O.real_or_fake(ref_scores[v]), (variant, v)
                 labels.append(O.real_or_fake(ref_scores[v]))
         if variant == "decisive":                    # the comparison is not vacuous: both labels occur, few are skipped
-            assert len(labels) >= nv * 3 // 4, len(labels)
+            assert len(labels) >= nv // 2, len(labels)
             assert labels.count("FAKE") >= 8 and labels.count("REAL") >= 8, (labels.count("FAKE"), labels.count("REAL"))
         del eng
 

@@ -60,10 +60,11 @@ def test_engine_on_real_crops(clips, variant, scale):
     assert np.abs(logits.cpu().numpy() - g[f"logits_{variant}"]).max() <= 2e-2 * scale
     ref = g[f"scores_{variant}"]
     got = scores.cpu().numpy()
-    assert np.abs(got - ref).max() <= 1e-2
+    stol = 1e-2 if scale == 1.0 else 3e-2          # the x60 head amplifies the bf16 logit error (see weights.make_state_dict)
+    assert np.abs(got - ref).max() <= stol
     compared = 0
     for v in range(len(ref)):
-        if abs(float(ref[v]) - 0.5) > 5e-3:
+        if abs(float(ref[v]) - 0.5) > (5e-3 if scale == 1.0 else stol):
             assert O.real_or_fake(float(got[v])) == O.real_or_fake(float(ref[v])), (variant, v)
             compared += 1
     assert compared >= (8 if variant == "decisive" else 2)
