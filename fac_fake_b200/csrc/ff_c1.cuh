@@ -22,14 +22,15 @@ struct C1Args {
   float shift[32];
 };
 
-static __global__ void __launch_bounds__(128, 6)
+template <bool F16 = false>
+__global__ void __launch_bounds__(128, 6)
 conv1_f32_kernel(const __grid_constant__ C1Args a) {
   constexpr int HW = 224, TW = 8, TH = 16, PW = TW + 2, PH = TH + 2;
   constexpr int TILES_W = HW / TW, TILES_H = HW / TH, TILES = TILES_W * TILES_H;
   constexpr int NELEM = PH * PW * 3;
   __shared__ __align__(1024) uint8_t sA[128 * 128];
   __shared__ __align__(1024) uint8_t sB[32 * 128];
-  __shared__ __align__(16) __nv_bfloat16 s_in[PH * PW * 4];
+  __shared__ __align__(16) unsigned short s_in[PH * PW * 4];     // bf16 or fp16 bit patterns
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
 
@@ -52,7 +53,7 @@ conv1_f32_kernel(const __grid_constant__ C1Args a) {
   if (tid == 0) pdl_trigger();
   pdl_wait();                      // inputs may come from, and bufA may still be read by, the previous kernel
   const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-  constexpr uint32_t idesc = make_idesc_bf16(128, 32);
+  constexpr uint32_t idesc = make_idesc_16<F16>(128, 32);
 
   const int num_tiles = TILES * a.n_img;
   const int hl = tid >> 3, wl = tid & 7;
@@ -98,7 +99,7 @@ conv1_f32_kernel(const __grid_constant__ C1Args a) {
         decode(i, &py, &px, &c);
         const int gy = h0 - 1 + py, gx = w0 - 1 + px;
         const bool ok = gy >= 0 && gy < HW && gx >= 0 && gx < HW;
-        s_in[(py * PW + px) * 4 + c] = __float2bfloat16_rn(ok ? pf[j] : 0.0f);
+        s_in[(py * PW + px) * 4 + c] = static_cast<unsigned short>(pack16x2<F16>(ok ? pf[j] : 0.0f, 0.0f) & 0xffffu);
       }
     }
     __syncthreads();
@@ -137,7 +138,7 @@ conv1_f32_kernel(const __grid_constant__ C1Args a) {
     for (int c = 0; c < 32; c += 2) {
       const float x0 = fmaf(__uint_as_float(v[c]), a.scale[c], a.shift[c]);
       const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale[c + 1], a.shift[c + 1]);
-      p[c >> 1] = pack_bf16x2_relu(x0, x1);
+      p[c >> 1] = pack16x2_relu<F16>(x0, x1);
     }
     __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * HW + (h0 + hl)) * HW + (w0 + wl)) * 32;
     st_global_v8(o, p);
@@ -179,7 +180,8 @@ __device__ __forceinline__ uint64_t make_kmajor_desc_noswz(uint32_t smem_addr, u
   return d;
 }
 
-static __global__ void __launch_bounds__(128, 8)
+template <bool F16 = false>
+__global__ void __launch_bounds__(128, 8)
 conv1_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C1PairArgs a) {
   constexpr int HW = 224, TW = 16, TH = 16, PW = TW + 2, PH = TH + 2;
   constexpr int TILES_W = HW / TW, TILES_H = HW / TH, TILES = TILES_W * TILES_H;
@@ -215,7 +217,7 @@ conv1_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (tid == 0) pdl_trigger();
   pdl_wait();
   const uint32_t sin_addr = smem_u32(s_in), sB_addr = smem_u32(sB);
-  constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+  constexpr uint32_t idesc = make_idesc_16<F16>(128, 64);
   const int num_tiles = TILES * a.n_img;
   const int hl = tid >> 3, jl = tid & 7;
 
@@ -262,7 +264,7 @@ conv1_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const float v0 = ok ? fmaf(static_cast<float>(rp[0]), a.na[0], a.nb[0]) : 0.0f;
         const float v1 = ok ? fmaf(static_cast<float>(rp[1]), a.na[1], a.nb[1]) : 0.0f;
         const float v2 = ok ? fmaf(static_cast<float>(rp[2]), a.na[2], a.nb[2]) : 0.0f;
-        *reinterpret_cast<uint2*>(s_in + job_py[j] * SPITCH + job_px[j] * 8) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, 0.0f));
+        *reinterpret_cast<uint2*>(s_in + job_py[j] * SPITCH + job_px[j] * 8) = make_uint2(pack16x2<F16>(v0, v1), pack16x2<F16>(v2, 0.0f));
       }
     }
     fence_proxy_async_smem();
@@ -295,7 +297,7 @@ conv1_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int c = 0; c < 32; c += 2) {
         const float x0 = fmaf(__uint_as_float(v[c]), a.scale[c], a.shift[c]);
         const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale[c + 1], a.shift[c + 1]);
-        pk[c >> 1] = pack_bf16x2_relu(x0, x1);
+        pk[c >> 1] = pack16x2_relu<F16>(x0, x1);
       }
       st_global_v8(o + p * 32, pk);
       st_global_v8(o + p * 32 + 16, pk + 8);

@@ -66,7 +66,8 @@ struct C12Smem {
 };
 
 constexpr int C12_THREADS = 288;      // 8 worker warps + 1 MMA-issuing warp
-static __global__ void __launch_bounds__(C12_THREADS, 2)
+template <bool F16 = false>
+__global__ void __launch_bounds__(C12_THREADS, 2)
 c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ C12Args a) {
   using L = C12Smem;
   constexpr int HW = 224, TW = 16, TH = 14;
@@ -125,7 +126,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   }
   pdl_wait();
   const uint32_t sin_addr = base + L::SIN_OFF, b1_addr = base + L::B1_OFF, patch_addr = base + L::PATCH_OFF;
-  constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+  constexpr uint32_t idesc = make_idesc_16<F16>(128, 64);
   // base descriptors, built once: the issuing thread only adds compile-time offsets between MMAs (a single thread that
   // rebuilds descriptors between tcgen05.mma issues at ~104 cycles per MMA instead of 53, tools/umma_rate_test.cu)
   const uint64_t ad1 = make_kmajor_desc_noswz(sin_addr, 16, L::SIN_PITCH);
@@ -221,7 +222,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         const float v0 = ok ? fmaf(static_cast<float>(rp[0]), a.na[0], a.nb[0]) : 0.0f;
         const float v1 = ok ? fmaf(static_cast<float>(rp[1]), a.na[1], a.nb[1]) : 0.0f;
         const float v2 = ok ? fmaf(static_cast<float>(rp[2]), a.na[2], a.nb[2]) : 0.0f;
-        *reinterpret_cast<uint2*>(s_in + py * L::SIN_PITCH + px * 8) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, 0.0f));
+        *reinterpret_cast<uint2*>(s_in + py * L::SIN_PITCH + px * 8) = make_uint2(pack16x2<F16>(v0, v1), pack16x2<F16>(v2, 0.0f));
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
@@ -242,7 +243,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       for (int c = 0; c < 32; c += 2) {
         const float x0 = fmaf(__uint_as_float(v[c]), a.scale2[c], a.shift2[c]);
         const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale2[c + 1], a.shift2[c + 1]);
-        pk[c >> 1] = pack_bf16x2_relu(x0, x1);
+        pk[c >> 1] = pack16x2_relu<F16>(x0, x1);
       }
       if (hl < TH) {
         st_global_v8(o, pk);
@@ -281,7 +282,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           for (int c = 0; c < 32; c += 2) {
             const float x0 = fmaf(__uint_as_float(v[c]), a.scale1[c], a.shift1[c]);
             const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale1[c + 1], a.shift1[c + 1]);
-            pk[c >> 1] = inside ? pack_bf16x2_relu(x0, x1) : 0u;
+            pk[c >> 1] = inside ? pack16x2_relu<F16>(x0, x1) : 0u;
           }
           if (keep) {
 #pragma unroll
@@ -306,8 +307,9 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   if (warp == 8) { tcgen05_fence_after(); tmem_dealloc<256>(tmem); }
 }
 
+template <bool F16 = false>
 inline cudaError_t launch_c12(int grid, cudaStream_t st, const CUtensorMap& x, const CUtensorMap& w2, const C12Args& args) {
-  return ffh::launch_smem(c12_kernel, dim3(grid), dim3(C12_THREADS), C12Smem::TOTAL, st, true, x, w2, args);
+  return ffh::launch_smem(c12_kernel<F16>, dim3(grid), dim3(C12_THREADS), C12Smem::TOTAL, st, true, x, w2, args);
 }
 
 }  // namespace ff

@@ -283,7 +283,13 @@ int finalize(ff_cvit* h) {
           for (int u = 0; u < 256; ++u) {
             const std::vector<float> two = {std::fmaf((float)u, h->c1_na[c], h->c1_nb[c]), ((float)u / 255.0f - mean[c]) / sd[c]};
             const std::vector<bf16> r = to_act16(h, two);
-            if (memcmp(&r[0], &r[1], sizeof(bf16)) != 0)
+            unsigned short b0, b1;
+            memcpy(&b0, &r[0], 2);
+            memcpy(&b1, &r[1], 2);
+            // bf16: bit-identical for all 768 codes.  fp16 (11-bit mantissa): the two roundings of values 1e-7 apart may
+            // land on neighbouring codes; accept one unit in the last place (2^-11 relative, below the type's own rounding)
+            const int ulp = b0 > b1 ? b0 - b1 : b1 - b0;
+            if (ulp > (h->act_f16 ? 1 : 0))
               return fail(h, FF_ERR_STATE, "internal: single-FMA normalisation differs from (u/255-mean)/std at code %d channel %d", u, c);
           }
         }
@@ -502,13 +508,15 @@ int run_conv(ff_cvit* h, int li, int n_img, int img_off_out, int set, cudaStream
   a.out = conv_output_buffer(h, li, set);
   ProfScope ps(h, st, KC_TC_CONV + li - 1);
   cudaError_t e;
+  const bool f16 = h->act_f16;     // GGCA variant: fp16 activations / filters (same kernels, other operand-format template)
   if (L.ws2x) {
     a.tiles_w = p.hw / 16; a.tiles_h = p.hw / 16;
     a.out_blocked = (li == 4) ? 1 : 0;          // layer 5 feeds layer 6 (also a pair kernel); layer 6 writes plain NHWC
     const int tiles = a.tiles_w * a.tiles_h * n_img;
     const int g = std::min(2 * ((tiles + 1) / 2), h->num_sms & ~1);
-    e = p.pool ? launch_ws2x<true>(g, st, L.tmA_ws2x, L.tmW_ws2x, a, reinterpret_cast<const WsEpi&>(L.epi))
-               : launch_ws2x<false>(g, st, L.tmA_ws2x, L.tmW_ws2x, a, reinterpret_cast<const WsEpi&>(L.epi));
+    const WsEpi& epi = reinterpret_cast<const WsEpi&>(L.epi);
+    if (f16) e = p.pool ? launch_ws2x<true, true>(g, st, L.tmA_ws2x, L.tmW_ws2x, a, epi) : launch_ws2x<false, true>(g, st, L.tmA_ws2x, L.tmW_ws2x, a, epi);
+    else e = p.pool ? launch_ws2x<true>(g, st, L.tmA_ws2x, L.tmW_ws2x, a, epi) : launch_ws2x<false>(g, st, L.tmA_ws2x, L.tmW_ws2x, a, epi);
   } else if (L.ws2) {
     a.out_blocked = (li == 3) ? 1 : 0;          // layer 4 feeds the CTA-pair kernel of layer 5
     a.tiles_w = p.hw / 16; a.tiles_h = p.hw / 16;
@@ -516,9 +524,11 @@ int run_conv(ff_cvit* h, int li, int n_img, int img_off_out, int set, cudaStream
     const WsEpi& epi = reinterpret_cast<const WsEpi&>(L.epi);
     if (p.cout == 32) {
       const int g = std::min(tiles, h->num_sms * 2);
-      e = p.pool ? launch_ws2<64, true, 2>(g, st, L.tmA_ws2, L.tmW_ws2, a, epi) : launch_ws2<64, false, 2>(g, st, L.tmA_ws2, L.tmW_ws2, a, epi);
+      if (f16) e = p.pool ? launch_ws2<64, true, 2, true>(g, st, L.tmA_ws2, L.tmW_ws2, a, epi) : launch_ws2<64, false, 2, true>(g, st, L.tmA_ws2, L.tmW_ws2, a, epi);
+      else e = p.pool ? launch_ws2<64, true, 2>(g, st, L.tmA_ws2, L.tmW_ws2, a, epi) : launch_ws2<64, false, 2>(g, st, L.tmA_ws2, L.tmW_ws2, a, epi);
     } else {
-      e = launch_ws2<128, false, 4>(std::min(tiles, h->num_sms), st, L.tmA_ws2, L.tmW_ws2, a, epi);
+      e = f16 ? launch_ws2<128, false, 4, true>(std::min(tiles, h->num_sms), st, L.tmA_ws2, L.tmW_ws2, a, epi)
+              : launch_ws2<128, false, 4>(std::min(tiles, h->num_sms), st, L.tmA_ws2, L.tmW_ws2, a, epi);
     }
   } else {
     a.tiles_w = p.hw / L.bw; a.tiles_h = p.hw / L.bh;
@@ -530,11 +540,13 @@ int run_conv(ff_cvit* h, int li, int n_img, int img_off_out, int set, cudaStream
     if (L.pair2) {         // one item = two pixel tiles x one 256-channel tile on a CTA pair
       const int items = ((m_tiles + 1) / 2) * (p.cout / 256);
       const int g2 = std::min(2 * items, h->num_sms & ~1);
-      e = p.pool ? launch_ptc2<true>(g2, st, L.tmA, L.tmB_half, a) : launch_ptc2<false>(g2, st, L.tmA, L.tmB_half, a);
+      if (f16) e = p.pool ? launch_ptc2<true, true>(g2, st, L.tmA, L.tmB_half, a) : launch_ptc2<false, true>(g2, st, L.tmA, L.tmB_half, a);
+      else e = p.pool ? launch_ptc2<true>(g2, st, L.tmA, L.tmB_half, a) : launch_ptc2<false>(g2, st, L.tmA, L.tmB_half, a);
     } else {               // Cout = 128: two pixel sub-tiles share one 128-channel filter tile
       const int tiles = ((m_tiles + 1) / 2) * (p.cout / 128);
       const int g = std::min(tiles, h->num_sms);
-      e = p.pool ? launch_ptc<128, 2, true, 4>(g, st, L.tmA, L.tmB, a) : launch_ptc<128, 2, false, 4>(g, st, L.tmA, L.tmB, a);
+      if (f16) e = p.pool ? launch_ptc<128, 2, true, 4, true>(g, st, L.tmA, L.tmB, a) : launch_ptc<128, 2, false, 4, true>(g, st, L.tmA, L.tmB, a);
+      else e = p.pool ? launch_ptc<128, 2, true, 4>(g, st, L.tmA, L.tmB, a) : launch_ptc<128, 2, false, 4>(g, st, L.tmA, L.tmB, a);
     }
   }
   if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of conv layer %d failed: %s", li + 1, cudaGetErrorString(e));
@@ -597,7 +609,7 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
         }
         const ConvLayerDev& L2 = set ? h->conv_alt[1] : h->conv[1];
         const int grid = std::min(16 * 14 * ns, h->num_sms * 2);
-        cudaError_t e = launch_c12(grid, sst, tmX, L2.tmW_ws2, ca);
+        cudaError_t e = h->act_f16 ? launch_c12<true>(grid, sst, tmX, L2.tmW_ws2, ca) : launch_c12<false>(grid, sst, tmX, L2.tmW_ws2, ca);
         if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of the fused layer-1/2 kernel failed: %s", cudaGetErrorString(e));
         ++h->launches;
       } else {
@@ -610,12 +622,14 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
           ca.out = bufA; ca.w = h->c1_wp; ca.n_img = ns;
           for (int c = 0; c < 3; ++c) { ca.na[c] = h->c1_na[c]; ca.nb[c] = h->c1_nb[c]; }
           for (int o = 0; o < 32; ++o) { ca.scale[o] = h->c1_scale[o]; ca.shift[o] = h->c1_shift[o]; }
-          e = ffh::launch_k(conv1_pair_kernel, dim3(std::min(196 * ns, h->num_sms * 8)), dim3(128), 0, sst, true, tmX, ca);
+          e = h->act_f16 ? ffh::launch_k(conv1_pair_kernel<true>, dim3(std::min(196 * ns, h->num_sms * 8)), dim3(128), 0, sst, true, tmX, ca)
+                         : ffh::launch_k(conv1_pair_kernel<false>, dim3(std::min(196 * ns, h->num_sms * 8)), dim3(128), 0, sst, true, tmX, ca);
         } else {
           C1Args ca;
           ca.x = reinterpret_cast<const float*>(xin); ca.out = bufA; ca.w = h->c1_w; ca.n_img = ns;
           for (int o = 0; o < 32; ++o) { ca.scale[o] = h->c1_scale[o]; ca.shift[o] = h->c1_shift[o]; }
-          e = ffh::launch_k(conv1_f32_kernel, dim3(std::min(392 * ns, h->num_sms * 8)), dim3(128), 0, sst, true, ca);
+          e = h->act_f16 ? ffh::launch_k(conv1_f32_kernel<true>, dim3(std::min(392 * ns, h->num_sms * 8)), dim3(128), 0, sst, true, ca)
+                         : ffh::launch_k(conv1_f32_kernel<false>, dim3(std::min(392 * ns, h->num_sms * 8)), dim3(128), 0, sst, true, ca);
         }
         if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of conv1 failed: %s", cudaGetErrorString(e));
         ++h->launches;
@@ -864,6 +878,7 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
   h->device = device;
   h->compute = compute_dtype;
   h->kind = kind;
+  h->act_f16 = kind == 2;
   h->ln2_eps = kind == 2 ? 1e-6f : 1e-5f;
   h->cap = (max_crops + 31) / 32 * 32;
   h->rows_cap = (2 * h->cap + 127) / 128 * 128;

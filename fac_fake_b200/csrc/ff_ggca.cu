@@ -125,7 +125,7 @@ int finalize_ggca_extras(ff_cvit* h) {
 // x = x * ggca(x)  (cvit_GGCA_ADD_DEConv_RepBn8.py:447-448), in place on the [n,7,7,512] feature map
 int ggca_gate(ff_cvit* h, int n, cudaStream_t st) {
   ProfScope ps(h, st, KC_SMALL);
-  ggca_gate_kernel<<<n, 512, 0, st>>>(h->feat, h->ggca_w1, h->ggca_b1, h->ggca_w2, h->ggca_b2, n);
+  ggca_gate_kernel<<<n, 512, 0, st>>>(h->feat, h->ggca_w1, h->ggca_b1, h->ggca_w2, h->ggca_b2, n, h->act_f16 ? 1 : 0);
   FF_LAUNCH_CHECK(h, "ggca_gate");
   return FF_OK;
 }

@@ -38,7 +38,7 @@ struct Ptc2Smem {
   static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
 };
 
-template <bool POOL>
+template <bool POOL, bool F16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 ptc2_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   using L = Ptc2Smem;
@@ -128,7 +128,7 @@ ptc2_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      constexpr uint32_t idesc = make_idesc_16<F16>(256, BN);
       int s = 0, ph = 0, it = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
         const int acc = it & 1;
@@ -187,17 +187,13 @@ ptc2_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = 0; c < 32; c += 2) {
           const float x0 = fmaf(__uint_as_float(v[c]), ss[col0 + c0 + c], ss[512 + col0 + c0 + c]);
           const float x1 = fmaf(__uint_as_float(v[c + 1]), ss[col0 + c0 + c + 1], ss[512 + col0 + c0 + c + 1]);
-          p[c >> 1] = pack_bf16x2_relu(x0, x1);
+          p[c >> 1] = pack16x2_relu<F16>(x0, x1);
         }
         if (POOL) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            uint32_t o1 = __shfl_xor_sync(0xffffffffu, p[i], 1);
-            __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&p[i]), *reinterpret_cast<__nv_bfloat162*>(&o1));
-            uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
-            uint32_t o2 = __shfl_xor_sync(0xffffffffu, mu, BW);
-            m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o2));
-            p[i] = *reinterpret_cast<uint32_t*>(&m);
+            const uint32_t mu = max16x2<F16>(p[i], __shfl_xor_sync(0xffffffffu, p[i], 1));
+            p[i] = max16x2<F16>(mu, __shfl_xor_sync(0xffffffffu, mu, BW));
           }
         }
         if (writer) {
@@ -216,9 +212,9 @@ ptc2_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <bool POOL>
+template <bool POOL, bool F16 = false>
 inline cudaError_t launch_ptc2(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
-  return ffh::launch_smem(ptc2_conv_kernel<POOL>, dim3(grid), dim3(192), Ptc2Smem::TOTAL, st, true, a, b, args);
+  return ffh::launch_smem(ptc2_conv_kernel<POOL, F16>, dim3(grid), dim3(192), Ptc2Smem::TOTAL, st, true, a, b, args);
 }
 
 }  // namespace ff

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -139,6 +140,14 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | (static_cast<uint32_t>(N >> 3) << 17) // N
          | (static_cast<uint32_t>(M >> 4) << 24);
 }
+// Same shape with A = B = fp16 (format code 0 instead of 1 in both operand fields); D stays fp32.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return make_idesc_bf16(M, N) & ~((1u << 7) | (1u << 10));
+}
+// 16-bit activation type of a conv-stack kernel instance: bf16 (default) or fp16 (F16 = true: the GGCA / DEConv variant,
+// whose difference filters need the three extra mantissa bits — DESIGN.md §10).
+template <bool F16>
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N) { return F16 ? make_idesc_f16(M, N) : make_idesc_bf16(M, N); }
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -240,6 +249,33 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  if (F16) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  return pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2_relu(float lo, float hi) {
+  if (F16) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  return pack_bf16x2_relu(lo, hi);
+}
+// element-wise max of two packed pairs (the 2x2 max-pool of the epilogues)
+template <bool F16>
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b) {
+  if (F16) {
+    __half2 m = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&m);
+  }
+  __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&m);
 }
 // 32-byte (one full L2 sector) global store, sm_100+: STG.E.256.  ptr must be 32-byte aligned.
 __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* v) {

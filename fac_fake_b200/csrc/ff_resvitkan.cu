@@ -189,6 +189,7 @@ int rvk_launch_op(ff_cvit* h, const ff_cvit::RvkOp& op, int n, cudaStream_t st, 
   cudaError_t e;
   if (op.resid >= 0 && op.bn == 128) e = launch_rvk_conv2<128, 2, true>(grid, st, op.tmA, op.tmB, op.tmO, op.tmR, a);
   else if (op.resid >= 0) return fail(h, FF_ERR_STATE, "%s: residual epilogue needs cout >= 128", op.name.c_str());
+  else if (op.bn == 128 && h->act_f16) e = launch_rvk_conv2<128, 3, false, true>(grid, st, op.tmA, op.tmB, op.tmO, op.tmO, a);
   else if (op.bn == 128) e = launch_rvk_conv2<128, 3, false>(grid, st, op.tmA, op.tmB, op.tmO, op.tmO, a);
   else e = launch_rvk_conv2<64, 4, false>(grid, st, op.tmA, op.tmB, op.tmO, op.tmO, a);
   if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of %s failed: %s", op.name.c_str(), cudaGetErrorString(e));

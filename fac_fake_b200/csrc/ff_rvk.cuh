@@ -190,7 +190,7 @@ struct Rvk2Smem {
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-template <int BN, int STAGES, bool RESID>
+template <int BN, int STAGES, bool RESID, bool F16 = false>
 __global__ void __launch_bounds__(320, 1)
 rvk_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const TcArgs a) {
@@ -200,6 +200,7 @@ rvk_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int HALF = BN / 2, NCH = HALF / 32;
   constexpr int PANELS = BN / 64;
   static_assert(BN == 64 || BN == 128, "BN");
+  static_assert(!(RESID && F16), "the residual epilogue reads bf16");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -289,7 +290,7 @@ rvk_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = make_idesc_16<F16>(128, BN);
       int s = 0, ph = 0, it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -379,7 +380,7 @@ rvk_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 x0 = fmaxf(x0 + rf.x, 0.0f);
                 x1 = fmaxf(x1 + rf.y, 0.0f);
               }
-              p[e] = pack_bf16x2(x0, x1);
+              p[e] = pack16x2<F16>(x0, x1);
             }
             *sp = make_uint4(p[0], p[1], p[2], p[3]);
           }
@@ -419,10 +420,10 @@ inline void rvk_tile_geometry(int out_hw, int* bw, int* bh, int* bi) {
   else { *bw = 8; *bh = 8; *bi = 2; }                         // 7x7: one masked 8x8 box per image
 }
 
-template <int BN, int STAGES, bool RESID>
+template <int BN, int STAGES, bool RESID, bool F16 = false>
 inline cudaError_t launch_rvk_conv2(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o,
                                     const CUtensorMap& r, const TcArgs& args) {
-  return ffh::launch_smem(rvk_conv2_kernel<BN, STAGES, RESID>, dim3(grid), dim3(320), Rvk2Smem<BN, STAGES, RESID>::TOTAL, st, true, a, b, o, r, args);
+  return ffh::launch_smem(rvk_conv2_kernel<BN, STAGES, RESID, F16>, dim3(grid), dim3(320), Rvk2Smem<BN, STAGES, RESID>::TOTAL, st, true, a, b, o, r, args);
 }
 
 // ---- MaxPool2d(kernel 3, stride 2, pad 1) on NHWC bf16 with C = 64 (ResVitKan.py:194,232): [n,112,112,64] -> [n,56,56,64]
@@ -560,10 +561,11 @@ kan_l1_kernel(const float* __restrict__ part, const float* __restrict__ w1, cons
 //   att_h[c][h] = sigmoid(S(mean_w x) + S(max_w x)),  att_w[c][w] likewise over h,  S = shared 1x1 convs per group of
 //   128 channels: 128 -> 8 (+BN, folded on the host) -> ReLU -> 128;  out = x * (x * att_h * att_w).
 // One block per crop, one thread per channel; the 7x7 map of the thread's channel lives in registers, the pooled
-// vectors and the hidden units go through shared memory.  In place on the bf16 NHWC feature map [n][7][7][512].
+// vectors and the hidden units go through shared memory.  In place on the NHWC feature map [n][7][7][512]: read in the
+// conv stack's 16-bit type (fp16 when in_f16 != 0), written as bf16 — the patch-embedding GEMM that follows is bf16.
 static __global__ void __launch_bounds__(512)
 ggca_gate_kernel(__nv_bfloat16* __restrict__ feat, const float* __restrict__ w1, const float* __restrict__ b1,
-                 const float* __restrict__ w2, const float* __restrict__ b2, int n) {
+                 const float* __restrict__ w2, const float* __restrict__ b2, int n, int in_f16) {
   __shared__ float s_pool[7][512];             // pooled vectors of one type: [pos][channel]
   __shared__ float s_hid[28][4][8];            // [type*7 + pos][group][hidden unit]; type 0 = h_avg, 1 = h_max, 2 = w_avg, 3 = w_max
   const int b = blockIdx.x;
@@ -572,7 +574,7 @@ ggca_gate_kernel(__nv_bfloat16* __restrict__ feat, const float* __restrict__ w1,
   __nv_bfloat16* f = feat + static_cast<size_t>(b) * 49 * 512 + c;
   float x[49];
 #pragma unroll
-  for (int i = 0; i < 49; ++i) x[i] = __bfloat162float(f[i * 512]);
+  for (int i = 0; i < 49; ++i) x[i] = in_f16 ? __half2float(reinterpret_cast<const __half*>(f)[i * 512]) : __bfloat162float(f[i * 512]);
 #pragma unroll
   for (int type = 0; type < 4; ++type) {
 #pragma unroll

@@ -244,7 +244,7 @@ struct PtcSmem {
 // MSUB = 2 (used for Cout = 128): one CTA tile is two 128-pixel sub-tiles against the same 128 output channels,
 // i.e. 48 KB of operands per 8 MMAs — the same bytes-per-MMA-cycle ratio as the 128 x 256 tile (with a single
 // 128 x 128 tile the smem ring could not be refilled at the rate the N=128 MMAs drain it).
-template <int BN, int MSUB, bool POOL, int STAGES>
+template <int BN, int MSUB, bool POOL, int STAGES, bool F16 = false>
 __global__ void __launch_bounds__(192, 1)
 ptc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   using L = PtcSmem<BN, MSUB, STAGES>;
@@ -333,7 +333,7 @@ ptc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = make_idesc_16<F16>(128, BN);
       int s = 0, ph = 0, it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -396,17 +396,13 @@ ptc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int c = 0; c < 32; c += 2) {
             const float x0 = fmaf(__uint_as_float(v[c]), ss[col0 + c0 + c], ss[512 + col0 + c0 + c]);
             const float x1 = fmaf(__uint_as_float(v[c + 1]), ss[col0 + c0 + c + 1], ss[512 + col0 + c0 + c + 1]);
-            p[c >> 1] = pack_bf16x2_relu(x0, x1);
+            p[c >> 1] = pack16x2_relu<F16>(x0, x1);
           }
           if (POOL) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              uint32_t o1 = __shfl_xor_sync(0xffffffffu, p[i], 1);
-              __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&p[i]), *reinterpret_cast<__nv_bfloat162*>(&o1));
-              uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
-              uint32_t o2 = __shfl_xor_sync(0xffffffffu, mu, BW);
-              m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o2));
-              p[i] = *reinterpret_cast<uint32_t*>(&m);
+              const uint32_t mu = max16x2<F16>(p[i], __shfl_xor_sync(0xffffffffu, p[i], 1));
+              p[i] = max16x2<F16>(mu, __shfl_xor_sync(0xffffffffu, mu, BW));
             }
           }
           if (writer) {
@@ -433,9 +429,9 @@ inline cudaError_t launch_tc_gemm(dim3 grid, cudaStream_t st, const CUtensorMap&
   // (a deeper TMA ring - 8 stages - was measured slower: 192 KB of smem leaves one CTA per SM instead of two)
   return ffh::launch_smem(tc_gemm_kernel<BN, 4>, grid, dim3(192), TcSmem<128, BN, 4>::TOTAL, st, true, a, b, args);
 }
-template <int BN, int MSUB, bool POOL, int STAGES>
+template <int BN, int MSUB, bool POOL, int STAGES, bool F16 = false>
 inline cudaError_t launch_ptc(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
-  return ffh::launch_smem(ptc_conv_kernel<BN, MSUB, POOL, STAGES>, dim3(grid), dim3(192), PtcSmem<BN, MSUB, STAGES>::TOTAL, st, true, a, b, args);
+  return ffh::launch_smem(ptc_conv_kernel<BN, MSUB, POOL, STAGES, F16>, dim3(grid), dim3(192), PtcSmem<BN, MSUB, STAGES>::TOTAL, st, true, a, b, args);
 }
 
 }  // namespace ff

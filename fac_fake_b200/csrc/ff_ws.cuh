@@ -68,7 +68,7 @@ struct Ws2Smem {
 
 // Epilogue for one accumulator row = one pixel pair.  COUT = BN/2.  Processes the pair one pixel (COUT columns) at
 // a time to bound registers.  POOL: horizontal max = the two pixels of the pair, vertical max = lane ^ 8.
-template <int BN, bool POOL, bool ARRIVE_ON_LEADER = false>
+template <int BN, bool POOL, bool ARRIVE_ON_LEADER = false, bool F16 = false>
 __device__ __forceinline__ void ws2_epilogue(uint32_t taddr, const WsEpi& ss, const TcArgs& a, int pw0, int h0, int n, int r,
                                              int lane, uint32_t arrive_bar) {
   constexpr int COUT = BN / 2;
@@ -91,7 +91,7 @@ __device__ __forceinline__ void ws2_epilogue(uint32_t taddr, const WsEpi& ss, co
     for (int c = 0; c < COUT; c += 2) {
       const float x0 = fmaf(__uint_as_float(v[c]), ss.scale[c], ss.shift[c]);
       const float x1 = fmaf(__uint_as_float(v[c + 1]), ss.scale[c + 1], ss.shift[c + 1]);
-      pk[p][c >> 1] = pack_bf16x2_relu(x0, x1);
+      pk[p][c >> 1] = pack16x2_relu<F16>(x0, x1);
     }
     if (!POOL && n < a.n_img) {
       if (COUT == 64 && a.out_blocked) {
@@ -114,11 +114,8 @@ __device__ __forceinline__ void ws2_epilogue(uint32_t taddr, const WsEpi& ss, co
   if (POOL) {
 #pragma unroll
     for (int i = 0; i < COUT / 2; ++i) {
-      __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[0][i]), *reinterpret_cast<__nv_bfloat162*>(&pk[1][i]));
-      uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
-      uint32_t o2 = __shfl_xor_sync(0xffffffffu, mu, 8);
-      m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o2));
-      pk[0][i] = *reinterpret_cast<uint32_t*>(&m);
+      const uint32_t mu = max16x2<F16>(pk[0][i], pk[1][i]);
+      pk[0][i] = max16x2<F16>(mu, __shfl_xor_sync(0xffffffffu, mu, 8));
     }
     if ((lane & 8) == 0 && n < a.n_img) {
       const size_t pix = (static_cast<size_t>(a.img_off_out + n) * (a.H >> 1) + ((h0 + hl) >> 1)) * Wp + (pw0 + jl);
@@ -134,7 +131,7 @@ __device__ __forceinline__ void ws2_epilogue(uint32_t taddr, const WsEpi& ss, co
 // store is one 64-byte run.  ncu on the 4-warp epilogue (profiles/r02_ncu_stage12_before.txt): with 128 columns per
 // thread the N = 128 kernels kept the tensor pipe's shared-memory port only 48-50 % busy — the MMA thread waited for
 // TMEM to drain.  HALF is a template parameter so that the folded BN constants stay immediate constant-bank operands.
-template <int HALF, bool POOL, bool ARRIVE_ON_LEADER>
+template <int HALF, bool POOL, bool ARRIVE_ON_LEADER, bool F16>
 __device__ __forceinline__ void ws2_epilogue_c64_half(uint32_t taddr, const WsEpi& ss, const TcArgs& a, int pw0, int h0, int n, int r,
                                                       int lane, uint32_t arrive_bar) {
   constexpr int COUT = 64, C0 = 32 * HALF;
@@ -158,7 +155,7 @@ __device__ __forceinline__ void ws2_epilogue_c64_half(uint32_t taddr, const WsEp
     for (int c = 0; c < 32; c += 2) {
       const float x0 = fmaf(__uint_as_float(v[c]), ss.scale[C0 + c], ss.shift[C0 + c]);
       const float x1 = fmaf(__uint_as_float(v[c + 1]), ss.scale[C0 + c + 1], ss.shift[C0 + c + 1]);
-      pk[p][c >> 1] = pack_bf16x2_relu(x0, x1);
+      pk[p][c >> 1] = pack16x2_relu<F16>(x0, x1);
     }
     if (!POOL && n < a.n_img) {
       __nv_bfloat16* o;
@@ -176,11 +173,8 @@ __device__ __forceinline__ void ws2_epilogue_c64_half(uint32_t taddr, const WsEp
   if (POOL) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[0][i]), *reinterpret_cast<__nv_bfloat162*>(&pk[1][i]));
-      uint32_t mu = *reinterpret_cast<uint32_t*>(&m);
-      uint32_t o2 = __shfl_xor_sync(0xffffffffu, mu, 8);
-      m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o2));
-      pk[0][i] = *reinterpret_cast<uint32_t*>(&m);
+      const uint32_t mu = max16x2<F16>(pk[0][i], pk[1][i]);
+      pk[0][i] = max16x2<F16>(mu, __shfl_xor_sync(0xffffffffu, mu, 8));
     }
     if ((lane & 8) == 0 && n < a.n_img) {
       const size_t pix = (static_cast<size_t>(a.img_off_out + n) * (a.H >> 1) + ((h0 + hl) >> 1)) * Wp + (pw0 + jl);
@@ -192,7 +186,7 @@ __device__ __forceinline__ void ws2_epilogue_c64_half(uint32_t taddr, const WsEp
 }
 
 // TcArgs: H, W, tiles_w (= W/16), tiles_h (= H/16), n_img, img_off_out, out.  epi.scale/shift indexed by cout.
-template <int BN, bool POOL, int STAGES>
+template <int BN, bool POOL, int STAGES, bool F16 = false>
 __global__ void __launch_bounds__(BN == 128 ? 320 : 192, 1)
 ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs a,
                const __grid_constant__ WsEpi epi) {
@@ -255,7 +249,7 @@ ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = make_idesc_16<F16>(128, BN);
       const uint64_t bdesc0 = make_kmajor_desc<128>(base + L::W_OFF);
       mbar_wait(bar_w, 0);
       int it = 0;
@@ -298,10 +292,10 @@ ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN;
       if (BN == 128) {
-        if (warp < 6) ws2_epilogue_c64_half<0, POOL, false>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
-        else ws2_epilogue_c64_half<1, POOL, false>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
+        if (warp < 6) ws2_epilogue_c64_half<0, POOL, false, F16>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
+        else ws2_epilogue_c64_half<1, POOL, false, F16>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
       } else {
-        ws2_epilogue<BN, POOL>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
+        ws2_epilogue<BN, POOL, false, F16>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
       }
     }
   }
@@ -341,7 +335,7 @@ struct Ws2xSmem {
   static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
 };
 
-template <bool POOL>
+template <bool POOL, bool F16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs a,
                  const __grid_constant__ WsEpi epi) {
@@ -421,7 +415,7 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      constexpr uint32_t idesc = make_idesc_16<F16>(256, BN);
       int it = 0;
       for (int pi = cluster_id; pi < num_pairs; pi += num_clusters, ++it) {
         const int s = it & 1;
@@ -458,8 +452,8 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + acc * BN;
-      if (warp < 6) ws2_epilogue_c64_half<0, POOL, true>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
-      else ws2_epilogue_c64_half<1, POOL, true>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
+      if (warp < 6) ws2_epilogue_c64_half<0, POOL, true, F16>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
+      else ws2_epilogue_c64_half<1, POOL, true, F16>(taddr, epi, a, tw * 8, th * 16, n, r, lane, bar_tempty + 8 * acc);
     }
   }
 
@@ -472,13 +466,13 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 
-template <int BN, bool POOL, int STAGES>
+template <int BN, bool POOL, int STAGES, bool F16 = false>
 inline cudaError_t launch_ws2(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args, const WsEpi& epi) {
-  return ffh::launch_smem(ws2conv_kernel<BN, POOL, STAGES>, dim3(grid), dim3(BN == 128 ? 320 : 192), Ws2Smem<BN, STAGES>::TOTAL, st, true, a, w, args, epi);
+  return ffh::launch_smem(ws2conv_kernel<BN, POOL, STAGES, F16>, dim3(grid), dim3(BN == 128 ? 320 : 192), Ws2Smem<BN, STAGES>::TOTAL, st, true, a, w, args, epi);
 }
-template <bool POOL>
+template <bool POOL, bool F16 = false>
 inline cudaError_t launch_ws2x(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w, const TcArgs& args, const WsEpi& epi) {
-  return ffh::launch_smem(ws2x_conv_kernel<POOL>, dim3(grid), dim3(320), Ws2xSmem::TOTAL, st, true, a, w, args, epi);
+  return ffh::launch_smem(ws2x_conv_kernel<POOL, F16>, dim3(grid), dim3(320), Ws2xSmem::TOTAL, st, true, a, w, args, epi);
 }
 
 }  // namespace ff

@@ -12,10 +12,11 @@ from oracle import ggca_oracle as G
 
 pytestmark = pytest.mark.gpu
 
-# Per-frame logits vs the fp32 reference.  The CViT path meets 2e-2; this variant's difference convolutions amplify the
-# rounding of bf16 activations (see test_conv_chain_and_gate_against_fp32_oracle), measured 2.6e-2 on these weights.
-# Gate: 5e-2, and REAL/FAKE decisions must agree.  An fp16-activation path would restore 2e-2.
-BF16_TOL = 5e-2
+# Per-frame logits vs the fp32 reference: the north-star gate, 2e-2.  This variant's difference convolutions amplify the
+# rounding of their input activations (see test_conv_chain_and_gate_against_fp32_oracle); with bf16 activations the
+# logits landed 2.6e-2 away, so its conv stack runs on fp16 activations and filters (kind::f16 MMAs, same tensor rate,
+# three more mantissa bits).
+BF16_TOL = 2e-2
 
 
 def _engine(variant, max_crops=64):
@@ -39,7 +40,8 @@ STEP_OF_ENTRY = [1, 2, 3, 4, 5, 6, 7, 8, 26, 9, 10, 11, 12, 13, 14, 15, 16, 17]
 
 
 def _q(t):
-    return t.to(torch.bfloat16).to(torch.float32)
+    """round to the conv stack's 16-bit operand type of this variant (fp16)"""
+    return t.to(torch.float16).to(torch.float32)
 
 
 def _nchw(flat, n, c):
@@ -49,8 +51,8 @@ def _nchw(flat, n, c):
 
 @pytest.mark.parametrize("variant", ["default", "bn"])
 def test_each_conv_layer_in_isolation(variant, ggca_bn, ggca_default):
-    """Implementation check, one layer at a time: the oracle layer (fp32 accumulate, bf16-rounded folded kernel) applied
-    to the ENGINE's previous activation must reproduce the engine's next activation to one bf16 rounding.  Covers the
+    """Implementation check, one layer at a time: the oracle layer (fp32 accumulate, fp16-rounded folded kernel) applied
+    to the ENGINE's previous activation must reproduce the engine's next activation to one fp16 rounding.  Covers the
     DEConv folding done in C++ from the five branch tensors, the BN-less conv pair and every pool."""
     eng, sd = ggca_bn if variant == "bn" else ggca_default
     torch.set_num_threads(os.cpu_count() or 4)
@@ -77,17 +79,18 @@ def test_each_conv_layer_in_isolation(variant, ggca_bn, ggca_default):
             scale = ref.abs().max().item()
             err = (got - ref).abs().max().item()
             rel_rms = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
-            assert err <= 0.008 * scale and rel_rms <= 0.004, f"plan entry {entry} (step {step}): err {err} scale {scale} rms {rel_rms}"
+            assert err <= 0.002 * scale and rel_rms <= 0.001, f"plan entry {entry} (step {step}): err {err} scale {scale} rms {rel_rms}"
             prev = got
 
 
 @pytest.mark.parametrize("variant", ["default", "bn"])
 def test_conv_chain_and_gate_against_fp32_oracle(variant, ggca_bn, ggca_default):
     """End to end against the fp32 oracle.  The DEConv kernels are difference filters (centre tap = minus the sum of
-    the others): they pass the bf16 rounding noise of their input at full gain while attenuating the signal, so the
-    relative error of a bf16-activation pipeline grows at every DEConv — a CPU simulation of bf16 operands / fp32
-    accumulation on these weights gives 1.9 % rms after entry 7, 4.5 % after entry 12 and 9 % at the feature map.
-    The gates below are 1.5x that curve; the implementation itself is pinned by the isolation test above."""
+    the others): they pass the rounding noise of their input at full gain while attenuating the signal, so the relative
+    error of a 16-bit-activation pipeline grows at every DEConv — with bf16 activations a CPU simulation on these weights
+    gave 1.9 % rms after entry 7, 4.5 % after entry 12 and 9 % at the feature map (and the engine matched that curve).
+    With fp16 activations (8x finer) the gates below are that curve / 4; the implementation itself is pinned by the
+    isolation test above."""
     eng, sd = ggca_bn if variant == "bn" else ggca_default
     torch.set_num_threads(os.cpu_count() or 4)
     crops = W.synthetic_crops(3, seed=41)
@@ -100,15 +103,16 @@ def test_conv_chain_and_gate_against_fp32_oracle(variant, ggca_bn, ggca_default)
             got = eng.debug_activation(xg, step)
             assert got.numel() == ref.numel() and torch.isfinite(got).all(), entry
             rel_rms = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
-            gate = 0.03 if entry <= 10 else (0.07 if entry <= 14 else 0.15)
+            gate = 0.008 if entry <= 10 else (0.018 if entry <= 14 else 0.04)
+            print(f"ggca {variant} entry {entry}: rel rms {rel_rms:.5f}")
             assert rel_rms <= gate, f"plan entry {entry} (step {step}): relative rms error {rel_rms}"
         gated = (h * G.ggca(h, sd)).permute(0, 2, 3, 1).contiguous().flatten()
     got = eng.debug_activation(xg, 27)
-    assert ((got - gated).pow(2).mean().sqrt() / gated.pow(2).mean().sqrt()).item() <= 0.3     # the gate squares x
+    assert ((got - gated).pow(2).mean().sqrt() / gated.pow(2).mean().sqrt()).item() <= 0.08    # the gate squares x; bf16 store
 
 
 def test_gate_alone_on_engine_features(ggca_bn):
-    """GGCA kernel in isolation: oracle gate applied to the ENGINE's own (bf16) feature map."""
+    """GGCA kernel in isolation: oracle gate applied to the ENGINE's own (fp16) feature map; the result is stored as bf16."""
     eng, sd = ggca_bn
     crops = W.synthetic_crops(4, seed=42).cuda()
     f = eng.debug_activation(crops, 17).view(4, 7, 7, 512).permute(0, 3, 1, 2).contiguous()
