@@ -1149,7 +1149,8 @@ int64_t ff_cvit_debug_activation(ff_cvit_t* h, const void* x, int x_layout, cons
         e = cudaMalloc(&tmp, (size_t)tap.elems * sizeof(float));
         if (e == cudaSuccess) {
           const unsigned short* src = reinterpret_cast<const unsigned short*>(tap.ptr);
-          const int f16 = h->act_f16 ? 1 : 0;     // every 16-bit tap is a conv-stack activation
+          // every 16-bit tap is a conv-stack activation in the handle's 16-bit type, except the gated map (always bf16)
+          const int f16 = (h->act_f16 && stop_after != 27) ? 1 : 0;
           if (tap.blocked_hw)
             unblock_act16_to_f32_kernel<<<(unsigned)((tap.elems + 255) / 256), 256, 0, st>>>(src, tmp, n, tap.blocked_hw, f16);
           else

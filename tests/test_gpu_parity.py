@@ -400,6 +400,11 @@ def test_config2_video_decisions_at_scale():
         ref_scores = O.video_scores(ref, offsets)
         labels = []
         for v in range(nv):
+            # the reference rule `f if f > r else |1 - r|` (cvit_prediction.py:274-279) jumps where the two means cross:
+            # a video whose reference means are within the gate of each other has no well-defined score to compare
+            pm = torch.sigmoid(ref[offsets[v]:offsets[v + 1]]).mean(0)
+            if abs(float(pm[0] - pm[1])) <= stol:
+                continue
             assert abs(scores[v].item() - ref_scores[v]) <= stol, (variant, v)
             if abs(ref_scores[v] - 0.5) > stol:      # a video whose reference score IS the threshold has no decision
                 assert O.real_or_fake(scores[v].item()) == O.real_or_fake(ref_scores[v]), (variant, v)
