@@ -264,6 +264,18 @@ def main_s3d():
         np.savez_compressed(os.path.join(out_dir, f"s3d_{variant}.npz"), logits=logits.numpy(), layer_stats=np.array(stats),
                             feat_sample=h[0, :32, 0].numpy().astype(np.float32), seed_weights=0, seed_clips=4, b=2, t=16)
         print("s3d", variant, "logits", logits.flatten().tolist(), "last stats", stats[-1])
+        # BASELINE configs[4] geometry: 64-frame clips (t1 = 32, t2 = 16, t3 = 8 frames at the head)
+        x64 = clips_to_reference_input(W.synthetic_clips(1, 64, seed=5))
+        with torch.no_grad():
+            logits64 = model(x64)
+            stats64 = []
+            h = x64
+            for m in model.base:
+                h = m(h)
+                stats64.append([h.double().mean().item(), h.double().abs().mean().item(), h.double().pow(2).mean().sqrt().item()])
+        np.savez_compressed(os.path.join(out_dir, f"s3d_t64_{variant}.npz"), logits=logits64.numpy(), layer_stats=np.array(stats64),
+                            seed_weights=0, seed_clips=5, b=1, t=64)
+        print("s3d T=64", variant, "logits", logits64.flatten().tolist())
 
 
 if __name__ == "__main__" and os.environ.get("FF_GOLDEN_S3D", "1") == "1":

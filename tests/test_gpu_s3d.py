@@ -91,3 +91,34 @@ def test_video_score_and_errors(s3d_bn):
         S3DEngine(1, "yes")
     with pytest.raises(ValueError):
         S3DEngine(1, "no", frames_per_clip=8).to("cuda:0").load_state_dict(sd)    # head would see < 2 frames
+
+
+# ---- BASELINE configs[4] geometry: 64-frame clips (the benchmarked shape: t1 = 32, t2 = 16, t3 = 8 frames at the head,
+#      other temporal TMA extents than T = 16)
+@pytest.mark.parametrize("variant", ["default", "bn"])
+def test_t64_every_base_module_and_logits(golden_dir, variant):
+    from fac_fake_b200 import S3DEngine
+    T64 = 64
+    sd = W.make_s3d_state_dict(0, variant)
+    eng = S3DEngine(1, "no", frames_per_clip=T64, max_clips=2).to("cuda:0").load_state_dict(sd)
+    torch.set_num_threads(os.cpu_count() or 4)
+    g = np.load(os.path.join(golden_dir, f"s3d_t64_{variant}.npz"))
+    clips = W.synthetic_clips(int(g["b"]), T64, seed=int(g["seed_clips"]))
+    taps = {}
+    ref_logits = S.forward(_ref_input(clips), sd, taps)
+    assert np.abs(ref_logits.numpy() - g["logits"]).max() <= 1e-4            # oracle == reference class at T = 64
+    xg = clips.cuda()
+    for idx in range(16):
+        ref = taps[idx].permute(0, 2, 3, 4, 1).contiguous().flatten()
+        got = eng.debug_activation(xg, idx)
+        assert got.numel() == ref.numel(), idx
+        assert torch.isfinite(got).all(), idx
+        rel_rms = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+        assert rel_rms <= 0.004 * (idx + 2), f"base.{idx}: rms {rel_rms}"
+    got = eng(xg).cpu().numpy()
+    tol = 3e-2 * max(1.0, np.abs(g["logits"]).max())
+    assert np.isfinite(got).all() and np.abs(got - g["logits"]).max() <= tol
+    # two clips in one pass and the same clips one by one give the same bits
+    two = torch.cat([clips, W.synthetic_clips(1, T64, seed=6)]).cuda()
+    both = eng(two).cpu().numpy()
+    assert np.array_equal(both[0], got[0])
