@@ -41,7 +41,7 @@ SYMBOLS = [
     ("ff_blazeface_predict", _i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     ("ff_blazeface_nms", _i, [_vp, _vp, _i, C.c_float, C.c_float, _vp, _vp, _vp]),
     ("ff_blazeface_launch_count", _i64, [_vp]),
-    ("ff_s3d_create", _i, [C.POINTER(_vp), _i, _i, _i, _i]),
+    ("ff_s3d_create", _i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
     ("ff_s3d_destroy", None, [_vp]),
     ("ff_s3d_last_error", C.c_char_p, [_vp]),
     ("ff_s3d_load_weight", _i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i]),

@@ -10,7 +10,7 @@ namespace ff {
 
 // ---- input -> normalised bf16 NHWC4 [n,224,224,4] (channel 3 = 0), 8 bytes per pixel.
 // IN_KIND 2: uint8 NHWC with (x/255-mean)/std (cvit_prediction.py:41-45 convention); IN_KIND 0: fp32 NCHW as given.
-template <int IN_KIND>
+template <int IN_KIND, bool F16 = false>
 __global__ void __launch_bounds__(256)
 rvk_convert_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int n_img, float a0, float b0, float a1, float b1,
                    float a2, float b2) {
@@ -29,8 +29,8 @@ rvk_convert_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, 
       const float v0 = fmaf(static_cast<float>(by[3 * k]), a0, b0);
       const float v1 = fmaf(static_cast<float>(by[3 * k + 1]), a1, b1);
       const float v2 = fmaf(static_cast<float>(by[3 * k + 2]), a2, b2);
-      o[2 * k] = pack_bf16x2(v0, v1);
-      o[2 * k + 1] = pack_bf16x2(v2, 0.0f);
+      o[2 * k] = pack16x2<F16>(v0, v1);
+      o[2 * k + 1] = pack16x2<F16>(v2, 0.0f);
     }
     uint4* q = reinterpret_cast<uint4*>(out + i * 4);
     q[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -40,7 +40,7 @@ rvk_convert_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, 
     if (i >= total) return;
     const size_t img = i / (224 * 224), pix = i % (224 * 224);
     const float* p = reinterpret_cast<const float*>(x) + img * 3 * 224 * 224 + pix;
-    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(p[0], p[224 * 224]), pack_bf16x2(p[2 * 224 * 224], 0.0f));
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack16x2<F16>(p[0], p[224 * 224]), pack16x2<F16>(p[2 * 224 * 224], 0.0f));
   }
 }
 
@@ -276,10 +276,11 @@ rvk_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive_expect_tx(bar, L::STAGE_BYTES);
           const int tap = kb / a.kb_per_tap;
           const int cc = kb - tap * a.kb_per_tap;
-          // taps: 9 = 3x3 (pad 1); 1 = 1x1; 3 / 7 = a 1-D filter along the H coordinate (pad 1 / 3), which is the time
+          // taps: 9 = 3x3 (pad 1); 49 = 7x7 (pad 3); 1 = 1x1; 3 / 7 = a 1-D filter along the H coordinate (pad 1 / 3), which is the time
           // axis of the S3D temporal convolutions — their stride applies to that axis only
           int dx = 0, dy = 0, sdw = sd;
           if (a.taps == 9) { const int kh = tap / 3; dy = kh - 1; dx = tap - kh * 3 - 1; }
+          else if (a.taps == 49) { const int kh = tap / 7; dy = kh - 3; dx = tap - kh * 7 - 3; }      // 7x7, pad 3 (S3D SRM stem)
           else if (a.taps == 3 || a.taps == 7) { dy = tap - (a.taps >> 1); sdw = 1; }
 #pragma unroll
           for (int j = 0; j < MSUB; ++j) tma_load_4d(sa + j * 128 * 128, &tmA, bar, cc * BKE, sdw * w0[j] + dx, sd * h0[j] + dy, n0[j]);

@@ -1,5 +1,6 @@
 // ff_s3d.cuh — S3D clip classifier on the GPU (SURVEY.md §8f-2;
-// /root/reference/sx_exp_deepfakedetect-master/S3D/model.py:6-342, SRM_net == 'no').
+// /root/reference/sx_exp_deepfakedetect-master/S3D/model.py:6-342; both SRM_net == 'no' and the SRM high-pass front-end
+// SRM_net == 'yes', SRM/HPF.py:11-37).
 //
 // Activations are bf16 [clip][frame][h][w][channel] (NDHWC) with the TRUE channel count of each tensor.  Every
 // convolution is one launch of rvk_conv2_kernel (ff_rvk.cuh: persistent tcgen05 implicit GEMM, TMA-store epilogue):
@@ -85,6 +86,11 @@ struct ff_s3d {
   CUtensorMap tm_x4;
   float *fc_w = nullptr, *fc_b = nullptr;
   const bf16* final_feat = nullptr;              // [clip][t3][7][7][1024]
+  // SRM_net == 'yes' (model.py:38-39, SRM/HPF.py:11-37): x4 holds fp16, hpf = Conv3d(3,30,(1,5,5)) output [frames][224][224][32] bf16
+  int srm = 0;
+  bf16* hpf = nullptr;
+  bf16* hpf_w = nullptr;                         // pair-expanded 5x5 filter [5 kh][64 (p,co)][8 px x 4 ch] fp16 bits
+  CUtensorMap tm_x4_hpf;
   int64_t launches = 0;
 };
 
@@ -298,6 +304,7 @@ s3d_maxpool_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int n, i
 }
 
 // ---- fp32 NCDHW clip [b,3,T,224,224] (the reference module's input) -> bf16 NHWC4 frames
+template <bool F16>
 __global__ void __launch_bounds__(256)
 s3d_convert_ncdhw_kernel(const float* __restrict__ x, bf16* __restrict__ out, int n, int t) {
   const size_t total = (size_t)n * t * 224 * 224;
@@ -307,7 +314,122 @@ s3d_convert_ncdhw_kernel(const float* __restrict__ x, bf16* __restrict__ out, in
   const size_t f = (i / (224 * 224)) % t, b = i / ((size_t)224 * 224 * t);
   const float* p = x + ((b * 3) * t + f) * 224 * 224 + pix;
   const size_t cs = (size_t)t * 224 * 224;
-  reinterpret_cast<uint2*>(out)[i] = make_uint2(ff::pack_bf16x2(p[0], p[cs]), ff::pack_bf16x2(p[2 * cs], 0.0f));
+  reinterpret_cast<uint2*>(out)[i] = make_uint2(ff::pack16x2<F16>(p[0], p[cs]), ff::pack16x2<F16>(p[2 * cs], 0.0f));
+}
+
+// ---- SRM high-pass front-end: Conv3d(3, 30, (1,5,5), padding (0,2,2), bias=False) on every frame (SRM/HPF.py:11-37;
+// the 30 SRM residual filters arrive as `SRM.hpf.weight` of the checkpoint).  No im2col, same scheme as rvk_stem_kernel /
+// conv1_pair_kernel: the frame is fp16 NHWC4 (raw 0..255 are exact in fp16; the filter taps keep 11 mantissa bits, which
+// matters for residual filters whose taps sum to zero), TMA brings a 20-row x 24-pixel patch, non-swizzled K-major
+// descriptors read it as overlapping windows: accumulator row = a PAIR of output pixels (rows 16 bytes = 2 pixels
+// apart), K window of a filter row = the 8 pixels starting two left of the pair (64 bytes = two K=16 steps), N = 2 x 32
+// with the pair-expanded filter B[kh][(p,co)][(q,c)] = W[co][c][kh][q-p] (0 <= q-p <= 4).  Tile = 16 x 16 output pixels,
+// 10 tcgen05.mma (kind::f16, M=128, N=64) per tile.  Output bf16 NHWC with 32 channels (30 + 2 zero) = the A operand of
+// the 7x7 stem convolution that follows; no BatchNorm / activation here (HPF.forward returns the raw filter output).
+struct HpfArgs {
+  __nv_bfloat16* out;            // [frames,224,224,32] bf16
+  const __nv_bfloat16* w;        // [5 kh][64][32] fp16 bit patterns
+  int n_img;
+};
+constexpr int HPF_RING = 3, HPF_PROW = 192, HPF_PROWS = 20, HPF_PSLOT = 3840;
+constexpr int HPF_SMEM = HPF_RING * HPF_PSLOT + 5 * 4096 + 128;
+__global__ void __launch_bounds__(128, 4)
+s3d_hpf_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ HpfArgs a) {
+  constexpr int OW = 224, TW = 16, TH = 16, TILES_W = OW / TW, TILES_H = OW / TH, TILES = TILES_W * TILES_H;
+  constexpr int RING = HPF_RING, PROW = HPF_PROW, PBYTES = HPF_PROWS * HPF_PROW, PSLOT = HPF_PSLOT;
+  extern __shared__ uint8_t hpf_smem_raw[];
+  uint8_t* sm = hpf_smem_raw + ((128u - (smem_u32(hpf_smem_raw) & 127u)) & 127u);
+  uint8_t (*s_patch)[PSLOT] = reinterpret_cast<uint8_t (*)[PSLOT]>(sm);
+  uint8_t* sB = sm + RING * PSLOT;
+  __shared__ __align__(8) uint64_t s_bar[1 + RING];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar_mma = smem_u32(&s_bar[0]);
+  const uint32_t bar_raw = smem_u32(&s_bar[1]);
+  // filter -> core-matrix layout: (n, 16-byte chunk c) at ((n/8)*4 + c)*128 + (n%8)*16
+  for (int i = tid; i < 5 * 64 * 4; i += 128) {
+    const int kh = i / 256, rem = i % 256, n = rem >> 2, c = rem & 3;
+    *reinterpret_cast<uint4*>(sB + kh * 4096 + ((n >> 3) * 4 + c) * 128 + (n & 7) * 16) = reinterpret_cast<const uint4*>(a.w)[i];
+  }
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    mbar_init(bar_mma, 1);
+    for (int s = 0; s < RING; ++s) mbar_init(bar_raw + 8 * s, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<64>(smem_u32(&s_tmem));
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (tid == 0) pdl_trigger();
+  pdl_wait();
+  const uint32_t sB_addr = smem_u32(sB);
+  constexpr uint32_t idesc = make_idesc_f16(128, 64);
+  const int num_tiles = TILES * a.n_img;
+  const int hl = tid >> 3, jl = tid & 7;
+  auto issue = [&](int t, int slot) {
+    const int n = t / TILES;
+    const int rem = t - n * TILES;
+    const int th = rem / TILES_W, tw = rem - th * TILES_W;
+    mbar_arrive_expect_tx(bar_raw + 8 * slot, PBYTES);
+    // patch = pixels w0-2 .. w0+21 (96 fp16 = 192 B; the start is 16-byte aligned), rows h0-2 .. h0+17; zero fill = padding
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(&s_patch[slot][0])),
+        "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar_raw + 8 * slot), "r"((tw * TW - 2) * 4), "r"(th * TH - 2), "r"(n)
+        : "memory");
+  };
+  if (tid == 0)
+    for (int s = 0; s < RING - 1; ++s) {
+      const int t = blockIdx.x + s * gridDim.x;
+      if (t < num_tiles) issue(t, s);
+    }
+  int it = 0;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    const int n = t / TILES;
+    const int rem = t - n * TILES;
+    const int th = rem / TILES_W, tw = rem - th * TILES_W;
+    const int slot = it % RING;
+    if (tid == 0) {
+      const int tn = t + (RING - 1) * gridDim.x;        // slot (it+2)%3 was consumed by tile it-1 (all threads passed bar_mma)
+      if (tn < num_tiles) issue(tn, (it + RING - 1) % RING);
+      mbar_wait(bar_raw + 8 * slot, (it / RING) & 1);
+      tcgen05_fence_after();
+      const uint32_t patch = smem_u32(&s_patch[slot][0]);
+#pragma unroll
+      for (int kh = 0; kh < 5; ++kh) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          // A: row (h_l, pair j_l) at patch + (h_l + kh)*192 + j_l*16; K chunks 16 B apart; groups (h_l) one patch row apart
+          const uint64_t ad = make_kmajor_desc_noswz(patch + kh * PROW + 32 * j, 16, PROW);
+          const uint64_t bd = make_kmajor_desc_noswz(sB_addr + kh * 4096 + 2 * j * 128, 128, 512);
+          umma_bf16_ss(tmem, ad, bd, idesc, (kh > 0 || j > 0) ? 1u : 0u);
+        }
+      }
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, it & 1);
+    tcgen05_fence_after();
+    // thread = pixel pair (h_l, j_l): columns 0..31 = pixel 2j, 32..63 = pixel 2j+1 -> 128 contiguous bytes of NHWC32
+    __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * OW + (th * TH + hl)) * OW + (tw * TW + 2 * jl)) * 32;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + p * 32, v);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) pk[c >> 1] = pack_bf16x2(__uint_as_float(v[c]), __uint_as_float(v[c + 1]));
+      st_global_v8(o + p * 32, pk);
+      st_global_v8(o + p * 32 + 16, pk + 8);
+    }
+    tcgen05_fence_before();
+    __syncthreads();               // every thread has read TMEM and passed bar_mma before the next tile's MMAs / TMA reuse
+  }
+  __syncthreads();
+  if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<64>(tmem); }
 }
 
 // ---- head (model.py:40-46): avg_pool3d((2,7,7), stride 1) -> 1x1x1 conv fc (+bias) -> mean over time.  One block per clip.
@@ -353,7 +475,7 @@ int s3d_finalize(ff_s3d* h) {
   h->t3 = h->t2 / 2;                             // MaxPool3d(2, 2, 0)
   if (h->t3 < 2 || h->t3 > 8) return sfail(h, FF_ERR_BAD_ARG, "frames per clip must give 2..8 frames at the head, i.e. T = 16..71 (got %d from T = %d)", h->t3, T);
   // ---- stem spatial conv (1,7,7)/2, 3 -> 64: rvk_stem_kernel's [kh][cout][8 px][4 ch] layout, kw = px - 1
-  {
+  if (!h->srm) {
     const auto* w = sget(h, "base.0.conv_s.weight", {64, 3, 1, 7, 7});
     if (!w) return bad();
     std::vector<float> ws((size_t)7 * 64 * 32, 0.0f), scale, shift;
@@ -374,6 +496,58 @@ int s3d_finalize(ff_s3d* h) {
   }
   h->ops.clear();
   bf16 *A = h->buf[0], *B = h->buf[1], *t1b = h->buf[2], *t2b = h->buf[3], *t3b = h->buf[4];
+  if (h->srm) {
+    // ---- SRM front-end (model.py:38-39): HPF = Conv3d(3,30,(1,5,5)) -> s3d_hpf_kernel, then base.0.conv_s = (1,7,7)/2 on
+    //      30 channels as an implicit GEMM of the persistent kernel (49 taps, one half-filled 64-channel k-block per tap:
+    //      the hpf tensor has 32 channels, TMA zero-fills the rest of the box)
+    const auto* hw_ = sget(h, "SRM.hpf.weight", {30, 3, 1, 5, 5});
+    if (!hw_) return bad();
+    std::vector<float> wp((size_t)5 * 64 * 32, 0.0f);     // B[kh][(p,co)][(q,c)] = W[co][c][kh][q-p]
+    for (int kh = 0; kh < 5; ++kh)
+      for (int p = 0; p < 2; ++p)
+        for (int o = 0; o < 30; ++o)
+          for (int kw = 0; kw < 5; ++kw)
+            for (int c = 0; c < 3; ++c)
+              wp[((size_t)kh * 64 + p * 32 + o) * 32 + (p + kw) * 4 + c] = (*hw_)[(((size_t)o * 3 + c) * 5 + kh) * 5 + kw];
+    if ((rc = supload(h, &h->hpf_w, ffh::to_f16_bits(wp)))) return rc;
+    {
+      cuuint64_t dims[3] = {896, 224, (cuuint64_t)h->cap * T};
+      cuuint64_t strides[2] = {896 * 2, (cuuint64_t)224 * 896 * 2};
+      cuuint32_t box[3] = {96, (cuuint32_t)HPF_PROWS, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = ffh::encode_tiled()(&h->tm_x4_hpf, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, h->x4, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return sfail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(HPF input) failed: %d", (int)r);
+    }
+    const auto* w = sget(h, "base.0.conv_s.weight", {64, 30, 1, 7, 7});
+    if (!w) return bad();
+    ff_s3d::Op op;
+    op.kind = ff_s3d::OP_CONV;
+    op.name = "base.0.conv_s.weight";
+    op.mode = ff_s3d::SPATIAL; op.cin = 32; op.cout = 64; op.cout_pad = 64; op.bn = 64; op.taps = 49; op.stride = 2;
+    op.hw = 112; op.t_in = T; op.t_out = T;
+    std::vector<float> wr((size_t)64 * 49 * 64, 0.0f), scale, shift;
+    for (int o = 0; o < 64; ++o)
+      for (int ci = 0; ci < 30; ++ci)
+        for (int t = 0; t < 49; ++t) wr[((size_t)o * 49 + t) * 64 + ci] = (*w)[((size_t)o * 30 + ci) * 49 + t];
+    if ((rc = s3d_fold_bn(h, "base.0.bn_s", 64, 64, &scale, &shift))) return rc;
+    if ((rc = supload(h, &op.w, to_bf16(wr)))) return rc;
+    if ((rc = supload(h, &op.scale, scale))) return rc;
+    if ((rc = supload(h, &op.shift, shift))) return rc;
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)49 * 64, 64};
+      cuuint64_t strides[1] = {(cuuint64_t)49 * 64 * 2};
+      cuuint32_t box[2] = {64, 64};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = ffh::encode_tiled()(&op.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, op.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return sfail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(SRM stem filter) failed: %d", (int)r);
+    }
+    rvk_tile_geometry(112, &op.bw, &op.bh, &op.bi);
+    if ((rc = s3d_tmap(h, &op.tmA, h->hpf, 32, 32, 224, 224, h->cap * T, op.bw, op.bh, op.bi, 2, 2))) return rc;
+    if ((rc = s3d_tmap(h, &op.tmO, A, 64, 64, 112, 112, h->cap * T, op.bw, op.bh, op.bi))) return rc;
+    h->ops.push_back(op);
+  }
   auto mark = [&](int base_idx, const bf16* p, int c) { h->ops.back().tap_after = base_idx; h->ops.back().tap_ptr = p; h->ops.back().tap_c = c; };
   // base.0: the spatial half runs in rvk_stem_kernel (frames -> A [.,112,112,64]); temporal (7,1,1)/2 -> B
   if ((rc = s3d_add_conv(h, "base.0.conv_t.weight", "base.0.bn_t", ff_s3d::TEMPORAL, 64, 64, 7, 2, 112, T, A, B, 64, 0))) return rc;
@@ -475,15 +649,25 @@ int s3d_forward(ff_s3d* h, const void* x, int layout, int n, float* logits, cuda
                 int64_t* tap_elems) {
   const int T = h->frames, frames = n * T;
   const unsigned blocks = (unsigned)(((size_t)frames * 224 * 224 + 255) / 256);
-  if (layout == FF_X_NHWC_U8) rvk_convert_kernel<2><<<(blocks + 3) / 4, 256, 0, st>>>(x, h->x4, frames, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f);
-  else s3d_convert_ncdhw_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), h->x4, n, T);
-  S3_CUDA(h, cudaGetLastError());
-  S3_CUDA(h, ffh::ensure_dyn_smem(reinterpret_cast<const void*>(rvk_stem_kernel), RVK_STEM_SMEM));
-  RvkStemArgs sa;
-  sa.out = h->buf[0]; sa.w = h->stem_w; sa.n_img = frames;
-  for (int o = 0; o < 64; ++o) { sa.scale[o] = h->stem_scale[o]; sa.shift[o] = h->stem_shift[o]; }
-  cudaError_t e = launch_k(rvk_stem_kernel, dim3(std::min(14 * 7 * frames, h->num_sms * 4)), dim3(128), RVK_STEM_SMEM, st, false, h->tm_x4, sa);
-  if (e != cudaSuccess) return sfail(h, FF_ERR_CUDA, "launch of the stem failed: %s", cudaGetErrorString(e));
+  cudaError_t e;
+  if (h->srm) {
+    if (layout == FF_X_NHWC_U8) rvk_convert_kernel<2, true><<<(blocks + 3) / 4, 256, 0, st>>>(x, h->x4, frames, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f);
+    else s3d_convert_ncdhw_kernel<true><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), h->x4, n, T);
+    S3_CUDA(h, cudaGetLastError());
+    HpfArgs ha;
+    ha.out = h->hpf; ha.w = h->hpf_w; ha.n_img = frames;
+    e = ffh::launch_smem(s3d_hpf_kernel, dim3(std::min(14 * 14 * frames, h->num_sms * 4)), dim3(128), HPF_SMEM, st, false, h->tm_x4_hpf, ha);
+    if (e != cudaSuccess) return sfail(h, FF_ERR_CUDA, "launch of the SRM high-pass kernel failed: %s", cudaGetErrorString(e));
+  } else {
+    if (layout == FF_X_NHWC_U8) rvk_convert_kernel<2><<<(blocks + 3) / 4, 256, 0, st>>>(x, h->x4, frames, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f);
+    else s3d_convert_ncdhw_kernel<false><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), h->x4, n, T);
+    S3_CUDA(h, cudaGetLastError());
+    RvkStemArgs sa;
+    sa.out = h->buf[0]; sa.w = h->stem_w; sa.n_img = frames;
+    for (int o = 0; o < 64; ++o) { sa.scale[o] = h->stem_scale[o]; sa.shift[o] = h->stem_shift[o]; }
+    e = ffh::launch_smem(rvk_stem_kernel, dim3(std::min(14 * 7 * frames, h->num_sms * 4)), dim3(128), RVK_STEM_SMEM, st, false, h->tm_x4, sa);
+    if (e != cudaSuccess) return sfail(h, FF_ERR_CUDA, "launch of the stem failed: %s", cudaGetErrorString(e));
+  }
   h->launches += 2;
   for (const ff_s3d::Op& op : h->ops) {
     if (op.kind == ff_s3d::OP_CONV) {
@@ -519,8 +703,8 @@ int s3d_forward(ff_s3d* h, const void* x, int layout, int n, float* logits, cuda
 
 extern "C" {
 
-int ff_s3d_create(ff_s3d_t** out, int device, int max_clips, int frames_per_clip, int num_class) {
-  if (!out || max_clips <= 0 || frames_per_clip <= 0 || num_class <= 0 || num_class > 16) return sfail(nullptr, FF_ERR_BAD_ARG, "ff_s3d_create: bad arguments");
+int ff_s3d_create(ff_s3d_t** out, int device, int max_clips, int frames_per_clip, int num_class, int srm_net) {
+  if (!out || max_clips <= 0 || frames_per_clip <= 0 || num_class <= 0 || num_class > 16 || (srm_net != 0 && srm_net != 1)) return sfail(nullptr, FF_ERR_BAD_ARG, "ff_s3d_create: bad arguments");
   *out = nullptr;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -538,6 +722,7 @@ int ff_s3d_create(ff_s3d_t** out, int device, int max_clips, int frames_per_clip
   h->cap = max_clips;
   h->frames = frames_per_clip;
   h->num_class = num_class;
+  h->srm = srm_net;
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   // largest tensor: the stem's spatial output [clips*T][112][112][64]
   const size_t act = (size_t)max_clips * frames_per_clip * 112 * 112 * 64;
@@ -547,6 +732,7 @@ int ff_s3d_create(ff_s3d_t** out, int device, int max_clips, int frames_per_clip
     rc = salloc(h, &h->buf[i], i < 2 ? act : act / 2);
   }
   if (rc == FF_OK) rc = salloc(h, &h->x4, (size_t)max_clips * frames_per_clip * 224 * 224 * 4);
+  if (rc == FF_OK && srm_net) rc = salloc(h, &h->hpf, (size_t)max_clips * frames_per_clip * 224 * 224 * 32);
   if (rc != FF_OK) {
     g_s3d_create_error = h->err;
     ff_s3d_destroy(h);

@@ -3,7 +3,7 @@
 Used where the reference builds and calls its module
 (/root/reference/sx_exp_deepfakedetect-master/S3D/S3D-test.py:199-212,267-279):
 
-    model = S3DEngine(num_class=1, SRM_net='no', frames_per_clip=64)
+    model = S3DEngine(num_class=1, SRM_net='no', frames_per_clip=64)      # or SRM_net='yes'
     model.load_state_dict(state_dict)          # 'module.' prefixes of DataParallel checkpoints are stripped (:199-205)
     logits = model(video_faces)                # fp32 [b,3,T,224,224], raw 0..255 BGR  ->  [b, num_class]
 
@@ -22,8 +22,9 @@ from .engine import EngineError, _stream_ptr
 
 class S3DEngine:
     def __init__(self, num_class: int = 1, SRM_net: str = "no", *, frames_per_clip: int = 64, max_clips: int = 8):
-        if SRM_net != "no":
-            raise ValueError("S3DEngine implements the SRM_net == 'no' path (model.py:37-41); the SRM front-end is not built")
+        if SRM_net not in ("no", "yes"):
+            raise ValueError("SRM_net must be 'no' or 'yes' (model.py:10-14)")
+        self.SRM_net = SRM_net                      # 'yes': 30 SRM high-pass filters in front of `base` (model.py:38-39)
         self.num_class = int(num_class)
         self.frames_per_clip = int(frames_per_clip)
         self._max_clips = int(max_clips)
@@ -62,7 +63,8 @@ class S3DEngine:
             self._lib.ff_s3d_destroy(self._h)
             self._h = None
         h = C.c_void_p()
-        rc = self._lib.ff_s3d_create(C.byref(h), self._device.index, self._max_clips, self.frames_per_clip, self.num_class)
+        rc = self._lib.ff_s3d_create(C.byref(h), self._device.index, self._max_clips, self.frames_per_clip, self.num_class,
+                                     1 if self.SRM_net == "yes" else 0)
         if rc != L.FF_OK:
             msg = self._lib.ff_s3d_last_error(None)
             raise (ValueError if rc == L.FF_ERR_BAD_ARG else EngineError)(f"ff_s3d_create failed: {msg.decode() if msg else ''} (code {rc})")

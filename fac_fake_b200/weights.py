@@ -324,15 +324,23 @@ def _s3d_sep(gen, sd, p, cin, cout, k, variant, gain=1.0):
     _bn3(gen, sd, p + ".bn_t", cout, variant)
 
 
-def make_s3d_state_dict(seed: int = 0, variant: str = "default", num_class: int = 1) -> "OrderedDict[str, torch.Tensor]":
+def make_s3d_state_dict(seed: int = 0, variant: str = "default", num_class: int = 1, srm: bool = False) -> "OrderedDict[str, torch.Tensor]":
     """state_dict of the reference `S3D(num_class, 'no')` (model.py:6-48), key names as in the reference (incl. the
-    always-constructed, unused-without-SRM `SRM.hpf.weight`)."""
+    always-constructed, unused-without-SRM `SRM.hpf.weight`).  ``srm=True``: `S3D(num_class, 'yes')` — the first
+    convolution takes the 30 high-pass channels; `SRM.hpf.weight` is a set of zero-sum (high-pass) 5x5 kernels replicated
+    over the three input channels / 3, the structure of the reference's SRM bank (SRM/HPF.py:17-28)."""
     gen = torch.Generator(device="cpu")
     gen.manual_seed(5000011 * seed + 53)
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
-    sd["SRM.hpf.weight"] = torch.randn((30, 3, 1, 5, 5), generator=gen) * 0.1
-    # the input is raw 0..255 pixels: scale the first kernel so that activations are O(1) after the stem
-    _s3d_sep(gen, sd, "base.0", 3, 64, 7, variant, gain=1.0 / 128.0)
+    if srm:
+        k = torch.randn((30, 1, 1, 5, 5), generator=gen)
+        k = (k - k.mean(dim=(3, 4), keepdim=True)) * 0.25           # zero-sum residual filters
+        sd["SRM.hpf.weight"] = (k / 3.0).repeat(1, 3, 1, 1, 1).contiguous()
+        _s3d_sep(gen, sd, "base.0", 30, 64, 7, variant, gain=1.0 / 64.0)
+    else:
+        sd["SRM.hpf.weight"] = torch.randn((30, 3, 1, 5, 5), generator=gen) * 0.1
+        # the input is raw 0..255 pixels: scale the first kernel so that activations are O(1) after the stem
+        _s3d_sep(gen, sd, "base.0", 3, 64, 7, variant, gain=1.0 / 128.0)
     _s3d_basic(gen, sd, "base.2", 64, 64, variant)
     _s3d_sep(gen, sd, "base.3", 64, 192, 3, variant)
     for idx, name in S3D_BASE_MIXED.items():

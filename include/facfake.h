@@ -196,15 +196,18 @@ int64_t ff_blazeface_launch_count(const ff_blazeface_t* h);
 /* ---- S3D clip classifier ------------------------------------------------------------------
  * Replaces `S3D(num_class, 'no')` + `load_state_dict` + `model(video_faces)` of
  * sx_exp_deepfakedetect-master/S3D/S3D-test.py:210-212,199-205,267-272 (S3D/model.py:6-342).  Weight keys are that
- * module's state_dict names (`base.N...`, `fc.0.*`; `SRM.hpf.weight` and `num_batches_tracked` are accepted and
- * ignored: the SRM front-end is not implemented).  Clips are 224x224, `frames_per_clip` in 16..71.
+ * module's state_dict names (`base.N...`, `fc.0.*`, `SRM.hpf.weight`; `num_batches_tracked` is accepted and ignored).
+ * `srm_net` = 1 builds the SRM front-end of `S3D(num_class, 'yes')` (model.py:11-16,38-39; SRM/HPF.py:11-37): the 30
+ * high-pass residual filters `SRM.hpf.weight` [30,3,1,5,5] run before `base`, whose first convolution then takes 30
+ * channels (`base.0.conv_s.weight` [64,30,1,7,7]); with `srm_net` = 0 `SRM.hpf.weight` is accepted and ignored, as the
+ * reference module itself ignores it.  Clips are 224x224, `frames_per_clip` in 16..71.
  *   forward   x: DEVICE, x_layout FF_X_NCHW_F32 = fp32 [n,3,T,224,224] (the module's own input: raw 0..255 BGR,
  *             S3D-test.py:94-96) or FF_X_NHWC_U8 = uint8 [n,T,224,224,3] (frames as decoded);
  *             logits: DEVICE fp32 [n,num_class] (temporal mean of the per-window fc outputs, model.py:40-46).
  *   debug     activation after `base[base_index]` (0..15, model.py:17-34) as fp32 [n,T',H',W',C] on the HOST.
  * bf16 tensor-core path only.                                                                                   */
 typedef struct ff_s3d ff_s3d_t;
-int ff_s3d_create(ff_s3d_t** out, int device, int max_clips, int frames_per_clip, int num_class);
+int ff_s3d_create(ff_s3d_t** out, int device, int max_clips, int frames_per_clip, int num_class, int srm_net);
 void ff_s3d_destroy(ff_s3d_t* h);
 const char* ff_s3d_last_error(const ff_s3d_t* h); /* h may be NULL: last create() error */
 int ff_s3d_load_weight(ff_s3d_t* h, const char* key, const float* host_fp32, const int64_t* shape, int ndim);

@@ -351,3 +351,33 @@ def main_sample_clips():
 
 if __name__ == "__main__" and os.environ.get("FF_GOLDEN_SAMPLE_CLIPS", "1") == "1":
     main_sample_clips()
+
+
+def main_s3d_srm():
+    """tests/golden/s3d_srm.npz — the SRM front-end (`S3D(1, 'yes')`, model.py:11-16,38-39): logits of the reference class
+    for (a) the synthetic state_dict with synthetic zero-sum residual filters and (b) the same state_dict with the
+    reference's OWN 30 SRM filters (the value `HPF()` builds from SRM/srm_filter_kernel.py, stored here as data)."""
+    from oracle import s3d_oracle as S  # noqa: E402
+    S3D = load_reference_s3d_class()
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    model = S3D(1, "yes").eval()
+    real_bank = model.SRM.hpf.weight.detach().clone()
+    out = {"hpf_weight_reference": real_bank.numpy().astype(np.float32), "seed_weights": 0, "seed_clips": 8, "b": 1, "t": 16}
+    x = clips_to_reference_input(W.synthetic_clips(1, 16, seed=8))
+    for tag, bank in (("synthetic", None), ("reference_bank", real_bank)):
+        sd = W.make_s3d_state_dict(0, "bn", srm=True)
+        if bank is not None:
+            sd["SRM.hpf.weight"] = bank
+        model.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            logits = model(x)
+            h0 = model.SRM(x)
+        assert (S.forward(x, sd, srm=True) - logits).abs().max().item() <= 1e-4
+        out[f"logits_{tag}"] = logits.numpy()
+        out[f"hpf_rms_{tag}"] = np.float32(h0.double().pow(2).mean().sqrt().item())
+        print("s3d srm", tag, "logits", logits.flatten().tolist(), "hpf rms", float(out[f"hpf_rms_{tag}"]))
+    np.savez_compressed(os.path.join(out_dir, "s3d_srm.npz"), **out)
+
+
+if __name__ == "__main__" and os.environ.get("FF_GOLDEN_S3D_SRM", "1") == "1":
+    main_s3d_srm()

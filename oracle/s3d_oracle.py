@@ -1,7 +1,9 @@
 """CPU oracle for the S3D clip classifier — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-Restates /root/reference/sx_exp_deepfakedetect-master/S3D/model.py (SRM_net == 'no' path) in fp32 torch functional ops:
+Restates /root/reference/sx_exp_deepfakedetect-master/S3D/model.py in fp32 torch functional ops (SRM_net == 'no', and
+SRM_net == 'yes' = ``hpf`` below in front of ``features``):
 
+* ``hpf``                         SRM/HPF.py:11-37  Conv3d(3, 30, (1,5,5), padding (0,2,2), bias=False) with `SRM.hpf.weight`
 * ``basic_conv`` / ``sep_conv``   :50-82   Conv3d(bias=False) + BatchNorm3d(eps 1e-3, eval) + ReLU; separable = (1,k,k) then (k,1,1)
 * ``mixed``                       :84-342  four branches (1x1x1 | 1x1x1+sep3 | 1x1x1+sep3 | MaxPool3d(3,1,1)+1x1x1), channel concat
 * ``features``                    :17-34   stem sep7/2, pools, 9 Mixed blocks
@@ -75,9 +77,18 @@ def features(x, sd, taps=None, upto: int = 16):
     return x
 
 
-def forward(x, sd, taps=None):
-    """Raw clip [b,3,T,224,224] (0..255 BGR floats) -> logits [b, classes]."""
+def hpf(x, sd):
+    """SRM/HPF.py:30-35 (model.py:38-39): the 30 high-pass residual maps of every frame."""
+    return F.conv3d(x, sd["SRM.hpf.weight"], padding=(0, 2, 2))
+
+
+def forward(x, sd, taps=None, srm: bool = False):
+    """Raw clip [b,3,T,224,224] (0..255 BGR floats) -> logits [b, classes].  srm=True: S3D(num_class, 'yes')."""
     with torch.no_grad():
+        if srm:
+            x = hpf(x, sd)
+            if taps is not None:
+                taps["hpf"] = x
         y = features(x, sd, taps)
         y = F.avg_pool3d(y, (2, y.size(3), y.size(4)), stride=1)
         y = F.conv3d(y, sd["fc.0.weight"], sd["fc.0.bias"])

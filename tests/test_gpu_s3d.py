@@ -88,7 +88,7 @@ def test_video_score_and_errors(s3d_bn):
         eng(torch.zeros((1, 3, T + 1, 224, 224)))
     from fac_fake_b200 import S3DEngine
     with pytest.raises(ValueError):
-        S3DEngine(1, "yes")
+        S3DEngine(1, "maybe")
     with pytest.raises(ValueError):
         S3DEngine(1, "no", frames_per_clip=8).to("cuda:0").load_state_dict(sd)    # head would see < 2 frames
 
@@ -122,3 +122,34 @@ def test_t64_every_base_module_and_logits(golden_dir, variant):
     two = torch.cat([clips, W.synthetic_clips(1, T64, seed=6)]).cuda()
     both = eng(two).cpu().numpy()
     assert np.array_equal(both[0], got[0])
+
+
+# ---- SRM front-end: S3D(num_class, 'yes') — 30 high-pass residual filters in front of `base` (model.py:38-39, SRM/HPF.py)
+@pytest.mark.parametrize("bank", ["synthetic", "reference_bank"])
+def test_srm_front_end(golden_dir, bank):
+    from fac_fake_b200 import S3DEngine
+    g = np.load(os.path.join(golden_dir, "s3d_srm.npz"))
+    sd = W.make_s3d_state_dict(0, "bn", srm=True)
+    if bank == "reference_bank":                       # the reference's own 30 SRM filters (data fixture)
+        sd["SRM.hpf.weight"] = torch.from_numpy(g["hpf_weight_reference"])
+    eng = S3DEngine(1, "yes", frames_per_clip=int(g["t"]), max_clips=2).to("cuda:0").load_state_dict(sd)
+    torch.set_num_threads(os.cpu_count() or 4)
+    clips = W.synthetic_clips(int(g["b"]), int(g["t"]), seed=int(g["seed_clips"]))
+    taps = {}
+    ref_logits = S.forward(_ref_input(clips), sd, taps, srm=True)
+    assert np.abs(ref_logits.numpy() - g[f"logits_{bank}"]).max() <= 1e-4            # oracle == reference class
+    xg = clips.cuda()
+    for idx in range(16):
+        ref = taps[idx].permute(0, 2, 3, 4, 1).contiguous().flatten()
+        got = eng.debug_activation(xg, idx)
+        assert got.numel() == ref.numel() and torch.isfinite(got).all(), idx
+        rel_rms = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+        assert rel_rms <= 0.004 * (idx + 3), f"base.{idx}: rms {rel_rms}"
+    got = eng(xg).cpu().numpy()
+    tol = 3e-2 * max(1.0, np.abs(g[f"logits_{bank}"]).max())
+    assert np.isfinite(got).all() and np.abs(got - g[f"logits_{bank}"]).max() <= tol
+    got2 = eng(_ref_input(clips).cuda()).cpu().numpy()                                # fp32 NCDHW entry
+    assert np.abs(got2 - got).max() <= 1e-6
+    # a no-SRM checkpoint must not load into an SRM engine (first conv has 30 input channels)
+    with pytest.raises(ValueError):
+        S3DEngine(1, "yes", frames_per_clip=16).to("cuda:0").load_state_dict(W.make_s3d_state_dict(0, "bn"))
