@@ -250,7 +250,8 @@ def run_s3d(args):
     T, n = args.frames, args.clips
     warmup, steps = max(3, args.warmup), max(1, args.steps)
     peaks = read_peaks()
-    eng = S3DEngine(1, "no", frames_per_clip=T, max_clips=n).to(dev).load_state_dict(W.make_s3d_state_dict(0, "default"))
+    eng = S3DEngine(1, "yes" if args.srm else "no", frames_per_clip=T, max_clips=n).to(dev).load_state_dict(
+        W.make_s3d_state_dict(0, "default", srm=args.srm))
     ROT = 2                                           # 2 x 308 MB of uint8 clips > 126 MB L2; > 10 GB of activations per step
     host = [W.synthetic_clips(n, T, seed=200 + 13 * rank + i).pin_memory() for i in range(ROT)]
     devb = [b.to(dev) for b in host]
@@ -304,12 +305,14 @@ def run_s3d(args):
     e2e_value = world * n * e2e_steps / float(t.item())
     if rank == 0:
         fl = s3d_flops_per_clip(T)
+        if args.srm:      # HPF 3->30 5x5 on every frame, and the stem's spatial conv on 30 instead of 3 channels
+            fl += 2 * T * 224 * 224 * 30 * 75 + 2 * T * 112 * 112 * 64 * 27 * 49
         tfl = value / world * fl / 1e12
         out = {
             "metric": "S3D clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"S3D bf16 inference, synthetic {T}-frame 224x224 uint8 clips, {n} clips per GPU per step "
+            "config": {"workload": f"S3D{' + SRM front-end' if args.srm else ''} bf16 inference, synthetic {T}-frame 224x224 uint8 clips, {n} clips per GPU per step "
                                    f"(BASELINE configs[4]), random-init weights", "clips_per_step_per_gpu": n, "frames_per_clip": T,
                        "parallelism": f"clip-sharded x{world} (no data-path collective)",
                        "l2": "inputs rotate over 2 batches (616 MB > 126 MB L2); > 10 GB of activations per step sweep L2",
@@ -326,12 +329,12 @@ def run_s3d(args):
         if world == 1 and not args.no_cpu_baseline:
             from oracle import s3d_oracle as S
             torch.set_num_threads(os.cpu_count() or 1)
-            sd = W.make_s3d_state_dict(0, "default")
+            sd = W.make_s3d_state_dict(0, "default", srm=args.srm)
             x = W.synthetic_clips(1, T, seed=3).permute(0, 4, 1, 2, 3).contiguous().float()
-            S.forward(x, sd)
+            S.forward(x, sd, srm=args.srm)
             t0 = time.perf_counter()
             for _ in range(2):
-                S.forward(x, sd)
+                S.forward(x, sd, srm=args.srm)
             dt = (time.perf_counter() - t0) / 2
             out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"1 clip of {T} frames x 2 runs; torch {torch.__version__} fp32 CPU oracle", "seconds_per_run": dt}
@@ -504,6 +507,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=512, help="--model blazeface: 128x128 tiles per step")
     ap.add_argument("--clips", type=int, default=32, help="--model s3d: clips per GPU per step")
     ap.add_argument("--frames", type=int, default=64, help="--model s3d: frames per clip")
+    ap.add_argument("--srm", action="store_true", help="--model s3d: S3D(num_class, 'yes'), the SRM high-pass front-end")
     ap.add_argument("--model", default="cvit", choices=sorted(MODELS) + ["s3d", "blazeface"],
                     help="cvit = the north-star path (default, what the driver runs); resvitkan = SURVEY 8f-1 / BASELINE configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
