@@ -742,8 +742,8 @@ def main():
         gemm_ms = prof["tcgen05_gemm"][0]
         by_kernel["ff::xf_kernel + ff::tc_gemm_kernel (embed, encoder, head)"] = {
             "ms_per_step": gemm_ms / steps, "launches_per_step": prof["tcgen05_gemm"][1] / steps,
-            "tflops": (flops_per_crop - CONV_FLOPS) * n * steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0,
-            "flops_per_crop": flops_per_crop - CONV_FLOPS}
+            "tflops": (FLOPS_PER_CROP - CONV_FLOPS) * n * steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0,
+            "flops_per_crop": FLOPS_PER_CROP - CONV_FLOPS}
         by_kernel[list(by_kernel)[-1]]["frac"] = by_kernel[list(by_kernel)[-1]]["tflops"] / peak
         dom_name = max(fams, key=lambda k: by_kernel[k]["ms_per_step"])
         dom = by_kernel[dom_name]
