@@ -276,11 +276,13 @@ rvk_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive_expect_tx(bar, L::STAGE_BYTES);
           const int tap = kb / a.kb_per_tap;
           const int cc = kb - tap * a.kb_per_tap;
-          // taps: 9 = 3x3 (pad 1); 49 = 7x7 (pad 3); 1 = 1x1; 3 / 7 = a 1-D filter along the H coordinate (pad 1 / 3), which is the time
+          // taps: 9 = 3x3 (pad 1); 28 = 7x7/2 over pixel pairs; 1 = 1x1; 3 / 7 = a 1-D filter along the H coordinate (pad 1 / 3), which is the time
           // axis of the S3D temporal convolutions — their stride applies to that axis only
           int dx = 0, dy = 0, sdw = sd;
           if (a.taps == 9) { const int kh = tap / 3; dy = kh - 1; dx = tap - kh * 3 - 1; }
-          else if (a.taps == 49) { const int kh = tap / 7; dy = kh - 3; dx = tap - kh * 7 - 3; }      // 7x7, pad 3 (S3D SRM stem)
+          // 28 = 7x7 / stride 2 on a 32-channel tensor viewed as pixel PAIRS of 64 channels (S3D SRM stem): output pixel x
+          // reads input pixels 2x-3 .. 2x+3 = pairs x-2 (second half) .. x+1, so the pair axis has unit stride
+          else if (a.taps == 28) { const int kh = tap >> 2; dy = kh - 3; dx = (tap & 3) - 2; sdw = 1; }
           else if (a.taps == 3 || a.taps == 7) { dy = tap - (a.taps >> 1); sdw = 1; }
 #pragma unroll
           for (int j = 0; j < MSUB; ++j) tma_load_4d(sa + j * 128 * 128, &tmA, bar, cc * BKE, sdw * w0[j] + dx, sd * h0[j] + dy, n0[j]);

@@ -498,8 +498,10 @@ int s3d_finalize(ff_s3d* h) {
   bf16 *A = h->buf[0], *B = h->buf[1], *t1b = h->buf[2], *t2b = h->buf[3], *t3b = h->buf[4];
   if (h->srm) {
     // ---- SRM front-end (model.py:38-39): HPF = Conv3d(3,30,(1,5,5)) -> s3d_hpf_kernel, then base.0.conv_s = (1,7,7)/2 on
-    //      30 channels as an implicit GEMM of the persistent kernel (49 taps, one half-filled 64-channel k-block per tap:
-    //      the hpf tensor has 32 channels, TMA zero-fills the rest of the box)
+    //      30 channels as an implicit GEMM of the persistent kernel.  The hpf tensor has 32 channels per pixel, so two
+    //      horizontally adjacent pixels are one 64-channel k-block: output pixel x needs input pixels 2x-3 .. 2x+3 = the
+    //      pixel pairs x-2 (second pixel only) .. x+1 — 7 x 4 = 28 full k-blocks instead of 49 half-empty ones, and the
+    //      pair axis is read with unit stride (only the row axis keeps elementStride 2)
     const auto* hw_ = sget(h, "SRM.hpf.weight", {30, 3, 1, 5, 5});
     if (!hw_) return bad();
     std::vector<float> wp((size_t)5 * 64 * 32, 0.0f);     // B[kh][(p,co)][(q,c)] = W[co][c][kh][q-p]
@@ -524,19 +526,25 @@ int s3d_finalize(ff_s3d* h) {
     ff_s3d::Op op;
     op.kind = ff_s3d::OP_CONV;
     op.name = "base.0.conv_s.weight";
-    op.mode = ff_s3d::SPATIAL; op.cin = 32; op.cout = 64; op.cout_pad = 64; op.bn = 64; op.taps = 49; op.stride = 2;
+    op.mode = ff_s3d::SPATIAL; op.cin = 64; op.cout = 64; op.cout_pad = 64; op.bn = 64; op.taps = 28; op.stride = 2;
     op.hw = 112; op.t_in = T; op.t_out = T;
-    std::vector<float> wr((size_t)64 * 49 * 64, 0.0f), scale, shift;
+    std::vector<float> wr((size_t)64 * 28 * 64, 0.0f), scale, shift;      // [cout][kh][pair tap dp = -2..1][pixel of the pair][32 ch]
     for (int o = 0; o < 64; ++o)
-      for (int ci = 0; ci < 30; ++ci)
-        for (int t = 0; t < 49; ++t) wr[((size_t)o * 49 + t) * 64 + ci] = (*w)[((size_t)o * 30 + ci) * 49 + t];
+      for (int kh = 0; kh < 7; ++kh)
+        for (int dpi = 0; dpi < 4; ++dpi)
+          for (int half = 0; half < 2; ++half) {
+            const int kw = 2 * (dpi - 2) + half + 3;                         // input pixel 2x + 2dp + half = 2x - 3 + kw
+            if (kw < 0 || kw > 6) continue;
+            for (int ci = 0; ci < 30; ++ci)
+              wr[((size_t)o * 28 + kh * 4 + dpi) * 64 + half * 32 + ci] = (*w)[(((size_t)o * 30 + ci) * 7 + kh) * 7 + kw];
+          }
     if ((rc = s3d_fold_bn(h, "base.0.bn_s", 64, 64, &scale, &shift))) return rc;
     if ((rc = supload(h, &op.w, to_bf16(wr)))) return rc;
     if ((rc = supload(h, &op.scale, scale))) return rc;
     if ((rc = supload(h, &op.shift, shift))) return rc;
     {
-      cuuint64_t dims[2] = {(cuuint64_t)49 * 64, 64};
-      cuuint64_t strides[1] = {(cuuint64_t)49 * 64 * 2};
+      cuuint64_t dims[2] = {(cuuint64_t)28 * 64, 64};
+      cuuint64_t strides[1] = {(cuuint64_t)28 * 64 * 2};
       cuuint32_t box[2] = {64, 64};
       cuuint32_t estr[2] = {1, 1};
       CUresult r = ffh::encode_tiled()(&op.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, op.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -544,7 +552,7 @@ int s3d_finalize(ff_s3d* h) {
       if (r != CUDA_SUCCESS) return sfail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(SRM stem filter) failed: %d", (int)r);
     }
     rvk_tile_geometry(112, &op.bw, &op.bh, &op.bi);
-    if ((rc = s3d_tmap(h, &op.tmA, h->hpf, 32, 32, 224, 224, h->cap * T, op.bw, op.bh, op.bi, 2, 2))) return rc;
+    if ((rc = s3d_tmap(h, &op.tmA, h->hpf, 64, 64, 112, 224, h->cap * T, op.bw, op.bh, op.bi, 1, 2))) return rc;
     if ((rc = s3d_tmap(h, &op.tmO, A, 64, 64, 112, 112, h->cap * T, op.bw, op.bh, op.bi))) return rc;
     h->ops.push_back(op);
   }
