@@ -73,7 +73,8 @@ int ff_resvitkan_create(ff_cvit_t** out, int device, int max_crops);
  * `ggca.shared_conv.*`, `transformer.layers.L.1.fn.norm.norm1.*`; RepBN / schedule buffers and the unused
  * `Deconv.*` are accepted and ignored).  Every DEConv is folded into one 3x3 kernel at finalize (:337-351),
  * LinearNorm is its eval() form LayerNorm(eps 1e-6) (:22-47), the gate is x * GGCA(x) (:143-213,447-448).
- * bf16 path only.  Debug steps: 1..17 = the 17 pooled-plan conv layers (step 9 = features1.27), 26 = the extra
+ * Tensor-core path only; its conv stack runs on fp16 activations and filters (the difference filters need the extra
+ * mantissa bits to hold the 2e-2 logit gate), the shared embedding / encoder / head on bf16.  Debug steps: 1..17 = the 17 pooled-plan conv layers (step 9 = features1.27), 26 = the extra
  * BN-less Conv2d(128,128) features1.26 (between steps 8 and 9), 27 = gated feature map, 18..25 as for CViT. */
 int ff_cvit_ggca_create(ff_cvit_t** out, int device, int max_crops);
 void ff_cvit_destroy(ff_cvit_t* h);
@@ -153,7 +154,8 @@ int64_t ff_cvit_debug_activation(ff_cvit_t* h, const void* x, int x_layout, cons
                                  void* stream);
 /* Per-launch timing for bench.py's roofline: when enabled every kernel launch is bracketed by a CUDA event
  * pair on the launching stream.  ff_cvit_get_profile synchronises and returns accumulated milliseconds and
- * launch counts in 21 slots: 0 = conv1 (CUDA cores), 1..16 = tcgen05 conv of feature layer 2..17,
+ * launch counts in 21 slots: 0 = stand-alone conv1 (fp32 input / debug tap; on the uint8 path layers 1+2 are one kernel
+ * counted in slot 1), 1..16 = tcgen05 conv of feature layer 2..17,
  * 17 = patch-embedding GEMM, 18 = transformer GEMMs, 19 = head GEMM, 20 = small kernels.
  * enable == 2 selects a coarse mode that only times three phases per pass (slot 0 = feature layers 1-6,
  * slot 1 = feature layers 7-17, slot 2 = embedding + transformer + head) and leaves the launches PDL-chained.
