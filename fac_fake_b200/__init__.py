@@ -6,7 +6,8 @@ There is no CPU / PyTorch fallback: without the CUDA library the package raises.
 """
 from .engine import CViTEngine, CViTGGCAEngine, EngineError, ResVitKanEngine  # noqa: F401
 from .blazeface import BlazeFaceEngine  # noqa: F401
+from .face_extract import FaceExtractorEngine  # noqa: F401
 from .s3d import S3DEngine  # noqa: F401
 from . import weights  # noqa: F401
 
-__all__ = ["CViTEngine", "CViTGGCAEngine", "ResVitKanEngine", "BlazeFaceEngine", "S3DEngine", "EngineError", "weights"]
+__all__ = ["CViTEngine", "CViTGGCAEngine", "ResVitKanEngine", "BlazeFaceEngine", "FaceExtractorEngine", "S3DEngine", "EngineError", "weights"]

@@ -40,6 +40,8 @@ SYMBOLS = [
     ("ff_blazeface_finalize", _i, [_vp]),
     ("ff_blazeface_predict", _i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     ("ff_blazeface_nms", _i, [_vp, _vp, _i, C.c_float, C.c_float, _vp, _vp, _vp]),
+    ("ff_blazeface_tile_frames", _i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    ("ff_blazeface_frame_faces", _i, [_vp, _vp, _i, _i, _i, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
     ("ff_blazeface_launch_count", _i64, [_vp]),
     ("ff_s3d_create", _i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
     ("ff_s3d_destroy", None, [_vp]),

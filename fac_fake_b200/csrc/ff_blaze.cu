@@ -24,6 +24,7 @@
 
 #include "../../include/facfake.h"
 #include "ff_host.h"
+#include "ff_pre.cuh"
 
 namespace {
 
@@ -59,7 +60,7 @@ struct ff_blazeface {
   float *act_a = nullptr, *act_b = nullptr, *feat8 = nullptr;   // ping-pong activations; 16x16x88 map kept for the heads
   float *raw_boxes = nullptr, *raw_scores = nullptr;      // [cap][896][16], [cap][896]
   int64_t launches = 0;
-  int use_chains = 1;                                    // FF_BLAZE_CHAINS=0: one launch per BlazeBlock
+  void* tile_desc = nullptr; size_t tile_desc_cap = 0;    // crop descriptors of ff_blazeface_tile_frames
 };
 
 namespace {
@@ -486,6 +487,130 @@ blaze_nms_kernel(const float* __restrict__ det, int n, float min_score, float io
   if (lane == 0) counts[tile] = nfaces <= NMS_MAX_FACES ? nfaces : -1;
 }
 
+
+// ---- per-FRAME detections for the reference's FaceExtractor (helpers_face_extract_1.py:87-124): the dense detections
+// of a frame's T tiles (T = 3 overlapping square windows of a landscape frame, 1 of a portrait one, :185-205) are masked
+// (score >= min_score, blazeface.py:262), mapped back to frame coordinates — `_resize_detections` (:207-233: tile
+// coordinate * 128 * split/128) then `_untile_detections` (:235-272: + the window's x / y offset) — merged by the blending
+// NMS of blazeface.py:305-358 over the whole frame, and expanded by `_add_margin_to_detections` (:274-294: 20 % of the
+// box height, twice that above, clamped to the frame) into the integer crop rectangle `_crop_faces` cuts (:296-312).
+// One warp per frame; same candidate / face limits and the same fall-back contract (count = -1) as blaze_nms_kernel.
+struct FrameGeom {
+  int tiles;            // T
+  float scale;          // split_size / 128 as fp32 (what `detection * target - 0) * scale` multiplies by)
+  int x_step;           // window t starts at (t * x_step, 0): num_v = 1 in the reference
+  int frame_w, frame_h;
+};
+__global__ void __launch_bounds__(128)
+blaze_frame_nms_kernel(const float* __restrict__ det, int n_frames, FrameGeom g, float min_score, float iou_thr, float margin,
+                       float* __restrict__ faces, int* __restrict__ boxes, int* __restrict__ counts) {
+  __shared__ int s_idx[4][NMS_MAX_CAND];            // tile * 896 + anchor
+  __shared__ float s_score[4][NMS_MAX_CAND];
+  __shared__ float s_box[4][NMS_MAX_CAND][4];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int frame = blockIdx.x * 4 + w;
+  if (frame >= n_frames) return;
+  const float* d = det + (size_t)frame * g.tiles * NUM_ANCHORS * 17;
+  // coordinate k of detection (tile t, anchor a) in frame coordinates, in the reference's fp32 order of operations
+  auto coord = [&](int ta, int k) {
+    const int t = ta / NUM_ANCHORS;
+    const float v = __fmul_rn(__fsub_rn(__fmul_rn(d[(size_t)ta * 17 + k], 128.0f), 0.0f), g.scale);
+    const bool is_x = k < 4 ? (k & 1) : !(k & 1);           // box: ymin xmin ymax xmax; keypoints: x y pairs
+    return __fadd_rn(v, is_x ? (float)(t * g.x_step) : 0.0f);     // num_v = 1: every window starts at y = 0 (:248-268)
+  };
+  int ncand = 0;
+  for (int a0 = 0; a0 < g.tiles * NUM_ANCHORS; a0 += 32) {
+    const int a = a0 + lane;
+    const float sc = a < g.tiles * NUM_ANCHORS ? d[(size_t)a * 17 + 16] : -1.0f;
+    const bool keep = sc >= min_score;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    const int pos = ncand + __popc(m & ((1u << lane) - 1u));
+    if (keep && pos < NMS_MAX_CAND) { s_idx[w][pos] = a; s_score[w][pos] = sc; }
+    ncand += __popc(m);
+  }
+  __syncwarp();
+  if (ncand > NMS_MAX_CAND) { if (lane == 0) counts[frame] = -1; return; }
+  int my_rank[2] = {-1, -1};
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h;
+    if (i < ncand) {
+      const float si = s_score[w][i];
+      int r = 0;
+      for (int j = 0; j < ncand; ++j) { const float sj = s_score[w][j]; r += (sj > si || (sj == si && j < i)) ? 1 : 0; }
+      my_rank[h] = r;
+    }
+  }
+  int my_anchor[2]; float my_sc[2];
+  for (int h = 0; h < 2; ++h) { const int i = lane + 32 * h; my_anchor[h] = i < ncand ? s_idx[w][i] : 0; my_sc[h] = i < ncand ? s_score[w][i] : 0.f; }
+  __syncwarp();
+  for (int h = 0; h < 2; ++h)
+    if (my_rank[h] >= 0) { s_idx[w][my_rank[h]] = my_anchor[h]; s_score[w][my_rank[h]] = my_sc[h]; }
+  __syncwarp();
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h;
+    if (i < ncand)
+      for (int k = 0; k < 4; ++k) s_box[w][i][k] = coord(s_idx[w][i], k);
+  }
+  __syncwarp();
+  unsigned alive[2] = {ncand >= 32 ? 0xffffffffu : ((1u << ncand) - 1u), ncand > 32 ? ((ncand >= 64) ? 0xffffffffu : ((1u << (ncand - 32)) - 1u)) : 0u};
+  int nfaces = 0;
+  float* out = faces + (size_t)frame * NMS_MAX_FACES * 17;
+  int* bout = boxes + (size_t)frame * NMS_MAX_FACES * 4;
+  while ((alive[0] | alive[1]) != 0u) {
+    const int first = alive[0] ? __ffs(alive[0]) - 1 : 32 + __ffs(alive[1]) - 1;
+    const float fy0 = s_box[w][first][0], fx0 = s_box[w][first][1], fy1 = s_box[w][first][2], fx1 = s_box[w][first][3];
+    const float farea = (fy1 - fy0) * (fx1 - fx0);
+    unsigned ov[2];
+    for (int h = 0; h < 2; ++h) {
+      const int i = lane + 32 * h;
+      bool o = false;
+      if (i < ncand && ((alive[h] >> lane) & 1u)) {
+        const float ih = fmaxf(fminf(fy1, s_box[w][i][2]) - fmaxf(fy0, s_box[w][i][0]), 0.f);
+        const float iw = fmaxf(fminf(fx1, s_box[w][i][3]) - fmaxf(fx0, s_box[w][i][1]), 0.f);
+        const float inter = ih * iw;
+        const float area = (s_box[w][i][2] - s_box[w][i][0]) * (s_box[w][i][3] - s_box[w][i][1]);
+        o = inter / (farea + area - inter) > iou_thr;
+      }
+      ov[h] = __ballot_sync(0xffffffffu, o);
+    }
+    ov[first >> 5] |= 1u << (first & 31);
+    const int cnt = __popc(ov[0]) + __popc(ov[1]);
+    if (nfaces < NMS_MAX_FACES) {
+      float val = 0.f;
+      if (lane < 17) {
+        if (cnt > 1) {
+          float num = 0.f, tot = 0.f;
+          for (int h = 0; h < 2; ++h)
+            for (unsigned m = ov[h]; m; m &= m - 1) {
+              const int i = 32 * h + __ffs(m) - 1;
+              const float sc = s_score[w][i];
+              tot += sc;
+              if (lane < 16) num += coord(s_idx[w][i], lane) * sc;
+            }
+          val = lane < 16 ? num / tot : tot / (float)cnt;
+        } else {
+          val = lane < 16 ? coord(s_idx[w][first], lane) : s_score[w][first];
+        }
+        out[nfaces * 17 + lane] = val;
+      }
+      // margin + integer crop rectangle (ymin, xmin, ymax, xmax): lanes 0..3 hold the merged box
+      const float ymin = __shfl_sync(0xffffffffu, val, 0), xmin = __shfl_sync(0xffffffffu, val, 1);
+      const float ymax = __shfl_sync(0xffffffffu, val, 2), xmax = __shfl_sync(0xffffffffu, val, 3);
+      if (lane == 0) {
+        const float off = rintf(__fmul_rn(margin, __fsub_rn(ymax, ymin)));          // torch.round = half to even
+        bout[nfaces * 4 + 0] = (int)fmaxf(__fsub_rn(ymin, __fmul_rn(off, 2.0f)), 0.0f);
+        bout[nfaces * 4 + 1] = (int)fmaxf(__fsub_rn(xmin, off), 0.0f);
+        bout[nfaces * 4 + 2] = (int)fminf(__fadd_rn(ymax, off), (float)g.frame_h);
+        bout[nfaces * 4 + 3] = (int)fminf(__fadd_rn(xmax, off), (float)g.frame_w);
+      }
+    }
+    ++nfaces;
+    alive[0] &= ~ov[0];
+    alive[1] &= ~ov[1];
+  }
+  if (lane == 0) counts[frame] = nfaces <= NMS_MAX_FACES ? nfaces : -1;
+}
+
 template <typename T>
 int balloc(ff_blazeface* h, T** p, size_t count) {
   void* q = nullptr;
@@ -590,7 +715,7 @@ int bforward(ff_blazeface* h, const uint8_t* tiles, int n, float* det, cudaStrea
     return ch;
   };
   for (int i = 0; i < 16; ++i) {
-    if (h->use_chains && i == 6) {             // blocks 6..10: the whole 16x16 stage -> feat8
+    if (i == 6) {             // blocks 6..10: the whole 16x16 stage -> feat8
       constexpr int SM = (256 * 89 + 88 * 260 + 4) * 4;
       BZ_CUDA(h, ffh::ensure_dyn_smem(reinterpret_cast<const void*>(blaze_chain_kernel<16, 88, 512>), SM));
       blaze_chain_kernel<16, 88, 512><<<n, 512, SM, st>>>(cur, h->feat8, make_chain(6, 5));
@@ -600,7 +725,7 @@ int bforward(ff_blazeface* h, const uint8_t* tiles, int n, float* det, cudaStrea
       i = 10;
       continue;
     }
-    if (h->use_chains && i == 12) {            // blocks 12..15: the 8x8 stage after the stride-2 block 11
+    if (i == 12) {            // blocks 12..15: the 8x8 stage after the stride-2 block 11
       constexpr int SM = (64 * 97 + 96 * 68 + 4) * 4;
       BZ_CUDA(h, ffh::ensure_dyn_smem(reinterpret_cast<const void*>(blaze_chain_kernel<8, 96, 256>), SM));
       blaze_chain_kernel<8, 96, 256><<<n, 256, SM, st>>>(cur, nxt, make_chain(12, 4));
@@ -653,7 +778,6 @@ int ff_blazeface_create(ff_blazeface_t** out, int device, int max_tiles) {
   ff_blazeface* h = new ff_blazeface();
   h->device = device;
   h->cap = max_tiles;
-  if (const char* v = getenv("FF_BLAZE_CHAINS")) h->use_chains = atoi(v);
   int rc = FF_OK;
   do {
     if ((rc = balloc(h, &h->act_a, (size_t)h->cap * ACT_ELEMS))) break;
@@ -677,6 +801,7 @@ void ff_blazeface_destroy(ff_blazeface_t* h) {
     ffh::DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
+    if (h->tile_desc) cudaFree(h->tile_desc);
   }
   delete h;
 }
@@ -730,6 +855,55 @@ int ff_blazeface_nms(ff_blazeface_t* h, const float* detections, int n, float mi
   ffh::DeviceGuard guard(h->device);
   if (n == 0) return FF_OK;
   blaze_nms_kernel<<<(n + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(detections, n, min_score, iou_threshold, faces, counts);
+  BZ_CUDA(h, cudaGetLastError());
+  ++h->launches;
+  return FF_OK;
+}
+
+int ff_blazeface_tile_frames(ff_blazeface_t* h, const uint8_t* frames, int n_frames, int frame_h, int frame_w, uint8_t* tiles,
+                             void* stream) {
+  if (!h || n_frames < 0 || frame_h <= 0 || frame_w <= 0 || (n_frames > 0 && (!frames || !tiles)))
+    return bfail(h, FF_ERR_BAD_ARG, "ff_blazeface_tile_frames: bad arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  ffh::DeviceGuard guard(h->device);
+  if (n_frames == 0) return FF_OK;
+  // helpers_face_extract_1.py:185-205: square windows of side min(H, W); three of them, (W - side) / 2 apart, for a
+  // landscape frame, one for a portrait frame; each resized to 128 x 128 with cv2.INTER_AREA
+  const int split = std::min(frame_h, frame_w), x_step = (frame_w - split) / 2, T = frame_w > frame_h ? 3 : 1;
+  const int n = n_frames * T;
+  std::vector<ff::CropDesc> d(n);
+  for (int f = 0; f < n_frames; ++f)
+    for (int t = 0; t < T; ++t)
+      d[f * T + t] = ff::make_crop_desc(frames + ((size_t)f * frame_h * frame_w + (size_t)t * x_step) * 3, split, split, frame_w * 3, 128);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((size_t)n > h->tile_desc_cap) {
+    if (h->tile_desc) cudaFree(h->tile_desc);
+    h->tile_desc = nullptr; h->tile_desc_cap = 0;
+    BZ_CUDA(h, cudaMalloc(&h->tile_desc, sizeof(ff::CropDesc) * n));
+    h->tile_desc_cap = n;
+  }
+  BZ_CUDA(h, cudaMemcpyAsync(h->tile_desc, d.data(), sizeof(ff::CropDesc) * n, cudaMemcpyHostToDevice, st));
+  ff::preprocess_kernel<128><<<dim3(128 / 4, n), 256, 0, st>>>(reinterpret_cast<const ff::CropDesc*>(h->tile_desc), n, 0, tiles, nullptr);
+  BZ_CUDA(h, cudaGetLastError());
+  ++h->launches;
+  return FF_OK;
+}
+
+int ff_blazeface_frame_faces(ff_blazeface_t* h, const float* detections, int n_frames, int frame_h, int frame_w, float min_score,
+                             float iou_threshold, float margin, float* faces, int32_t* boxes, int32_t* counts, void* stream) {
+  if (!h || n_frames < 0 || frame_h <= 0 || frame_w <= 0 || (n_frames > 0 && (!detections || !faces || !boxes || !counts)))
+    return bfail(h, FF_ERR_BAD_ARG, "ff_blazeface_frame_faces: bad arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  ffh::DeviceGuard guard(h->device);
+  if (n_frames == 0) return FF_OK;
+  FrameGeom g;
+  const int split = std::min(frame_h, frame_w);
+  g.tiles = frame_w > frame_h ? 3 : 1;
+  g.scale = (float)((double)split / 128.0);
+  g.x_step = (frame_w - split) / 2;
+  g.frame_w = frame_w; g.frame_h = frame_h;
+  blaze_frame_nms_kernel<<<(n_frames + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(detections, n_frames, g, min_score, iou_threshold,
+                                                                                               margin, faces, boxes, counts);
   BZ_CUDA(h, cudaGetLastError());
   ++h->launches;
   return FF_OK;

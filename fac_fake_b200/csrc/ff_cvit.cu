@@ -1097,15 +1097,7 @@ int ff_preprocess_crops(ff_cvit_t* h, const uint8_t* const* crop_ptrs, const int
   for (int i = 0; i < n; ++i) {
     const int ch = hw[2 * i], cw = hw[2 * i + 1];
     if (!crop_ptrs[i] || ch <= 0 || cw <= 0 || pitch[i] < cw * 3) return fail(h, FF_ERR_SHAPE, "crop %d: bad pointer/size/pitch", i);
-    d[i].ptr = crop_ptrs[i]; d[i].h = ch; d[i].w = cw; d[i].pitch = pitch[i];
-    const double sx = (double)cw / 224.0, sy = (double)ch / 224.0;
-    if (sx >= 1.0 && sy >= 1.0) {
-      const int isx = (int)std::lrint(sx), isy = (int)std::lrint(sy);
-      const bool fast = std::fabs(sx - isx) < 2.220446049250313e-16 && std::fabs(sy - isy) < 2.220446049250313e-16;
-      d[i].mode = fast ? PRE_FAST : PRE_FRAC; d[i].isx = isx; d[i].isy = isy;
-    } else {
-      d[i].mode = PRE_LINEAR; d[i].isx = d[i].isy = 1;
-    }
+    d[i] = make_crop_desc(crop_ptrs[i], ch, cw, pitch[i], 224);
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ffh::DeviceGuard guard(h->device);
@@ -1118,7 +1110,7 @@ int ff_preprocess_crops(ff_cvit_t* h, const uint8_t* const* crop_ptrs, const int
   FF_CUDA(h, cudaMemcpyAsync(dd, d.data(), sizeof(CropDesc) * n, cudaMemcpyHostToDevice, st));
   {
     ProfScope ps(h, st, KC_SMALL);
-    preprocess_kernel<<<dim3(224 / 4, n), 256, 0, st>>>(dd, n, swap_rb, out_u8, out_norm_nchw);
+    preprocess_kernel<224><<<dim3(224 / 4, n), 256, 0, st>>>(dd, n, swap_rb, out_u8, out_norm_nchw);
   }
   FF_LAUNCH_CHECK(h, "preprocess");
   return FF_OK;

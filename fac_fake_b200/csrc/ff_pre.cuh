@@ -8,6 +8,7 @@
 //   FRAC   both scales >= 1         : computeResizeAreaTab weights (fp64 -> fp32), fp32 accumulate in table order
 //   LINEAR any up-scaling           : bilinear in "area mode", 11-bit fixed-point taps, integer arithmetic
 #pragma once
+#include <cmath>
 #include "ff_ptx.cuh"
 
 namespace ff {
@@ -29,8 +30,8 @@ struct AreaSpan {
 
 __device__ __forceinline__ AreaSpan area_span(int d, double scale, int ssize) {
   AreaSpan s;
-  s.fs1 = d * scale;
-  s.fs2 = s.fs1 + scale;
+  s.fs1 = __dmul_rn(static_cast<double>(d), scale);      // explicit roundings: an fma contraction of d*scale + scale
+  s.fs2 = __dadd_rn(s.fs1, scale);                         // would move a table boundary by one ulp
   s.cell = fmin(scale, ssize - s.fs1);
   int sx1 = static_cast<int>(ceil(s.fs1)), sx2 = static_cast<int>(floor(s.fs2));
   sx2 = min(sx2, ssize - 1);
@@ -61,8 +62,8 @@ __device__ __forceinline__ void area_entry(const AreaSpan& s, int e, int* si, fl
 
 __device__ __forceinline__ void linear_tap(int d, int ssize, int dsize, int* sx, int* a0, int* a1, bool* edge) {
   const double scale = static_cast<double>(ssize) / dsize, inv = static_cast<double>(dsize) / ssize;
-  int s = static_cast<int>(floor(d * scale));
-  float fx = static_cast<float>((d + 1) - (s + 1) * inv);
+  int s = static_cast<int>(floor(__dmul_rn(static_cast<double>(d), scale)));
+  float fx = static_cast<float>(__dsub_rn(static_cast<double>(d + 1), __dmul_rn(static_cast<double>(s + 1), inv)));
   fx = fx <= 0.0f ? 0.0f : fx - floorf(fx);
   if (s < 0) { fx = 0.0f; s = 0; }
   bool e = false;
@@ -107,12 +108,15 @@ __device__ __forceinline__ float area_alpha(const AreaTabEntry& t, int e) {
   return e == 0 ? t.a_first : (e == t.n - 1 ? t.a_last : t.a_mid);
 }
 
-// Block = 4 output rows of one crop (896 pixels); one thread produces 4 consecutive output pixels of one row
+// Destination size D x D: 224 for the CViT crops, 128 for the BlazeFace tiles (helpers_face_extract_1.py:195).
+// Block = 4 output rows of one crop; one thread produces 4 consecutive output pixels of one row
 // (12 output bytes = three aligned 32-bit stores), so a warp covers 128 consecutive output pixels.
+template <int D>
 __global__ void __launch_bounds__(256)
 preprocess_kernel(const CropDesc* __restrict__ crops, int n, int swap_rb, uint8_t* __restrict__ out_u8,
                   float* __restrict__ out_norm) {
-  constexpr int D = 224, ROWS = 4;
+  constexpr int ROWS = 4;
+  static_assert(D % 4 == 0 && ROWS * D / 4 <= 256 && D + ROWS <= 256, "block shape");
   __shared__ AreaTabEntry s_ax[D];
   __shared__ AreaTabEntry s_ay[ROWS];
   __shared__ LinTabEntry s_lx[D];
@@ -207,6 +211,22 @@ preprocess_kernel(const CropDesc* __restrict__ crops, int n, int swap_rb, uint8_
     uint32_t* o = reinterpret_cast<uint32_t*>(out_u8 + (static_cast<size_t>(i) * D * D + pix0) * 3);   // 12-byte aligned
     o[0] = packed[0]; o[1] = packed[1]; o[2] = packed[2];
   }
+}
+
+// Which of OpenCV's three INTER_AREA regimes a (h x w) -> (D x D) resize falls into (resize.cpp: integer scale ->
+// resizeAreaFast_, fractional down-scale -> resizeArea_, any up-scaling -> the bilinear kernel in area mode).
+inline CropDesc make_crop_desc(const uint8_t* ptr, int h, int w, int pitch, int D) {
+  CropDesc d;
+  d.ptr = ptr; d.h = h; d.w = w; d.pitch = pitch;
+  const double sx = static_cast<double>(w) / D, sy = static_cast<double>(h) / D;
+  if (sx >= 1.0 && sy >= 1.0) {
+    const int isx = static_cast<int>(lrint(sx)), isy = static_cast<int>(lrint(sy));
+    const bool fast = fabs(sx - isx) < 2.220446049250313e-16 && fabs(sy - isy) < 2.220446049250313e-16;
+    d.mode = fast ? PRE_FAST : PRE_FRAC; d.isx = isx; d.isy = isy;
+  } else {
+    d.mode = PRE_LINEAR; d.isx = d.isy = 1;
+  }
+  return d;
 }
 
 }  // namespace ff

@@ -193,6 +193,22 @@ int ff_blazeface_predict(ff_blazeface_t* h, const uint8_t* tiles, int n, float* 
  * reference's host loop on that tile).                                                                      */
 int ff_blazeface_nms(ff_blazeface_t* h, const float* detections, int n, float min_score, float iou_threshold, float* faces,
                      int32_t* counts, void* stream);
+/* The tiling / untiling / cropping around the detector that the reference's FaceExtractor does on the host
+ * (helpers/helpers_face_extract_1.py), on the device:
+ *   tile_frames   `_tile_frames` (:139-205): frames = DEVICE uint8 [n_frames, H, W, 3]; every frame is cut into square
+ *                 windows of side min(H, W) — three, (W - side) / 2 apart, when W > H, else one — and each is resized to
+ *                 128 x 128 with cv2.INTER_AREA semantics (bit-exact).  tiles = DEVICE uint8 [n_frames * T, 128, 128, 3].
+ *   frame_faces   `_resize_detections` + `_untile_detections` + `facedet.nms` + `_add_margin_to_detections` + the integer
+ *                 rectangle of `_crop_faces` (:207-312) for every frame: detections = DEVICE [n_frames * T, 896, 17] from
+ *                 ff_blazeface_predict on those tiles; faces = DEVICE fp32 [n_frames, 16, 17] in frame coordinates;
+ *                 boxes = DEVICE int32 [n_frames, 16, 4] = (ymin, xmin, ymax, xmax) of the crop incl. the margin;
+ *                 counts = DEVICE int32 [n_frames], -1 when a frame has more than 64 candidates / 16 faces.
+ * The crops themselves are then views of the frame on the device (`frame[ymin:ymax, xmin:xmax]`, pitch = W * 3) handed to
+ * ff_preprocess_crops: pixels never return to the host between the decoder's upload and the CViT scores.          */
+int ff_blazeface_tile_frames(ff_blazeface_t* h, const uint8_t* frames, int n_frames, int frame_h, int frame_w, uint8_t* tiles,
+                             void* stream);
+int ff_blazeface_frame_faces(ff_blazeface_t* h, const float* detections, int n_frames, int frame_h, int frame_w, float min_score,
+                             float iou_threshold, float margin, float* faces, int32_t* boxes, int32_t* counts, void* stream);
 int64_t ff_blazeface_launch_count(const ff_blazeface_t* h);
 
 /* ---- S3D clip classifier ------------------------------------------------------------------

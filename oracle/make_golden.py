@@ -381,3 +381,54 @@ def main_s3d_srm():
 
 if __name__ == "__main__" and os.environ.get("FF_GOLDEN_S3D_SRM", "1") == "1":
     main_s3d_srm()
+
+
+def main_face_extract():
+    """tests/golden/face_extract.npz — the reference FaceExtractor (helpers/helpers_face_extract_1.py) with the reference
+    BlazeFace and its shipped weights on frames of two small sample clips: a landscape one (3 tiles per frame) and a
+    portrait one (1 tile).  Stored: the frames, the 128x128 tiles of `_tile_frames`, per frame the detections after
+    `_resize_detections` / `_untile_detections` / `nms` and the crop rectangles after `_add_margin_to_detections`."""
+    helpers = os.path.join(REF, "helpers")
+    sys.path.insert(0, helpers)
+    from blazeface import BlazeFace  # noqa: E402
+    from helpers_face_extract_1 import FaceExtractor  # noqa: E402
+    from helpers_read_video_1 import VideoReader  # noqa: E402
+    net = BlazeFace()
+    net.load_weights(os.path.join(helpers, "blazeface.pth"))
+    net.load_anchors(os.path.join(helpers, "anchors.npy"))
+    net.train(False)
+    reader = VideoReader(verbose=False)
+    out = {}
+    for tag, name, idxs in (("land", "0017_fake.mp4.mp4", [0, 30, 60, 90]), ("port", "0048_fake.mp4.mp4", [0, 200, 400, 800])):
+        path = os.path.join(REF, "sample__prediction_data", name)
+        fx = FaceExtractor(lambda p: reader.read_frames_at_indices(p, idxs), net)
+        frames, got_idxs = reader.read_frames_at_indices(path, idxs)
+        tiles, resize_info = fx._tile_frames(frames, net.input_size)
+        det = net.predict_on_batch(tiles, apply_nms=False)
+        det = fx._resize_detections(det, net.input_size, resize_info)
+        det = fx._untile_detections(frames.shape[0], (frames.shape[2], frames.shape[1]), det)
+        det = net.nms(det)
+        F = frames.shape[0]
+        faces = np.zeros((F, 16, 17), np.float32)
+        rects = np.zeros((F, 16, 4), np.int32)
+        counts = np.zeros((F,), np.int32)
+        for i in range(F):
+            k = len(det[i])
+            counts[i] = k
+            faces[i, :k] = det[i].numpy()
+            m = fx._add_margin_to_detections(det[i], (frames.shape[2], frames.shape[1]), 0.2)
+            rects[i, :k] = m[:, :4].cpu().numpy().astype(int)
+        res = fx.process_video(path)
+        shapes = [[f.shape[:2] for f in r["faces"]] for r in res]
+        out.update({f"{tag}_frames": frames, f"{tag}_tiles": tiles, f"{tag}_faces": faces, f"{tag}_rects": rects, f"{tag}_counts": counts,
+                    f"{tag}_idxs": np.array(got_idxs)})
+        print("face_extract", tag, frames.shape, "tiles", tiles.shape, "faces per frame", counts.tolist(), "crop shapes", shapes)
+        for i, r in enumerate(res):      # the public result agrees with the internal steps replayed above
+            assert [tuple(f.shape[:2]) for f in r["faces"]] == [(int(y1 - y0), int(x1 - x0)) for y0, x0, y1, x1 in rects[i, :counts[i]]]
+    path = os.path.join(ROOT, "tests", "golden", "face_extract.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) / 1e6, "MB")
+
+
+if __name__ == "__main__" and os.environ.get("FF_GOLDEN_FACE_EXTRACT", "1") == "1":
+    main_face_extract()
