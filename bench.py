@@ -402,6 +402,28 @@ def run_blazeface(args):
     for _ in range(5):
         B.predict_on_batch(sample, sd, torch.from_numpy(w["anchors"]))
     cpu_s = (time.perf_counter() - t0) / 5
+    # the whole front-end of SURVEY 8f-3: frames -> tiles -> detector -> untile / NMS / margin -> 224x224 crops -> CViT scores
+    from fac_fake_b200 import CViTEngine, FaceExtractorEngine, weights as W
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "face_extract.npz"))
+    n_frames = 60
+    fr_host = torch.from_numpy(np.concatenate([fx["land_frames"]] * (n_frames // len(fx["land_frames"])))).pin_memory()
+    small = BlazeFaceEngine(max_tiles=3 * n_frames).to("cuda:0")
+    small.load_weights(sd)
+    small.load_anchors(w["anchors"])
+    ex = FaceExtractorEngine(None, small)
+    model = CViTEngine(max_crops=n_frames * 2).to("cuda:0").load_state_dict(W.make_state_dict(0, "bn"))
+
+    def front_end(frames_host):
+        frames = frames_host.cuda(non_blocking=True)
+        crops = ex.extract_crops_device(frames, model)
+        return model.predict_videos(crops, [0, crops.shape[0]]).cpu(), crops.shape[0]
+    for _ in range(3):
+        front_end(fr_host)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, n_crops = front_end(fr_host)
+    fe_s = (time.perf_counter() - t0) / args.steps
     fl, by = blazeface_work_per_tile()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
     gbs = by * args.tiles / (ms * 1e-3) / 1e9
@@ -409,6 +431,9 @@ def run_blazeface(args):
         "metric": "BlazeFace tiles/sec", "value": args.tiles / ms * 1e3, "unit": "tiles/s", "ms_per_step": ms, "tiles_per_step": args.tiles,
         "gpu_launches_per_step": int(launches), "dtype": "f32", "faces_found": int(sum(len(f) for f in faces)),
         "e2e": {"value": args.tiles / e2e_s, "unit": "tiles/s", "what": "pinned host uint8 tiles -> H2D -> network + decode -> mask + blending NMS on the device (ff_blazeface_nms) -> D2H of [n,16,17] faces + counts"},
+        "face_front_end": {"value": n_frames / fe_s, "unit": "frames/s", "frames": n_frames, "frame_hw": list(fr_host.shape[1:3]), "crops": int(n_crops),
+                           "what": "pinned host uint8 frames (536x500, 3 tiles each) -> H2D -> ff_blazeface_tile_frames -> detector -> ff_blazeface_frame_faces "
+                                   "-> D2H of detections/rectangles -> ff_preprocess_crops on device views -> CViT -> per-video score on the host"},
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                      "algorithmic_bytes_per_tile": by, "flops_per_tile": fl, "gflops": fl * args.tiles / (ms * 1e-3) / 1e9},
         "cpu_baseline": {"value": len(sample) / cpu_s, "unit": "tiles/s", "cores": os.cpu_count(), "kind": "port",
