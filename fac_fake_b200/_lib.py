@@ -16,8 +16,8 @@ FF_REDUCE_REFERENCE, FF_REDUCE_SOFTMAX_MEAN, FF_REDUCE_REFERENCE_PROBS = 0, 1, 2
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 SYMBOLS = [
     ("ff_cvit_create", _i, [C.POINTER(_vp), _i, _i, _i]),
-    ("ff_resvitkan_create", _i, [C.POINTER(_vp), _i, _i]),
-    ("ff_cvit_ggca_create", _i, [C.POINTER(_vp), _i, _i]),
+    ("ff_resvitkan_create", _i, [C.POINTER(_vp), _i, _i, _i]),
+    ("ff_cvit_ggca_create", _i, [C.POINTER(_vp), _i, _i, _i]),
     ("ff_cvit_destroy", None, [_vp]),
     ("ff_last_error", C.c_char_p, [_vp]),
     ("ff_cvit_load_weight", _i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i]),
@@ -40,6 +40,7 @@ SYMBOLS = [
     ("ff_blazeface_finalize", _i, [_vp]),
     ("ff_blazeface_predict", _i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     ("ff_blazeface_nms", _i, [_vp, _vp, _i, C.c_float, C.c_float, _vp, _vp, _vp]),
+    ("ff_blazeface_nms_lists", _i, [_vp, _vp, _vp, _i, C.c_float, _vp, _vp, _vp]),
     ("ff_blazeface_tile_frames", _i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     ("ff_blazeface_frame_faces", _i, [_vp, _vp, _i, _i, _i, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
     ("ff_blazeface_launch_count", _i64, [_vp]),

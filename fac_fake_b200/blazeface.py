@@ -182,11 +182,33 @@ class BlazeFaceEngine:
         return out
 
     def nms(self, detections: List[torch.Tensor]) -> List[torch.Tensor]:
-        """blazeface.py:225-234."""
-        out = []
-        for det in detections:
-            faces = self._weighted_non_max_suppression(det.cpu())
-            out.append(torch.stack(faces) if len(faces) > 0 else torch.zeros((0, 17)))
+        """blazeface.py:225-234: blending NMS of every list in one kernel (``ff_blazeface_nms_lists``); a list it cannot
+        hold (> 64 detections or > 16 faces) is merged by the same algorithm on the host."""
+        n = len(detections)
+        if n == 0:
+            return []
+        sizes = [int(d.shape[0]) for d in detections]
+        offs = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32)
+        out: List[Optional[torch.Tensor]] = [None] * n
+        if offs[-1] > 0:
+            self._ensure_ready()
+            flat = torch.cat([d.reshape(-1, 17).to(torch.float32) for d in detections]).to(self._device).contiguous()
+            offs_d = offs.to(self._device)
+            faces = torch.empty((n, 16, 17), dtype=torch.float32, device=self._device)
+            counts = torch.empty((n,), dtype=torch.int32, device=self._device)
+            with torch.cuda.device(self._device):
+                rc = self._lib.ff_blazeface_nms_lists(self._h, C.c_void_p(flat.data_ptr()), C.c_void_p(offs_d.data_ptr()), n,
+                                                      C.c_float(self.min_suppression_threshold), C.c_void_p(faces.data_ptr()),
+                                                      C.c_void_p(counts.data_ptr()), C.c_void_p(_stream_ptr(self._device)))
+            self._check(rc, "ff_blazeface_nms_lists")
+            faces_h, counts_h = faces.cpu(), counts.cpu().tolist()
+            for i, k in enumerate(counts_h):
+                if k >= 0:
+                    out[i] = faces_h[i, :k].clone()
+        for i in range(n):
+            if out[i] is None:
+                f = self._weighted_non_max_suppression(detections[i].cpu()) if sizes[i] else []
+                out[i] = torch.stack(f) if f else torch.zeros((0, 17))
         return out
 
     def _weighted_non_max_suppression(self, detections: torch.Tensor) -> List[torch.Tensor]:

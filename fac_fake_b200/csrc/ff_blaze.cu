@@ -391,21 +391,25 @@ blaze_decode_kernel(const float* __restrict__ raw_boxes, const float* __restrict
 // the host loop for that tile.
 constexpr int NMS_MAX_CAND = 64, NMS_MAX_FACES = 16;
 __global__ void __launch_bounds__(128)
-blaze_nms_kernel(const float* __restrict__ det, int n, float min_score, float iou_thr, float* __restrict__ faces, int* __restrict__ counts) {
+blaze_nms_kernel(const float* __restrict__ det, const int* __restrict__ list_offsets, int n, float min_score, float iou_thr,
+                 float* __restrict__ faces, int* __restrict__ counts) {
   __shared__ int s_idx[4][NMS_MAX_CAND];
   __shared__ float s_score[4][NMS_MAX_CAND];
   __shared__ float s_box[4][NMS_MAX_CAND][4];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x * 4 + w;
   if (tile >= n) return;
-  const float* d = det + (size_t)tile * NUM_ANCHORS * 17;
+  // dense mode: the tile's 896 decoded anchors, masked by score;  list mode (`nms(list)`, blazeface.py:225-234): rows
+  // list_offsets[tile] .. list_offsets[tile+1] of a packed [total,17] array, every one a candidate
+  const float* d = det + (list_offsets ? (size_t)list_offsets[tile] * 17 : (size_t)tile * NUM_ANCHORS * 17);
+  const int rows = list_offsets ? list_offsets[tile + 1] - list_offsets[tile] : NUM_ANCHORS;
   // 1. candidates in anchor order
   int ncand = 0;
   bool overflow = false;
-  for (int a0 = 0; a0 < NUM_ANCHORS; a0 += 32) {
+  for (int a0 = 0; a0 < rows; a0 += 32) {
     const int a = a0 + lane;
-    const float sc = d[a * 17 + 16];
-    const bool keep = sc >= min_score;
+    const float sc = a < rows ? d[a * 17 + 16] : 0.f;
+    const bool keep = a < rows && (list_offsets != nullptr || sc >= min_score);
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     const int pos = ncand + __popc(m & ((1u << lane) - 1u));
     if (keep && pos < NMS_MAX_CAND) { s_idx[w][pos] = a; s_score[w][pos] = sc; }
@@ -854,7 +858,20 @@ int ff_blazeface_nms(ff_blazeface_t* h, const float* detections, int n, float mi
   std::lock_guard<std::mutex> lk(h->mu);
   ffh::DeviceGuard guard(h->device);
   if (n == 0) return FF_OK;
-  blaze_nms_kernel<<<(n + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(detections, n, min_score, iou_threshold, faces, counts);
+  blaze_nms_kernel<<<(n + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(detections, nullptr, n, min_score, iou_threshold, faces, counts);
+  BZ_CUDA(h, cudaGetLastError());
+  ++h->launches;
+  return FF_OK;
+}
+
+int ff_blazeface_nms_lists(ff_blazeface_t* h, const float* detections, const int32_t* offsets, int n, float iou_threshold,
+                           float* faces, int32_t* counts, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!detections || !offsets || !faces || !counts)))
+    return bfail(h, FF_ERR_BAD_ARG, "ff_blazeface_nms_lists: bad arguments");
+  std::lock_guard<std::mutex> lk(h->mu);
+  ffh::DeviceGuard guard(h->device);
+  if (n == 0) return FF_OK;
+  blaze_nms_kernel<<<(n + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(detections, offsets, n, 0.f, iou_threshold, faces, counts);
   BZ_CUDA(h, cudaGetLastError());
   ++h->launches;
   return FF_OK;

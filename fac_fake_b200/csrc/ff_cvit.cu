@@ -362,9 +362,9 @@ int finalize(ff_cvit* h) {
     if ((rc = upload_linear(h, &h->head2, "mlp_head.2", 2, MLP, true, 64))) return rc;
   }
 
+  if (h->kind == 2 && (rc = finalize_ggca_extras(h))) return rc;
   if (h->compute == FF_COMPUTE_BF16) {
     if (h->kind != 1 && (rc = build_conv_maps(h))) return rc;
-    if (h->kind == 2 && (rc = finalize_ggca_extras(h))) return rc;
     const int cap128 = (h->cap + 127) / 128 * 128;
     if ((rc = tmap_2d(h, &h->tm_feat, h->feat, PATCH, cap128, 64, 128))) return rc;
     if ((rc = tmap_2d(h, &h->tm_xn, h->xn, DIM, h->rows_cap, 64, 128))) return rc;
@@ -729,8 +729,13 @@ int forward_fp32(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   // conv stack, NHWC fp32, ping-pong fA/fB; processed `chunk` crops at a time to bound the workspace
   const int chunk = h->s12_cap;
   const size_t crop_in_bytes = layout == FF_X_NHWC_U8 ? (size_t)224 * 224 * 3 : (size_t)224 * 224 * 3 * 4;
-  float* featf = h->fB + (size_t)chunk * 224 * 224 * 32;    // tail of fB is reserved for [cap][25088]
+  float* featf = h->featf;                                  // tail of fB is reserved for [cap][25088]
   if (stop && n > chunk) return fail(h, FF_ERR_BAD_ARG, "debug tap needs n <= %d", chunk);
+  if (stop && h->kind != 0 && stop != 25) return fail(h, FF_ERR_BAD_ARG, "the fp32 path of this variant taps the logits (25) only");
+  if (h->kind == 1) {
+    int rc1 = rvk_features_fp32(h, x, layout, n, featf, st);
+    if (rc1) return rc1;
+  } else
   for (int s0 = 0; s0 < n; s0 += chunk) {
     const int ns = std::min(chunk, n - s0);
     const uint8_t* xin = reinterpret_cast<const uint8_t*>(x) + (size_t)s0 * crop_in_bytes;
@@ -745,14 +750,24 @@ int forward_fp32(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
       const int blocks = (int)std::min<size_t>((total + 255) / 256, 1u << 30);
       if (li == 0)
         conv3x3_fp32_kernel<<<blocks, 256, 0, st>>>(xin, layout == FF_X_NHWC_U8 ? 2 : 1, nullptr, L.wf, L.scale, L.shift, dst,
-                                                   ns, p.hw, p.cin, p.cout, p.pool ? 1 : 0);
+                                                   ns, p.hw, p.cin, p.cout, p.pool ? 1 : 0, 1);
       else
         conv3x3_fp32_kernel<<<blocks, 256, 0, st>>>(nullptr, 0, cur, L.wf, L.scale, L.shift, dst, ns, p.hw, p.cin, p.cout,
-                                                   p.pool ? 1 : 0);
+                                                   p.pool ? 1 : 0, 1);
       FF_LAUNCH_CHECK(h, "conv3x3_fp32");
       if (tap_hit(li + 1, dst, (int64_t)total)) return FF_OK;
       std::swap(cur, nxt);
+      if (h->kind == 2 && li == 7) {     // features1.26: Conv2d(128,128) without BN / activation
+        const ff_cvit::RvkOp& op = h->rvk_ops[0];
+        conv3x3_fp32_kernel<<<blocks, 256, 0, st>>>(nullptr, 0, cur, op.wf, op.scale, op.shift, nxt, ns, 56, 128, 128, 0, 0);
+        FF_LAUNCH_CHECK(h, "features1.26_fp32");
+        std::swap(cur, nxt);
+      }
     }
+  }
+  if (h->kind == 2) {                    // x = x * ggca(x)
+    int rc2 = ggca_gate_fp32(h, featf, n, st);
+    if (rc2) return rc2;
   }
   const int rows = 2 * n;
   float* xn = reinterpret_cast<float*>(h->fA);                  // [rows][1024]
@@ -771,13 +786,13 @@ int forward_fp32(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   if (tap_hit(18, h->x, (int64_t)rows * DIM)) return FF_OK;
   for (int l = 0; l < DEPTH; ++l) {
     const XfLayerDev& X = h->xf[l];
-    layernorm_f32_kernel<<<(rows + 7) / 8, 256, 0, st>>>(h->x, X.ln1_g, X.ln1_b, xn, rows);
+    layernorm_f32_kernel<<<(rows + 7) / 8, 256, 0, st>>>(h->x, X.ln1_g, X.ln1_b, xn, rows, 1e-5f);
     FF_LAUNCH_CHECK(h, "layernorm_f32");
     if ((rc = lin(xn, X.qkv, rows, h->qkv, 0, 0, "qkv_fp32"))) return rc;
     attention2_f32_kernel<<<(n * 8 + 7) / 8, 256, 0, st>>>(h->qkv, att, n);
     FF_LAUNCH_CHECK(h, "attention2_f32");
     if ((rc = lin(att, X.out, rows, h->x, 0, 1, "out_fp32"))) return rc;
-    layernorm_f32_kernel<<<(rows + 7) / 8, 256, 0, st>>>(h->x, X.ln2_g, X.ln2_b, xn, rows);
+    layernorm_f32_kernel<<<(rows + 7) / 8, 256, 0, st>>>(h->x, X.ln2_g, X.ln2_b, xn, rows, h->ln2_eps);
     FF_LAUNCH_CHECK(h, "layernorm_f32");
     if ((rc = lin(xn, X.ff1, rows, ffh, 2, 0, "ff1_fp32"))) return rc;
     if ((rc = lin(ffh, X.ff2, rows, h->x, 0, 1, "ff2_fp32"))) return rc;
@@ -786,8 +801,12 @@ int forward_fp32(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   cls_gather_f32_kernel<<<n, 256, 0, st>>>(h->x, xn, n);
   FF_LAUNCH_CHECK(h, "cls_gather_f32");
   if ((rc = lin(xn, h->head1, n, h->hid, 1, 0, "head1_fp32"))) return rc;
-  head2_kernel<<<(n + 7) / 8, 256, 0, st>>>(h->hid, h->head2.wf, h->head2.b, logits, n);
-  FF_LAUNCH_CHECK(h, "head2");
+  if (h->kind == 1) {
+    if ((rc = kan_head(h, n, logits, st))) return rc;
+  } else {
+    head2_kernel<<<(n + 7) / 8, 256, 0, st>>>(h->hid, h->head2.wf, h->head2.b, logits, n);
+    FF_LAUNCH_CHECK(h, "head2");
+  }
   if (tap_hit(25, logits, (int64_t)n * 2)) return FF_OK;
   return FF_OK;
 }
@@ -858,8 +877,6 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
   if (!out || max_crops <= 0) return fail(nullptr, FF_ERR_BAD_ARG, "ff_cvit_create: bad arguments");
   if (compute_dtype != FF_COMPUTE_BF16 && compute_dtype != FF_COMPUTE_FP32)
     return fail(nullptr, FF_ERR_BAD_ARG, "ff_cvit_create: unknown compute_dtype %d", compute_dtype);
-  if (kind != 0 && compute_dtype != FF_COMPUTE_BF16)
-    return fail(nullptr, FF_ERR_BAD_ARG, "only the tensor-core path is implemented for the ResVitKan / GGCA variants");
   *out = nullptr;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -878,7 +895,7 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
   h->device = device;
   h->compute = compute_dtype;
   h->kind = kind;
-  h->act_f16 = kind == 2;
+  h->act_f16 = kind == 2 && compute_dtype == FF_COMPUTE_BF16;
   h->ln2_eps = kind == 2 ? 1e-6f : 1e-5f;
   h->cap = (max_crops + 31) / 32 * 32;
   h->rows_cap = (2 * h->cap + 127) / 128 * 128;
@@ -895,12 +912,19 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
     if ((rc = dev_alloc(h, &h->hid, (size_t)cap128 * MLP))) break;
     if (kind == 1) {
       constexpr size_t kRvkActElems = (size_t)112 * 112 * 64;      // largest activation per crop (stem / layer1 output)
-      for (int i = 0; i < 5 && rc == FF_OK; ++i) rc = dev_alloc(h, &h->rvk_buf[i], (size_t)h->cap * kRvkActElems);
-      if (rc) break;
-      if ((rc = dev_alloc(h, &h->rvk_x4, (size_t)h->cap * 224 * 224 * 4))) break;
+      if (compute_dtype == FF_COMPUTE_BF16) {
+        for (int i = 0; i < 5 && rc == FF_OK; ++i) rc = dev_alloc(h, &h->rvk_buf[i], (size_t)h->cap * kRvkActElems);
+        if (rc) break;
+        if ((rc = dev_alloc(h, &h->rvk_x4, (size_t)h->cap * 224 * 224 * 4))) break;
+      } else {
+        h->rvk_f32_chunk = std::min(h->cap, 32);
+        for (int i = 0; i < 5 && rc == FF_OK; ++i) rc = dev_alloc(h, &h->rvk_f32[i], (size_t)h->rvk_f32_chunk * kRvkActElems);
+        if (rc) break;
+        if ((rc = dev_alloc(h, &h->rvk_x4f, (size_t)h->rvk_f32_chunk * 224 * 224 * 4))) break;
+      }
       if ((rc = dev_alloc(h, &h->kan_part, (size_t)KAN_PART_CHUNKS * h->cap * 64))) break;
     }
-    if (kind == 2 && (rc = dev_alloc(h, &h->bufR, (size_t)h->cap * 56 * 56 * 128))) break;
+    if (kind == 2 && compute_dtype == FF_COMPUTE_BF16 && (rc = dev_alloc(h, &h->bufR, (size_t)h->cap * 56 * 56 * 128))) break;
     if (compute_dtype == FF_COMPUTE_BF16 && kind != 1) {
       if ((rc = dev_alloc(h, &h->bufA, (size_t)h->s12_cap * 224 * 224 * 32))) break;
       if ((rc = dev_alloc(h, &h->bufB, (size_t)h->s12_cap * 224 * 224 * 32))) break;
@@ -926,10 +950,11 @@ int create_impl(ff_cvit_t** out, int device, int max_crops, int compute_dtype, i
       cudaMemset(h->ffh_buf, 0, (size_t)h->rows_cap * MLP * 2);
       cudaMemset(h->clsb, 0, (size_t)cap128 * DIM * 2);
     } else {
-      const size_t act = (size_t)h->s12_cap * 224 * 224 * 32;
+      const size_t act = kind == 1 ? 0 : (size_t)h->s12_cap * 224 * 224 * 32;   // the ResNet trunk has its own fp32 buffers
       const size_t tail = std::max((size_t)h->rows_cap * DIM * 4, (size_t)1);
       if ((rc = dev_alloc(h, &h->fA, std::max(act, tail)))) break;
       if ((rc = dev_alloc(h, &h->fB, act + (size_t)h->cap * PATCH))) break;
+      h->featf = h->fB + act;
     }
   } while (0);
   if (rc != FF_OK) {
@@ -954,11 +979,11 @@ const char* ff_last_error(const ff_cvit_t* h) { return h ? h->err.c_str() : g_cr
 int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype) {
   return create_impl(out, device, max_crops, compute_dtype, 0);
 }
-int ff_resvitkan_create(ff_cvit_t** out, int device, int max_crops) {
-  return create_impl(out, device, max_crops, FF_COMPUTE_BF16, 1);
+int ff_resvitkan_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype) {
+  return create_impl(out, device, max_crops, compute_dtype, 1);
 }
-int ff_cvit_ggca_create(ff_cvit_t** out, int device, int max_crops) {
-  return create_impl(out, device, max_crops, FF_COMPUTE_BF16, 2);
+int ff_cvit_ggca_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype) {
+  return create_impl(out, device, max_crops, compute_dtype, 2);
 }
 
 void ff_cvit_destroy(ff_cvit_t* h) {

@@ -127,6 +127,7 @@ struct ff_cvit {
   bool xf_ready = false;             // false: the per-op GPU launches run the encoder (cooperative launch unavailable)
   float* fA = nullptr;               // fp32-path workspace
   float* fB = nullptr;
+  float* featf = nullptr;            // [cap][25088] fp32 patch vectors (tail of fB)
 
   // ---- GGCA / DEConv / RepBN variant (kind == 2): the CViT plan + one BN-less linear conv + the gate
   ffh::bf16* bufR = nullptr;         // output of the extra Conv2d(128,128) (features1.26), read by layer 9
@@ -142,6 +143,7 @@ struct ff_cvit {
     int in_buf = 0, out_buf = 0;
     int bn = 64, bw = 8, bh = 8, bi = 2;
     ffh::bf16* w = nullptr;
+    float* wf = nullptr;            // FF_COMPUTE_FP32: [cout][taps][cin] fp32
     ffh::bf16* out_ptr = nullptr;   // explicit output (kind 2); otherwise rvk_buf[out_buf] / feat
     float *scale = nullptr, *shift = nullptr;
     CUtensorMap tmA, tmB;
@@ -157,6 +159,11 @@ struct ff_cvit {
   CUtensorMap rvk_tm_x4;
   float *kan_w0 = nullptr, *kan_w1 = nullptr, *kan_g0 = nullptr, *kan_g1 = nullptr;
   float* kan_part = nullptr;             // layer-0 split-K slabs [KAN_CHUNKS][cap][64]
+  // FF_COMPUTE_FP32 trunk: same buffer roles as rvk_buf, `rvk_f32_chunk` crops at a time
+  float* rvk_f32[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* rvk_x4f = nullptr;              // normalised fp32 NHWC4 input
+  float *rvk_stem_wf = nullptr, *rvk_stem_scale_d = nullptr, *rvk_stem_shift_d = nullptr;
+  int rvk_f32_chunk = 0;
 
   // ---- grow-only scratch for predict()
   int32_t* slot_buf = nullptr; size_t slot_cap = 0;
@@ -248,6 +255,7 @@ struct DebugTap {
 // ---- ff_resvitkan.cu
 int finalize_rvk_features(ff_cvit* h);
 int rvk_features(ff_cvit* h, const void* x, int layout, int slot_base, int n, cudaStream_t st, DebugTap* tap);
+int rvk_features_fp32(ff_cvit* h, const void* x, int layout, int n, float* featf, cudaStream_t st);
 int rvk_launch_op(ff_cvit* h, const ff_cvit::RvkOp& op, int n, cudaStream_t st, int prof_cls);
 int kan_head(ff_cvit* h, int n, float* logits, cudaStream_t st);
 // ---- ff_ggca.cu
@@ -256,5 +264,6 @@ extern const GgcaPlan kGgcaPlan[18];
 int ggca_conv_weights(ff_cvit* h, const GgcaPlan& gp, int cin, int cout, std::vector<float>* w_out, std::vector<float>* b_out);
 int finalize_ggca_extras(ff_cvit* h);
 int ggca_gate(ff_cvit* h, int n, cudaStream_t st);
+int ggca_gate_fp32(ff_cvit* h, float* featf, int n, cudaStream_t st);
 
 }  // namespace ffe

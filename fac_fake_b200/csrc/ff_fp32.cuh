@@ -10,10 +10,10 @@ namespace ff {
 // conv3x3 pad 1 + (scale, shift) + ReLU [+ 2x2 max-pool], NHWC fp32 -> NHWC fp32 (cvit.py:88-147).
 // One thread per output element (channel fastest).  in_kind 0: NHWC fp32 `in`; 1: fp32 NCHW raw input (cin=3);
 // 2: uint8 NHWC raw crops with (x/255-mean)/std fused (cvit_prediction.py:41-45,214-215).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 conv3x3_fp32_kernel(const void* __restrict__ raw, int in_kind, const float* __restrict__ in, const float* __restrict__ w,
                     const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out, int n_img,
-                    int hw, int cin, int cout, int pool) {
+                    int hw, int cin, int cout, int pool, int relu) {
   const int ohw = pool ? hw / 2 : hw;
   const size_t total = static_cast<size_t>(n_img) * ohw * ohw * cout;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -24,7 +24,7 @@ conv3x3_fp32_kernel(const void* __restrict__ raw, int in_kind, const float* __re
     const int oh = static_cast<int>(t % ohw);
     const int n = static_cast<int>(t / ohw);
     const float* wr = w + static_cast<size_t>(co) * 9 * cin;
-    float best = 0.0f;   // ReLU output is >= 0, so 0 is a valid identity for the max
+    float best = relu ? 0.0f : -INFINITY;   // ReLU output is >= 0, so 0 is a valid identity for the max
     const int reps = pool ? 2 : 1;
     for (int dy = 0; dy < reps; ++dy)
       for (int dx = 0; dx < reps; ++dx) {
@@ -67,7 +67,7 @@ conv3x3_fp32_kernel(const void* __restrict__ raw, int in_kind, const float* __re
 }
 
 // out[M][N] (=|+=) act(A[M][K] * W[N][K]^T + bias).  64x64 tile, 256 threads, 4x4 per thread, K step 16.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 linear_fp32_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
                    float* __restrict__ out, int M, int N, int K, int act, int resid) {
   __shared__ float sa[16][64 + 4];
@@ -113,9 +113,9 @@ linear_fp32_kernel(const float* __restrict__ A, const float* __restrict__ W, con
   }
 }
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     float* __restrict__ y, int rows) {
+                     float* __restrict__ y, int rows, float eps) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -128,13 +128,13 @@ layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   float q = 0.0f;
 #pragma unroll
   for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; q += d * d; }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / 1024.0f) + 1e-5f);
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / 1024.0f) + eps);
   float* yr = y + static_cast<size_t>(row) * 1024;
 #pragma unroll
   for (int i = 0; i < 32; ++i) yr[i * 32 + lane] = (v[i] - mean) * rstd * gamma[i * 32 + lane] + beta[i * 32 + lane];
 }
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 attention2_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int n_crops) {
   const int wid = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -158,7 +158,91 @@ attention2_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, in
   *reinterpret_cast<float4*>(o0 + 1024) = make_float4(a10 * v0.x + a11 * v1.x, a10 * v0.y + a11 * v1.y, a10 * v0.z + a11 * v1.z, a10 * v0.w + a11 * v1.w);
 }
 
-__global__ void __launch_bounds__(256)
+// ---- fp32 path of the ResVitKan trunk (ResVitKan/ResVitKan.py:150-240)
+// raw input -> normalised NHWC fp32 with 4 channels (4th = 0).  in_kind 1: fp32 NCHW (already normalised);
+// 2: uint8 NHWC crops, (u/255 - mean)/std in the reference's operation order (cvit_prediction.py:41-45,214-215).
+static __global__ void __launch_bounds__(256)
+nhwc4_f32_kernel(const void* __restrict__ raw, int in_kind, float4* __restrict__ out, int n_img) {
+  const size_t total = static_cast<size_t>(n_img) * 224 * 224;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  float v[3];
+  if (in_kind == 2) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(raw) + i * 3;
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = __fdiv_rn(__fdiv_rn(static_cast<float>(p[c]), 255.0f) - mean[c], sd[c]);
+  } else {
+    const size_t n = i / (224 * 224), px = i % (224 * 224);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = reinterpret_cast<const float*>(raw)[(n * 3 + c) * 224 * 224 + px];
+  }
+  out[i] = make_float4(v[0], v[1], v[2], 0.0f);
+}
+
+// Any k x k convolution (pad = k/2, stride 1 or 2) + (scale, shift) [+ ReLU] [+ residual, ReLU], NHWC fp32, cin % 4 == 0.
+// One thread per output element; w = [cout][k*k][cin].  The bottleneck's two ReLUs (before and after the residual add,
+// ResVitKan.py:169-176) are `relu` and the one implied by `resid`.
+static __global__ void __launch_bounds__(256)
+conv_fp32_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ scale,
+                 const float* __restrict__ shift, const float* __restrict__ resid, float* __restrict__ out, int n_img,
+                 int in_hw, int out_hw, int cin, int cout, int k, int stride, int relu) {
+  const size_t total = static_cast<size_t>(n_img) * out_hw * out_hw * cout;
+  const int pad = k / 2;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(idx % cout);
+    size_t t = idx / cout;
+    const int ow = static_cast<int>(t % out_hw); t /= out_hw;
+    const int oh = static_cast<int>(t % out_hw);
+    const size_t n = t / out_hw;
+    const float* wr = w + static_cast<size_t>(co) * k * k * cin;
+    float acc = 0.0f;
+    for (int kh = 0; kh < k; ++kh) {
+      const int iy = oh * stride + kh - pad;
+      if (iy < 0 || iy >= in_hw) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int ix = ow * stride + kw - pad;
+        if (ix < 0 || ix >= in_hw) continue;
+        const float* p = in + ((n * in_hw + iy) * in_hw + ix) * cin;
+        const float* wt = wr + (kh * k + kw) * cin;
+        for (int c = 0; c < cin; c += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(p + c);
+          const float4 b = *reinterpret_cast<const float4*>(wt + c);
+          acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+        }
+      }
+    }
+    float v = fmaf(acc, scale[co], shift[co]);
+    if (relu) v = fmaxf(v, 0.0f);
+    if (resid) v = fmaxf(v + resid[idx], 0.0f);
+    out[idx] = v;
+  }
+}
+
+// MaxPool2d(3, stride 2, pad 1), NHWC fp32 (ResVitKan.py:194,232)
+static __global__ void __launch_bounds__(256)
+maxpool3s2_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int n_img, int in_hw, int c) {
+  const int out_hw = in_hw / 2;
+  const size_t total = static_cast<size_t>(n_img) * out_hw * out_hw * c;
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = static_cast<int>(idx % c);
+  size_t t = idx / c;
+  const int ow = static_cast<int>(t % out_hw); t /= out_hw;
+  const int oh = static_cast<int>(t % out_hw);
+  const size_t n = t / out_hw;
+  float m = -INFINITY;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int iy = 2 * oh + dy, ix = 2 * ow + dx;
+      if (iy < 0 || iy >= in_hw || ix < 0 || ix >= in_hw) continue;
+      m = fmaxf(m, in[((n * in_hw + iy) * in_hw + ix) * c + ch]);
+    }
+  out[idx] = m;
+}
+
+static __global__ void __launch_bounds__(256)
 cls_gather_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int n) {
   const int b = blockIdx.x;
   if (b >= n) return;

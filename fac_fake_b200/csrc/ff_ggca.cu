@@ -89,13 +89,17 @@ int finalize_ggca_extras(ff_cvit* h) {
   for (int o = 0; o < 128; ++o)
     for (int ci = 0; ci < 128; ++ci)
       for (int t = 0; t < 9; ++t) wr[((size_t)o * 9 + t) * 128 + ci] = wsrc[((size_t)o * 128 + ci) * 9 + t];
-  if ((rc = dev_upload(h, &op.w, to_act16(h, wr)))) return rc;
   if ((rc = dev_upload(h, &op.scale, ones))) return rc;
   if ((rc = dev_upload(h, &op.shift, bias))) return rc;
-  if ((rc = tmap_2d(h, &op.tmB, op.w, 9 * 128, 128, 64, 128))) return rc;
-  if ((rc = tmap_4d(h, &op.tmA, conv_output_buffer(h, 7), 128, 56, 56, h->cap, 64, 8, 8, 2))) return rc;
-  if ((rc = tmap_4d(h, &op.tmO, h->bufR, 128, 56, 56, h->cap, 64, 8, 8, 2))) return rc;
-  op.tmR = op.tmO;
+  if (h->compute == FF_COMPUTE_FP32) {
+    if ((rc = dev_upload(h, &op.wf, wr))) return rc;
+  } else {
+    if ((rc = dev_upload(h, &op.w, to_act16(h, wr)))) return rc;
+    if ((rc = tmap_2d(h, &op.tmB, op.w, 9 * 128, 128, 64, 128))) return rc;
+    if ((rc = tmap_4d(h, &op.tmA, conv_output_buffer(h, 7), 128, 56, 56, h->cap, 64, 8, 8, 2))) return rc;
+    if ((rc = tmap_4d(h, &op.tmO, h->bufR, 128, 56, 56, h->cap, 64, 8, 8, 2))) return rc;
+    op.tmR = op.tmO;
+  }
   h->rvk_ops.clear();
   h->rvk_ops.push_back(op);
   // GGCA(512,7,7).shared_conv: Conv2d(128,8,1) + BatchNorm2d(8) + ReLU + Conv2d(8,128,1)  (:159-166)
@@ -125,8 +129,15 @@ int finalize_ggca_extras(ff_cvit* h) {
 // x = x * ggca(x)  (cvit_GGCA_ADD_DEConv_RepBn8.py:447-448), in place on the [n,7,7,512] feature map
 int ggca_gate(ff_cvit* h, int n, cudaStream_t st) {
   ProfScope ps(h, st, KC_SMALL);
-  ggca_gate_kernel<<<n, 512, 0, st>>>(h->feat, h->ggca_w1, h->ggca_b1, h->ggca_w2, h->ggca_b2, n, h->act_f16 ? 1 : 0);
+  if (h->act_f16) ggca_gate_kernel<1><<<n, 512, 0, st>>>(h->feat, h->ggca_w1, h->ggca_b1, h->ggca_w2, h->ggca_b2, n);
+  else ggca_gate_kernel<0><<<n, 512, 0, st>>>(h->feat, h->ggca_w1, h->ggca_b1, h->ggca_w2, h->ggca_b2, n);
   FF_LAUNCH_CHECK(h, "ggca_gate");
+  return FF_OK;
+}
+
+int ggca_gate_fp32(ff_cvit* h, float* featf, int n, cudaStream_t st) {
+  ggca_gate_kernel<2><<<n, 512, 0, st>>>(featf, h->ggca_w1, h->ggca_b1, h->ggca_w2, h->ggca_b2, n);
+  FF_LAUNCH_CHECK(h, "ggca_gate_fp32");
   return FF_OK;
 }
 

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "ff_cvit.h"
+#include "ff_fp32.cuh"
 #include "ff_rvk.cuh"
 
 namespace ffe {
@@ -53,9 +54,14 @@ int rvk_add_op(ff_cvit* h, const std::string& conv, const std::string& bn, int c
   for (int o = 0; o < cout; ++o)
     for (int ci = 0; ci < cin; ++ci)
       for (int t = 0; t < k * k; ++t) wr[((size_t)o * k * k + t) * cin + ci] = (*w)[((size_t)o * cin + ci) * k * k + t];
-  if ((rc = dev_upload(h, &op.w, ffh::to_bf16(wr)))) return rc;
   if ((rc = dev_upload(h, &op.scale, scale))) return rc;
   if ((rc = dev_upload(h, &op.shift, shift))) return rc;
+  if (h->compute == FF_COMPUTE_FP32) {           // CUDA-core path: fp32 filters, no tensor maps
+    if ((rc = dev_upload(h, &op.wf, wr))) return rc;
+    h->rvk_ops.push_back(op);
+    return FF_OK;
+  }
+  if ((rc = dev_upload(h, &op.w, ffh::to_bf16(wr)))) return rc;
   if ((rc = tmap_2d(h, &op.tmB, op.w, (uint64_t)k * k * cin, cout, 64, op.bn))) return rc;
   const bf16* in = h->rvk_buf[in_buf];
   if (op.type == 0) {
@@ -91,9 +97,18 @@ int finalize_rvk_features(ff_cvit* h) {
       for (int o = 0; o < 64; ++o)
         for (int kw = 0; kw < 7; ++kw)
           for (int c = 0; c < 3; ++c) ws[((size_t)kh * 64 + o) * 32 + (kw + 1) * 4 + c] = (*w)[(((size_t)o * 3 + c) * 7 + kh) * 7 + kw];
-    if ((rc = dev_upload(h, &h->rvk_stem_w, ffh::to_bf16(ws)))) return rc;
     if ((rc = rvk_fold_bn(h, "features.bn1", 64, &scale, &shift))) return rc;
     for (int o = 0; o < 64; ++o) { h->rvk_stem_scale[o] = scale[o]; h->rvk_stem_shift[o] = shift[o]; }
+    if (h->compute == FF_COMPUTE_FP32) {
+      std::vector<float> wf((size_t)64 * 49 * 4, 0.0f);      // [cout][kh*7+kw][4]
+      for (int o = 0; o < 64; ++o)
+        for (int t = 0; t < 49; ++t)
+          for (int c = 0; c < 3; ++c) wf[((size_t)o * 49 + t) * 4 + c] = (*w)[((size_t)o * 3 + c) * 49 + t];
+      if ((rc = dev_upload(h, &h->rvk_stem_wf, wf))) return rc;
+      if ((rc = dev_upload(h, &h->rvk_stem_scale_d, scale))) return rc;
+      if ((rc = dev_upload(h, &h->rvk_stem_shift_d, shift))) return rc;
+    } else {
+    if ((rc = dev_upload(h, &h->rvk_stem_w, ffh::to_bf16(ws)))) return rc;
     cuuint64_t dims[3] = {896, 224, (cuuint64_t)h->cap};
     cuuint64_t strides[2] = {896 * 2, (cuuint64_t)224 * 896 * 2};
     cuuint32_t box[3] = {96, 37, 1};
@@ -102,6 +117,7 @@ int finalize_rvk_features(ff_cvit* h) {
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, FF_ERR_CUDA, "cuTensorMapEncodeTiled(stem input) failed: %d", (int)r);
+    }
   }
   // ---- bottlenecks.  Buffers: X in {0,1} (block input / output, alternating), 2 = conv1 out, 3 = conv2 out, 4 = downsample
   h->rvk_ops.clear();
@@ -242,6 +258,33 @@ int rvk_features(ff_cvit* h, const void* x, int layout, int slot_base, int n, cu
     }
   }
   if (tap_hit(6, h->feat, (int64_t)n * PATCH)) return FF_OK;
+  return FF_OK;
+}
+
+// The same trunk on the fp32 CUDA-core path (FF_COMPUTE_FP32): one thread per output element, `rvk_f32_chunk` crops at
+// a time; featf = [n][49][512] fp32.
+int rvk_features_fp32(ff_cvit* h, const void* x, int layout, int n, float* featf, cudaStream_t st) {
+  const size_t crop_in_bytes = layout == FF_X_NHWC_U8 ? (size_t)224 * 224 * 3 : (size_t)224 * 224 * 3 * 4;
+  auto blocks = [](size_t total) { return (unsigned)std::min<size_t>((total + 255) / 256, 1u << 30); };
+  for (int c0 = 0; c0 < n; c0 += h->rvk_f32_chunk) {
+    const int ns = std::min(h->rvk_f32_chunk, n - c0);
+    const uint8_t* xin = reinterpret_cast<const uint8_t*>(x) + (size_t)c0 * crop_in_bytes;
+    nhwc4_f32_kernel<<<blocks((size_t)ns * 224 * 224), 256, 0, st>>>(xin, layout == FF_X_NHWC_U8 ? 2 : 1, reinterpret_cast<float4*>(h->rvk_x4f), ns);
+    FF_LAUNCH_CHECK(h, "nhwc4_f32");
+    conv_fp32_kernel<<<blocks((size_t)ns * 112 * 112 * 64), 256, 0, st>>>(h->rvk_x4f, h->rvk_stem_wf, h->rvk_stem_scale_d, h->rvk_stem_shift_d,
+                                                                         nullptr, h->rvk_f32[0], ns, 224, 112, 4, 64, 7, 2, 1);
+    FF_LAUNCH_CHECK(h, "stem_fp32");
+    maxpool3s2_f32_kernel<<<blocks((size_t)ns * 56 * 56 * 64), 256, 0, st>>>(h->rvk_f32[0], h->rvk_f32[1], ns, 112, 64);
+    FF_LAUNCH_CHECK(h, "maxpool_fp32");
+    for (const ff_cvit::RvkOp& op : h->rvk_ops) {
+      float* out = op.out_buf < 0 ? featf + (size_t)c0 * PATCH : h->rvk_f32[op.out_buf];
+      const int k = op.taps == 9 ? 3 : 1;
+      conv_fp32_kernel<<<blocks((size_t)ns * op.out_hw * op.out_hw * op.cout), 256, 0, st>>>(
+          h->rvk_f32[op.in_buf], op.wf, op.scale, op.shift, op.resid >= 0 ? h->rvk_f32[op.resid] : nullptr, out, ns, op.in_hw, op.out_hw,
+          op.cin, op.cout, k, op.stride, op.act);
+      FF_LAUNCH_CHECK(h, op.name.c_str());
+    }
+  }
   return FF_OK;
 }
 

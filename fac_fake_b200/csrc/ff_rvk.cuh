@@ -3,6 +3,7 @@
 // (7x7 stride 2, no im2col), the 3x3 stride-2 max-pool, rvk_conv2_kernel (every bottleneck convolution; also used by
 // the S3D and GGCA engines), the KAN head and the GGCA gate.
 #pragma once
+#include <type_traits>
 #include "ff_c1.cuh"
 #include "ff_small.cuh"
 
@@ -566,18 +567,26 @@ kan_l1_kernel(const float* __restrict__ part, const float* __restrict__ w1, cons
 // One block per crop, one thread per channel; the 7x7 map of the thread's channel lives in registers, the pooled
 // vectors and the hidden units go through shared memory.  In place on the NHWC feature map [n][7][7][512]: read in the
 // conv stack's 16-bit type (fp16 when in_f16 != 0), written as bf16 — the patch-embedding GEMM that follows is bf16.
-static __global__ void __launch_bounds__(512)
-ggca_gate_kernel(__nv_bfloat16* __restrict__ feat, const float* __restrict__ w1, const float* __restrict__ b1,
-                 const float* __restrict__ w2, const float* __restrict__ b2, int n, int in_f16) {
+// KIND 0: bf16 map;  1: fp16 in, bf16 out;  2: fp32 map (FF_COMPUTE_FP32 path).
+template <int KIND>
+__global__ void __launch_bounds__(512)
+ggca_gate_kernel(void* __restrict__ feat_v, const float* __restrict__ w1, const float* __restrict__ b1,
+                 const float* __restrict__ w2, const float* __restrict__ b2, int n) {
+  using T = typename std::conditional<KIND == 2, float, __nv_bfloat16>::type;
+  T* feat = reinterpret_cast<T*>(feat_v);
   __shared__ float s_pool[7][512];             // pooled vectors of one type: [pos][channel]
   __shared__ float s_hid[28][4][8];            // [type*7 + pos][group][hidden unit]; type 0 = h_avg, 1 = h_max, 2 = w_avg, 3 = w_max
   const int b = blockIdx.x;
   if (b >= n) return;
   const int c = threadIdx.x, grp = c >> 7, cg = c & 127;
-  __nv_bfloat16* f = feat + static_cast<size_t>(b) * 49 * 512 + c;
+  T* f = feat + static_cast<size_t>(b) * 49 * 512 + c;
   float x[49];
 #pragma unroll
-  for (int i = 0; i < 49; ++i) x[i] = in_f16 ? __half2float(reinterpret_cast<const __half*>(f)[i * 512]) : __bfloat162float(f[i * 512]);
+  for (int i = 0; i < 49; ++i) {
+    if constexpr (KIND == 2) x[i] = f[i * 512];
+    else if constexpr (KIND == 1) x[i] = __half2float(reinterpret_cast<const __half*>(f)[i * 512]);
+    else x[i] = __bfloat162float(f[i * 512]);
+  }
 #pragma unroll
   for (int type = 0; type < 4; ++type) {
 #pragma unroll
@@ -625,7 +634,9 @@ ggca_gate_kernel(__nv_bfloat16* __restrict__ feat, const float* __restrict__ w1,
 #pragma unroll
     for (int ww = 0; ww < 7; ++ww) {
       const float v = x[hh * 7 + ww];
-      f[(hh * 7 + ww) * 512] = __float2bfloat16(v * (v * att[hh] * att[7 + ww]));
+      const float g = v * (v * att[hh] * att[7 + ww]);
+      if constexpr (KIND == 2) f[(hh * 7 + ww) * 512] = g;
+      else f[(hh * 7 + ww) * 512] = __float2bfloat16(g);
     }
 }
 

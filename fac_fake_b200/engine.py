@@ -363,25 +363,26 @@ class ResVitKanEngine(CViTEngine):
 
     Same surface as ``CViTEngine`` (``.to()``, ``.load_state_dict()``, ``.eval()``, ``model(x)``,
     ``forward_slots``, ``predict_videos``...); the state_dict keys are the reference module's.
-    Only the bf16 tensor-core path exists for this variant.
+    ``compute_dtype='fp32'`` selects the CUDA-core path (logits within 1e-4 of the reference, slow).
     """
 
     _IGNORED_KEYS = ("mlp_head.*",)      # defined by the module, not on its forward path (ResVitKan.py:296-300)
 
     def __init__(self, image_size=224, patch_size=7, num_classes=2, channels=512, dim=1024, depth=6, heads=8,
-                 mlp_dim=2048, *, max_crops: int = 256):
+                 mlp_dim=2048, *, max_crops: int = 256, compute_dtype: str = "bf16"):
         super().__init__(image_size, patch_size, num_classes, channels, dim, depth, heads, mlp_dim,
-                         max_crops=max_crops, compute_dtype="bf16")
+                         max_crops=max_crops, compute_dtype=compute_dtype)
 
     def _create(self, h) -> int:
-        return self._lib.ff_resvitkan_create(C.byref(h), self._device.index, self._max_crops)
+        return self._lib.ff_resvitkan_create(C.byref(h), self._device.index, self._max_crops, self._compute)
 
 
 class CViTGGCAEngine(CViTEngine):
     """Drop-in for ``cvit_GGCA_ADD_DEConv_RepBn8.CViT`` at inference time
     (/root/reference/CViT-main/model/cvit_GGCA_ADD_DEConv_RepBn8.py:353-455): the CViT conv plan with DEConv blocks
     (folded to plain 3x3 kernels at load), one BN-less conv pair, the GGCA gate on the 7x7x512 map and
-    LinearNorm (= LayerNorm eps 1e-6 in eval) in the MLP branches.  Same surface as ``CViTEngine``; bf16 path only.
+    LinearNorm (= LayerNorm eps 1e-6 in eval) in the MLP branches.  Same surface as ``CViTEngine``;
+    ``compute_dtype='bf16'`` = tensor-core path (fp16 conv stack, logits within 2e-2), ``'fp32'`` = CUDA-core path (1e-4).
     """
 
     # RepBN / LinearNorm training-schedule state and the unused Deconv block (cvit_GGCA_ADD_DEConv_RepBn8.py:22-60,425)
@@ -390,9 +391,9 @@ class CViTGGCAEngine(CViTEngine):
                      "transformer.layers.*.1.fn.norm.r0", "*.num_batches_tracked")
 
     def __init__(self, image_size=224, patch_size=7, num_classes=2, channels=512, dim=1024, depth=6, heads=8,
-                 mlp_dim=2048, *, max_crops: int = 512):
+                 mlp_dim=2048, *, max_crops: int = 512, compute_dtype: str = "bf16"):
         super().__init__(image_size, patch_size, num_classes, channels, dim, depth, heads, mlp_dim,
-                         max_crops=max_crops, compute_dtype="bf16")
+                         max_crops=max_crops, compute_dtype=compute_dtype)
 
     def _create(self, h) -> int:
-        return self._lib.ff_cvit_ggca_create(C.byref(h), self._device.index, self._max_crops)
+        return self._lib.ff_cvit_ggca_create(C.byref(h), self._device.index, self._max_crops, self._compute)

@@ -63,20 +63,22 @@ int ff_cvit_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype
  * ResVitKan/ResVitKan.py:284-329 — ResNet-50 `features` (:185-240), the same patch embedding and
  * 6-layer ViT, and `kan_head` = Linear, Dropout, ReLU, KAN([2048,64,2]) (kan.py:90-206).  Weight keys are
  * that module's state_dict names (`features.layer{L}.{b}.conv{1,2,3}.weight`, `kan_head.3.layers.{0,1}.*`, …;
- * `mlp_head.*` and `num_batches_tracked` are accepted and ignored).  bf16 tensor-core path only.  Every
+ * `mlp_head.*` and `num_batches_tracked` are accepted and ignored).  compute_dtype as for ff_cvit_create
+ * (FF_COMPUTE_FP32 = CUDA-core path, logits within 1e-4, debug tap 25 only).  Every
  * other entry point below works unchanged on such a handle; ff_cvit_debug_activation steps are
  * 1 = stem + max-pool, 2..5 = layer1..layer4, 6 = channel conv + bn2, 18..25 as for CViT.            */
-int ff_resvitkan_create(ff_cvit_t** out, int device, int max_crops);
+int ff_resvitkan_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype);
 /* The `cvit_GGCA_ADD_DEConv_RepBn8` variant: replaces `CViT(...)` of
  * model/cvit_GGCA_ADD_DEConv_RepBn8.py:353-455.  Weight keys are that module's state_dict names
  * (`features1.N.*`, `features2.N.*`, DEConv branches `….conv1_{1..4}.conv.*` / `….conv1_5.*`,
  * `ggca.shared_conv.*`, `transformer.layers.L.1.fn.norm.norm1.*`; RepBN / schedule buffers and the unused
  * `Deconv.*` are accepted and ignored).  Every DEConv is folded into one 3x3 kernel at finalize (:337-351),
  * LinearNorm is its eval() form LayerNorm(eps 1e-6) (:22-47), the gate is x * GGCA(x) (:143-213,447-448).
- * Tensor-core path only; its conv stack runs on fp16 activations and filters (the difference filters need the extra
- * mantissa bits to hold the 2e-2 logit gate), the shared embedding / encoder / head on bf16.  Debug steps: 1..17 = the 17 pooled-plan conv layers (step 9 = features1.27), 26 = the extra
+ * FF_COMPUTE_BF16: the conv stack runs on fp16 activations and filters (the difference filters need the extra
+ * mantissa bits to hold the 2e-2 logit gate), the shared embedding / encoder / head on bf16.  FF_COMPUTE_FP32: CUDA-core
+ * path, logits within 1e-4, debug tap 25 only.  Debug steps: 1..17 = the 17 pooled-plan conv layers (step 9 = features1.27), 26 = the extra
  * BN-less Conv2d(128,128) features1.26 (between steps 8 and 9), 27 = gated feature map, 18..25 as for CViT. */
-int ff_cvit_ggca_create(ff_cvit_t** out, int device, int max_crops);
+int ff_cvit_ggca_create(ff_cvit_t** out, int device, int max_crops, int compute_dtype);
 void ff_cvit_destroy(ff_cvit_t* h);
 const char* ff_last_error(const ff_cvit_t* h); /* h may be NULL: last create() error */
 
@@ -193,6 +195,11 @@ int ff_blazeface_predict(ff_blazeface_t* h, const uint8_t* tiles, int n, float* 
  * reference's host loop on that tile).                                                                      */
 int ff_blazeface_nms(ff_blazeface_t* h, const float* detections, int n, float min_score, float iou_threshold, float* faces,
                      int32_t* counts, void* stream);
+/* `BlazeFace.nms(detections)` (blazeface.py:225-234): the same blending NMS over n caller-supplied detection lists.
+ * detections: DEVICE [offsets[n],17] (the lists back to back);  offsets: DEVICE int32 [n+1];  faces / counts as above
+ * (count -1: more than 64 detections in the list or more than 16 faces; run the host loop for that list).        */
+int ff_blazeface_nms_lists(ff_blazeface_t* h, const float* detections, const int32_t* offsets, int n, float iou_threshold,
+                           float* faces, int32_t* counts, void* stream);
 /* The tiling / untiling / cropping around the detector that the reference's FaceExtractor does on the host
  * (helpers/helpers_face_extract_1.py), on the device:
  *   tile_frames   `_tile_frames` (:139-205): frames = DEVICE uint8 [n_frames, H, W, 3]; every frame is cut into square

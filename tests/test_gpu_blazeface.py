@@ -86,6 +86,19 @@ def test_device_nms_matches_oracle_on_crowded_tiles(blaze):
         assert len(got[t]) == len(ref), t
         if ref:
             assert torch.allclose(got[t], torch.stack(ref), atol=2e-6), t
+    # `nms(list)` (blazeface.py:225-234) = the same kernel in list mode, on the masked detections in arbitrary order
+    lists = []
+    for t in range(n):
+        d = dense[t][dense[t][:, 16] >= B.MIN_SCORE]
+        lists.append(d[torch.randperm(d.shape[0], generator=gen)])
+    got = eng.nms(lists)
+    assert len(got) == n
+    for t in range(n):
+        ref = B.weighted_nms(lists[t])
+        assert got[t].shape == (len(ref), 17), t
+        if ref:
+            assert torch.allclose(got[t], torch.stack(ref), atol=2e-6), t
+    assert eng.nms([]) == [] and eng.nms([torch.zeros((0, 17))])[0].shape == (0, 17)
 
 
 def test_errors_are_loud(blaze):

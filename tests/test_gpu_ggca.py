@@ -138,6 +138,23 @@ def test_logits_match_reference_golden(golden_dir, variant, ggca_bn, ggca_defaul
         eng(torch.zeros((33, 3, 224, 224), device="cuda"))
 
 
+@pytest.mark.parametrize("variant", ["default", "bn"])
+def test_fp32_path_logits(golden_dir, variant):
+    """compute_dtype='fp32' (CUDA-core conv stack, gate, encoder): the north-star fp32 gate, 1e-4, against the reference
+    class's golden logits; uint8 and reference-style fp32 NCHW input."""
+    from fac_fake_b200 import CViTGGCAEngine
+    sd = W.make_ggca_state_dict(0, variant)
+    eng = CViTGGCAEngine(max_crops=32, compute_dtype="fp32").to("cuda:0").load_state_dict(sd)
+    g = np.load(os.path.join(golden_dir, f"ggca_{variant}.npz"))
+    n = min(int(g["n"]), 6)
+    crops = W.synthetic_crops(int(g["n"]), seed=int(g["seed_crops"]))[:n]
+    tol = 1e-4 * max(1.0, np.abs(g["logits"]).max())
+    got = eng.forward_slots(crops.cuda(), torch.arange(n)).cpu().numpy()
+    assert np.abs(got - g["logits"][:n]).max() <= tol
+    got2 = eng(O.normalize_crops(crops).cuda()).cpu().numpy()
+    assert np.abs(got2 - g["logits"][:n]).max() <= tol
+
+
 def test_tokens_and_transformer_match_oracle(ggca_bn):
     """LinearNorm (eps 1e-6) in the MLP branch, nn.LayerNorm (eps 1e-5) in the attention branch."""
     eng, sd = ggca_bn
