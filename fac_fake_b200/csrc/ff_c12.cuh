@@ -167,20 +167,25 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   };
 
   if (warp == 8) {
-    if (tid == 256) {
+    // The issuing warp runs in uniform control flow and elects one lane around the TMA / MMA instructions only: inside
+    // `if (tid == 256)` every UTCHMMA was preceded by 2-4 R2UR moves of its descriptors plus an ELECT loop.
+    {
       // conv1 of tile k on 16 rows x 10 pairs: strip 0 = pairs 0..7, strip 1 = pairs 2..9 (32 bytes further)
       auto issue_conv1 = [&](int t, int it) {
         mbar_wait(bar_sin, it & 1);          // all 256 workers: s_in(k) written — and, by their program order, epilogue 1
         tcgen05_fence_after();               // of tile k-1 finished (the conv1 accumulators are free again)
         const int tn = t + (L::RING - 1) * gridDim.x;      // every worker has consumed the raw window of tile k
-        if (tn < num_tiles) issue(tn, (it + L::RING - 1) % L::RING);
+        if (elect_one()) {
+          if (tn < num_tiles) issue(tn, (it + L::RING - 1) % L::RING);
 #pragma unroll
-        for (int strip = 0; strip < 2; ++strip)
+          for (int strip = 0; strip < 2; ++strip)
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh)     // descriptors = per-kernel constants + compile-time offsets (16-byte units)
-            umma_bf16_ss(tm_c1 + strip * 64, ad1 + static_cast<uint64_t>((kh * L::SIN_PITCH + strip * 32) >> 4),
-                         bd1 + static_cast<uint64_t>((kh * 2048) >> 4), idesc, kh > 0 ? 1u : 0u);
-        umma_commit(bar_mma1);
+            for (int kh = 0; kh < 3; ++kh)     // descriptors = per-kernel constants + compile-time offsets (16-byte units)
+              umma_bf16_ss(tm_c1 + strip * 64, ad1 + static_cast<uint64_t>((kh * L::SIN_PITCH + strip * 32) >> 4),
+                           bd1 + static_cast<uint64_t>((kh * 2048) >> 4), idesc, kh > 0 ? 1u : 0u);
+          umma_commit(bar_mma1);
+        }
+        __syncwarp();
       };
       // Order in the tensor pipe: conv1(0), [conv1(k+1), conv2(k)] ...  conv1(k+1) goes in FRONT of conv2(k) so that the
       // workers' epilogue 1 of tile k+1 runs while the pipe executes the 24 conv2 MMAs of tile k (before, conv1(k+1) was
@@ -190,7 +195,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       if (static_cast<int>(blockIdx.x) < num_tiles) issue_conv1(blockIdx.x, 0);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         // patch(k) is waited for first (it completes before sin(k+1) in every worker's program order): no barrier
-        // phase can then run ahead of this thread
+        // phase can then run ahead of this warp
         mbar_wait(bar_patch, it & 1);
         if (t + static_cast<int>(gridDim.x) < num_tiles) issue_conv1(t + gridDim.x, it + 1);
         // conv2 of tile k: as ws2conv_kernel<64> over patch[k & 1] into accumulator c2[k & 1]
@@ -198,14 +203,17 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         tcgen05_fence_after();
         const uint64_t adesc0 = ad2 + static_cast<uint64_t>(((it & 1) * L::PATCH_STRIDE) >> 4);
         const uint32_t d2 = tm_c2 + (it & 1) * 64;
+        if (elect_one()) {
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
+          for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            umma_bf16_ss(d2, adesc0 + static_cast<uint64_t>(((kh * 10 * 128 + 32 * c) >> 4)),
-                         bd2 + static_cast<uint64_t>(((kh * 2 + (c >> 2)) * 8192 + 32 * (c & 3)) >> 4), idesc, (kh > 0 || c > 0) ? 1u : 0u);
+            for (int c = 0; c < 8; ++c)
+              umma_bf16_ss(d2, adesc0 + static_cast<uint64_t>(((kh * 10 * 128 + 32 * c) >> 4)),
+                           bd2 + static_cast<uint64_t>(((kh * 2 + (c >> 2)) * 8192 + 32 * (c & 3)) >> 4), idesc, (kh > 0 || c > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_mma2 + 8 * (it & 1));
         }
-        umma_commit(bar_mma2 + 8 * (it & 1));
+        __syncwarp();
       }
     }
   } else {

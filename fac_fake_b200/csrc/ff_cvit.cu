@@ -128,6 +128,40 @@ int upload_linear(ff_cvit* h, LinearDev* L, const std::string& name, int out_f, 
   return FF_OK;
 }
 
+// LayerNorm folded into the linear that follows it (encoder kernel, ff_xf.cuh):
+//   LN(x) . W^T + b = rstd * (x . W'^T - mean * c1) + c2,   W' = W * gamma (per input column), c1 = W' . 1, c2 = W . beta + b.
+// c1 is summed over the bf16-rounded W' the tensor core multiplies, so the mean term cancels exactly.
+int upload_folded_linear(ff_cvit* h, LinearDev* L, float** c1, float** c2, const std::string& name, const std::string& norm,
+                         int out_f, int in_f, bool bias) {
+  const auto* w = get_w(h, name + ".weight", {out_f, in_f});
+  const auto* g = w ? get_w(h, norm + ".weight", {in_f}) : nullptr;
+  const auto* be = g ? get_w(h, norm + ".bias", {in_f}) : nullptr;
+  const auto* b = (be && bias) ? get_w(h, name + ".bias", {out_f}) : nullptr;
+  if (!w || !g || !be || (bias && !b)) return weight_rc(h);
+  std::vector<float> wg((size_t)out_f * in_f);
+  for (int n = 0; n < out_f; ++n)
+    for (int k = 0; k < in_f; ++k) wg[(size_t)n * in_f + k] = (*w)[(size_t)n * in_f + k] * (*g)[k];
+  const std::vector<bf16> wq = ffh::to_bf16(wg);
+  std::vector<float> v1(out_f), v2(out_f);
+  for (int n = 0; n < out_f; ++n) {
+    double s1 = 0.0, s2 = bias ? (double)(*b)[n] : 0.0;
+    for (int k = 0; k < in_f; ++k) {
+      s1 += (double)__bfloat162float(wq[(size_t)n * in_f + k]);
+      s2 += (double)(*be)[k] * (double)(*w)[(size_t)n * in_f + k];
+    }
+    v1[n] = (float)s1;
+    v2[n] = (float)s2;
+  }
+  L->out_f = out_f;
+  L->in_f = in_f;
+  L->bn = 64;
+  int rc;
+  if ((rc = dev_upload(h, &L->w, wq))) return rc;
+  if ((rc = tmap_2d(h, &L->tmB, L->w, in_f, out_f, 64, 64))) return rc;
+  if ((rc = dev_upload(h, c1, v1))) return rc;
+  return dev_upload(h, c2, v2);
+}
+
 int upload_vec(ff_cvit* h, float** p, const std::string& key, int64_t n) {
   const auto* v = get_w(h, key, {n});
   if (!v) return weight_rc(h);
@@ -354,6 +388,10 @@ int finalize(ff_cvit* h) {
     if ((rc = upload_linear(h, &X.out, p + ".0.fn.fn.to_out", DIM, DIM, true, 64))) return rc;
     if ((rc = upload_linear(h, &X.ff1, p + ".1.fn.fn.net.0", MLP, DIM, true, 64))) return rc;
     if ((rc = upload_linear(h, &X.ff2, p + ".1.fn.fn.net.2", DIM, MLP, true, 64))) return rc;
+    if (h->compute == FF_COMPUTE_BF16) {
+      if ((rc = upload_folded_linear(h, &X.qkv_f, &X.c1q, &X.c2q, p + ".0.fn.fn.to_qkv", p + ".0.fn.norm", 3 * DIM, DIM, false))) return rc;
+      if ((rc = upload_folded_linear(h, &X.ff1_f, &X.c1f, &X.c2f, p + ".1.fn.fn.net.0", ln2, MLP, DIM, true))) return rc;
+    }
   }
   if (h->kind == 1) {     // kan_head = Linear, Dropout, ReLU, KAN (ResVitKan.py:302-307); mlp_head is not on the forward path
     if ((rc = upload_linear(h, &h->head1, "kan_head.0", MLP, DIM, true, 64))) return rc;
@@ -396,16 +434,17 @@ int xf_setup(ff_cvit* h) {
   maps[1] = h->tm_att;
   maps[2] = h->tm_ffh;
   for (int l = 0; l < DEPTH; ++l) {
-    maps[3 + 4 * l + 0] = h->xf[l].qkv.tmB;
+    maps[3 + 4 * l + 0] = h->xf[l].qkv_f.tmB;     // LayerNorm-folded weights (upload_folded_linear)
     maps[3 + 4 * l + 1] = h->xf[l].out.tmB;
-    maps[3 + 4 * l + 2] = h->xf[l].ff1.tmB;
+    maps[3 + 4 * l + 2] = h->xf[l].ff1_f.tmB;
     maps[3 + 4 * l + 3] = h->xf[l].ff2.tmB;
   }
-  int rc = dev_alloc(h, &h->xf_maps, maps.size());
-  if (rc) return rc;
-  FF_CUDA(h, cudaMemcpy(h->xf_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  h->xf_maps = maps;
+  int rc;
   if ((rc = dev_alloc(h, &h->xf_sync, (size_t)2 * XF_MAX_GROUPS))) return rc;
   FF_CUDA(h, cudaMemset(h->xf_sync, 0, 2 * XF_MAX_GROUPS * sizeof(unsigned int)));   // the kernel re-arms them itself
+  if ((rc = dev_alloc(h, &h->xf_stats, (size_t)2 * h->rows_cap * 64))) return rc;
+  FF_CUDA(h, cudaMemset(h->xf_stats, 0, (size_t)2 * h->rows_cap * 64 * sizeof(float)));
   FF_CUDA(h, ffh::ensure_dyn_smem(reinterpret_cast<const void*>(xf_kernel), XF_SMEM_TOTAL));
   int per_sm = 0;
   FF_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, xf_kernel, XF_THREADS, XF_SMEM_TOTAL));
@@ -419,13 +458,16 @@ int launch_xf(ff_cvit* h, cudaStream_t st, int n, int depth) {
   XfArgs a;
   memset(&a, 0, sizeof(a));
   a.x = h->x; a.xn = h->xn; a.qkv = h->qkvb; a.att = h->att; a.ffh = h->ffh_buf;
-  a.maps = h->xf_maps;
+  static_assert(sizeof(XfArgs) <= 4096, "XfArgs must fit the kernel parameter space");
+  memcpy(a.maps, h->xf_maps.data(), sizeof(a.maps));
   a.sync = h->xf_sync;
+  a.stats = reinterpret_cast<float2*>(h->xf_stats);
+  a.stats_stride = (long long)h->rows_cap * 32;
   a.rows = 2 * n; a.n_crops = n; a.depth = depth;
   a.eps1 = 1e-5f; a.eps2 = h->ln2_eps;
   for (int l = 0; l < DEPTH; ++l) {
     const XfLayerDev& X = h->xf[l];
-    a.L[l] = XfLayerP{X.ln1_g, X.ln1_b, X.ln2_g, X.ln2_b, X.out.b, X.ff1.b, X.ff2.b};
+    a.L[l] = XfLayerP{X.c1q, X.c2q, X.c1f, X.c2f, X.out.b, X.ff2.b};
   }
   const int tiles = (a.rows + 127) / 128;
   cudaLaunchConfig_t cfg;
@@ -672,7 +714,9 @@ int forward_pass(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   // ---- patch embedding (split-K, deterministic slabs) + token assembly
   rc = launch_gemm(h, st, h->tm_feat, h->embed, n, h->emb, DIM, EPI_STORE_F32, ACT_NONE, EMBED_SPLITS, "patch_to_embedding");
   if (rc) return rc;
-  { ProfScope ps(h, st, KC_SMALL); ffh::launch_k(tokens_kernel, dim3(n), dim3(256), 0, st, true, (const float*)h->emb, (int)EMBED_SPLITS, (long long)h->cap * DIM, (const float*)h->embed.b, (const float*)h->cls, (const float*)h->pos, slot, slot_base, h->x, n); }
+  { ProfScope ps(h, st, KC_SMALL); ffh::launch_k(tokens_kernel, dim3(n), dim3(256), 0, st, true, (const float*)h->emb, (int)EMBED_SPLITS, (long long)h->cap * DIM, (const float*)h->embed.b, (const float*)h->cls, (const float*)h->pos, slot, slot_base, h->x, n,
+                                                   h->xf_ready ? h->xn : (bf16*)nullptr, reinterpret_cast<float2*>(h->xf_stats),
+                                                   reinterpret_cast<float2*>(h->xf_stats) + (size_t)h->rows_cap * 32); }
   FF_LAUNCH_CHECK(h, "tokens");
   const int rows = 2 * n;
   if (tap_hit(18, h->x, (int64_t)rows * DIM, false)) return FF_OK;
@@ -781,7 +825,7 @@ int forward_fp32(ff_cvit* h, const void* x, int layout, const int32_t* slot, int
   };
   int rc;
   if ((rc = lin(featf, h->embed, n, h->emb, 0, 0, "embed_fp32"))) return rc;
-  tokens_kernel<<<n, 256, 0, st>>>(h->emb, 1, 0, nullptr, h->cls, h->pos, slot, slot_base, h->x, n);
+  tokens_kernel<<<n, 256, 0, st>>>(h->emb, 1, 0, nullptr, h->cls, h->pos, slot, slot_base, h->x, n, nullptr, nullptr, nullptr);
   FF_LAUNCH_CHECK(h, "tokens");
   if (tap_hit(18, h->x, (int64_t)rows * DIM)) return FF_OK;
   for (int l = 0; l < DEPTH; ++l) {

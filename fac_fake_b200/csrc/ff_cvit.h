@@ -62,6 +62,10 @@ struct LinearDev {
 struct XfLayerDev {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   LinearDev qkv, out, ff1, ff2;
+  // encoder kernel (ff_xf.cuh): LayerNorm folded into the two linears that follow it.  W'[n][k] = W[n][k] * gamma[k] (bf16),
+  // c1[n] = sum_k bf16(W'[n][k]), c2[n] = sum_k beta[k] * W[n][k] (+ bias[n])
+  LinearDev qkv_f, ff1_f;
+  float *c1q = nullptr, *c2q = nullptr, *c1f = nullptr, *c2f = nullptr;
 };
 
 // profile slots: 0 = conv1, 1..16 = tcgen05 conv layer (index li), 17 = embed GEMM, 18 = transformer GEMMs,
@@ -121,8 +125,9 @@ struct ff_cvit {
   float* hid = nullptr;                           // [cap128][2048]
   CUtensorMap tm_feat, tm_xn, tm_att, tm_ffh, tm_cls;
   // whole-encoder cooperative kernel (ff_xf.cuh): device copy of the tensor maps it indexes, readiness
-  CUtensorMap* xf_maps = nullptr;
+  std::vector<CUtensorMap> xf_maps;  // host copy; passed by value in the kernel parameters
   unsigned int* xf_sync = nullptr;   // group-barrier counters
+  float* xf_stats = nullptr;         // [2][rows_cap][32] (sum, centred sum of squares) of 32-column segments of the residual stream
   int xf_groups = 0;                 // co-resident groups of 16 CTAs
   bool xf_ready = false;             // false: the per-op GPU launches run the encoder (cooperative launch unavailable)
   float* fA = nullptr;               // fp32-path workspace

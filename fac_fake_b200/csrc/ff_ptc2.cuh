@@ -127,7 +127,9 @@ ptc2_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    // Whole warp in uniform control flow, one elected lane around the MMAs: under `if (lane == 0)` the stage-dependent
+    // descriptors live in vector registers and every UTCHMMA is wrapped in an ELECT + 8x R2UR.BROADCAST loop.
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_16<F16>(256, BN);
       int s = 0, ph = 0, it = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
@@ -141,13 +143,17 @@ ptc2_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sa = base + s * L::STAGE_BYTES;
           const uint64_t adesc = make_kmajor_desc<128>(sa);
           const uint64_t bdesc = make_kmajor_desc<128>(sa + L::A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_2cta(bar_empty + 8 * s, 0x3);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2cta(bar_empty + 8 * s, 0x3);
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit_2cta(bar_tfull + 8 * acc, 0x3);
+        if (elect_one()) umma_commit_2cta(bar_tfull + 8 * acc, 0x3);
+        __syncwarp();
       }
     }
   } else {

@@ -91,12 +91,25 @@ attention2_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restri
                                                      pack_bf16x2(a10 * v0.z + a11 * v1.z, a10 * v0.w + a11 * v1.w));
 }
 
+// Sum over the 32 lanes of a warp in xor-butterfly order: every lane ends with the same bits.  The encoder's row mean is
+// defined as this sum of the row's 32 segment sums / 1024 wherever it is (re)computed (tokens_kernel, ff_xf.cuh).
+__device__ __forceinline__ float warp_sum_bfly(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // Token assembly (cvit.py:171-175): tok0 = cls + pos[slot], tok1 = (patch embedding + bias) + pos[slot].
 // The patch embedding arrives as n_splits split-K partial slabs that are summed here in a fixed order.
+// For the encoder kernel (xb != nullptr) it also writes what the first LayerNorm-folded GEMM reads: xb = bf16(x - mean(x))
+// and, per 32-column segment, (sum, centred sum of squares) into stats_a; stats_b receives the same sums (its row mean is
+// the shift xb was written with, ff_xf.cuh).
 static __global__ void __launch_bounds__(256)
 tokens_kernel(const float* __restrict__ emb, int n_splits, long long split_stride, const float* __restrict__ bias,
               const float* __restrict__ cls, const float* __restrict__ pos, const int* __restrict__ slot, int slot_base,
-              float* __restrict__ x, int n) {
+              float* __restrict__ x, int n, __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats_a,
+              float2* __restrict__ stats_b) {
+  __shared__ float s_seg[2][32];
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.x;
@@ -112,8 +125,39 @@ tokens_kernel(const float* __restrict__ emb, int n_splits, long long split_strid
   }
   const float4 bb = bias ? reinterpret_cast<const float4*>(bias)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   float4* x0 = reinterpret_cast<float4*>(x + static_cast<size_t>(2 * b) * 1024);
-  x0[i] = make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);
-  x0[256 + i] = make_float4((e.x + bb.x) + p.x, (e.y + bb.y) + p.y, (e.z + bb.z) + p.z, (e.w + bb.w) + p.w);
+  const float4 t0 = make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);
+  const float4 t1 = make_float4((e.x + bb.x) + p.x, (e.y + bb.y) + p.y, (e.z + bb.z) + p.z, (e.w + bb.w) + p.w);
+  x0[i] = t0;
+  x0[256 + i] = t1;
+  if (xb == nullptr) return;
+  const float4 tok[2] = {t0, t1};
+  const int seg = i >> 3;               // 8 threads x 4 columns = one 32-column segment
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float sum = (tok[r].x + tok[r].y) + (tok[r].z + tok[r].w);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    const float mu = sum * (1.0f / 32.0f);
+    const float d0 = tok[r].x - mu, d1 = tok[r].y - mu, d2 = tok[r].z - mu, d3 = tok[r].w - mu;
+    float m2 = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+    m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+    m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
+    if ((i & 7) == 0) {
+      const size_t o = static_cast<size_t>(2 * b + r) * 32 + seg;
+      stats_a[o] = make_float2(sum, m2);
+      stats_b[o] = make_float2(sum, 0.0f);
+      s_seg[r][seg] = sum;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const float mean = warp_sum_bfly(s_seg[r][i & 31]) * (1.0f / 1024.0f);
+    reinterpret_cast<uint2*>(xb + static_cast<size_t>(2 * b + r) * 1024)[i] =
+        make_uint2(pack_bf16x2(tok[r].x - mean, tok[r].y - mean), pack_bf16x2(tok[r].z - mean, tok[r].w - mean));
+  }
 }
 
 // cls select (cvit.py:177): bf16 copy of token 0 of every crop -> A operand of mlp_head.0.

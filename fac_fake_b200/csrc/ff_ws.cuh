@@ -248,7 +248,9 @@ ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // whole warp in uniform control flow, one elected lane around the MMAs (keeps the descriptors in uniform registers:
+    // under `if (lane == 0)` every UTCHMMA was preceded by R2UR moves and an ELECT loop)
+    {
       constexpr uint32_t idesc = make_idesc_16<F16>(128, BN);
       const uint64_t bdesc0 = make_kmajor_desc<128>(base + L::W_OFF);
       mbar_wait(bar_w, 0);
@@ -265,18 +267,21 @@ ws2conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // thread must not spend more scalar work per MMA than the tensor pipe needs to execute it (tools/umma_rate_test.cu:
         // 53-64 cycles per MMA with ready descriptors, 104 when they are rebuilt between the MMAs).
         const uint64_t adesc0 = make_kmajor_desc_sbo<128>(patch + 64, 10 * 128);
+        if (elect_one()) {
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
+          for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            // A: window starts 64 bytes (one pixel) into pair j of patch row (h_l + kh); 32 bytes per k-step
-            const uint64_t adesc = adesc0 + static_cast<uint64_t>((kh * 10 * 128 + 32 * c) >> 4);
-            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(((kh * 2 + (c >> 2)) * L::W_TILE + 32 * (c & 3)) >> 4);
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kh > 0 || c > 0) ? 1u : 0u);
+            for (int c = 0; c < 8; ++c) {
+              // A: window starts 64 bytes (one pixel) into pair j of patch row (h_l + kh); 32 bytes per k-step
+              const uint64_t adesc = adesc0 + static_cast<uint64_t>((kh * 10 * 128 + 32 * c) >> 4);
+              const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(((kh * 2 + (c >> 2)) * L::W_TILE + 32 * (c & 3)) >> 4);
+              umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kh > 0 || c > 0) ? 1u : 0u);
+            }
           }
+          umma_commit(bar_empty + 8 * s);
+          umma_commit(bar_tfull + 8 * acc);
         }
-        umma_commit(bar_empty + 8 * s);
-        umma_commit(bar_tfull + 8 * acc);
+        __syncwarp();
       }
     }
   } else {
@@ -414,7 +419,10 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    // The whole warp walks the tiles in uniform control flow and elects one lane around the MMAs only: under
+    // `if (lane == 0)` ptxas keeps the descriptors in vector registers and wraps every UTCHMMA in an ELECT + R2UR.BROADCAST
+    // loop (3 per instruction here; ~150 cycles per MMA in the encoder kernel, ff_xf.cuh).
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_16<F16>(256, BN);
       int it = 0;
       for (int pi = cluster_id; pi < num_pairs; pi += num_clusters, ++it) {
@@ -425,20 +433,23 @@ ws2x_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tcgen05_fence_after();
         const uint32_t patch = base + L::P_OFF + s * L::PATCH_STRIDE;
         const uint32_t d_tmem = tmem_base + acc * BN;
+        if (elect_one()) {
 #pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
+          for (int cb = 0; cb < 2; ++cb) {
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
+            for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint64_t adesc = make_kmajor_desc_sbo<128>(patch + cb * L::PATCH_ONE + kh * 10 * 128 + 64 + 32 * c, 10 * 128);
-              const uint64_t bdesc = make_kmajor_desc<128>(base + L::W_OFF + (cb * 6 + kh * 2 + (c >> 2)) * L::W_TILE) + 2 * (c & 3);
-              umma_bf16_ss_2cta(d_tmem, adesc, bdesc, idesc, (cb > 0 || kh > 0 || c > 0) ? 1u : 0u);
+              for (int c = 0; c < 8; ++c) {
+                const uint64_t adesc = make_kmajor_desc_sbo<128>(patch + cb * L::PATCH_ONE + kh * 10 * 128 + 64 + 32 * c, 10 * 128);
+                const uint64_t bdesc = make_kmajor_desc<128>(base + L::W_OFF + (cb * 6 + kh * 2 + (c >> 2)) * L::W_TILE) + 2 * (c & 3);
+                umma_bf16_ss_2cta(d_tmem, adesc, bdesc, idesc, (cb > 0 || kh > 0 || c > 0) ? 1u : 0u);
+              }
             }
           }
+          umma_commit_2cta(bar_empty + 8 * s, 0x3);
+          umma_commit_2cta(bar_tfull + 8 * acc, 0x3);
         }
-        umma_commit_2cta(bar_empty + 8 * s, 0x3);
-        umma_commit_2cta(bar_tfull + 8 * acc, 0x3);
+        __syncwarp();
       }
     }
   } else {

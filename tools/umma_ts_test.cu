@@ -134,8 +134,57 @@ void run2(int grid, long long* d) {
          cudaGetErrorString(e), (double)BM * BN * 16 / cyc / 2);
 }
 
+// Third experiment: does a tcgen05.commit after every CE MMAs (the per-stage "empty" arrival of a pipelined mainloop)
+// slow the tensor pipe down?  Commits go to mbarriers nobody waits on (count 1, phases just flip).
+template <int BN, int CE>
+__global__ void __launch_bounds__(128, 1) commit_kernel(int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sa = base, sb = base + 32 * 1024, bar = sb + 64 * 1024;
+  volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(bp + (bar - base) + 64);
+  for (int i = threadIdx.x; i < (int)((bar - base) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(bp)[i] = 0;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { for (int i = 0; i < 5; ++i) mbar_init(bar + 8 * i, 1); fence_mbar_init(); }
+  if (warp == 1) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(slot)));
+  fence_proxy_async_smem();
+  tcgen05_fence_before(); __syncthreads(); tcgen05_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+    const uint64_t adesc = make_kmajor_desc<128>(sa);
+    const uint64_t bdesc = make_kmajor_desc<128>(sb);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        umma_bf16_ss(tmem, adesc + 2 * (k % 4) + (k / 4) * 1024, bdesc + 2 * (k % 4) + ((k / 4) & 1) * (BN * 8), idesc, 1u);
+        if (CE > 0 && (k % CE) == CE - 1) umma_commit(bar + 8 * (1 + (k / CE) % 4));
+      }
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tcgen05_fence_before(); __syncthreads();
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc<512>(tmem); }
+}
+template <int BN, int CE>
+void run3(long long* d) {
+  const int smem = 32 * 1024 + 64 * 1024 + 128 + 2048;
+  cudaFuncSetAttribute(commit_kernel<BN, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int iters = 400;
+  commit_kernel<BN, CE><<<1, 128, smem>>>(iters, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long c = 0;
+  cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+  printf("SS M 128 N %3d, commit every %2d MMAs: %7.1f cycles/MMA (%s)\n", BN, CE, (double)c / (iters * 16), cudaGetErrorString(e));
+}
+
 int main() {
   long long* d; cudaMalloc(&d, 16);
+  run3<64, 0>(d); run3<64, 4>(d); run3<64, 1>(d); run3<128, 4>(d); run3<192, 4>(d); run3<256, 4>(d);
   for (int grid : {1, 148}) {
     run1<0, 128, 32>(grid, d); run1<0, 128, 64>(grid, d); run1<0, 128, 128>(grid, d); run1<0, 128, 256>(grid, d);
     run1<1, 128, 32>(grid, d); run1<1, 128, 64>(grid, d); run1<1, 128, 128>(grid, d); run1<1, 128, 256>(grid, d);
