@@ -340,9 +340,15 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
     const uint32_t idesc = g == XF_G_QKV ? make_idesc_bf16(128, 192) : (g == XF_G_FF1 ? make_idesc_bf16(128, 128) : make_idesc_bf16(128, 64));
     tcgen05_fence_after();
     int sM = 0;
+    // The state of the NEXT stage's barrier is polled (non-blocking test_wait) before this stage's MMAs are issued: a
+    // try_wait on a long-complete barrier still costs ~200 cycles in the issuing warp (measured), as much as the four
+    // N = 64 MMAs it gates, and the tensor pipe ran dry between k-blocks.
+    bool ready = mbar_test_wait(bar_full, pf & 1u);
     for (int kb = 0; kb < kbt; ++kb) {
-      mbar_wait(bar_full + 8 * sM, (pf >> sM) & 1u);
+      if (!ready) mbar_wait(bar_full + 8 * sM, (pf >> sM) & 1u);
       pf ^= 1u << sM;
+      const int sN = sM + 1 == ns ? 0 : sM + 1;
+      ready = kb + 1 < kbt && mbar_test_wait(bar_full + 8 * sN, (pf >> sN) & 1u);
       tcgen05_fence_after();
       if (lane == 0 && kb == 0) XF_TRACE(3, trace_mma++);
       if (lane == 0 && trace_mma == 6) XF_TRACE(6, kb);
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
         umma_commit(bar_empty + 8 * sM);
       }
       __syncwarp();
-      if (++sM == ns) sM = 0;
+      sM = sN;
     }
     if (elect_one()) umma_commit(bar_acc);
     __syncwarp();
