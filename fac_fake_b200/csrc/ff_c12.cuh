@@ -66,6 +66,13 @@ struct C12Smem {
 };
 
 constexpr int C12_THREADS = 288;      // 8 worker warps + 1 MMA-issuing warp
+// Developer aid (-DFF_C12_TRACE, never shipped): block 0 stamps clock64 at the pipeline hand-offs of tiles 6..9 and prints them.
+#ifdef FF_C12_TRACE
+__device__ long long c12_trace_buf[10][16];
+#define C12_TRACE(ev, it) do { if (blockIdx.x == 0 && (it) >= 6 && (it) < 10) c12_trace_buf[ev][(it)] = clock64(); } while (0)
+#else
+#define C12_TRACE(ev, it) do { } while (0)
+#endif
 template <bool F16 = false>
 __global__ void __launch_bounds__(C12_THREADS, 2)
 c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ C12Args a) {
@@ -76,6 +83,9 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   constexpr int PW = 22, PH = 18;                                     // conv1 input patch, pixels x rows
 
   extern __shared__ uint8_t smem_raw[];
+#ifdef FF_C12_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) c12_trace_buf[9][0] = clock64();
+#endif
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* s_in = base_ptr + L::SIN_OFF;
@@ -125,6 +135,9 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     pdl_trigger();
   }
   pdl_wait();
+#ifdef FF_C12_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) c12_trace_buf[9][1] = clock64();
+#endif
   const uint32_t sin_addr = base + L::SIN_OFF, b1_addr = base + L::B1_OFF, patch_addr = base + L::PATCH_OFF;
   constexpr uint32_t idesc = make_idesc_16<F16>(128, 64);
   // base descriptors, built once: the issuing thread only adds compile-time offsets between MMAs (a single thread that
@@ -174,6 +187,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       auto issue_conv1 = [&](int t, int it) {
         mbar_wait(bar_sin, it & 1);          // all 256 workers: s_in(k) written — and, by their program order, epilogue 1
         tcgen05_fence_after();               // of tile k-1 finished (the conv1 accumulators are free again)
+        if (tid == 256) C12_TRACE(0, it);
         const int tn = t + (L::RING - 1) * gridDim.x;      // every worker has consumed the raw window of tile k
         if (elect_one()) {
           if (tn < num_tiles) issue(tn, (it + L::RING - 1) % L::RING);
@@ -186,6 +200,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           umma_commit(bar_mma1);
         }
         __syncwarp();
+        if (tid == 256) C12_TRACE(1, it);
       };
       // Order in the tensor pipe: conv1(0), [conv1(k+1), conv2(k)] ...  conv1(k+1) goes in FRONT of conv2(k) so that the
       // workers' epilogue 1 of tile k+1 runs while the pipe executes the 24 conv2 MMAs of tile k (before, conv1(k+1) was
@@ -197,6 +212,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         // patch(k) is waited for first (it completes before sin(k+1) in every worker's program order): no barrier
         // phase can then run ahead of this warp
         mbar_wait(bar_patch, it & 1);
+        if (tid == 256) C12_TRACE(2, it);
         if (t + static_cast<int>(gridDim.x) < num_tiles) issue_conv1(t + gridDim.x, it + 1);
         // conv2 of tile k: as ws2conv_kernel<64> over patch[k & 1] into accumulator c2[k & 1]
         if (!w2_ready) { mbar_wait(bar_w2, 0); w2_ready = true; }
@@ -213,6 +229,8 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           }
           umma_commit(bar_mma2 + 8 * (it & 1));
         }
+        __syncwarp();
+        if (tid == 256) C12_TRACE(3, it);
         __syncwarp();
       }
     }
@@ -242,6 +260,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       tile_coords(t, &n, &h0, &w0);
       mbar_wait(bar_mma2 + 8 * (it & 1), (it >> 1) & 1);
       tcgen05_fence_after();
+      if (tid == 0) C12_TRACE(7, it);
       __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * HW + (h0 + hl)) * HW + (w0 + 2 * jl)) * 32 + half * 32;
       uint32_t v[32];
       tmem_ld_32x32(tm_c2 + (it & 1) * 64 + (static_cast<uint32_t>(lane_grp * 32) << 16) + half * 32, v);
@@ -271,6 +290,7 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       //         pixels w0-2+2j, +1; positions outside the image are conv2's zero padding.
       mbar_wait(bar_mma1, it & 1);
       tcgen05_fence_after();
+      if (tid == 0) C12_TRACE(4, it);
       {
         const int gy = h0 - 1 + hl;
 #pragma unroll
@@ -303,15 +323,32 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       tcgen05_fence_before();
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(bar_patch);
+      if (tid == 0) C12_TRACE(5, it);
       // ---- c. next tile: conversion (s_in was released by the conv1 MMAs of tile k, waited for in step a)
       const int tn = t + gridDim.x;
       if (tn < num_tiles) convert(tn, it + 1);
+      if (tid == 0) C12_TRACE(6, it);
       // ---- d. previous tile: output epilogue while the issuer feeds the conv2 MMAs of tile k
       if (it >= 1) epilogue2(t - gridDim.x, it - 1);
+      if (tid == 0) C12_TRACE(8, it);
     }
     if (it >= 1) epilogue2(blockIdx.x + (it - 1) * gridDim.x, it - 1);
   }
   __syncthreads();
+#ifdef FF_C12_TRACE
+  if (blockIdx.x == 0 && tid == 0 && num_tiles > 10 * static_cast<int>(gridDim.x)) {
+    printf("c12 block 0: %d tiles; start -> after pdl_wait %lld cycles; -> patch(6) ready %lld; whole kernel %lld cycles\n",
+           (num_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1, c12_trace_buf[9][1] - c12_trace_buf[9][0],
+           c12_trace_buf[2][6] - c12_trace_buf[9][0], clock64() - c12_trace_buf[9][0]);
+    const long long t0 = c12_trace_buf[2][6];
+    const char* nm[9] = {"issuer: s_in(k) ready", "issuer: conv1(k) issued", "issuer: patch(k) ready", "issuer: conv2(k) issued",
+                         "worker: conv1(k) done", "worker: epilogue1(k) done", "worker: convert(k+1) done", "worker: conv2(k) done (seen in it k+1)",
+                         "worker: epilogue2(k-1) done"};
+    printf("c12 trace, block 0, cycles since patch(6) was ready at the issuer:\n");
+    for (int e = 0; e < 9; ++e) printf("  %-40s k=6: %7lld  k=7: %7lld  k=8: %7lld  k=9: %7lld\n", nm[e], c12_trace_buf[e][6] - t0,
+                                       c12_trace_buf[e][7] - t0, c12_trace_buf[e][8] - t0, c12_trace_buf[e][9] - t0);
+  }
+#endif
   if (warp == 8) { tcgen05_fence_after(); tmem_dealloc<256>(tmem); }
 }
 
