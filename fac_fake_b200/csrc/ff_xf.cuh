@@ -24,8 +24,8 @@
 //     read while they are rewritten.  Plain stores, fixed summation order: deterministic.
 //     The launch is cooperative, so all CTAs are co-resident and the spin cannot deadlock.  (16-CTA thread-block
 //     clusters were tried first: only 7 such clusters are co-resident on a B200, the 8th tile ran as a second wave.)
-//   * the 200 KB TMA ring and the TMEM allocation live for the whole kernel.  Every GEMM re-cuts the ring into as many
-//     stages as its stage size allows: 5 x 40 KB (qkv), 6 x 32 KB (ff1), 8 x 24 KB (out, ff2).  Weights do not depend
+//   * the 200 KB TMA ring and the TMEM allocation live for the whole kernel.  Every GEMM re-cuts the ring: 5 stages of one
+//     k-block (40 KB, qkv), 3 stages of two k-blocks (64 KB, ff1), 4 stages of two k-blocks (48 KB, out, ff2).  Weights do not depend
 //     on the previous phase: once the MMAs of a GEMM are complete the producer re-cuts the ring, loads the first B
 //     tiles of the NEXT GEMM under the epilogue and the group barrier and L2-prefetches the rest of that GEMM's weight
 //     slice — after the barrier only L2 hits are on the critical path.
@@ -45,13 +45,13 @@
 namespace ff {
 
 constexpr int XF_CS = 16;        // CTAs per group = N-slices per 128-row token tile
-constexpr int XF_STAGES = 8;        // mbarrier pairs; a GEMM uses 5, 6 or 8 of them (stage = A tile + its 3, 2 or 1 weight boxes)
+constexpr int XF_STAGES = 8;        // mbarrier pairs; a GEMM uses 3 to 5 of them
 constexpr int XF_THREADS = 320;
 constexpr int XF_MAX_DEPTH = 6;
 constexpr int XF_MAX_GROUPS = 64;
 constexpr int XF_A_BYTES = 128 * 128;          // 128 token rows x 64 bf16
 constexpr int XF_BBOX_BYTES = 64 * 128;        // one weight box: 64 output features x 64 bf16
-constexpr int XF_RING_BYTES = 5 * (XF_A_BYTES + 3 * XF_BBOX_BYTES);   // 200 KB = 5 x 40 KB (qkv) >= 6 x 32 KB (ff1), 8 x 24 KB (out, ff2)
+constexpr int XF_RING_BYTES = 5 * (XF_A_BYTES + 3 * XF_BBOX_BYTES);   // 200 KB = 5 x 40 KB (qkv) >= 3 x 64 KB (ff1), 4 x 48 KB (out, ff2)
 constexpr int XF_BAR_OFF = XF_RING_BYTES;                // full[S], empty[S], acc
 constexpr int XF_SLOT_OFF = XF_BAR_OFF + (2 * XF_STAGES + 1) * 8;
 constexpr int XF_VEC_OFF = ((XF_SLOT_OFF + 16 + 15) / 16) * 16;      // c1 | c2 slice of the current folded GEMM (2 x 192 floats)
@@ -278,41 +278,54 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
 
   int trace_mma = 0, trace_mma2 = 0, trace_prod = 0;
   (void)trace_mma; (void)trace_mma2; (void)trace_prod;
-  auto gemm_stages = [](int g) { return g == XF_G_QKV ? 5 : (g == XF_G_FF1 ? 6 : 8); };
-  auto gemm_stage_bytes = [&](int g) { return XF_A_BYTES + gemm_nb(g) * XF_BBOX_BYTES; };
+  // A stage holds gemm_kps(g) k-blocks (each = A tile + its weight boxes, back to back) behind ONE full/empty barrier pair:
+  // the N = 64 / 128 GEMMs take two k-blocks per stage, i.e. eight MMAs per barrier wait and per tcgen05.commit
+  // (one k-block per stage left the tensor pipe dry between k-blocks: wait + commit cost as much as four N = 64 MMAs).
+  auto gemm_kps = [](int g) { return g == XF_G_QKV ? 1 : 2; };
+  auto gemm_units = [&](int g) { return gemm_kb(g) / gemm_kps(g); };
+  auto gemm_kblock_bytes = [&](int g) { return XF_A_BYTES + gemm_nb(g) * XF_BBOX_BYTES; };
+  auto gemm_stage_bytes = [&](int g) { return gemm_kps(g) * gemm_kblock_bytes(g); };
+  auto gemm_stages = [](int g) { return g == XF_G_QKV ? 5 : (g == XF_G_FF1 ? 3 : 4); };   // 5 x 40, 3 x 64, 4 x 48 KB
   // ---- producer state: B pointer runs ahead (acquires stages), A pointer follows.  Stage geometry belongs to the GEMM
   //      being loaded; bit s of pe = parity of the next acquisition of stage s (stages are used unevenly)
   int sB = 0, sA = 0, npre = 0, acc_phase_p = 0;
   uint32_t pe = 0;
-  auto issue_b = [&](int layer, int g, int kb) {     // acquire the next stage and load the weight boxes of k-block kb
+  auto issue_b = [&](int layer, int g, int u) {     // acquire the next stage and load the weight boxes of stage unit u
     mbar_wait(bar_empty + 8 * sB, ((pe >> sB) & 1u) ^ 1u);
     pe ^= 1u << sB;
-    if (lane == 0 && trace_prod == 5 && g == XF_G_OUT) XF_TRACE(7, kb);
-    const int nb = gemm_nb(g);
+    if (lane == 0 && trace_prod == 5 && g == XF_G_OUT) XF_TRACE(7, u);
+    const int nb = gemm_nb(g), kps = gemm_kps(g);
     const uint32_t bar = bar_full + 8 * sB;
     if (elect_one()) {
-      mbar_arrive_expect_tx(bar, XF_A_BYTES + nb * XF_BBOX_BYTES);
+      mbar_arrive_expect_tx(bar, gemm_stage_bytes(g));
       const CUtensorMap* tmB = a.maps + 3 + 4 * layer + g;
-      const uint32_t sb = base + sB * gemm_stage_bytes(g) + XF_A_BYTES;
-      for (int j = 0; j < nb; ++j) tma_load_2d(sb + j * XF_BBOX_BYTES, tmB, bar, kb * 64, (rank * nb + j) * 64);
+      for (int sub = 0; sub < kps; ++sub) {
+        const uint32_t sb = base + sB * gemm_stage_bytes(g) + sub * gemm_kblock_bytes(g) + XF_A_BYTES;
+        for (int j = 0; j < nb; ++j) tma_load_2d(sb + j * XF_BBOX_BYTES, tmB, bar, (u * kps + sub) * 64, (rank * nb + j) * 64);
+      }
     }
     __syncwarp();
     if (++sB == gemm_stages(g)) sB = 0;
   };
-  auto issue_a = [&](int g, int kb, int m0) {
-    if (elect_one()) tma_load_2d(base + sA * gemm_stage_bytes(g), a.maps + gemm_amap(g), bar_full + 8 * sA, kb * 64, m0);
+  auto issue_a = [&](int g, int u, int m0) {
+    if (elect_one()) {
+      const int kps = gemm_kps(g);
+      for (int sub = 0; sub < kps; ++sub)
+        tma_load_2d(base + sA * gemm_stage_bytes(g) + sub * gemm_kblock_bytes(g), a.maps + gemm_amap(g), bar_full + 8 * sA,
+                    (u * kps + sub) * 64, m0);
+    }
     __syncwarp();
     if (++sA == gemm_stages(g)) sA = 0;
   };
-  // weights of GEMM (layer, g) — the ring is empty: re-cut it, first k-blocks into the ring, the rest of this CTA's slice into L2
+  // weights of GEMM (layer, g) — the ring is empty: re-cut it, first stage units into the ring, the rest of this CTA's slice into L2
   auto preissue = [&](int layer, int g) {
-    const int kbt = gemm_kb(g), nb = gemm_nb(g);
+    const int ut = gemm_units(g), nb = gemm_nb(g), kps = gemm_kps(g);
     const CUtensorMap* tmB = a.maps + 3 + 4 * layer + g;
     sB = 0; sA = 0;
-    npre = min(gemm_stages(g), kbt);
-    for (int kb = 0; kb < npre; ++kb) issue_b(layer, g, kb);
+    npre = min(gemm_stages(g), ut);
+    for (int u = 0; u < npre; ++u) issue_b(layer, g, u);
     if (elect_one())
-      for (int kb = npre; kb < kbt; ++kb)
+      for (int kb = npre * kps; kb < ut * kps; ++kb)
         for (int j = 0; j < nb; ++j) xf_prefetch_l2_2d(tmB, kb * 64, (rank * nb + j) * 64);
     __syncwarp();
   };
@@ -320,10 +333,10 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
   // (the ring is empty again) run ahead into the next GEMM
   auto produce = [&](int layer, int g, int m0, bool more_tiles) {
     xf_fence_proxy_async();
-    const int kbt = gemm_kb(g);
-    for (int kb = 0; kb < kbt; ++kb) {
-      if (kb >= npre) issue_b(layer, g, kb);
-      issue_a(g, kb, m0);
+    const int ut = gemm_units(g);
+    for (int u = 0; u < ut; ++u) {
+      if (u >= npre) issue_b(layer, g, u);
+      issue_a(g, u, m0);
     }
     if (lane == 0) XF_TRACE(5, trace_prod++);
     mbar_wait(bar_acc, acc_phase_p);
@@ -336,29 +349,30 @@ __global__ void __launch_bounds__(XF_THREADS, 1) xf_kernel(const __grid_constant
   // ---- MMA state: bit s of pf = parity of the next completion of full[s]
   uint32_t pf = 0;
   auto mma = [&](int g) {
-    const int kbt = gemm_kb(g), ns = gemm_stages(g), sbytes = gemm_stage_bytes(g);
+    const int ut = gemm_units(g), ns = gemm_stages(g), sbytes = gemm_stage_bytes(g), kbytes = gemm_kblock_bytes(g), kps = gemm_kps(g);
     const uint32_t idesc = g == XF_G_QKV ? make_idesc_bf16(128, 192) : (g == XF_G_FF1 ? make_idesc_bf16(128, 128) : make_idesc_bf16(128, 64));
     tcgen05_fence_after();
     int sM = 0;
-    // The state of the NEXT stage's barrier is polled (non-blocking test_wait) before this stage's MMAs are issued: a
-    // try_wait on a long-complete barrier still costs ~200 cycles in the issuing warp (measured), as much as the four
-    // N = 64 MMAs it gates, and the tensor pipe ran dry between k-blocks.
+    // The state of the NEXT stage's barrier is polled (non-blocking test_wait) before this stage's MMAs are issued, so the
+    // latency of the poll overlaps the issue.
     bool ready = mbar_test_wait(bar_full, pf & 1u);
-    for (int kb = 0; kb < kbt; ++kb) {
+    for (int u = 0; u < ut; ++u) {
       if (!ready) mbar_wait(bar_full + 8 * sM, (pf >> sM) & 1u);
       pf ^= 1u << sM;
       const int sN = sM + 1 == ns ? 0 : sM + 1;
-      ready = kb + 1 < kbt && mbar_test_wait(bar_full + 8 * sN, (pf >> sN) & 1u);
+      ready = u + 1 < ut && mbar_test_wait(bar_full + 8 * sN, (pf >> sN) & 1u);
       tcgen05_fence_after();
-      if (lane == 0 && kb == 0) XF_TRACE(3, trace_mma++);
-      if (lane == 0 && trace_mma == 6) XF_TRACE(6, kb);
-      if (lane == 0 && kb == kbt - 1) XF_TRACE(4, trace_mma2++);
+      if (lane == 0 && u == 0) XF_TRACE(3, trace_mma++);
+      if (lane == 0 && trace_mma == 6) XF_TRACE(6, u);
+      if (lane == 0 && u == ut - 1) XF_TRACE(4, trace_mma2++);
       const uint32_t sa = base + sM * sbytes;
-      const uint64_t adesc = make_kmajor_desc<128>(sa);
-      const uint64_t bdesc = make_kmajor_desc<128>(sa + XF_A_BYTES);
       if (elect_one()) {
+        for (int sub = 0; sub < kps; ++sub) {
+          const uint64_t adesc = make_kmajor_desc<128>(sa + sub * kbytes);
+          const uint64_t bdesc = make_kmajor_desc<128>(sa + sub * kbytes + XF_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (u > 0 || sub > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(bar_empty + 8 * sM);
       }
       __syncwarp();
