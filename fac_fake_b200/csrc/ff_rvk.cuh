@@ -293,7 +293,9 @@ rvk_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // whole warp in uniform control flow, one elected lane around the MMAs (descriptors stay in uniform registers, no
+    // ELECT loop per UTCHMMA); the next stage's barrier is polled before this stage's MMAs are issued
+    {
       constexpr uint32_t idesc = make_idesc_16<F16>(128, BN);
       int s = 0, ph = 0, it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -301,22 +303,30 @@ rvk_conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (it >= 2) mbar_wait(bar_tempty + 8 * acc, ((it >> 1) - 1) & 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * MSUB * BN;
+        bool ready = mbar_test_wait(bar_full + 8 * s, ph);
         for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(bar_full + 8 * s, ph);
+          if (!ready) mbar_wait(bar_full + 8 * s, ph);
+          const int sn = s + 1 == STAGES ? 0 : s + 1;
+          const int phn = s + 1 == STAGES ? ph ^ 1 : ph;
+          ready = kb + 1 < kb_total && mbar_test_wait(bar_full + 8 * sn, phn);
           tcgen05_fence_after();
           const uint32_t sa = base + s * L::STAGE_BYTES;
           const uint64_t bdesc = make_kmajor_desc<128>(sa + L::A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < MSUB; ++j) {
-            const uint64_t adesc = make_kmajor_desc<128>(sa + j * 128 * 128);
+            for (int j = 0; j < MSUB; ++j) {
+              const uint64_t adesc = make_kmajor_desc<128>(sa + j * 128 * 128);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(d_tmem + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss(d_tmem + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(bar_empty + 8 * s);
           }
-          umma_commit(bar_empty + 8 * s);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          __syncwarp();
+          s = sn; ph = phn;
         }
-        umma_commit(bar_tfull + 8 * acc);
+        if (elect_one()) umma_commit(bar_tfull + 8 * acc);
+        __syncwarp();
       }
     }
   } else {

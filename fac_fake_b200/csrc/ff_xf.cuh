@@ -29,14 +29,14 @@
 //     on the previous phase: once the MMAs of a GEMM are complete the producer re-cuts the ring, loads the first B
 //     tiles of the NEXT GEMM under the epilogue and the group barrier and L2-prefetches the rest of that GEMM's weight
 //     slice — after the barrier only L2 hits are on the critical path.
-//   * what paces the mainloops (clock64 traces, tools/xf_trace.py, profiles/r02_xf_trace.txt): the 128-row A tiles —
-//     activations another SM wrote a moment ago — complete ~595 cycles apart although they are issued back to back,
-//     whatever the stage size, the ring depth, the number of CTAs, the k-block order across the 16 CTAs (rotating it
-//     changed nothing) and the number of TMA operations per tile; weight boxes arrive underneath.  Before this round's
-//     fix the same ~600 cycles per k-block came from the MMA issue itself (below).
+//   * what paces the mainloops (clock64 traces, tools/xf_trace.py, profiles/r02_xf_trace.txt): with one k-block per
+//     stage a k-block completed every ~550-600 cycles (4 MMAs need 192-384) whatever the stage size, the ring depth, the
+//     number of CTAs, the k-block order across the 16 CTAs, the source of the A tile (fresh activations or static
+//     memory) and the number of TMA operations per tile — a fixed cost per full/empty hand-off (barrier poll + commit in
+//     the issuing warp, ~300 cycles), first hidden behind a slow MMA issue (below).  Two k-blocks per stage: ~390.
 //
 //   warp 0    TMA producer (one elected lane)        warp 1   tcgen05.mma issuer (one elected lane), TMEM owner
-//   warps 2-9 epilogues (two warps per TMEM lane group, half of the columns each) + LayerNorm + 2-token attention
+//   warps 2-9 epilogues (two warps per TMEM lane group, half of the columns each) + row statistics + 2-token attention
 #pragma once
 #include "ff_ptx.cuh"
 #include "ff_small.cuh"
@@ -45,7 +45,7 @@
 namespace ff {
 
 constexpr int XF_CS = 16;        // CTAs per group = N-slices per 128-row token tile
-constexpr int XF_STAGES = 8;        // mbarrier pairs; a GEMM uses 3 to 5 of them
+constexpr int XF_STAGES = 8;     // mbarrier pairs; a GEMM uses 3 to 5 of them
 constexpr int XF_THREADS = 320;
 constexpr int XF_MAX_DEPTH = 6;
 constexpr int XF_MAX_GROUPS = 64;
