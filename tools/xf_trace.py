@@ -1,4 +1,4 @@
-"""Developer aid: run the encoder once with the -DFF_XF_TRACE build of the library (build/libfacfake_trace.so) and let
+"""Developer aid: run the encoder once with the trace build of the library (`make trace` -> build/libfacfake_trace.so) and let
 block 0 print the cycle stamps of one layer's barriers / accumulators.  python tools/xf_trace.py [n_crops]"""
 import os
 import sys
