@@ -336,6 +336,30 @@ def test_encoder_kernel_tiles_and_launch_count():
     assert per_call == 10 * 5 + 11 + 6, per_call
 
 
+def test_encoder_folded_layernorm_with_a_large_row_mean():
+    """The encoder kernel folds LayerNorm into to_qkv / net.0 and feeds the GEMMs bf16(x - previous row mean) (ff_xf.cuh).
+    A residual stream whose rows sit 6 sigma away from zero (pos_embedding + 6) must stay as close to the fp32 oracle as
+    a centred one: the shift, not the raw value, sets the bf16 rounding error."""
+    from fac_fake_b200 import CViTEngine
+    sd = {k: v.clone() for k, v in W.make_state_dict(0, "bn").items()}
+    sd["pos_embedding"] = sd["pos_embedding"] + 6.0
+    eng = CViTEngine(max_crops=32).to("cuda:0").load_state_dict(sd)
+    crops = W.synthetic_crops(4, seed=41)
+    slots = torch.tensor([0, 5, 17, 31])
+    with torch.no_grad():
+        t = O.embed_tokens(O.features(O.normalize_crops(crops), sd), sd, slots)
+        assert t.mean().abs().item() > 4.0
+        for depth in (1, 3, 6):
+            ref = O.transformer(t, sd, depth=depth)
+            got = eng.debug_activation(crops.cuda(), 18 + depth, slots).view(4, 2, 1024)
+            centred = ref - ref.mean(-1, keepdim=True)
+            # gate on the scale of the deviations from the row mean (what LayerNorm sees), not on the 6-sigma offset
+            assert (got - ref).abs().max().item() <= 2e-2 * max(1.0, centred.abs().max().item()), depth
+    logits = eng.forward_slots(crops.cuda(), slots).cpu()
+    ref_logits = O.forward_slots(O.normalize_crops(crops), sd, slots)
+    assert (logits - ref_logits).abs().max().item() <= BF16_TOL
+
+
 def test_cta_pair_conv_kernel_odd_tile_counts():
     """Feature layers 10..17 run on ptc2_conv_kernel (cta_group::2, 256 pixels x 256 channels per CTA pair).  33 crops
     give odd pixel-tile counts (the pair's second tile falls off the end): activations against the oracle."""
