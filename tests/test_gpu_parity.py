@@ -360,6 +360,22 @@ def test_encoder_folded_layernorm_with_a_large_row_mean():
     assert (logits - ref_logits).abs().max().item() <= BF16_TOL
 
 
+def test_repeated_mixed_size_calls_are_bitwise_reproducible():
+    """One handle, 48 calls of mixed batch sizes (1 ... 640 crops: partial tiles, more tiles than co-resident encoder
+    groups): every repetition of a size returns the same bits.  The encoder's group barriers, its alternating statistics
+    buffers and the self-re-arming counters carry state from launch to launch; a protocol race would show up here."""
+    eng, _ = _engine("bn", max_crops=640)
+    ref = {}
+    for it in range(48):
+        n = [1, 31, 32, 64, 65, 200, 512, 640][it % 8]
+        out = eng.forward_slots(W.synthetic_crops(n, seed=n).cuda()).cpu()
+        assert torch.isfinite(out).all()
+        if n in ref:
+            assert torch.equal(ref[n], out), (it, n)
+        else:
+            ref[n] = out
+
+
 def test_cta_pair_conv_kernel_odd_tile_counts():
     """Feature layers 10..17 run on ptc2_conv_kernel (cta_group::2, 256 pixels x 256 channels per CTA pair).  33 crops
     give odd pixel-tile counts (the pair's second tile falls off the end): activations against the oracle."""
