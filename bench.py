@@ -234,6 +234,30 @@ def s3d_flops_per_clip(T: int) -> int:
     return fl + 2 * 1024 * (t3 - 1)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPU cores NVML reports as local to its GPU, BEFORE the pinned host buffers of the e2e leg are
+    allocated (first touch puts them on that NUMA node): at 8 ranks the 8 x 77 MB per step of H2D otherwise all cross
+    from the node torchrun happened to start on.  Best effort: returns the number of cores, 0 when NVML / affinity
+    are unavailable."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        # NVML numbers the physical GPUs; CUDA_VISIBLE_DEVICES may renumber them for this process: go through the UUID
+        props = torch.cuda.get_device_properties(local_rank)
+        uuid = str(props.uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID((uuid if uuid.startswith("GPU-") else "GPU-" + uuid).encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cores = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return 0
+
+
 def run_s3d(args):
     """--model s3d: BASELINE configs[4] — 64-frame 224x224 clips, 32 clips per GPU per step."""
     keep_stdout_clean()
@@ -565,6 +589,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cores = bind_to_gpu_numa_node(local_rank) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(3, args.warmup)
@@ -813,7 +838,8 @@ def main():
                        "videos_per_s_30f": value / 30.0,
                        "parallelism": f"video-sharded x{world} (no data-path collective; one gather of the per-video scores after the last step, inside the timed region)",
                        "l2": "inputs rotate over 4 distinct batches (308 MB > 126 MB L2); >1.6 GB of activations per step sweep L2",
-                       "timing": "CUDA events on the launching stream, max over ranks"},
+                       "timing": "CUDA events on the launching stream, max over ranks",
+                       "host": f"rank bound to the {numa_cores} cores NVML reports local to its GPU" if numa_cores else "no CPU binding"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 224 * 224 * 3 + 4 * (n_videos + 1),
                     "d2h_bytes_per_step": 4 * n_videos, "steps": e2e_steps,
