@@ -255,26 +255,53 @@ c12_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(bar_sin);
     };
-    auto epilogue2 = [&](int t, int it) {      // thread = one pixel of pair (hl, jl) of the 14 x 16 tile: 32 channels = 64 bytes
+    // Output epilogue of tile `it`: done by the FOUR warps whose half equals the tile's parity (= its accumulator), each
+    // thread converting BOTH pixels of pair (hl, jl) = 128 contiguous bytes.  With one pixel per thread (the two halves
+    // of a pair in different warps) every store instruction scattered 32 quarter-lines: a timing experiment with one
+    // contiguous KB per instruction made the kernel 13 % faster.  Now the four 32-byte pieces are transposed across the
+    // four lanes that hold neighbouring pairs, and instruction q writes piece b of pair 4a+q from lane (a, b): four
+    // consecutive lanes fill one 128-byte line.  The other four warps do the next tile; every warp still finishes its
+    // share of tile k-2 before it arrives on patch_ready(k), which is what frees accumulator k & 1 for the issuer.
+    auto epilogue2 = [&](int t, int it) {
+      if (half != (it & 1)) return;
       int n, h0, w0;
       tile_coords(t, &n, &h0, &w0);
       mbar_wait(bar_mma2 + 8 * (it & 1), (it >> 1) & 1);
       tcgen05_fence_after();
-      if (tid == 0) C12_TRACE(7, it);
-      __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * HW + (h0 + hl)) * HW + (w0 + 2 * jl)) * 32 + half * 32;
-      uint32_t v[32];
-      tmem_ld_32x32(tm_c2 + (it & 1) * 64 + (static_cast<uint32_t>(lane_grp * 32) << 16) + half * 32, v);
-      tmem_ld_wait();
-      uint32_t pk[16];
+      if ((tid & 127) == 0) C12_TRACE(7, it);
+      uint32_t pk[2][16];
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        const float x0 = fmaf(__uint_as_float(v[c]), a.scale2[c], a.shift2[c]);
-        const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale2[c + 1], a.shift2[c + 1]);
-        pk[c >> 1] = pack16x2_relu<F16>(x0, x1);
+      for (int p = 0; p < 2; ++p) {
+        uint32_t v[32];
+        tmem_ld_32x32(tm_c2 + (it & 1) * 64 + (static_cast<uint32_t>(lane_grp * 32) << 16) + p * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float x0 = fmaf(__uint_as_float(v[c]), a.scale2[c], a.shift2[c]);
+          const float x1 = fmaf(__uint_as_float(v[c + 1]), a.scale2[c + 1], a.shift2[c + 1]);
+          pk[p][c >> 1] = pack16x2_relu<F16>(x0, x1);
+        }
       }
-      if (hl < TH) {
-        st_global_v8(o, pk);
-        st_global_v8(o + 16, pk + 8);
+      uint32_t (*pc)[8] = reinterpret_cast<uint32_t (*)[8]>(&pk[0][0]);     // pc[k] = 32-byte piece k of the pair's 128 bytes
+      const int b4 = tid & 3;
+#pragma unroll
+      for (int m = 2; m >= 1; m >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q & m) continue;
+          const bool up = (b4 & m) != 0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t send = up ? pc[q][e] : pc[q | m][e];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, m);
+            if (up) pc[q][e] = recv; else pc[q | m][e] = recv;
+          }
+        }
+      }
+      if (hl < TH) {      // pc[q] = piece b4 of pair (jl & ~3) + q of row hl
+        __nv_bfloat16* o = a.out + ((static_cast<size_t>(n) * HW + (h0 + hl)) * HW + (w0 + 2 * (jl & ~3))) * 32 + b4 * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) st_global_v8(o + q * 64, pc[q]);
       }
       tcgen05_fence_before();
     };

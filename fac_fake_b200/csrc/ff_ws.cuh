@@ -157,17 +157,40 @@ __device__ __forceinline__ void ws2_epilogue_c64_half(uint32_t taddr, const WsEp
       const float x1 = fmaf(__uint_as_float(v[c + 1]), ss.scale[C0 + c + 1], ss.shift[C0 + c + 1]);
       pk[p][c >> 1] = pack16x2_relu<F16>(x0, x1);
     }
-    if (!POOL && n < a.n_img) {
-      __nv_bfloat16* o;
-      if (a.out_blocked) {   // channel-blocked [n][2][H][W][32]: block HALF, pixel 2j+p
-        const size_t pix = (static_cast<size_t>((a.img_off_out + n) * 2 + HALF) * a.H + (h0 + hl)) * a.W + (2 * (pw0 + jl) + p);
-        o = out + pix * 32;
-      } else {
-        const size_t pair = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * Wp + (pw0 + jl);
-        o = out + pair * (2 * COUT) + p * COUT + C0;
-      }
+    if (!POOL && !a.out_blocked && n < a.n_img) {
+      const size_t pair = (static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * Wp + (pw0 + jl);
+      __nv_bfloat16* o = out + pair * (2 * COUT) + p * COUT + C0;
       st_global_v8(o, &pk[p][0]);
       st_global_v8(o + 16, &pk[p][8]);
+    }
+  }
+  if (!POOL && a.out_blocked) {
+    // Channel-blocked [n][2][H][W][32]: this thread owns 128 contiguous bytes (pixels 2j, 2j+1 of block HALF) = four
+    // 32-byte pieces.  Written directly, every store instruction scatters 32 quarter-lines (32 sectors per request:
+    // measured 13 % of conv4, 3 % of conv5).  A 4x4 transpose of the pieces across the four lanes that hold neighbouring
+    // pairs lets instruction q write piece b of pair 4a+q from lane (a, b): four consecutive lanes fill one 128-byte line.
+    uint32_t (*pc)[8] = reinterpret_cast<uint32_t (*)[8]>(&pk[0][0]);     // pc[k] = piece k = pk[k >> 1][8 * (k & 1) ..]
+    const int b = lane & 3;
+#pragma unroll
+    for (int m = 2; m >= 1; m >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q & m) continue;
+        const bool up = (b & m) != 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t send = up ? pc[q][e] : pc[q | m][e];
+          const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, m);
+          if (up) pc[q][e] = recv; else pc[q | m][e] = recv;
+        }
+      }
+    }
+    if (n < a.n_img) {
+      // pc[q] now holds piece b of pair (jl & ~3) + q of this row
+      const size_t row = (static_cast<size_t>((a.img_off_out + n) * 2 + HALF) * a.H + (h0 + hl)) * a.W;
+      __nv_bfloat16* o = out + (row + 2 * (pw0 + (jl & ~3))) * 32 + b * 16;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st_global_v8(o + q * 64, pc[q]);
     }
   }
   if (POOL) {
