@@ -63,11 +63,13 @@ struct TcSmem {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN, int STAGES>
+// KPS = k-blocks per stage (one full/empty barrier pair per stage): a wait + commit per FOUR MMAs left the tensor pipe dry
+// between k-blocks when one CTA owns the SM (ff_xf.cuh, profiles/r02_xf_trace.txt); with KPS = 2 it is eight.
+template <int BN, int STAGES, int KPS = 1>
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   constexpr int ROWB = 128;
-  using L = TcSmem<ROWB, BN, STAGES>;
+  using L = TcSmem<ROWB, BN, STAGES * KPS>;      // STAGES * KPS k-block slots; barrier pair s guards slots s*KPS .. s*KPS+KPS-1
   constexpr int BKE = ROWB / 2;        // bf16 elements per k-block row
   constexpr int KSTEPS = ROWB / 32;    // UMMA K=16 steps per k-block
   constexpr int TMEM_COLS = BN;
@@ -122,37 +124,51 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       pdl_wait();                  // A (activations) is produced by the previous kernel
       int it = 0, s = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; kb += KPS) {
         if (it > 0) mbar_wait(bar_empty + 8 * s, (it - 1) & 1);
-        const uint32_t sa = base + s * L::STAGE_BYTES;
-        const uint32_t sb = sa + L::A_BYTES;
+        const int nk = min(KPS, kb_end - kb);
         const uint32_t bar = bar_full + 8 * s;
-        mbar_arrive_expect_tx(bar, L::STAGE_BYTES);
-        tma_load_2d(sa, &tmA, bar, kb * BKE, m0);
-        tma_load_2d(sb, &tmB, bar, kb * BKE, col0);
+        mbar_arrive_expect_tx(bar, nk * L::STAGE_BYTES);
+        for (int sub = 0; sub < nk; ++sub) {
+          const uint32_t sa = base + (s * KPS + sub) * L::STAGE_BYTES;
+          tma_load_2d(sa, &tmA, bar, (kb + sub) * BKE, m0);
+          tma_load_2d(sa + L::A_BYTES, &tmB, bar, (kb + sub) * BKE, col0);
+        }
         if (++s == STAGES) { s = 0; ++it; }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // whole warp in uniform control flow, one elected lane around the MMAs; the next stage's barrier is polled early
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN);
       int it = 0, s = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(bar_full + 8 * s, it & 1);
+      bool ready = kb_begin < kb_end && mbar_test_wait(bar_full, 0);
+      for (int kb = kb_begin; kb < kb_end; kb += KPS) {
+        if (!ready) mbar_wait(bar_full + 8 * s, it & 1);
+        const int sn = s + 1 == STAGES ? 0 : s + 1;
+        const int itn = s + 1 == STAGES ? it + 1 : it;
+        ready = kb + KPS < kb_end && mbar_test_wait(bar_full + 8 * sn, itn & 1);
         tcgen05_fence_after();
-        const uint32_t sa = base + s * L::STAGE_BYTES;
-        const uint64_t adesc = make_kmajor_desc<ROWB>(sa);
-        const uint64_t bdesc = make_kmajor_desc<ROWB>(sa + L::A_BYTES);
+        const int nk = min(KPS, kb_end - kb);
+        if (elect_one()) {
+          for (int sub = 0; sub < nk; ++sub) {
+            const uint32_t sa = base + (s * KPS + sub) * L::STAGE_BYTES;
+            const uint64_t adesc = make_kmajor_desc<ROWB>(sa);
+            const uint64_t bdesc = make_kmajor_desc<ROWB>(sa + L::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < KSTEPS; ++k) {
-          // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the 16-byte address field
-          umma_bf16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            for (int k = 0; k < KSTEPS; ++k) {
+              // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the 16-byte address field
+              umma_bf16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || sub > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(bar_empty + 8 * s);   // frees this smem stage once the MMAs above have read it
         }
-        umma_commit(bar_empty + 8 * s);   // frees this smem stage once the MMAs above have read it
-        if (++s == STAGES) { s = 0; ++it; }
+        __syncwarp();
+        s = sn; it = itn;
       }
-      umma_commit(bar_tmem);              // accumulator complete
+      if (elect_one()) umma_commit(bar_tmem);              // accumulator complete
+      __syncwarp();
     }
   } else {
     // =========================== epilogue (warps 2..5) ===========================
@@ -440,7 +456,10 @@ ptc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int BN>
 inline cudaError_t launch_tc_gemm(dim3 grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
   // (a deeper TMA ring - 8 stages - was measured slower: 192 KB of smem leaves one CTA per SM instead of two)
-  return ffh::launch_smem(tc_gemm_kernel<BN, 4>, grid, dim3(192), TcSmem<128, BN, 4>::TOTAL, st, true, a, b, args);
+  // BN = 128: one CTA per SM anyway (4 x 32 KB) -> 3 stages of two k-blocks; BN = 64 keeps 4 x 24 KB and two CTAs per SM,
+  // whose hand-offs hide behind each other's MMAs
+  if (BN == 128) return ffh::launch_smem(tc_gemm_kernel<BN, 3, 2>, grid, dim3(192), TcSmem<128, BN, 6>::TOTAL, st, true, a, b, args);
+  return ffh::launch_smem(tc_gemm_kernel<BN, 4, 1>, grid, dim3(192), TcSmem<128, BN, 4>::TOTAL, st, true, a, b, args);
 }
 template <int BN, int MSUB, bool POOL, int STAGES, bool F16 = false>
 inline cudaError_t launch_ptc(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
