@@ -22,7 +22,7 @@ $(LIB): $(OBJ)
 # Developer build with the clock64 pipeline traces of the encoder and the fused layer-1/2 kernel compiled in
 # (tools/xf_trace.py loads it; profiles/r02_xf_trace.txt, profiles/r02_c12_trace.txt).  Never loaded by the package.
 trace: $(LIB)
-	$(NVCC) $(NVFLAGS) -DFF_XF_TRACE -DFF_C12_TRACE -c -o build/ff_cvit_trace.o $(CSRC)/ff_cvit.cu 2> build/ff_cvit_trace.ptxas.log
+	$(NVCC) $(NVFLAGS) -DFF_XF_TRACE -DFF_C12_TRACE -DFF_PTC_TRACE -c -o build/ff_cvit_trace.o $(CSRC)/ff_cvit.cu 2> build/ff_cvit_trace.ptxas.log
 	$(NVCC) $(ARCH) -shared -o build/libfacfake_trace.so build/ff_cvit_trace.o $(filter-out build/ff_cvit.o,$(OBJ))
 
 clean:

@@ -780,7 +780,7 @@ def main():
         lf = [2 * 9 * ci * co * hw * hw for ci, co, hw in plan]
         lt = list(prof_layers.values())
         fams = {"ff::c12_kernel (layers 1+2 fused)": ([1], lf[0] + lf[1]), "ff::ws2conv_kernel (layers 3, 4)": ([2, 3], lf[2] + lf[3]),
-                "ff::ws2x_conv_kernel (layers 5, 6)": ([4, 5], lf[4] + lf[5]), "ff::ptc_conv_kernel (layers 7-9)": ([6, 7, 8], sum(lf[6:9])),
+                "ff::ws2x_conv_kernel (layers 5, 6)": ([4, 5], lf[4] + lf[5]), "ff::ptcw_conv_kernel (layers 7-9)": ([6, 7, 8], sum(lf[6:9])),
                 "ff::ptc2_conv_kernel (layers 10-17)": (list(range(9, 17)), sum(lf[9:17]))}
         by_kernel = {}
         for name, (slots, fl) in fams.items():

@@ -18,6 +18,7 @@
 #include "ff_c12.cuh"
 #include "ff_xf.cuh"
 #include "ff_ptc2.cuh"
+#include "ff_ptcw.cuh"
 
 namespace ffe {
 
@@ -205,7 +206,7 @@ void conv_tile_geometry(int hw, int* bw, int* bh, int* bi) {
 // Kernel per feature layer li (0-based; li = 0 is conv1, fused into c12_kernel on the uint8 path):
 //   1..3   ws2conv_kernel   (Cin = 32: pixel-pair GEMM, N = 2*Cout)            ff_ws.cuh
 //   4, 5   ws2x_conv_kernel (Cin = 64: pixel-pair GEMM on a CTA pair, N = 128)  ff_ws.cuh
-//   6..8   ptc_conv_kernel  (Cout = 128: per-tap implicit GEMM, 2 x 128 pixels)  ff_tc.cuh
+//   6..8   ptcw_conv_kernel (Cout = 128: filter = M operand, 256 pixels = N operand)  ff_ptcw.cuh
 //   9..16  ptc2_conv_kernel (Cout >= 256: per-tap implicit GEMM on a CTA pair)   ff_ptc2.cuh
 int build_conv_maps(ff_cvit* h) {
   for (int pass = 0; pass < 2; ++pass)
@@ -227,11 +228,12 @@ int build_conv_maps(ff_cvit* h) {
       } else {
         L.bn = std::min(p.cout, 256);
         conv_tile_geometry(p.hw, &L.bw, &L.bh, &L.bi);
-        if ((rc = tmap_4d(h, &L.tmA, conv_input_buffer(h, li, set), p.cin, p.hw, p.hw, ncap, 64, L.bw, L.bh, L.bi))) return rc;
         L.pair2 = L.bn == 256;
+        if (L.pair2 && (rc = tmap_4d(h, &L.tmA, conv_input_buffer(h, li, set), p.cin, p.hw, p.hw, ncap, 64, L.bw, L.bh, L.bi))) return rc;
         if (L.pair2) rc = tmap_2d(h, &L.tmB_half, L.w, (uint64_t)9 * p.cin, p.cout, 64, 128);
         else rc = tmap_2d(h, &L.tmB, L.w, (uint64_t)9 * p.cin, p.cout, 64, L.bn);
         if (rc) return rc;
+        if (!L.pair2 && (rc = tmap_4d(h, &L.tmA_row, conv_input_buffer(h, li, set), p.cin, p.hw, p.hw, ncap, 64, L.bw + 2, L.bh, L.bi))) return rc;
       }
     }
   return FF_OK;
@@ -584,11 +586,11 @@ int run_conv(ff_cvit* h, int li, int n_img, int img_off_out, int set, cudaStream
       const int g2 = std::min(2 * items, h->num_sms & ~1);
       if (f16) e = p.pool ? launch_ptc2<true, true>(g2, st, L.tmA, L.tmB_half, a) : launch_ptc2<false, true>(g2, st, L.tmA, L.tmB_half, a);
       else e = p.pool ? launch_ptc2<true>(g2, st, L.tmA, L.tmB_half, a) : launch_ptc2<false>(g2, st, L.tmA, L.tmB_half, a);
-    } else {               // Cout = 128: two pixel sub-tiles share one 128-channel filter tile
+    } else {               // Cout = 128 at 56 x 56: the filter tile is the M operand, two pixel sub-tiles (256 pixels) the N operand
       const int tiles = ((m_tiles + 1) / 2) * (p.cout / 128);
       const int g = std::min(tiles, h->num_sms);
-      if (f16) e = p.pool ? launch_ptc<128, 2, true, 4, true>(g, st, L.tmA, L.tmB, a) : launch_ptc<128, 2, false, 4, true>(g, st, L.tmA, L.tmB, a);
-      else e = p.pool ? launch_ptc<128, 2, true, 4>(g, st, L.tmA, L.tmB, a) : launch_ptc<128, 2, false, 4>(g, st, L.tmA, L.tmB, a);
+      if (f16) e = p.pool ? launch_ptcw<true, true>(g, st, L.tmA_row, L.tmB, a) : launch_ptcw<false, true>(g, st, L.tmA_row, L.tmB, a);
+      else e = p.pool ? launch_ptcw<true>(g, st, L.tmA_row, L.tmB, a) : launch_ptcw<false>(g, st, L.tmA_row, L.tmB, a);
     }
   }
   if (e != cudaSuccess) return fail(h, FF_ERR_CUDA, "launch of conv layer %d failed: %s", li + 1, cudaGetErrorString(e));

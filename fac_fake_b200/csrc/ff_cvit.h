@@ -42,6 +42,7 @@ struct ConvLayerDev {
   int bn = 128;
   int bw = 16, bh = 8, bi = 1;
   bool pair2 = false;       // CTA-pair kernel (ff_ptc2.cuh): half filter tile per CTA
+  CUtensorMap tmA_row;      // Cout = 128 (ff_ptcw.cuh): boxes {64 ch, bw + 2, bh, bi} = the three taps of one filter row
   CUtensorMap tmB_half;     // box {64, 128}
   EpiParams epi;            // host copy of (scale, shift), cout <= 64
   bool ws2 = false;         // pixel-pair formulation (Cin = 32): N = 2*Cout

@@ -3,7 +3,7 @@
 // /root/reference/CViT-main/model/cvit.py:117-147) on a CTA PAIR, tcgen05.mma.cta_group::2, tile 256 pixels x 256
 // channels.
 //
-// Why: ptc_conv_kernel<256,1> fills 48 KB of shared memory per k-block per SM (16 KB of pixels + the whole 32 KB
+// Why: the single-CTA version of this kernel (128 pixels x 256 channels per CTA) filled 48 KB of shared memory per k-block per SM (16 KB of pixels + the whole 32 KB
 // filter tile); over layers 7..17 that is 51 GB of L2->SM traffic per 512-crop step on a power-capped
 // part.  With cta_group::2 each SM of the pair loads its own 128 pixel rows and only HALF of the filter tile
 // (128 of the 256 output channels; the MMA reads the peer's half through the pair datapath): 32 KB per k-block per

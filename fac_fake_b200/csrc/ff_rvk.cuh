@@ -164,7 +164,7 @@ rvk_stem_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
 
 // ---- persistent implicit-GEMM convolution for the ResNet bottlenecks (1x1 / 3x3, stride 1 / 2), the S3D convolutions
-// and the GGCA variant's BN-less conv.  Same skeleton as ptc_conv_kernel (ff_tc.cuh): one CTA per SM walks (2 pixel
+// and the GGCA variant's BN-less conv.  Same skeleton as ptc2_conv_kernel (ff_ptc2.cuh): one CTA per SM walks (2 pixel
 // tiles x BN channels) work items, warp 0 = TMA producer, warp 1 = tcgen05 issuer, double-buffered TMEM accumulators;
 //   * the tap loop and the TMA coordinates follow a.taps / a.stride (the strided maps carry elementStrides);
 //   * a stride-1 1x1 convolution is run "flat": W = all pixels of the batch, H = N = 1, boxes of 128 pixels;

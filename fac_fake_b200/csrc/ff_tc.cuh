@@ -1,4 +1,4 @@
-// ff_tc.cuh — the two generic tensor-core kernels of the engine:
+// ff_tc.cuh — the generic tensor-core GEMM kernel of the engine and the argument block the conv kernels share:
 //   * tc_gemm_kernel: y = x W^T (+bias, activation, residual) for the patch embedding, the per-op encoder linears
 //     (fallback when the one-launch encoder cannot be co-resident) and the MLP head (cvit.py:26-28,40-41,155,161-165):
 //     one 128 x BN tile per CTA, fp32 accumulator in TMEM, 64-element (SW128) k-blocks.
@@ -6,8 +6,8 @@
 //       warp 1   TMEM alloc + single-thread tcgen05.mma issue (cta_group::1, kind::f16, M=128, N=BN, K=16),
 //                tcgen05.commit releases smem stages / signals the epilogue
 //       warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns, bias / activation / residual, 32-byte global stores
-//   * ptc_conv_kernel: persistent implicit-GEMM 3x3 / pad 1 convolution over NHWC bf16 activations (reference op:
-//     nn.Conv2d + BatchNorm2d(eval) + ReLU [+ MaxPool2d(2)], /root/reference/CViT-main/model/cvit.py:110-119).
+//   * TcArgs: geometry / epilogue arguments of the persistent implicit-GEMM convolutions (ff_ptcw.cuh: layers 7-9,
+//     ff_ptc2.cuh: layers 10-17, ff_ws.cuh: layers 3-6, ff_rvk.cuh).
 #pragma once
 #include "ff_host.h"
 #include "ff_ptx.cuh"
@@ -236,222 +236,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-}  // namespace ff
-
-namespace ff {
-
-// =================================================================================================================
-// Persistent variant of the implicit-GEMM conv (feature layers 7..17): grid = #SMs, each CTA walks a static
-// round-robin list of (pixel tile, channel tile) pairs.  The smem ring keeps streaming across tile boundaries,
-// the fp32 accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs
-// of tile i+1, and the epilogue goes straight from registers to global memory: one thread = one output pixel =
-// one contiguous run of BN bf16; the 2x2 max-pool is two warp shuffles (w-neighbour lane^1, h-neighbour lane^BW).
-template <int BN, int MSUB, int STAGES>
-struct PtcSmem {
-  static constexpr int A_BYTES = MSUB * 128 * 128;                    // MSUB pixel sub-tiles share one B tile
-  static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SS_OFF = STAGES * STAGE_BYTES;                 // scale/shift floats [2][512]
-  static constexpr int BAR_OFF = SS_OFF + 2 * 512 * 4;                // full[S], empty[S], tfull[2], tempty[2]
-  static constexpr int SLOT_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
-  static constexpr int TOTAL = SLOT_OFF + 16 + 1024;
-};
-
-// MSUB = 2 (used for Cout = 128): one CTA tile is two 128-pixel sub-tiles against the same 128 output channels,
-// i.e. 48 KB of operands per 8 MMAs — the same bytes-per-MMA-cycle ratio as the 128 x 256 tile (with a single
-// 128 x 128 tile the smem ring could not be refilled at the rate the N=128 MMAs drain it).
-template <int BN, int MSUB, bool POOL, int STAGES, bool F16 = false>
-__global__ void __launch_bounds__(192, 1)
-ptc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-  using L = PtcSmem<BN, MSUB, STAGES>;
-  constexpr int BKE = 64;
-  constexpr int TMEM_COLS = 2 * MSUB * BN;
-  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns");
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  float* ss = reinterpret_cast<float*>(base_ptr + L::SS_OFF);
-  const uint32_t bar_full = base + L::BAR_OFF;
-  const uint32_t bar_empty = bar_full + STAGES * 8;
-  const uint32_t bar_tfull = bar_empty + STAGES * 8;
-  const uint32_t bar_tempty = bar_tfull + 16;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::SLOT_OFF);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int n_tiles = a.cout / BN;
-  const int lg_bi = 7 - a.lg_bw - a.lg_bh;
-  const int m_tiles = a.tiles_w * a.tiles_h * ((a.n_img + (1 << lg_bi) - 1) >> lg_bi);
-  const int num_tiles = ((m_tiles + MSUB - 1) / MSUB) * n_tiles;
-  const int kb_total = a.kb_total;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    mbar_init(bar_tfull, 1);
-    mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, 128);
-    mbar_init(bar_tempty + 8, 128);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  if (warp >= 2)
-    for (int i = threadIdx.x - 64; i < a.cout; i += 128) {
-      ss[2 * i] = a.scale[i];          // interleaved (scale, shift) pairs: the epilogue reads two channels per 16-byte load
-      ss[2 * i + 1] = a.shift[i];
-    }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // tile t -> channel tile and MSUB consecutive pixel tiles; a pixel tile past the end lands on an image index
-  // beyond the tensor (TMA zero-fills, the epilogue masks it by n < n_img)
-  auto tile_coords = [&](int t, int j, int* w0, int* h0, int* n0, int* col0) {
-    const int nt = t % n_tiles, mt = (t / n_tiles) * MSUB + j;
-    const int tw = mt % a.tiles_w;
-    const int th = (mt / a.tiles_w) % a.tiles_h;
-    const int nb = mt / (a.tiles_w * a.tiles_h);
-    *w0 = tw << a.lg_bw;
-    *h0 = th << a.lg_bh;
-    *n0 = nb << lg_bi;
-    *col0 = nt * BN;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      pdl_trigger();
-      pdl_wait();
-      int s = 0, ph = 0;     // ring position / phase carried across tiles
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int w0[MSUB], h0[MSUB], n0[MSUB], col0;
-#pragma unroll
-        for (int j = 0; j < MSUB; ++j) tile_coords(t, j, &w0[j], &h0[j], &n0[j], &col0);
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          const uint32_t sa = base + s * L::STAGE_BYTES;
-          const uint32_t bar = bar_full + 8 * s;
-          mbar_arrive_expect_tx(bar, L::STAGE_BYTES);
-          const int tap = kb / a.kb_per_tap;
-          const int cc = kb - tap * a.kb_per_tap;
-          const int kh = tap / 3, kw = tap - kh * 3;
-#pragma unroll
-          for (int j = 0; j < MSUB; ++j) tma_load_4d(sa + j * 128 * 128, &tmA, bar, cc * BKE, w0[j] + kw - 1, h0[j] + kh - 1, n0[j]);
-          tma_load_2d(sa + L::A_BYTES, &tmB, bar, kb * BKE, col0);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // whole warp in uniform control flow, one elected lane around the MMAs (descriptors stay in uniform registers, no
-    // ELECT loop per UTCHMMA); the next stage's barrier is polled before this stage's MMAs are issued
-    {
-      constexpr uint32_t idesc = make_idesc_16<F16>(128, BN);
-      int s = 0, ph = 0, it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        if (it >= 2) mbar_wait(bar_tempty + 8 * acc, ((it >> 1) - 1) & 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * MSUB * BN;
-        bool ready = mbar_test_wait(bar_full + 8 * s, ph);
-        for (int kb = 0; kb < kb_total; ++kb) {
-          if (!ready) mbar_wait(bar_full + 8 * s, ph);
-          const int sn = s + 1 == STAGES ? 0 : s + 1;
-          const int phn = s + 1 == STAGES ? ph ^ 1 : ph;
-          ready = kb + 1 < kb_total && mbar_test_wait(bar_full + 8 * sn, phn);
-          tcgen05_fence_after();
-          const uint32_t sa = base + s * L::STAGE_BYTES;
-          const uint64_t bdesc = make_kmajor_desc<128>(sa + L::A_BYTES);
-          if (elect_one()) {
-#pragma unroll
-            for (int j = 0; j < MSUB; ++j) {
-              const uint64_t adesc = make_kmajor_desc<128>(sa + j * 128 * 128);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_ss(d_tmem + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit(bar_empty + 8 * s);
-          }
-          __syncwarp();
-          s = sn; ph = phn;
-        }
-        if (elect_one()) umma_commit(bar_tfull + 8 * acc);
-        __syncwarp();
-      }
-    }
-  } else {
-    const int g = warp & 3;
-    const int r = g * 32 + lane;
-    const int BW = 1 << a.lg_bw, BH = 1 << a.lg_bh;
-    const int wl = r & (BW - 1);
-    const int hl = (r >> a.lg_bw) & (BH - 1);
-    const int nl = r >> (a.lg_bw + a.lg_bh);
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int acc = it & 1;
-      mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
-      tcgen05_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < MSUB; ++j) {
-        int w0, h0, n0, col0;
-        tile_coords(t, j, &w0, &h0, &n0, &col0);
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(g * 32) << 16) + (acc * MSUB + j) * BN;
-        const int n = n0 + nl;
-        const bool img_ok = n < a.n_img;
-        __nv_bfloat16* orow;
-        if (!POOL) orow = out + ((static_cast<size_t>(a.img_off_out + n) * a.H + (h0 + hl)) * a.W + (w0 + wl)) * a.cout + col0;
-        else orow = out + ((static_cast<size_t>(a.img_off_out + n) * (a.H >> 1) + ((h0 + hl) >> 1)) * (a.W >> 1) + ((w0 + wl) >> 1)) * a.cout + col0;
-        const bool writer = img_ok && (!POOL || (((wl | hl) & 1) == 0));
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c0, v);
-          tmem_ld_wait();
-          if (j == MSUB - 1 && c0 + 32 == BN) {   // accumulators fully read: hand the TMEM buffer back to the MMA warp
-            tcgen05_fence_before();
-            mbar_arrive(bar_tempty + 8 * acc);
-          }
-          uint32_t p[16];
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            // (scale, shift) of channels c, c+1 in ONE broadcast 16-byte load: with one 4-byte load per operand the
-            // epilogue's shared-memory wavefronts were 30 % of the smem pipe next to the MMA operand reads (ncu, conv7)
-            const float4 q = *reinterpret_cast<const float4*>(ss + 2 * (col0 + c0 + c));
-            const float x0 = fmaf(__uint_as_float(v[c]), q.x, q.y);
-            const float x1 = fmaf(__uint_as_float(v[c + 1]), q.z, q.w);
-            p[c >> 1] = pack16x2_relu<F16>(x0, x1);
-          }
-          if (POOL) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const uint32_t mu = max16x2<F16>(p[i], __shfl_xor_sync(0xffffffffu, p[i], 1));
-              p[i] = max16x2<F16>(mu, __shfl_xor_sync(0xffffffffu, mu, BW));
-            }
-          }
-          if (writer) {
-            st_global_v8(orow + c0, p);
-            st_global_v8(orow + c0 + 16, p + 8);
-          }
-        }
-      }
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
-  }
-}
-
-
 // ---- host launchers (opt the kernel in to its dynamic shared memory on the current device, PDL attribute set)
 template <int BN>
 inline cudaError_t launch_tc_gemm(dim3 grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
@@ -460,10 +244,6 @@ inline cudaError_t launch_tc_gemm(dim3 grid, cudaStream_t st, const CUtensorMap&
   // whose hand-offs hide behind each other's MMAs
   if (BN == 128) return ffh::launch_smem(tc_gemm_kernel<BN, 3, 2>, grid, dim3(192), TcSmem<128, BN, 6>::TOTAL, st, true, a, b, args);
   return ffh::launch_smem(tc_gemm_kernel<BN, 4, 1>, grid, dim3(192), TcSmem<128, BN, 4>::TOTAL, st, true, a, b, args);
-}
-template <int BN, int MSUB, bool POOL, int STAGES, bool F16 = false>
-inline cudaError_t launch_ptc(int grid, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const TcArgs& args) {
-  return ffh::launch_smem(ptc_conv_kernel<BN, MSUB, POOL, STAGES, F16>, dim3(grid), dim3(192), PtcSmem<BN, MSUB, STAGES>::TOTAL, st, true, a, b, args);
 }
 
 }  // namespace ff

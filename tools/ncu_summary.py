@@ -38,7 +38,7 @@ KEYS = [
     ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier / issue"),
     ("smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "stall membar / issue"),
 ]
-FAMILIES = ["c12_kernel", "ws2conv_kernel", "ws2x_conv_kernel", "ptc_conv_kernel", "ptc2_conv_kernel", "xf_kernel", "tc_gemm_kernel",
+FAMILIES = ["c12_kernel", "ws2conv_kernel", "ws2x_conv_kernel", "ptcw_conv_kernel", "ptc2_conv_kernel", "xf_kernel", "tc_gemm_kernel",
             "rvk_conv2_kernel"]
 
 
