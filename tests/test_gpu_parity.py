@@ -377,8 +377,10 @@ def test_repeated_mixed_size_calls_are_bitwise_reproducible():
 
 
 def test_cta_pair_conv_kernel_odd_tile_counts():
-    """Feature layers 10..17 run on ptc2_conv_kernel (cta_group::2, 256 pixels x 256 channels per CTA pair).  33 crops
-    give odd pixel-tile counts (the pair's second tile falls off the end): activations against the oracle."""
+    """Feature layers 7..9 run on ptcw_conv_kernel (128 channels x 256 pixels = two 8 x 8 x 2-image sub-tiles per CTA), layers
+    10..17 on ptc2_conv_kernel (cta_group::2, 256 pixels x 256 channels per CTA pair).  33 crops give an odd image count (the
+    second image of the last sub-tile does not exist) and odd pixel-tile counts (the second sub-tile / the pair's second tile
+    falls off the end): activations against the oracle."""
     eng, sd = _engine("bn", max_crops=64)
     crops = W.synthetic_crops(33, seed=74)
     acts = _oracle_layers(sd, O.normalize_crops(crops), 17)
