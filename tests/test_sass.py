@@ -2,6 +2,7 @@
 UTCHMMA (tcgen05.mma) and UTMALDG (TMA loads) in its SASS and no legacy HMMA (mma.sync).  Runs on CPU: cuobjdump only
 disassembles fac_fake_b200/libfacfake.so (profiles/r02_sass_table_final.txt is the same scan over the objects)."""
 import collections
+import os
 import re
 import shutil
 import subprocess
@@ -14,9 +15,12 @@ HOT = ["c12_kernel", "ws2conv_kernel", "ws2x_conv_kernel", "ptcw_conv_kernel", "
        "rvk_conv2_kernel", "rvk_stem_kernel"]
 
 
-@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+CUOBJDUMP = shutil.which("cuobjdump") or ("/usr/local/cuda/bin/cuobjdump" if os.path.exists("/usr/local/cuda/bin/cuobjdump") else None)
+
+
+@pytest.mark.skipif(CUOBJDUMP is None, reason="cuobjdump not found")
 def test_hot_kernels_are_tcgen05_and_tma():
-    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    sass = subprocess.run([CUOBJDUMP, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
     count = collections.defaultdict(lambda: collections.Counter())
     fn = None
     for line in sass.splitlines():
